@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — measures the VSOM hot path on B200 (contract: see DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload = BASELINE.json configs[1]: VSOM 64x64 grid, median-estimator transformation, synthetic 128-dim data,
+1M samples per step (one step = one pass of the online training hot path over one 1M-sample chunk at the
+epoch-0 schedule point eta=0.05, sigma=32).  `value` = training samples/s with the chunk already resident in HBM
+(CUDA events on the library's stream); `e2e` = the same through the host-buffer C-ABI call
+(vsom_train_chunk: H2D of the chunk + kernel + D2H of per-sample BMU / distance inside the timed region).
+A second object, `scoring`, reports batch BMU scoring rows/s on the config-4 shape (128x128 map, D=256).
+
+N > 1: the online step at this map size does not shard (per-sample dependency), so each
+rank trains an independent replica on its own stream of samples ("replicas only", weak scaling); scoring shards
+by rows with no communication.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+# ---- workload: BASELINE.json configs[1]
+W_, H_, D_ = 64, 64, 128
+ROWS_PER_STEP = 1_000_000
+ETA, SIGMA = 0.05, 32.0
+WORKLOAD = "VSOM 64x64 grid, median-estimator transformation, synthetic 128-dim data, 1M samples per step (BASELINE configs[1])"
+# ---- scoring side workload: BASELINE.json configs[3] shape, bounded rows
+SW_, SH_, SD_ = 128, 128, 256
+SCORE_ROWS = 1 << 20
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_chunk(n, d, seed):
+    """Config 2 data: x ~ N(mu_c, 1) from 64 cluster centres."""
+    rng = np.random.default_rng(seed)
+    centres = (rng.standard_normal((64, d)) * 3).astype(np.float32)
+    lab = rng.integers(0, 64, n)
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    x += centres[lab]
+    return x
+
+
+def init_map(n_nodes, dm, seed):
+    """Same distribution as Som::randomInitialize(seed, 1.0f) (src/Som.cpp:977-997): multiples of 1/1000 in [-1, 1)."""
+    rng = np.random.default_rng(seed)
+    return (rng.integers(-1000, 1000, (n_nodes, dm)).astype(np.float32) / np.float32(1000.0)).astype(np.float32)
+
+
+def window_nodes(w, h, sigma):
+    """Mean update-window size over BMU positions is data dependent; at sigma=32 on 64x64 the window is the whole map."""
+    r = 2.5 * sigma
+    if r >= max(w, h):
+        return w * h
+    side = int(np.ceil(r)) + int(np.floor(r))
+    return min(side, w) * min(side, h)
+
+
+def algorithmic_bytes_per_sample(n_nodes, dm, d_in, k):
+    """4*N*Dm (scan) + 20*K*Dm (window: read m,S; write m,S,sigma) + 4*D_in + 8*K."""
+    return 4 * n_nodes * dm + 20 * k * dm + 4 * d_in + 8 * k
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the same step, on the box's host cores.
+    Online training is single-threaded by construction (sample t+1 depends on sample t, src/Som.cpp:1161-1171),
+    so `cores` is 1.  Each step is a bounded sample of the 1M-sample chunk."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+
+    cls, kind = po.best_cpu_checker()
+    sample = 400
+    x = synth_chunk(sample * (args.steps + args.warmup), D_, 1234 + 2)
+    r = cls(W_, H_, D_, po.MEDIAN)
+    r.set_state(mean=init_map(W_ * H_, D_, 42))
+    for i in range(args.warmup):
+        r.train_rows(x[i * sample:(i + 1) * sample], ETA, SIGMA, po.EXPONENTIAL)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        r.train_rows(x[i * sample:(i + 1) * sample], ETA, SIGMA, po.EXPONENTIAL)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    sample_txt = f"{sample} samples per step of the 1M-sample chunk, 1 thread ({'reference TUs compiled unmodified, stand-in Eigen' if kind == 'reference' else 'C port'})"
+    print(json.dumps({
+        "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "eta": ETA, "sigma": SIGMA, "decay": "Exponential"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": 1, "kind": kind, "sample": sample_txt},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline_leg():
+    from oracle import pyoracle as po
+
+    cls, kind = po.best_cpu_checker()
+    sample = 1500
+    x = synth_chunk(sample + 100, D_, 1234 + 2)
+    r = cls(W_, H_, D_, po.MEDIAN)
+    r.set_state(mean=init_map(W_ * H_, D_, 42))
+    r.train_rows(x[:100], ETA, SIGMA, po.EXPONENTIAL)
+    t0 = time.perf_counter()
+    r.train_rows(x[100:], ETA, SIGMA, po.EXPONENTIAL)
+    dt = time.perf_counter() - t0
+    out = {"value": sample / dt, "unit": "samples/s", "cores": 1, "kind": kind,
+           "sample": f"first {sample} samples of the step's chunk after 100 warm-up samples, 1 thread (the path is sequential by construction)"}
+    # scoring side: Som::findBmu per row on the config-4 shape, 1 thread, bounded
+    rs = cls(SW_, SH_, SD_, po.STANDARD)
+    rs.set_state(mean=init_map(SW_ * SH_, SD_, 43))
+    q = synth_chunk(160, SD_, 1234 + 4)
+    t0 = time.perf_counter()
+    rs.find_bmu(q)
+    out["scoring"] = {"value": 160 / (time.perf_counter() - t0), "unit": "rows/s", "cores": 1, "sample": "160 rows, 128x128 map, D=256, 1 thread"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--order", default="reference", choices=["reference", "lanes"], help="reduction order of the online step's distances")
+    ap.add_argument("--rows", type=int, default=ROWS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    vsom = importlib.import_module("variational-self-organizing-maps_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.rows
+    order = vsom.ORDER_REFERENCE if args.order == "reference" else vsom.ORDER_LANES
+    ctx = vsom.VsomContext(W_, H_, D_, vsom.MEDIAN, order, device=local_rank)
+    ctx.upload_state(mean=init_map(W_ * H_, D_, 42 + rank))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    x_host = torch.from_numpy(synth_chunk(n, D_, 1234 + 2 + rank)).pin_memory()
+    x_dev = x_host.to(f"cuda:{local_rank}", non_blocking=False)
+    out_bmu = torch.empty(n, dtype=torch.int32, device=x_dev.device)
+    out_dist = torch.empty(n, dtype=torch.float32, device=x_dev.device)
+
+    # ---------------- value: chunk resident in HBM, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        ctx.train_chunk_device(x_dev, n, ETA, SIGMA, vsom.EXPONENTIAL, out_bmu, out_dist)
+    ctx.synchronize()
+    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            ctx.train_chunk_device(x_dev, n, ETA, SIGMA, vsom.EXPONENTIAL, out_bmu, out_dist)
+            ev[i + 1].record(stream)
+    ctx.synchronize()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=x_dev.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms / 1e3)
+
+    # ---------------- e2e: host buffers through the reference-facing C-ABI call, copies inside the timed region
+    x_np = x_host.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    ctx.train_chunk(x_np[: n // 8], ETA, SIGMA, vsom.EXPONENTIAL)  # warm the staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        bmu, d, r2, last = ctx.train_chunk(x_np, ETA, SIGMA, vsom.EXPONENTIAL)
+        mse = float(np.float32(r2.sum(dtype=np.float64) / n))  # the step's result (per-epoch MSE term), read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=x_dev.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+
+    # ---------------- scoring side (config-4 shape): exact batch BMU search, rows resident in HBM
+    sctx = vsom.VsomContext(SW_, SH_, SD_, vsom.STANDARD, device=local_rank)
+    sctx.upload_state(mean=init_map(SW_ * SH_, SD_, 43))
+    sstream = torch.cuda.ExternalStream(sctx.stream, device=local_rank)
+    q_dev = torch.from_numpy(synth_chunk(SCORE_ROWS, SD_, 1234 + 4 + rank)).to(x_dev.device)
+    s_bmu = torch.empty(SCORE_ROWS, dtype=torch.int32, device=x_dev.device)
+    s_dist = torch.empty(SCORE_ROWS, dtype=torch.float32, device=x_dev.device)
+    sctx.find_bmu_device(q_dev, SCORE_ROWS, s_bmu, s_dist)
+    sctx.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(sstream):
+        e0.record(sstream)
+        sctx.find_bmu_device(q_dev, SCORE_ROWS, s_bmu, s_dist)
+        e1.record(sstream)
+    sctx.synchronize()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=x_dev.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    score_ms = float(t.item())
+    score_rows_s = world * SCORE_ROWS / (score_ms / 1e3)
+
+    if rank == 0:
+        hbm_gbs, bf16_tf, peak_src = peaks()
+        k = window_nodes(W_, H_, SIGMA)
+        bps = algorithmic_bytes_per_sample(W_ * H_, D_, D_, k)
+        kern_s = statistics.mean(kernel_ms) / 1e3
+        achieved = bps * n / kern_s / 1e9
+        onchip_peak = 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else None
+        line = {
+            "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "eta": ETA, "sigma": SIGMA, "decay": "Exponential", "rows_per_step": n,
+                       "reduction_order": args.order, "parity": "bit-exact with the reference" if args.order == "reference" else "near-tie rule",
+                       "planes_resident_in_smem": ctx.planes_resident,
+                       "parallelism": "1 persistent kernel / chunk" if world == 1 else f"{world} independent replicas (online step does not shard at this map size)",
+                       "l2": "input chunk 512 MB > 126 MB L2; no flush needed"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": n * D_ * 4, "d2h_bytes_per_step": n * 12, "steps": e2e_steps,
+                    "result_read": "per-sample BMU, distance, residual^2 + MSE on host", "mse": mse},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": "online_step_kernel",
+                         "kernel_ms_per_launch": kern_s * 1e3,
+                         "note": "planes are shared-memory resident for this map, so the HBM figure is only the contract's denominator; "
+                                 "on-chip bound below", "onchip_peak_gbs": onchip_peak, "onchip_frac": (achieved / onchip_peak) if onchip_peak else None},
+            "scoring": {"metric": "bmu_scoring_rows_per_s", "value": score_rows_s, "unit": "rows/s", "rows": SCORE_ROWS * world, "ms": score_ms,
+                        "workload": "128x128 map, D=256 (BASELINE configs[3] shape), exact f32 scan in the reference's summation order",
+                        "flops_per_row": 2 * SW_ * SH_ * SD_, "tflops_equiv": score_rows_s * 2 * SW_ * SH_ * SD_ / 1e12,
+                        "tensor_peak_tflops": bf16_tf, "scaling": "row-sharded, no communication"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(line))
+    ctx.close()
+    sctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/* vsom_b200.h — C-ABI of libvsom_b200.so, the B200 (sm_100a) implementation of the VSOM training and
+ * scoring hot path.
+ *
+ * The reference (PereUbu7/Variational-Self-Organizing-Maps) has no FFI layer: its boundary is the C++
+ * class surface in include/SOM.hpp.  The host classes shipped in this repository's include/SOM.hpp keep
+ * that surface and forward the hot methods to the entry points below; each entry point names the
+ * reference method it replaces (file:line relative to the reference tree).  Only plain pointers and
+ * sizes cross this boundary — no Eigen, no torch, no C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 (VSOM_OK) or a negative vsom_status; vsom_last_error() gives the text.
+ *     Nothing throws, nothing calls exit().  There is NO CPU fallback: without a usable CUDA device
+ *     vsom_create() fails with VSOM_ERR_NO_DEVICE.
+ *   - one context is driven by one host thread at a time.
+ *   - "host" entry points take pageable or pinned host pointers, copy in/out on the context's stream and
+ *     are complete on return.  "_device" entry points take device pointers, only enqueue work on the
+ *     context's stream (vsom_stream) and return immediately; call vsom_synchronize() before reading.
+ *   - planes are row-major: node p = y*W + x (src/Som.cpp:119,191,895), N = W*H rows of Dm floats, where
+ *     Dm = vsom_model_length(d_in, transform) (Transformation::Length, src/Transformation.cpp:31-35,162-165).
+ */
+#ifndef VSOM_B200_H
+#define VSOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VSOM_API __attribute__((visibility("default")))
+#else
+#define VSOM_API
+#endif
+
+typedef struct vsom_ctx vsom_ctx;
+
+typedef enum vsom_status
+{
+    VSOM_OK = 0,
+    VSOM_ERR_INVALID = -1,     /* bad argument */
+    VSOM_ERR_CUDA = -2,        /* CUDA runtime error (text in vsom_last_error) */
+    VSOM_ERR_UNSUPPORTED = -3, /* a regime this build does not run on the device (never silently on the CPU) */
+    VSOM_ERR_TIMEOUT = -4,     /* a persistent kernel gave up waiting for a peer CTA / rank */
+    VSOM_ERR_NO_DEVICE = -5
+} vsom_status;
+
+/* The three shipped Transformation factories (src/Transformation.cpp:3-39, :41-77, :79-167). */
+typedef enum vsom_transform_kind
+{
+    VSOM_STANDARD = 0, /* Comparer m-v, Stepper v-m */
+    VSOM_MEDIAN = 1,   /* Comparer m-v, Stepper sign(v-m) */
+    VSOM_CLR = 2       /* combinatorial linear regression over the J(J-1)/2 pairs i<j */
+} vsom_transform_kind;
+
+/* Som::WeigthDecayFunction (include/SOM.hpp:70-75).  BatchMap is not an online mode. */
+typedef enum vsom_decay_kind
+{
+    VSOM_EXPONENTIAL = 0,
+    VSOM_INVERSE_PROPORTIONAL = 1
+} vsom_decay_kind;
+
+/* Order in which the squared residuals of one distance are summed (f32).
+ *   REFERENCE: k = 0,1,2,... sequentially — the order of `comparer.dot(comparer)` (src/Som.cpp:140) as the
+ *              reference compiles in this repository's oracle.  Distances, BMUs and the whole training
+ *              trajectory are then bit-identical to the reference.
+ *   LANES:     32 interleaved partial sums (k mod 32) each sequential, combined by a fixed xor-butterfly
+ *              (16,8,4,2,1).  Deterministic, faster for long vectors; BMUs can differ from the reference
+ *              only at near-ties (relative distance gap below 2*Dm*2^-24). */
+typedef enum vsom_reduction_order
+{
+    VSOM_ORDER_REFERENCE = 0,
+    VSOM_ORDER_LANES = 1
+} vsom_reduction_order;
+
+/* -------------------------------------------------------------------------------- context / state */
+
+/* Som::Som(width, height, depth, transformation) + Som::Construct (include/SOM.hpp:83-87, src/Som.cpp:11-48):
+ * all planes zero.  `device` is a CUDA ordinal. */
+VSOM_API int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order);
+VSOM_API void vsom_destroy(vsom_ctx *ctx);
+/* Text of the last error on ctx (or of the last failed vsom_create when ctx is NULL). */
+VSOM_API const char *vsom_last_error(const vsom_ctx *ctx);
+/* Transformation::Length (src/Transformation.cpp:31-35, :69-73, :162-165). */
+VSOM_API int vsom_model_length(int d_in, int transform);
+VSOM_API int vsom_depth(const vsom_ctx *ctx);      /* Som::getDepth  (src/Som.cpp:184-187) */
+VSOM_API int vsom_node_count(const vsom_ctx *ctx); /* width*height */
+/* cudaStream_t of the context, as void*: callers timing with CUDA events record on this stream. */
+VSOM_API void *vsom_stream(const vsom_ctx *ctx);
+VSOM_API int vsom_synchronize(vsom_ctx *ctx);
+/* Number of kernels this library has launched on ctx since creation (bench.py's gpu_launches). */
+VSOM_API uint64_t vsom_launch_count(const vsom_ctx *ctx);
+/* 1 when the online step keeps the three planes resident in shared memory for this map, else 0. */
+VSOM_API int vsom_planes_resident(const vsom_ctx *ctx);
+
+/* Replace / read the model state: Som::map, SMap, sigmaMap, weightMap, bmuHits (include/SOM.hpp:56-61).
+ * Any pointer may be NULL (skipped).  Initial planes come from the host (Som::randomInitialize,
+ * src/Som.cpp:977-997, runs on the host so that glibc's rand() sequence is the reference's). */
+VSOM_API int vsom_upload_state(vsom_ctx *ctx, const float *mean, const float *S, const float *sigma, const float *weight, const uint64_t *hits);
+VSOM_API int vsom_download_state(vsom_ctx *ctx, float *mean, float *S, float *sigma, float *weight, uint64_t *hits);
+
+/* -------------------------------------------------------------------------------- online training */
+
+/* n consecutive Som::trainSingle + Som::addBmu calls at fixed (eta, sigma): the inner loop of
+ * Som::trainBasicSom (src/Som.cpp:1161-1171; trainSingle :885-947, findBmu :291-309,
+ * euclidianWeightedDist :124-141, calculateNeighbourhoodWeight :949-975, addBmu :1189-1192), in row order.
+ *   x          n x d_in, row-major
+ *   last_bmu   in/out per row like DataSet::getLastBMU(j) (src/DataSet.cpp:60-69); may be NULL (= zeros).
+ *              Read only when sigma <= 1 (findLocalBmu regime, src/Som.cpp:335-454); always written.
+ *   out_bmu    linear BMU index per row; out_dist = (float)dist(bmu) on the updated map (:946);
+ *   out_resid2 = residual.squaredNorm() (the term of src/Som.cpp:1167).  Each may be NULL. */
+VSOM_API int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double sigma, int decay, uint64_t *last_bmu,
+                     uint32_t *out_bmu, float *out_dist, float *out_resid2);
+/* Same with x / outputs in device memory; enqueue only.  sigma must be > 1 (global-BMU regime). */
+VSOM_API int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n, double eta, double sigma, int decay,
+                            uint32_t *out_bmu_dev, float *out_dist_dev);
+
+/* -------------------------------------------------------------------------------- scoring */
+
+/* Per row: Som::findBmu (min_hits == 0, src/Som.cpp:291-309) or Som::findRestrictedBmu (src/Som.cpp:313-332),
+ * and out_dist = (float)euclidianWeightedDist(bmu, row) (src/Som.cpp:124-141).  Outputs may be NULL. */
+VSOM_API int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist);
+VSOM_API int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev);
+/* Som::evaluate for all-continuous columns (src/Som.cpp:490-523): f64 running mean of the BMU distance in row
+ * order.  (With binary columns the reference adds a cross-entropy term; that is host work on top of the
+ * BMU indices this call family returns.) */
+VSOM_API int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error);
+/* Distance of one row to every node: N x euclidianWeightedDist (src/Som.cpp:124-141), as the double it returns. */
+VSOM_API int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out);
+
+/* -------------------------------------------------------------------------------- U-matrix / index */
+
+/* Som::updateUMatrix + Som::getUMatrix (src/Som.cpp:999-1111, :159-162; euclidianWeightedDistRaw :143-157).
+ * out: N doubles, may be NULL (the matrix is kept on the device either way).  Needs width, height >= 2. */
+VSOM_API int vsom_update_umatrix(vsom_ctx *ctx, double *out);
+/* "SomIndex build": histogram of BMU ids (what Som::addBmu accumulates, src/Som.cpp:1189-1192) and the rows
+ * grouped by BMU in ascending row order (the per-neuron row set of src/Som.cpp:845-868).
+ * counts[N], offsets[N+1], row_ids[n]; each may be NULL. */
+VSOM_API int vsom_build_index(vsom_ctx *ctx, const uint32_t *bmu, size_t n, uint64_t *counts, uint64_t *offsets, uint32_t *row_ids);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSOM_B200_H */

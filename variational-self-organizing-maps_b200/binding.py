@@ -1,0 +1,214 @@
+"""ctypes binding of libvsom_b200.so (include/vsom_b200.h).  Product code: never imports oracle/."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from . import build as _build
+
+STANDARD, MEDIAN, CLR = 0, 1, 2
+EXPONENTIAL, INVERSE_PROPORTIONAL = 0, 1
+ORDER_REFERENCE, ORDER_LANES = 0, 1
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+
+_PROTOS = {
+    "vsom_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vsom_destroy": (None, [_vp]),
+    "vsom_last_error": (C.c_char_p, [_vp]),
+    "vsom_model_length": (C.c_int, [C.c_int, C.c_int]),
+    "vsom_depth": (C.c_int, [_vp]),
+    "vsom_node_count": (C.c_int, [_vp]),
+    "vsom_stream": (_vp, [_vp]),
+    "vsom_synchronize": (C.c_int, [_vp]),
+    "vsom_launch_count": (C.c_uint64, [_vp]),
+    "vsom_planes_resident": (C.c_int, [_vp]),
+    "vsom_upload_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
+    "vsom_download_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
+    "vsom_train_chunk": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_double, C.c_double, C.c_int, _u64p, _u32p, _f32p, _f32p]),
+    "vsom_train_chunk_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_double, C.c_double, C.c_int, _vp, _vp]),
+    "vsom_find_bmu": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
+    "vsom_find_bmu_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
+    "vsom_evaluate": (C.c_int, [_vp, _f32p, C.c_size_t, _f64p]),
+    "vsom_all_dists": (C.c_int, [_vp, _f32p, _f64p]),
+    "vsom_update_umatrix": (C.c_int, [_vp, _f64p]),
+    "vsom_build_index": (C.c_int, [_vp, _u32p, C.c_size_t, _u64p, _u64p, _u32p]),
+}
+
+_lib = None
+
+
+class VsomError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vsom_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def header_symbols():
+    """Every function include/vsom_b200.h declares."""
+    hdr = os.path.join(_build.REPO, "include", "vsom_b200.h")
+    return sorted(set(re.findall(r"VSOM_API[^;(]*?\b(vsom_\w+)\s*\(", open(hdr).read())))
+
+
+def lib():
+    """Load libvsom_b200.so (building it first when the sources are newer).  Fails loudly when it cannot."""
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    L = lib()
+    return [s for s in header_symbols() if hasattr(L, s)]
+
+
+def model_length(d_in: int, transform: int) -> int:
+    return int(lib().vsom_model_length(d_in, transform))
+
+
+def _p(a, t):
+    return C.cast(None, t) if a is None else a.ctypes.data_as(t)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class VsomContext:
+    """One map on one B200.  Method names follow the C-ABI; arrays are numpy (host entry points) or anything
+    with a ``data_ptr()`` (torch CUDA tensors; ``*_device`` entry points)."""
+
+    def __init__(self, width, height, d_in, transform=STANDARD, order=ORDER_REFERENCE, device=0):
+        L = lib()
+        h = _vp()
+        rc = L.vsom_create(C.byref(h), device, width, height, d_in, transform, order)
+        if rc != 0:
+            raise VsomError(rc, (L.vsom_last_error(None) or b"").decode())
+        self._h = h
+        self.W, self.H, self.N, self.Din = width, height, width * height, d_in
+        self.transform, self.order, self.device = transform, order, device
+        self.Dm = L.vsom_depth(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().vsom_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VsomError(rc, (lib().vsom_last_error(self._h) or b"").decode())
+
+    # ---- state
+    def upload_state(self, mean=None, S=None, sigma=None, weight=None, hits=None):
+        mean = None if mean is None else _f32(mean)
+        S = None if S is None else _f32(S)
+        sigma = None if sigma is None else _f32(sigma)
+        weight = None if weight is None else _f32(weight)
+        hits = None if hits is None else np.ascontiguousarray(hits, dtype=np.uint64)
+        for a in (mean, S, sigma):
+            if a is not None and a.size != self.N * self.Dm:
+                raise ValueError("plane must be N x Dm")
+        self._check(lib().vsom_upload_state(self._h, _p(mean, _f32p), _p(S, _f32p), _p(sigma, _f32p), _p(weight, _f32p), _p(hits, _u64p)))
+
+    def download_state(self):
+        mean = np.empty((self.N, self.Dm), np.float32)
+        S = np.empty_like(mean)
+        sigma = np.empty_like(mean)
+        weight = np.empty(self.N, np.float32)
+        hits = np.empty(self.N, np.uint64)
+        self._check(lib().vsom_download_state(self._h, _p(mean, _f32p), _p(S, _f32p), _p(sigma, _f32p), _p(weight, _f32p), _p(hits, _u64p)))
+        return dict(mean=mean, S=S, sigma=sigma, weight=weight, hits=hits)
+
+    # ---- online training
+    def train_chunk(self, x, eta, sigma, decay=EXPONENTIAL, last_bmu=None):
+        x = _f32(x).reshape(-1, self.Din)
+        n = x.shape[0]
+        bmu = np.empty(n, np.uint32)
+        dist = np.empty(n, np.float32)
+        resid2 = np.empty(n, np.float32)
+        last = np.zeros(n, np.uint64) if last_bmu is None else np.ascontiguousarray(last_bmu, dtype=np.uint64)
+        self._check(lib().vsom_train_chunk(self._h, _p(x, _f32p), n, eta, sigma, decay, _p(last, _u64p), _p(bmu, _u32p), _p(dist, _f32p),
+                                           _p(resid2, _f32p)))
+        return bmu, dist, resid2, last
+
+    def train_chunk_device(self, x_dev, n, eta, sigma, decay=EXPONENTIAL, out_bmu_dev=None, out_dist_dev=None):
+        self._check(lib().vsom_train_chunk_device(self._h, x_dev.data_ptr(), n, eta, sigma, decay,
+                                                  out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
+                                                  out_dist_dev.data_ptr() if out_dist_dev is not None else None))
+
+    # ---- scoring
+    def find_bmu(self, x, min_hits=0):
+        x = _f32(x).reshape(-1, self.Din)
+        n = x.shape[0]
+        bmu = np.empty(n, np.uint32)
+        dist = np.empty(n, np.float32)
+        self._check(lib().vsom_find_bmu(self._h, _p(x, _f32p), n, min_hits, _p(bmu, _u32p), _p(dist, _f32p)))
+        return bmu, dist
+
+    def find_bmu_device(self, x_dev, n, out_bmu_dev=None, out_dist_dev=None, min_hits=0):
+        self._check(lib().vsom_find_bmu_device(self._h, x_dev.data_ptr(), n, min_hits,
+                                               out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
+                                               out_dist_dev.data_ptr() if out_dist_dev is not None else None))
+
+    def evaluate(self, x):
+        x = _f32(x).reshape(-1, self.Din)
+        out = C.c_double(0)
+        self._check(lib().vsom_evaluate(self._h, _p(x, _f32p), x.shape[0], C.byref(out)))
+        return out.value
+
+    def all_dists(self, v):
+        v = _f32(v).reshape(self.Din)
+        out = np.empty(self.N, np.float64)
+        self._check(lib().vsom_all_dists(self._h, _p(v, _f32p), _p(out, _f64p)))
+        return out
+
+    # ---- U-matrix / index
+    def update_umatrix(self):
+        out = np.empty(self.N, np.float64)
+        self._check(lib().vsom_update_umatrix(self._h, _p(out, _f64p)))
+        return out
+
+    def build_index(self, bmu):
+        bmu = np.ascontiguousarray(bmu, dtype=np.uint32)
+        n = bmu.shape[0]
+        counts = np.empty(self.N, np.uint64)
+        offsets = np.empty(self.N + 1, np.uint64)
+        rows = np.empty(n, np.uint32)
+        self._check(lib().vsom_build_index(self._h, _p(bmu, _u32p), n, _p(counts, _u64p), _p(offsets, _u64p), _p(rows, _u32p)))
+        return counts, offsets, rows
+
+    # ---- plumbing
+    def synchronize(self):
+        self._check(lib().vsom_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().vsom_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().vsom_launch_count(self._h))
+
+    @property
+    def planes_resident(self) -> bool:
+        return bool(lib().vsom_planes_resident(self._h))

@@ -1,0 +1,429 @@
+// capi.cu — the extern "C" surface of libvsom_b200.so (include/vsom_b200.h): context, state transfer and the
+// host-buffer entry points that stage data through the context's stream around the kernel launchers.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace vsom
+{
+
+static std::string g_createError;
+
+int set_error(vsom_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_createError = msg;
+    return code;
+}
+
+int cuda_fail(vsom_ctx *ctx, cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    std::snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+    return set_error(ctx, VSOM_ERR_CUDA, buf);
+}
+
+int stage_reserve(vsom_ctx *ctx, int slot, size_t bytes)
+{
+    if (bytes <= ctx->stageCap[slot])
+        return VSOM_OK;
+    if (ctx->stage[slot])
+    {
+        VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        VSOM_CUDA(ctx, cudaFree(ctx->stage[slot]));
+        ctx->stage[slot] = nullptr;
+        ctx->stageCap[slot] = 0;
+    }
+    const size_t cap = bytes + bytes / 4 + 256;
+    VSOM_CUDA(ctx, cudaMalloc(&ctx->stage[slot], cap));
+    ctx->stageCap[slot] = cap;
+    return VSOM_OK;
+}
+
+static int check_error_flag(vsom_ctx *ctx, const char *what)
+{
+    int flag = 0;
+    VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag)
+        return set_error(ctx, VSOM_ERR_TIMEOUT, std::string(what) + ": device reported an error flag");
+    return VSOM_OK;
+}
+
+} // namespace vsom
+
+using namespace vsom;
+
+extern "C"
+{
+
+int vsom_model_length(int d_in, int transform) { return transform == VSOM_CLR ? d_in * (d_in - 1) : d_in; }
+
+int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order)
+{
+    if (!out)
+        return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: out is NULL");
+    *out = nullptr;
+    if (width < 1 || height < 1 || d_in < 1 || transform < VSOM_STANDARD || transform > VSOM_CLR || order < VSOM_ORDER_REFERENCE ||
+        order > VSOM_ORDER_LANES || (transform == VSOM_CLR && d_in < 2))
+        return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: bad width/height/d_in/transform/order");
+    if (static_cast<long long>(width) * height >= (1ll << 24))
+        return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: at most 2^24 - 1 nodes");
+    if (transform == VSOM_CLR && d_in > 65535)
+        return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: CLR pair tables are 16-bit");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1 || device < 0 || device >= count)
+    {
+        char buf[256];
+        std::snprintf(buf, sizeof(buf), "vsom_create: no usable CUDA device %d (%s; %d visible). This library has no CPU path.", device,
+                      e == cudaSuccess ? "ok" : cudaGetErrorString(e), count);
+        return set_error(nullptr, VSOM_ERR_NO_DEVICE, buf);
+    }
+    vsom_ctx *ctx = new vsom_ctx();
+    ctx->device = device;
+    ctx->W = width;
+    ctx->H = height;
+    ctx->N = width * height;
+    ctx->Din = d_in;
+    ctx->transform = transform;
+    ctx->order = order;
+    ctx->Dm = vsom_model_length(d_in, transform);
+    ctx->P = transform == VSOM_CLR ? ctx->Dm / 2 : 0;
+    ctx->Dr = transform == VSOM_CLR ? ctx->P : ctx->Dm;
+    ctx->rowStride = (ctx->Dm + 3) & ~3;
+
+    auto fail = [&](int rc) {
+        g_createError = ctx->err;
+        vsom_destroy(ctx);
+        return rc;
+    };
+#define CREATE_CUDA(call)                                                                  \
+    do                                                                                     \
+    {                                                                                      \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(cuda_fail(ctx, _e, #call, __FILE__, __LINE__));                    \
+    } while (0)
+
+    CREATE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+    {
+        ctx->err = "vsom_create: this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return fail(VSOM_ERR_NO_DEVICE);
+    }
+    ctx->numSMs = prop.multiProcessorCount;
+    ctx->smemOptin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    const size_t plane = sizeof(float) * static_cast<size_t>(ctx->N) * ctx->rowStride;
+    CREATE_CUDA(cudaMalloc(&ctx->mean, plane));
+    CREATE_CUDA(cudaMalloc(&ctx->S, plane));
+    CREATE_CUDA(cudaMalloc(&ctx->sigma, plane));
+    CREATE_CUDA(cudaMalloc(&ctx->weight, sizeof(float) * ctx->N));
+    CREATE_CUDA(cudaMalloc(&ctx->hits, sizeof(u64) * ctx->N));
+    CREATE_CUDA(cudaMalloc(&ctx->umatrix, sizeof(double) * ctx->N));
+    CREATE_CUDA(cudaMalloc(&ctx->slots, sizeof(u64) * 2 * static_cast<size_t>(ctx->numSMs)));
+    CREATE_CUDA(cudaMalloc(&ctx->errFlag, sizeof(int)));
+    CREATE_CUDA(cudaMemsetAsync(ctx->mean, 0, plane, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->S, 0, plane, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->sigma, 0, plane, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->weight, 0, sizeof(float) * ctx->N, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->hits, 0, sizeof(u64) * ctx->N, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->umatrix, 0, sizeof(double) * ctx->N, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
+    if (transform == VSOM_CLR)
+    {
+        // pairs (i<j) in row-major upper-triangle order: x'_q = v_i, y'_q = v_j (src/Transformation.cpp:94-101)
+        std::vector<unsigned short> pi(ctx->P), pj(ctx->P);
+        int q = 0;
+        for (int i = 0; i < d_in; ++i)
+            for (int j = i + 1; j < d_in; ++j)
+            {
+                pi[q] = static_cast<unsigned short>(i);
+                pj[q] = static_cast<unsigned short>(j);
+                ++q;
+            }
+        CREATE_CUDA(cudaMalloc(&ctx->pairI, sizeof(unsigned short) * ctx->P));
+        CREATE_CUDA(cudaMalloc(&ctx->pairJ, sizeof(unsigned short) * ctx->P));
+        CREATE_CUDA(cudaMemcpy(ctx->pairI, pi.data(), sizeof(unsigned short) * ctx->P, cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaMemcpy(ctx->pairJ, pj.data(), sizeof(unsigned short) * ctx->P, cudaMemcpyHostToDevice));
+    }
+    int rc = configure_online_step(ctx);
+    if (rc)
+        return fail(rc);
+    CREATE_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef CREATE_CUDA
+    *out = ctx;
+    return VSOM_OK;
+}
+
+void vsom_destroy(vsom_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->mean);
+    cudaFree(ctx->S);
+    cudaFree(ctx->sigma);
+    cudaFree(ctx->weight);
+    cudaFree(ctx->hits);
+    cudaFree(ctx->umatrix);
+    cudaFree(ctx->pairI);
+    cudaFree(ctx->pairJ);
+    cudaFree(ctx->slots);
+    cudaFree(ctx->errFlag);
+    cudaFree(ctx->lut);
+    for (void *p : ctx->stage)
+        cudaFree(p);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *vsom_last_error(const vsom_ctx *ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+int vsom_depth(const vsom_ctx *ctx) { return ctx ? ctx->Dm : 0; }
+int vsom_node_count(const vsom_ctx *ctx) { return ctx ? ctx->N : 0; }
+void *vsom_stream(const vsom_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+uint64_t vsom_launch_count(const vsom_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int vsom_planes_resident(const vsom_ctx *ctx) { return ctx ? ctx->residentTrain : 0; }
+
+int vsom_synchronize(vsom_ctx *ctx)
+{
+    if (!ctx)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+int vsom_upload_state(vsom_ctx *ctx, const float *mean, const float *S, const float *sigma, const float *weight, const uint64_t *hits)
+{
+    if (!ctx)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
+    if (mean)
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->mean, pitch, mean, w, w, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    if (S)
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->S, pitch, S, w, w, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    if (sigma)
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->sigma, pitch, sigma, w, w, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    if (weight)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->weight, weight, sizeof(float) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    if (hits)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->hits, hits, sizeof(u64) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+int vsom_download_state(vsom_ctx *ctx, float *mean, float *S, float *sigma, float *weight, uint64_t *hits)
+{
+    if (!ctx)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
+    if (mean)
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(mean, w, ctx->mean, pitch, w, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (S)
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(S, w, ctx->S, pitch, w, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sigma)
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(sigma, w, ctx->sigma, pitch, w, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (weight)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(weight, ctx->weight, sizeof(float) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hits)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(hits, ctx->hits, sizeof(u64) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n, double eta, double sigma, int decay, uint32_t *out_bmu_dev,
+                            float *out_dist_dev)
+{
+    if (!ctx || (!x_dev && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_train_chunk_device: x is NULL") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_online_step(ctx, x_dev, n, eta, sigma, decay, out_bmu_dev, out_dist_dev);
+}
+
+int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double sigma, int decay, uint64_t *last_bmu, uint32_t *out_bmu,
+                     float *out_dist, float *out_resid2)
+{
+    if (!ctx || (!x && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_train_chunk: x is NULL") : VSOM_ERR_INVALID;
+    if (n == 0)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 2, sizeof(float) * n);
+    if (rc)
+        return rc;
+    float *xDev = static_cast<float *>(ctx->stage[0]);
+    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
+    float *distDev = static_cast<float *>(ctx->stage[2]);
+    VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_online_step(ctx, xDev, n, eta, sigma, decay, bmuDev, distDev);
+    if (rc)
+        return rc;
+    std::vector<unsigned> tmp;
+    unsigned *bmuHost = out_bmu;
+    if (!bmuHost && last_bmu)
+    {
+        tmp.resize(n);
+        bmuHost = tmp.data();
+    }
+    if (bmuHost)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(bmuHost, bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_dist)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_dist, distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    // residual.squaredNorm() (src/Som.cpp:1167) and distanceError (:946) are the same f32 sum of the same residual
+    if (out_resid2)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_resid2, distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_error_flag(ctx, "vsom_train_chunk");
+    if (rc)
+        return rc;
+    if (last_bmu)
+        for (size_t r = 0; r < n; ++r)
+            last_bmu[r] = bmuHost[r]; // src/Som.cpp:895
+    return VSOM_OK;
+}
+
+int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev)
+{
+    if (!ctx || (!x_dev && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_device: x is NULL") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_find_bmu(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev);
+}
+
+int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist)
+{
+    if (!ctx || (!x && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu: x is NULL") : VSOM_ERR_INVALID;
+    if (n == 0)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 2, sizeof(float) * n);
+    if (rc)
+        return rc;
+    float *xDev = static_cast<float *>(ctx->stage[0]);
+    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
+    float *distDev = static_cast<float *>(ctx->stage[2]);
+    VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_find_bmu(ctx, xDev, n, min_hits, bmuDev, distDev);
+    if (rc)
+        return rc;
+    if (out_bmu)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_bmu, bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_dist)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_dist, distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)
+{
+    if (!ctx || !mean_error)
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_evaluate: mean_error is NULL") : VSOM_ERR_INVALID;
+    std::vector<float> dist(n);
+    int rc = vsom_find_bmu(ctx, x, n, 0, nullptr, dist.data());
+    if (rc)
+        return rc;
+    // src/Som.cpp:519 — Finch's incremental mean in double, in row order; with all-continuous columns the
+    // binary cross-entropy vector is multiplied by zeros, so its norm contributes sqrt(0) = 0.
+    double error = 0;
+    for (size_t i = 0; i < n; ++i)
+        error += 1. / (static_cast<double>(i) + 1.0) * (static_cast<double>(dist[i]) + 0.0 - error);
+    *mean_error = error;
+    return VSOM_OK;
+}
+
+int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out)
+{
+    if (!ctx || !v || !out)
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_all_dists: NULL argument") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_reserve(ctx, 0, sizeof(float) * ctx->Din);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 5, sizeof(double) * ctx->N);
+    if (rc)
+        return rc;
+    VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->stage[0], v, sizeof(float) * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_all_dists(ctx, static_cast<float *>(ctx->stage[0]), static_cast<double *>(ctx->stage[5]));
+    if (rc)
+        return rc;
+    VSOM_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage[5], sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+int vsom_update_umatrix(vsom_ctx *ctx, double *out)
+{
+    if (!ctx)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = launch_umatrix(ctx);
+    if (rc)
+        return rc;
+    if (out)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out, ctx->umatrix, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+int vsom_build_index(vsom_ctx *ctx, const uint32_t *bmu, size_t n, uint64_t *counts, uint64_t *offsets, uint32_t *row_ids)
+{
+    if (!ctx || (!bmu && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_build_index: bmu is NULL") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = ctx->N;
+    int rc = stage_reserve(ctx, 1, sizeof(unsigned) * (n ? n : 1));
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 2, sizeof(unsigned) * (n ? n : 1));
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 5, sizeof(u64) * (2 * N + 1));
+    if (rc)
+        return rc;
+    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
+    unsigned *rowDev = static_cast<unsigned *>(ctx->stage[2]);
+    u64 *countsDev = static_cast<u64 *>(ctx->stage[5]);
+    u64 *offsetsDev = countsDev + N;
+    if (n)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(bmuDev, bmu, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_build_index(ctx, bmuDev, n, countsDev, offsetsDev, row_ids ? rowDev : nullptr);
+    if (rc)
+        return rc;
+    if (counts)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(counts, countsDev, sizeof(u64) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (offsets)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(offsets, offsetsDev, sizeof(u64) * (N + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (row_ids && n)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(row_ids, rowDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_error_flag(ctx, "vsom_build_index");
+    if (rc)
+        return set_error(ctx, VSOM_ERR_INVALID, "vsom_build_index: a BMU id is >= width*height");
+    return VSOM_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,197 @@
+// common.cuh — context, error plumbing and device helpers shared by the sm_100a kernels of libvsom_b200.so.
+//
+// Arithmetic rule for every kernel in this library: the reference CPU build has no FMA (build/Makefile:18,
+// -msse2 only), so each float/double operation on a parity path is written with an explicit round-to-nearest
+// intrinsic (__fadd_rn, __fmul_rn, __fsub_rn, __fdiv_rn, __fsqrt_rn, __dadd_rn, ...) that nvcc never
+// contracts or reassociates; the library is additionally compiled with -fmad=false.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "vsom_b200.h"
+
+namespace vsom
+{
+
+typedef unsigned long long u64;
+
+// One neighbourhood-table entry per (|dy|, |dx|): Som::calculateNeighbourhoodWeight (src/Som.cpp:949-975)
+// evaluated on the host with the same libm exp() the reference calls, then pre-rounded the way
+// Som::trainSingle uses it (src/Som.cpp:922-941).
+struct LutEntry
+{
+    double nw;  // neighbourhood weight (f64)
+    float cexp; // (float)(nw * eta)  — Exponential decay: added to weightMap and multiplies the step
+    float nwf;  // (float)nw          — multiplies the Welford term; added to weightMap in InverseProportional
+};
+
+struct StepParams
+{
+    int W, H;                 // full grid
+    int node0, nodeCount;     // shard of the grid held by this device: global nodes [node0, node0+nodeCount)
+    int Din, Dm, Dr, P;       // sample length, model length, residual length (Dm or P), CLR pair count
+    int rowStride;            // floats between rows of the global planes
+    float *mean, *S, *sigma, *weight;
+    u64 *hits;
+    const float *x;           // n x Din samples (device)
+    u64 n;
+    int decay;
+    double radius;            // 2.5 * sigma (src/Som.cpp:899-903)
+    const LutEntry *lut;
+    int lutW;
+    const unsigned short *pairI, *pairJ; // CLR pair tables (src/Transformation.cpp:94-101)
+    u64 *slots;               // [2][gridDim.x] min-loc exchange
+    int *err;                 // set to 1 when a CTA gave up waiting
+    unsigned *outBmu;         // per sample, may be null
+    float *outDist;           // per sample, may be null
+    int resident;             // planes of the owned nodes live in shared memory for the whole chunk
+    int smStride;             // row stride (floats) of the resident copy
+    long long timeoutCycles;
+};
+
+} // namespace vsom
+
+struct vsom_ctx
+{
+    int device = 0;
+    int W = 0, H = 0, N = 0, Din = 0, Dm = 0, Dr = 0, P = 0;
+    int transform = 0, order = 0;
+    int rowStride = 0;
+    int numSMs = 0, smemOptin = 0;
+    cudaStream_t stream = nullptr;
+    float *mean = nullptr, *S = nullptr, *sigma = nullptr, *weight = nullptr;
+    vsom::u64 *hits = nullptr;
+    double *umatrix = nullptr;
+    unsigned short *pairI = nullptr, *pairJ = nullptr;
+    // online-step scratch
+    vsom::u64 *slots = nullptr;
+    int *errFlag = nullptr;
+    vsom::LutEntry *lut = nullptr;
+    size_t lutCap = 0;
+    std::vector<vsom::LutEntry> lutHost;
+    double lutEta = -1, lutSigma = -1;
+    int lutW = 0, lutH = 0;
+    // grow-only device staging for the host entry points
+    void *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stageCap[6] = {0, 0, 0, 0, 0, 0};
+    int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;
+    size_t smemTrain = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace vsom
+{
+
+int set_error(vsom_ctx *ctx, int code, const std::string &msg);
+int cuda_fail(vsom_ctx *ctx, cudaError_t e, const char *what, const char *file, int line);
+// grow-only device buffer `slot` of at least `bytes`
+int stage_reserve(vsom_ctx *ctx, int slot, size_t bytes);
+
+#define VSOM_CUDA(ctx, call)                                                   \
+    do                                                                         \
+    {                                                                          \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess)                                                 \
+            return ::vsom::cuda_fail((ctx), _e, #call, __FILE__, __LINE__);    \
+    } while (0)
+
+// kernels' host launchers (each returns a vsom_status)
+int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev);
+int configure_online_step(vsom_ctx *ctx);
+int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev);
+int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
+int launch_umatrix(vsom_ctx *ctx);
+int launch_build_index(vsom_ctx *ctx, const unsigned *bmuDev, size_t n, u64 *countsDev, u64 *offsetsDev, unsigned *rowIdsDev);
+
+// ------------------------------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ u64 ld_relaxed_gpu(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smemDst, const void *gmemSrc)
+{
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ u64 u64_min(u64 a, u64 b) { return a < b ? a : b; }
+__device__ __forceinline__ u64 warp_min_u64(u64 v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+        v = u64_min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// (distance, node) -> sortable key.  Distances are sums of squares (>= +0), so their IEEE bit patterns order
+// like the values; the node index in the low word reproduces findBmu's strict '<' / lowest-index-wins rule
+// (src/Som.cpp:296-304).  A NaN distance never wins, except at node 0 which seeds the search (:293).
+// Layout: [63:32] distance bits, [31:8] node, [7:0] tag (exchange sequence number; equal for all keys of a step).
+__device__ __forceinline__ u64 make_key(float d, unsigned node, unsigned tag)
+{
+    unsigned bits = __float_as_uint(d);
+    if (d != d)
+        bits = node == 0 ? 0u : 0x7fffffffu;
+    return (static_cast<u64>(bits) << 32) | (static_cast<u64>(node) << 8) | tag;
+}
+__device__ __forceinline__ unsigned key_node(u64 k) { return static_cast<unsigned>((k >> 8) & 0xffffffu); }
+
+// One residual of the Comparer, and its square accumulated in f32 (src/Som.cpp:136-140).
+//   Standard / Median: r = m - v           (src/Transformation.cpp:7-8, :45-46)
+//   CLR:               r = (A*x' + B) - y' (src/Transformation.cpp:104)
+template <int TR>
+__device__ __forceinline__ float residual(const float *m, const float *xs, int k, int P, const unsigned short *pi, const unsigned short *pj)
+{
+    if (TR != VSOM_CLR)
+        return __fsub_rn(m[k], xs[k]);
+    return __fsub_rn(__fadd_rn(__fmul_rn(m[k], xs[pi[k]]), m[P + k]), xs[pj[k]]);
+}
+
+// Squared distance in the reference's order: k = 0..Dr-1 sequentially (one thread).
+template <int TR>
+__device__ __forceinline__ float dist_sequential(const float *m, const float *xs, int Dr, int P, const unsigned short *pi, const unsigned short *pj)
+{
+    float s = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k < Dr; ++k)
+    {
+        const float r = residual<TR>(m, xs, k, P, pi, pj);
+        s = __fadd_rn(s, __fmul_rn(r, r));
+    }
+    return s;
+}
+
+// Squared distance with 32 interleaved partial sums and a fixed xor butterfly (all 32 lanes call; all get the value).
+template <int TR>
+__device__ __forceinline__ float dist_lanes(const float *m, const float *xs, int Dr, int P, const unsigned short *pi, const unsigned short *pj, int lane)
+{
+    float s = 0.0f;
+#pragma unroll 4
+    for (int k = lane; k < Dr; k += 32)
+    {
+        const float r = residual<TR>(m, xs, k, P, pi, pj);
+        s = __fadd_rn(s, __fmul_rn(r, r));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    return s;
+}
+
+#endif // __CUDACC__
+
+} // namespace vsom
