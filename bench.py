@@ -249,6 +249,13 @@ def main():
     total_ms = float(t.item())
     value = world * n * args.steps / (total_ms / 1e3)
 
+    # ---------------- diagnostics (untimed): per-phase cycles of the persistent kernel on a 100k-sample chunk
+    ctx.debug_profile(True)
+    ctx.train_chunk_device(x_dev, min(n, 100_000), ETA, SIGMA, vsom.EXPONENTIAL, out_bmu, out_dist)
+    ctx.synchronize()
+    phases = ctx.debug_phase_cycles()
+    ctx.debug_profile(False)
+
     # ---------------- e2e: host buffers through the reference-facing C-ABI call, copies inside the timed region
     x_np = x_host.numpy()
     e2e_steps = max(1, min(args.steps, 3))
@@ -306,6 +313,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": n * D_ * 4, "d2h_bytes_per_step": n * 12, "steps": e2e_steps,
                     "result_read": "per-sample BMU, distance, residual^2 + MSE on host", "mse": mse},
             "gpu_launches": launches,
+            "k1_phase_cycles_per_sample": phases,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": "online_step_kernel",

@@ -94,6 +94,12 @@ VSOM_API uint64_t vsom_launch_count(const vsom_ctx *ctx);
 /* 1 when the online step keeps the three planes resident in shared memory for this map, else 0. */
 VSOM_API int vsom_planes_resident(const vsom_ctx *ctx);
 
+/* Diagnostics of the online step (K1): when enabled, thread 0 of every CTA accumulates clock64() deltas of the
+ * five phases of each sample (wait-for-sample, scan + CTA min, grid-wide min-loc exchange, broadcast barrier,
+ * window update); vsom_debug_phase_cycles returns their mean over CTAs in cycles per sample for the last chunk. */
+VSOM_API int vsom_debug_profile(vsom_ctx *ctx, int enable);
+VSOM_API int vsom_debug_phase_cycles(vsom_ctx *ctx, double out[5]);
+
 /* Replace / read the model state: Som::map, SMap, sigmaMap, weightMap, bmuHits (include/SOM.hpp:56-61).
  * Any pointer may be NULL (skipped).  Initial planes come from the host (Som::randomInitialize,
  * src/Som.cpp:977-997, runs on the host so that glibc's rand() sequence is the reference's). */

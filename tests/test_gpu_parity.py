@@ -71,12 +71,13 @@ def test_scoring_umatrix_match_reference_fixture(vsom, name):
 
 
 # (W, H, Din, transform, rows, eta, sigma) — covers: fewer nodes than SMs, several nodes per CTA, planes resident
-# in shared memory and planes left in global memory (64x64x784 does not fit), CLR at J=32 (992 params / node).
+# in shared memory and planes left in global memory (100x100x784 does not fit), CLR at J=32 (992 params / node).
 SHAPES = [
     (4, 3, 3, 0, 64, 0.5, 1.5),
     (20, 20, 784, 0, 48, 0.1, 5.0),
     (64, 64, 128, 1, 96, 0.05, 16.0),
     (64, 64, 784, 0, 24, 0.1, 3.0),
+    (100, 100, 784, 0, 12, 0.1, 4.0),
     (50, 50, 32, 2, 32, 0.001, 12.0),
     (33, 7, 20, 2, 64, 0.002, 2.0),
 ]
@@ -123,7 +124,7 @@ def test_online_step_matches_oracle_bit_exact(vsom, po, shape, decay):
 
 def test_resident_and_global_plane_modes_are_both_exercised(vsom):
     a = vsom.VsomContext(64, 64, 128, vsom.MEDIAN)
-    b = vsom.VsomContext(64, 64, 784, vsom.STANDARD)
+    b = vsom.VsomContext(100, 100, 784, vsom.STANDARD)
     c = vsom.VsomContext(50, 50, 32, vsom.CLR)
     assert a.planes_resident and c.planes_resident and not b.planes_resident
     for k in (a, b, c):

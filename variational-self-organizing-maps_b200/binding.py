@@ -30,6 +30,8 @@ _PROTOS = {
     "vsom_synchronize": (C.c_int, [_vp]),
     "vsom_launch_count": (C.c_uint64, [_vp]),
     "vsom_planes_resident": (C.c_int, [_vp]),
+    "vsom_debug_profile": (C.c_int, [_vp, C.c_int]),
+    "vsom_debug_phase_cycles": (C.c_int, [_vp, _f64p]),
     "vsom_upload_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
     "vsom_download_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
     "vsom_train_chunk": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_double, C.c_double, C.c_int, _u64p, _u32p, _f32p, _f32p]),
@@ -196,6 +198,15 @@ class VsomContext:
         rows = np.empty(n, np.uint32)
         self._check(lib().vsom_build_index(self._h, _p(bmu, _u32p), n, _p(counts, _u64p), _p(offsets, _u64p), _p(rows, _u32p)))
         return counts, offsets, rows
+
+    # ---- diagnostics
+    def debug_profile(self, enable=True):
+        self._check(lib().vsom_debug_profile(self._h, int(enable)))
+
+    def debug_phase_cycles(self):
+        out = np.zeros(5, np.float64)
+        self._check(lib().vsom_debug_phase_cycles(self._h, _p(out, _f64p)))
+        return dict(zip(("wait_sample", "scan_min", "exchange", "broadcast", "update"), out.tolist()))
 
     # ---- plumbing
     def synchronize(self):

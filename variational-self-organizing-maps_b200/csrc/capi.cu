@@ -181,6 +181,7 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->slots);
     cudaFree(ctx->errFlag);
     cudaFree(ctx->lut);
+    cudaFree(ctx->profDev);
     for (void *p : ctx->stage)
         cudaFree(p);
     if (ctx->stream)
@@ -194,6 +195,45 @@ int vsom_node_count(const vsom_ctx *ctx) { return ctx ? ctx->N : 0; }
 void *vsom_stream(const vsom_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
 uint64_t vsom_launch_count(const vsom_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int vsom_planes_resident(const vsom_ctx *ctx) { return ctx ? ctx->residentTrain : 0; }
+
+int vsom_debug_profile(vsom_ctx *ctx, int enable)
+{
+    if (!ctx)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (enable && !ctx->profDev)
+    {
+        VSOM_CUDA(ctx, cudaMalloc(&ctx->profDev, sizeof(long long) * 5 * ctx->numSMs));
+        VSOM_CUDA(ctx, cudaMemset(ctx->profDev, 0, sizeof(long long) * 5 * ctx->numSMs));
+    }
+    else if (!enable && ctx->profDev)
+    {
+        VSOM_CUDA(ctx, cudaFree(ctx->profDev));
+        ctx->profDev = nullptr;
+    }
+    return VSOM_OK;
+}
+
+int vsom_debug_phase_cycles(vsom_ctx *ctx, double out[5])
+{
+    if (!ctx || !out)
+        return VSOM_ERR_INVALID;
+    if (!ctx->profDev || !ctx->profSamples || !ctx->gridTrain)
+        return set_error(ctx, VSOM_ERR_INVALID, "vsom_debug_phase_cycles: profiling not enabled or no chunk trained yet");
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<long long> h(static_cast<size_t>(5) * ctx->gridTrain);
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpy(h.data(), ctx->profDev, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i)
+    {
+        double s = 0;
+        for (int b = 0; b < ctx->gridTrain; ++b)
+            s += static_cast<double>(h[static_cast<size_t>(b) * 5 + i]);
+        out[i] = s / ctx->gridTrain / static_cast<double>(ctx->profSamples);
+    }
+    return VSOM_OK;
+}
 
 int vsom_synchronize(vsom_ctx *ctx)
 {

@@ -51,6 +51,7 @@ struct StepParams
     int resident;             // planes of the owned nodes live in shared memory for the whole chunk
     int smStride;             // row stride (floats) of the resident copy
     long long timeoutCycles;
+    long long *prof;          // optional [gridDim.x][5] per-phase cycle sums of thread 0 (diagnostics), else null
 };
 
 } // namespace vsom
@@ -81,6 +82,8 @@ struct vsom_ctx
     int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;
     size_t smemTrain = 0;
     uint64_t launches = 0;
+    long long *profDev = nullptr; // diagnostics: per-phase cycle sums of the last online-step launch
+    size_t profSamples = 0;
     std::string err;
 };
 

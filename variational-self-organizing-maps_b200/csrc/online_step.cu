@@ -7,15 +7,21 @@
 // Design
 //   * grid = one CTA per SM, launched cooperatively so that all CTAs are co-resident.  Grid nodes are dealt
 //     round-robin: CTA b owns shard-local nodes b, b+G, b+2G, ...  Ownership never changes, so a node's rows
-//     are read and written by exactly one CTA: when the owned rows of the three planes fit in shared memory
-//     they are loaded once, stay there for the whole chunk and are written back at the end (configs 1-3);
-//     otherwise they are addressed in global memory (large maps).
+//     are read and written by exactly one CTA: when the owned rows of the mean and S planes fit in shared
+//     memory they are loaded once, stay there for the whole chunk and are written back at the end
+//     (configs 1-3); otherwise they are addressed in global memory (large maps).
 //   * per sample there is exactly ONE grid-wide exchange: every CTA publishes the min (distance,node) key of
 //     its nodes in a tagged 64-bit slot, then reads all G slots and takes the min itself.  No second barrier
 //     is needed because the window update of a node is done by its owner, which is also the only CTA that
 //     scans it for the next sample.  Round-robin ownership spreads any update window evenly over the SMs.
+//   * sigmaMap is a pure function of the node's SMap and weightMap at its LAST visit
+//     (sigma = sqrt(|S / (W==0 ? 1e-6 : W)|), src/Som.cpp:939-942, overwritten at every visit), and nothing on
+//     this path reads it (all shipped Comparers ignore `dispersion`).  The kernel therefore only marks the
+//     visited nodes and evaluates that expression once per visited node at the end of the chunk — the stored
+//     plane is bit-identical, and the IEEE divide + square root leave the per-sample loop.
 //   * reduction order is a template parameter (vsom_reduction_order): REFERENCE sums the squared residuals
-//     sequentially like the reference's dot product, so BMUs and every plane stay bit-identical to it.
+//     sequentially like the reference's dot product (one thread per node), so BMUs and every plane stay
+//     bit-identical to it; LANES uses a warp per node.
 //   * the distance of the sample to its UPDATED BMU (trainSingle's return value, :946) is computed by an
 //     otherwise idle thread / warp of the owner CTA during the next sample's scan, off the critical path.
 #include "common.cuh"
@@ -25,7 +31,7 @@
 namespace vsom
 {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 
 template <int TR>
@@ -38,52 +44,92 @@ __device__ __forceinline__ float stepper_scalar(float xv, float m)
     return d;
 }
 
-template <int TR, int ORDER>
+// One element of the window update (src/Som.cpp:912-941) for Standard / Median; sigma is evaluated lazily.
+template <int TR>
+__device__ __forceinline__ void update_element(float xv, float c, float nwf, float &m, float &S)
+{
+    const float d0 = stepper_scalar<TR>(xv, m);                  // :912 (and :935, same value)
+    const float m1 = __fadd_rn(m, __fmul_rn(c, d0));             // :925 / :935
+    const float d1 = stepper_scalar<TR>(xv, m1);                 // :941 Stepper on the new mean
+    S = __fadd_rn(S, __fmul_rn(nwf, __fmul_rn(d0, d1)));         // :941
+    m = m1;
+}
+
+// Squared distance, reference order, over zero-padded rows with 128-bit loads (Standard / Median).
+__device__ __forceinline__ float dist_sequential_v4(const float *m, const float *xs, int n4)
+{
+    const float4 *m4 = reinterpret_cast<const float4 *>(m);
+    const float4 *x4 = reinterpret_cast<const float4 *>(xs);
+    float s = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < n4; ++c)
+    {
+        const float4 a = m4[c], b = x4[c];
+        float r = __fsub_rn(a.x, b.x);
+        s = __fadd_rn(s, __fmul_rn(r, r));
+        r = __fsub_rn(a.y, b.y);
+        s = __fadd_rn(s, __fmul_rn(r, r));
+        r = __fsub_rn(a.z, b.z);
+        s = __fadd_rn(s, __fmul_rn(r, r));
+        r = __fsub_rn(a.w, b.w);
+        s = __fadd_rn(s, __fmul_rn(r, r));
+    }
+    return s;
+}
+
+template <int TR>
+__device__ __forceinline__ float node_dist_reference(const float *m, const float *xs, const StepParams &p, int n4, const unsigned short *pi,
+                                                     const unsigned short *pj)
+{
+    if (TR != VSOM_CLR)
+        return dist_sequential_v4(m, xs, n4); // the zero padding adds +0 terms: s + 0 == s exactly
+    return dist_sequential<TR>(m, xs, p.Dr, p.P, pi, pj);
+}
+
+template <int TR, int ORDER, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepParams p)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 sWarpKey[kWarps];
     __shared__ u64 sBmuKey;
-    __shared__ int sCnt;
     __shared__ int sAbort;
-    __shared__ int sPendL;  // local node whose post-update distance is still owed (-1: none)
-    __shared__ u64 sPendT;  // ... for this sample
+    __shared__ int sPendL; // local node whose post-update distance is still owed (-1: none)
+    __shared__ u64 sPendT; // ... for this sample
 
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Lmax = (p.nodeCount + G - 1) / G;
     const int L = (p.nodeCount > b) ? (p.nodeCount - b + G - 1) / G : 0;
     const int DinPad = (p.Din + 3) & ~3;
+    const int DmPad = (p.Dm + 3) & ~3;
+    const int n4 = DmPad >> 2;
 
-    // ---- carve shared memory
-    float *xs = reinterpret_cast<float *>(smemRaw);       // [3][DinPad] sample ring
-    float *wloc = xs + 3 * DinPad;                        // [Lmax] weightMap of the owned nodes
-    float *coefC = wloc + Lmax;                           // [Lmax] per window node: step coefficient
-    float *coefN = coefC + Lmax;                          // [Lmax] (float)nw
-    float *coefT = coefN + Lmax;                          // [Lmax] (float)tempWeight
-    int *list = reinterpret_cast<int *>(coefT + Lmax);    // [Lmax] owned nodes inside the window
-    unsigned short *pi = reinterpret_cast<unsigned short *>(list + Lmax); // [P] CLR pair tables
-    unsigned short *pj = pi + ((p.P + 1) & ~1);
-    float *planes = reinterpret_cast<float *>(pj + ((p.P + 1) & ~1));     // resident rows: 3 x Lmax x smStride
-    // (P rounded to even keeps `planes` 4-byte aligned)
+    // ---- carve shared memory (every region 16-byte aligned)
+    float *xs = reinterpret_cast<float *>(smemRaw);                          // [3][DinPad] sample ring
+    float *wbuf = xs + 3 * DinPad;                                           // [2][Lpad] weightMap of the owned nodes
+    const int Lpad = (Lmax + 3) & ~3;
+    int2 *nodeXY = reinterpret_cast<int2 *>(wbuf + 2 * Lpad);                // [Lpad] grid position of the owned nodes
+    unsigned *touched = reinterpret_cast<unsigned *>(nodeXY + Lpad);         // [Lpad] visited in this chunk
+    unsigned short *pi = reinterpret_cast<unsigned short *>(touched + Lpad); // [Ppad] CLR pair tables
+    const int Ppad = (p.P + 7) & ~7;
+    unsigned short *pj = pi + Ppad;
+    float *planes = reinterpret_cast<float *>(pj + Ppad);                    // resident rows: 2 x Lmax x smStride
 
-    float *mBase, *sBase, *gBase;
+    float *mBase, *sBase;
     size_t stride;
-    if (p.resident)
+    if (RES)
     {
         stride = static_cast<size_t>(p.smStride);
         mBase = planes;
         sBase = planes + static_cast<size_t>(Lmax) * stride;
-        gBase = sBase + static_cast<size_t>(Lmax) * stride;
     }
     else
     {
         stride = static_cast<size_t>(G) * p.rowStride;
         mBase = p.mean + static_cast<size_t>(b) * p.rowStride;
         sBase = p.S + static_cast<size_t>(b) * p.rowStride;
-        gBase = p.sigma + static_cast<size_t>(b) * p.rowStride;
     }
 
-    // ---- prologue: pair tables, owned weights, resident rows, first sample
+    // ---- prologue: pair tables, owned weights / positions, resident rows, first sample
     if (TR == VSOM_CLR)
         for (int q = tid; q < p.P; q += kThreads)
         {
@@ -91,16 +137,23 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             pj[q] = p.pairJ[q];
         }
     for (int l = tid; l < L; l += kThreads)
-        wloc[l] = p.weight[static_cast<size_t>(l) * G + b];
-    if (p.resident)
+    {
+        const unsigned node = static_cast<unsigned>(p.node0 + l * G + b);
+        wbuf[l] = p.weight[static_cast<size_t>(l) * G + b];
+        nodeXY[l] = make_int2(static_cast<int>(node % static_cast<unsigned>(p.W)), static_cast<int>(node / static_cast<unsigned>(p.W)));
+        touched[l] = 0;
+    }
+    for (int k = tid; k < 3 * DinPad; k += kThreads)
+        xs[k] = 0.0f; // keeps the pad lanes of the 128-bit paths at zero
+    if (RES)
         for (int l = warp; l < L; l += kWarps)
         {
             const size_t g = (static_cast<size_t>(l) * G + b) * p.rowStride;
-            for (int k = lane; k < p.Dm; k += 32)
+            for (int k = lane; k < static_cast<int>(stride); k += 32)
             {
-                mBase[l * stride + k] = p.mean[g + k];
-                sBase[l * stride + k] = p.S[g + k];
-                gBase[l * stride + k] = p.sigma[g + k];
+                const bool in = k < p.Dm;
+                mBase[l * stride + k] = in ? p.mean[g + k] : 0.0f;
+                sBase[l * stride + k] = in ? p.S[g + k] : 0.0f;
             }
         }
     if (tid == 0)
@@ -109,19 +162,24 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         sPendL = -1;
         sPendT = 0;
     }
+    __syncthreads();
     if (p.n > 0)
         for (int k = tid; k < p.Din; k += kThreads)
             cp_async4(xs + k, p.x + k);
 
     const double dW = static_cast<double>(p.W), dH = static_cast<double>(p.H);
+    long long prof[5] = {0, 0, 0, 0, 0};
+    u64 done = 0;
 
     for (u64 t = 0; t < p.n; ++t)
     {
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+        if (p.prof && tid == 0)
+            c0 = clock64();
         const float *xt = xs + (t % 3) * DinPad;
+        float *wcur = wbuf + (t & 1) * Lpad, *wnext = wbuf + ((t + 1) & 1) * Lpad;
         cp_async_wait_all();
         __syncthreads(); // sample t landed; update of sample t-1 is complete; sPend* of t-1 visible
-        if (sAbort)
-            break;
         if (t + 1 < p.n)
         {
             float *xn = xs + ((t + 1) % 3) * DinPad;
@@ -129,6 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             for (int k = tid; k < p.Din; k += kThreads)
                 cp_async4(xn + k, src + k);
         }
+        if (p.prof && tid == 0)
+            c1 = clock64();
         const unsigned tag = static_cast<unsigned>((t >> 1) & 0xff);
 
         // ---- owed output of sample t-1: distance to its updated BMU (src/Som.cpp:946) + addBmu (:1189-1192)
@@ -142,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         {
             if (tid == kThreads - 1 && pendL >= 0)
             {
-                const float d = dist_sequential<TR>(mBase + pendL * stride, xprev, p.Dr, p.P, pi, pj);
+                const float d = node_dist_reference<TR>(mBase + pendL * stride, xprev, p, n4, pi, pj);
                 const size_t q = static_cast<size_t>(pendL) * G + b;
                 if (p.outBmu)
                     p.outBmu[pendT] = static_cast<unsigned>(p.node0 + q);
@@ -152,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             }
             for (int l = tid; l < L; l += kThreads)
             {
-                const float d = dist_sequential<TR>(mBase + l * stride, xt, p.Dr, p.P, pi, pj);
+                const float d = node_dist_reference<TR>(mBase + l * stride, xt, p, n4, pi, pj);
                 best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
             }
         }
@@ -178,18 +238,29 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             }
         }
         best = warp_min_u64(best);
-        if (lane == 0)
-            sWarpKey[warp] = best;
-        __syncthreads();
+        // REFERENCE order with at most 32 owned nodes: every key already sits in warp 0 — no CTA barrier
+        const bool crossWarp = ORDER != VSOM_ORDER_REFERENCE || L > 32;
+        if (crossWarp)
+        {
+            if (lane == 0)
+                sWarpKey[warp] = best;
+            __syncthreads();
+        }
 
         // ---- grid-wide min-loc: publish, then read every CTA's slot of this step
         if (warp == 0)
         {
-            u64 k = lane < kWarps ? sWarpKey[lane] : ~0ull;
-            k = warp_min_u64(k);
+            u64 k = best;
+            if (crossWarp)
+            {
+                k = lane < kWarps ? sWarpKey[lane] : ~0ull;
+                k = warp_min_u64(k);
+            }
             u64 *slots = p.slots + static_cast<size_t>(t & 1) * G;
             if (k == ~0ull) // CTA without nodes (cannot happen: G <= nodeCount) — still publish a tagged key
                 k = (~0ull << 8) | tag;
+            if (p.prof && tid == 0)
+                c2 = clock64();
             if (lane == 0)
                 st_relaxed_gpu(slots + b, k);
             const long long t0 = clock64();
@@ -217,7 +288,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             if (lane == 0)
             {
                 sBmuKey = m;
-                sCnt = 0;
                 sPendL = -1;
                 if (abort)
                 {
@@ -225,10 +295,14 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     *p.err = 1;
                 }
             }
+            if (p.prof && tid == 0)
+                c3 = clock64();
         }
         __syncthreads();
         if (sAbort)
             break;
+        if (p.prof && tid == 0)
+            c4 = clock64();
 
         // ---- window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric
         const unsigned bmu = key_node(sBmuKey);
@@ -243,99 +317,131 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         hi = __dadd_rn(static_cast<double>(by), p.radius);
         const int endY = static_cast<int>(static_cast<u64>(hi < dH ? hi : dH));
 
-        // ---- phase A: one thread per owned node inside the window: weightMap + the node's three coefficients
+        // Per window node: the neighbourhood entry and the step coefficient (src/Som.cpp:915-939).  Evaluated
+        // redundantly by every warp that works on the node — reading the OLD weight from wcur — so that no
+        // barrier is needed between "weights" and "vectors".
+#define VSOM_NODE_COEF(l_, inWin_, c_, nwf_, w1_)                                                                        \
+    {                                                                                                                    \
+        const int2 xy = nodeXY[l_];                                                                                      \
+        inWin_ = xy.x >= startX && xy.x < endX && xy.y >= startY && xy.y < endY;                                         \
+        if (inWin_)                                                                                                      \
+        {                                                                                                                \
+            const int dx = xy.x > bx ? xy.x - bx : bx - xy.x, dy = xy.y > by ? xy.y - by : by - xy.y;                    \
+            const float4 raw = __ldg(reinterpret_cast<const float4 *>(p.lut + dy * p.lutW + dx));                        \
+            const float cexp = raw.z;                                                                                    \
+            nwf_ = raw.w;                                                                                                \
+            const float w0 = wcur[l_];                                                                                   \
+            if (p.decay == VSOM_EXPONENTIAL)                                                                             \
+            {                                                                                                            \
+                w1_ = __fadd_rn(w0, cexp); /* :924 */                                                                    \
+                c_ = cexp;                 /* :925 */                                                                    \
+            }                                                                                                            \
+            else                                                                                                         \
+            {                                                                                                            \
+                w1_ = __fadd_rn(w0, nwf_); /* :930 */                                                                    \
+                const double nw = __hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x));                        \
+                const double tw = (w1_ == 0.0f) ? 1.0 : __ddiv_rn(nw, static_cast<double>(w1_)); /* :933 */              \
+                c_ = static_cast<float>(tw);                                                     /* :935 */              \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
+
+        // ---- phase A: one thread per owned node — the new weightMap value goes to the other weight buffer
         for (int l = tid; l < L; l += kThreads)
         {
-            const unsigned node = static_cast<unsigned>(p.node0 + l * G + b);
-            const int x = static_cast<int>(node % static_cast<unsigned>(p.W));
-            const int y = static_cast<int>(node / static_cast<unsigned>(p.W));
-            if (x >= startX && x < endX && y >= startY && y < endY)
+            bool inWin;
+            float c = 0.0f, nwf = 0.0f, w1 = wcur[l];
+            VSOM_NODE_COEF(l, inWin, c, nwf, w1);
+            wnext[l] = w1;
+            if (inWin)
             {
-                const int dx = x > bx ? x - bx : bx - x, dy = y > by ? y - by : by - y;
-                const LutEntry e = p.lut[dy * p.lutW + dx];
-                float w = wloc[l];
-                float c;
-                if (p.decay == VSOM_EXPONENTIAL)
-                {
-                    w = __fadd_rn(w, e.cexp); // :924
-                    c = e.cexp;               // :925
-                }
-                else
-                {
-                    w = __fadd_rn(w, e.nwf);                                                // :930
-                    const double tw = (w == 0.0f) ? 1.0 : __ddiv_rn(e.nw, static_cast<double>(w)); // :933
-                    c = static_cast<float>(tw);                                              // :935
-                }
-                wloc[l] = w;
-                const double tempWeight = (w == 0.0f) ? 0.000001 : static_cast<double>(w); // :939
-                const int slot = atomicAdd(&sCnt, 1);
-                list[slot] = l;
-                coefC[slot] = c;
-                coefN[slot] = e.nwf;
-                coefT[slot] = static_cast<float>(tempWeight);
-                if (node == bmu)
+                touched[l] = 1;
+                if (static_cast<unsigned>(p.node0 + l * G + b) == bmu)
                 {
                     sPendL = l;
                     sPendT = t;
                 }
             }
+            (void)c;
+            (void)nwf;
         }
-        __syncthreads();
 
-        // ---- phase B: one warp per window node, lanes over the model vector (src/Som.cpp:912-942)
-        const int cnt = sCnt;
-        for (int e = warp; e < cnt; e += kWarps)
+        // ---- phase B: one warp per (window node, 128-element slice) of the model vector (src/Som.cpp:912-941)
         {
-            const int l = list[e];
-            const float c = coefC[e], nwf = coefN[e], twf = coefT[e];
-            float *m = mBase + l * stride, *S = sBase + l * stride, *sg = gBase + l * stride;
-            if (TR != VSOM_CLR)
+            const int nq = TR == VSOM_CLR ? p.P : DmPad;
+            const int nCh = (nq + 127) >> 7;
+            const int items = L * nCh;
+            for (int it = warp; it < items; it += kWarps)
             {
-                for (int k = lane; k < p.Dm; k += 32)
+                const int l = it / nCh, ch = it - l * nCh;
+                bool inWin;
+                float c = 0.0f, nwf = 0.0f, w1 = 0.0f;
+                VSOM_NODE_COEF(l, inWin, c, nwf, w1);
+                (void)w1;
+                if (!inWin)
+                    continue;
+                float *m = mBase + l * stride, *S = sBase + l * stride;
+                if (TR != VSOM_CLR)
                 {
-                    const float xv = xt[k];
-                    const float m0 = m[k];
-                    const float d0 = stepper_scalar<TR>(xv, m0);               // :912 (and :935, same value)
-                    const float m1 = __fadd_rn(m0, __fmul_rn(c, d0));          // :925 / :935
-                    const float d1 = stepper_scalar<TR>(xv, m1);               // :941 Stepper on the new mean
-                    const float s1 = __fadd_rn(S[k], __fmul_rn(nwf, __fmul_rn(d0, d1)));
-                    m[k] = m1;
-                    S[k] = s1;
-                    sg[k] = __fsqrt_rn(fabsf(__fdiv_rn(s1, twf)));             // :942
+                    const int k = (ch << 7) + (lane << 2);
+                    if (k < DmPad)
+                    {
+                        float4 mv = *reinterpret_cast<float4 *>(m + k);
+                        float4 sv = *reinterpret_cast<float4 *>(S + k);
+                        const float4 xv = *reinterpret_cast<const float4 *>(xt + k);
+                        update_element<TR>(xv.x, c, nwf, mv.x, sv.x);
+                        update_element<TR>(xv.y, c, nwf, mv.y, sv.y);
+                        update_element<TR>(xv.z, c, nwf, mv.z, sv.z);
+                        update_element<TR>(xv.w, c, nwf, mv.w, sv.w);
+                        *reinterpret_cast<float4 *>(m + k) = mv;
+                        *reinterpret_cast<float4 *>(S + k) = sv;
+                    }
+                }
+                else
+                {
+                    // Stepper of CLR (src/Transformation.cpp:107-142): inner = (A x' + B) - y';
+                    // delta = [ (-2 inner) x' || -2 inner ]
+                    const int P = p.P;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const int q = (ch << 7) + (j << 5) + lane;
+                        if (q < P)
+                        {
+                            const float xi = xt[pi[q]], xj = xt[pj[q]];
+                            const float a0 = m[q], b0 = m[P + q];
+                            const float in0 = __fsub_rn(__fadd_rn(__fmul_rn(a0, xi), b0), xj);
+                            const float db0 = __fmul_rn(-2.0f, in0);
+                            const float da0 = __fmul_rn(db0, xi);
+                            const float a1 = __fadd_rn(a0, __fmul_rn(c, da0));
+                            const float b1 = __fadd_rn(b0, __fmul_rn(c, db0));
+                            const float in1 = __fsub_rn(__fadd_rn(__fmul_rn(a1, xi), b1), xj);
+                            const float db1 = __fmul_rn(-2.0f, in1);
+                            const float da1 = __fmul_rn(db1, xi);
+                            m[q] = a1;
+                            m[P + q] = b1;
+                            S[q] = __fadd_rn(S[q], __fmul_rn(nwf, __fmul_rn(da0, da1)));
+                            S[P + q] = __fadd_rn(S[P + q], __fmul_rn(nwf, __fmul_rn(db0, db1)));
+                        }
+                    }
                 }
             }
-            else
-            {
-                // Stepper of CLR (src/Transformation.cpp:107-142): inner = (A x' + B) - y';
-                // delta = [ (-2 inner) x' || -2 inner ]
-                const int P = p.P;
-                for (int q = lane; q < P; q += 32)
-                {
-                    const float xi = xt[pi[q]], xj = xt[pj[q]];
-                    const float a0 = m[q], b0 = m[P + q];
-                    const float in0 = __fsub_rn(__fadd_rn(__fmul_rn(a0, xi), b0), xj);
-                    const float db0 = __fmul_rn(-2.0f, in0);
-                    const float da0 = __fmul_rn(db0, xi);
-                    const float a1 = __fadd_rn(a0, __fmul_rn(c, da0));
-                    const float b1 = __fadd_rn(b0, __fmul_rn(c, db0));
-                    const float in1 = __fsub_rn(__fadd_rn(__fmul_rn(a1, xi), b1), xj);
-                    const float db1 = __fmul_rn(-2.0f, in1);
-                    const float da1 = __fmul_rn(db1, xi);
-                    const float sa = __fadd_rn(S[q], __fmul_rn(nwf, __fmul_rn(da0, da1)));
-                    const float sb = __fadd_rn(S[P + q], __fmul_rn(nwf, __fmul_rn(db0, db1)));
-                    m[q] = a1;
-                    m[P + q] = b1;
-                    S[q] = sa;
-                    S[P + q] = sb;
-                    sg[q] = __fsqrt_rn(fabsf(__fdiv_rn(sa, twf)));
-                    sg[P + q] = __fsqrt_rn(fabsf(__fdiv_rn(sb, twf)));
-                }
-            }
+        }
+#undef VSOM_NODE_COEF
+        done = t + 1;
+        if (p.prof && tid == 0)
+        {
+            const long long c5 = clock64();
+            prof[0] += c1 - c0;
+            prof[1] += c2 - c1;
+            prof[2] += c3 - c2;
+            prof[3] += c4 - c3;
+            prof[4] += c5 - c4;
         }
         // the __syncthreads at the top of the next iteration orders these writes before the next scan
     }
 
-    // ---- epilogue: last owed output, then write the owned rows back
+    // ---- epilogue: last owed output, lazy sigma, then write the owned rows back
     __syncthreads();
     if (sPendL >= 0)
     {
@@ -348,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         {
             if (tid == 0)
             {
-                d = dist_sequential<TR>(mBase + pendL * stride, xprev, p.Dr, p.P, pi, pj);
+                d = node_dist_reference<TR>(mBase + pendL * stride, xprev, p, n4, pi, pj);
                 writer = true;
             }
         }
@@ -367,52 +473,73 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             p.hits[q] += 1;
         }
     }
+    const float *wfin = wbuf + (done & 1) * Lpad;
     for (int l = tid; l < L; l += kThreads)
-        p.weight[static_cast<size_t>(l) * G + b] = wloc[l];
-    if (p.resident)
-        for (int l = warp; l < L; l += kWarps)
+        p.weight[static_cast<size_t>(l) * G + b] = wfin[l];
+    for (int l = warp; l < L; l += kWarps)
+    {
+        const size_t g = (static_cast<size_t>(l) * G + b) * p.rowStride;
+        const bool vis = touched[l] != 0;
+        // sigmaMap of a visited node: sqrt(|S / (float)(W == 0 ? 1e-6 : W)|) with its final S and W (src/Som.cpp:939-942)
+        const float w = wfin[l];
+        const float twf = static_cast<float>((w == 0.0f) ? 0.000001 : static_cast<double>(w));
+        for (int k = lane; k < p.Dm; k += 32)
         {
-            const size_t g = (static_cast<size_t>(l) * G + b) * p.rowStride;
-            for (int k = lane; k < p.Dm; k += 32)
+            const float sv = sBase[l * stride + k];
+            if (RES)
             {
                 p.mean[g + k] = mBase[l * stride + k];
-                p.S[g + k] = sBase[l * stride + k];
-                p.sigma[g + k] = gBase[l * stride + k];
+                p.S[g + k] = sv;
             }
+            if (vis)
+                p.sigma[g + k] = __fsqrt_rn(fabsf(__fdiv_rn(sv, twf)));
         }
+    }
+    if (p.prof && tid == 0)
+        for (int i = 0; i < 5; ++i)
+            p.prof[static_cast<size_t>(b) * 5 + i] = prof[i];
 }
 
 // --------------------------------------------------------------------------------------------- host side
 
+static int resident_stride(const vsom_ctx *ctx)
+{
+    // rows start 16-byte aligned and (stride / 4) is odd: the thread-per-node scan (lanes = nodes, 128-bit
+    // loads) and the warp-per-node update (lanes = consecutive words) are both bank-conflict free.
+    const int n4 = (ctx->Dm + 3) / 4;
+    return 4 * (n4 | 1);
+}
+
 static size_t online_step_smem(const vsom_ctx *ctx, int G, bool resident, int smStride)
 {
     const int Lmax = (ctx->N + G - 1) / G;
+    const int Lpad = (Lmax + 3) & ~3;
     const int DinPad = (ctx->Din + 3) & ~3;
-    size_t bytes = sizeof(float) * (3 * static_cast<size_t>(DinPad) + 4 * static_cast<size_t>(Lmax)) + sizeof(int) * static_cast<size_t>(Lmax);
-    bytes += 2 * sizeof(unsigned short) * static_cast<size_t>((ctx->P + 1) & ~1);
+    const int Ppad = (ctx->P + 7) & ~7;
+    size_t bytes = sizeof(float) * (3 * static_cast<size_t>(DinPad) + 2 * static_cast<size_t>(Lpad));
+    bytes += (sizeof(int2) + sizeof(unsigned)) * static_cast<size_t>(Lpad);
+    bytes += 2 * sizeof(unsigned short) * static_cast<size_t>(Ppad);
     if (resident)
-        bytes += sizeof(float) * 3 * static_cast<size_t>(Lmax) * smStride;
+        bytes += sizeof(float) * 2 * static_cast<size_t>(Lmax) * smStride;
     return bytes;
 }
 
 typedef void (*StepKernel)(const StepParams);
-static StepKernel pick_kernel(int transform, int order)
+static StepKernel pick_kernel(int transform, int order, int resident)
 {
-    static const StepKernel table[3][2] = {
-        {online_step_kernel<VSOM_STANDARD, VSOM_ORDER_REFERENCE>, online_step_kernel<VSOM_STANDARD, VSOM_ORDER_LANES>},
-        {online_step_kernel<VSOM_MEDIAN, VSOM_ORDER_REFERENCE>, online_step_kernel<VSOM_MEDIAN, VSOM_ORDER_LANES>},
-        {online_step_kernel<VSOM_CLR, VSOM_ORDER_REFERENCE>, online_step_kernel<VSOM_CLR, VSOM_ORDER_LANES>}};
-    return table[transform][order];
+#define VSOM_K(TR, ORD) {online_step_kernel<TR, ORD, false>, online_step_kernel<TR, ORD, true>}
+    static const StepKernel table[3][2][2] = {{VSOM_K(VSOM_STANDARD, VSOM_ORDER_REFERENCE), VSOM_K(VSOM_STANDARD, VSOM_ORDER_LANES)},
+                                              {VSOM_K(VSOM_MEDIAN, VSOM_ORDER_REFERENCE), VSOM_K(VSOM_MEDIAN, VSOM_ORDER_LANES)},
+                                              {VSOM_K(VSOM_CLR, VSOM_ORDER_REFERENCE), VSOM_K(VSOM_CLR, VSOM_ORDER_LANES)}};
+#undef VSOM_K
+    return table[transform][order][resident ? 1 : 0];
 }
 
 int configure_online_step(vsom_ctx *ctx)
 {
-    StepKernel k = pick_kernel(ctx->transform, ctx->order);
     const int G = ctx->N < ctx->numSMs ? ctx->N : ctx->numSMs;
-    // an odd row stride makes the thread-per-node sequential scan bank-conflict free; the warp-per-node
-    // paths read consecutive words and do not care.
-    const int smStride = ctx->Dm | 1;
-    const size_t statics = 512; // static __shared__ of the kernel, rounded up
+    const int smStride = resident_stride(ctx);
+    const size_t statics = 1024; // static __shared__ of the kernel, rounded up
     size_t bytes = online_step_smem(ctx, G, true, smStride);
     int resident = 1;
     if (bytes + statics > static_cast<size_t>(ctx->smemOptin))
@@ -422,6 +549,7 @@ int configure_online_step(vsom_ctx *ctx)
         if (bytes + statics > static_cast<size_t>(ctx->smemOptin))
             return set_error(ctx, VSOM_ERR_UNSUPPORTED, "online step: per-CTA bookkeeping does not fit in shared memory for this map");
     }
+    StepKernel k = pick_kernel(ctx->transform, ctx->order, resident);
     VSOM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
     int perSm = 0;
     VSOM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k, kThreads, bytes));
@@ -471,8 +599,8 @@ static int build_lut(vsom_ctx *ctx, double eta, double sigma)
         VSOM_CUDA(ctx, cudaMalloc(&ctx->lut, bytes));
         ctx->lutCap = bytes;
     }
-    // the previous chunk's kernel may still be reading the old table: stream-ordered copy from a pageable
-    // buffer is staged by the runtime before the call returns, so lutHost can be reused afterwards.
+    // the previous chunk's kernel may still be reading the old table: the copy is stream-ordered behind it, and
+    // a copy from pageable memory is staged by the runtime before the call returns, so lutHost can be reused.
     VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->lut, ctx->lutHost.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
     ctx->lutEta = eta;
     ctx->lutSigma = sigma;
@@ -533,8 +661,10 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.resident = ctx->residentTrain;
     p.smStride = ctx->smStrideTrain;
     p.timeoutCycles = 4000000000ll; // ~2 s at 1.9 GHz: a peer CTA that never publishes is a bug, not a wait
+    p.prof = ctx->profDev;
+    ctx->profSamples = n;
 
-    StepKernel k = pick_kernel(ctx->transform, ctx->order);
+    StepKernel k = pick_kernel(ctx->transform, ctx->order, ctx->residentTrain);
     void *args[] = {&p};
     VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k), dim3(G), dim3(kThreads), args, ctx->smemTrain, ctx->stream));
     ctx->launches += 1;
