@@ -128,7 +128,7 @@ int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int
     CREATE_CUDA(cudaMalloc(&ctx->weight, sizeof(float) * ctx->N));
     CREATE_CUDA(cudaMalloc(&ctx->hits, sizeof(u64) * ctx->N));
     CREATE_CUDA(cudaMalloc(&ctx->umatrix, sizeof(double) * ctx->N));
-    CREATE_CUDA(cudaMalloc(&ctx->slots, sizeof(u64) * 2 * static_cast<size_t>(ctx->numSMs)));
+    CREATE_CUDA(cudaMalloc(&ctx->slots, sizeof(u64) * 2 * static_cast<size_t>(ctx->numSMs) * ((ctx->numSMs + 15) & ~15)));
     CREATE_CUDA(cudaMalloc(&ctx->errFlag, sizeof(int)));
     CREATE_CUDA(cudaMemsetAsync(ctx->mean, 0, plane, ctx->stream));
     CREATE_CUDA(cudaMemsetAsync(ctx->S, 0, plane, ctx->stream));

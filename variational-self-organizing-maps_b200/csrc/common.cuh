@@ -44,13 +44,15 @@ struct StepParams
     const LutEntry *lut;
     int lutW;
     const unsigned short *pairI, *pairJ; // CLR pair tables (src/Transformation.cpp:94-101)
-    u64 *slots;               // [2][gridDim.x] min-loc exchange
+    u64 *slots;               // [2][G][pitch] min-loc exchange: slots[buffer][destination CTA][source CTA]
     int *err;                 // set to 1 when a CTA gave up waiting
     unsigned *outBmu;         // per sample, may be null
     float *outDist;           // per sample, may be null
     int resident;             // planes of the owned nodes live in shared memory for the whole chunk
     int smStride;             // row stride (floats) of the resident copy
     long long timeoutCycles;
+    int lutSmem, lutCount;    // copy the table into shared memory (it fits behind the resident rows)
+    int xVec;                 // sample rows are 16-byte aligned: 16-byte cp.async
     long long *prof;          // optional [gridDim.x][5] per-phase cycle sums of thread 0 (diagnostics), else null
 };
 
@@ -129,6 +131,11 @@ __device__ __forceinline__ void cp_async4(void *smemDst, const void *gmemSrc)
     unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smemDst, const void *gmemSrc)
+{
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ u64 u64_min(u64 a, u64 b) { return a < b ? a : b; }
@@ -138,6 +145,16 @@ __device__ __forceinline__ u64 warp_min_u64(u64 v)
     for (int o = 16; o; o >>= 1)
         v = u64_min(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// min over the warp of a 64-bit key with two REDUX instead of ten shuffles: min of the high words, then min of
+// the low words among the lanes that hold that high word.  All lanes get the result.
+__device__ __forceinline__ u64 warp_min_key(u64 k)
+{
+    const unsigned hi = static_cast<unsigned>(k >> 32), lo = static_cast<unsigned>(k);
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    return (static_cast<u64>(mhi) << 32) | mlo;
 }
 
 // (distance, node) -> sortable key.  Distances are sums of squares (>= +0), so their IEEE bit patterns order

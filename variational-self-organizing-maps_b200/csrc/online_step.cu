@@ -10,10 +10,13 @@
 //     are read and written by exactly one CTA: when the owned rows of the mean and S planes fit in shared
 //     memory they are loaded once, stay there for the whole chunk and are written back at the end
 //     (configs 1-3); otherwise they are addressed in global memory (large maps).
-//   * per sample there is exactly ONE grid-wide exchange: every CTA publishes the min (distance,node) key of
-//     its nodes in a tagged 64-bit slot, then reads all G slots and takes the min itself.  No second barrier
-//     is needed because the window update of a node is done by its owner, which is also the only CTA that
-//     scans it for the next sample.  Round-robin ownership spreads any update window evenly over the SMs.
+//   * per sample there is exactly ONE grid-wide exchange: every CTA pushes the min (distance,node) key of its
+//     nodes, tagged with the step number, into a private row of every other CTA (slots[dest][src]); each CTA
+//     then polls only its own row (G words, lines nobody else reads) and takes the min itself.  Pushing keeps
+//     the polling traffic off shared cache lines: with a single shared row, 148 pollers hammering the same
+//     ten L2 lines cost ~4000 cycles per sample (profiles/r01_bench_k1_v1.json).  No second barrier is needed
+//     because the window update of a node is done by its owner, which is also the only CTA that scans it for
+//     the next sample.  Round-robin ownership spreads any update window evenly over the SMs.
 //   * sigmaMap is a pure function of the node's SMap and weightMap at its LAST visit
 //     (sigma = sqrt(|S / (W==0 ? 1e-6 : W)|), src/Som.cpp:939-942, overwritten at every visit), and nothing on
 //     this path reads it (all shipped Comparers ignore `dispersion`).  The kernel therefore only marks the
@@ -33,6 +36,7 @@ namespace vsom
 
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
+constexpr size_t kStaticSmem = 1024; // static __shared__ of the kernel, rounded up
 
 template <int TR>
 __device__ __forceinline__ float stepper_scalar(float xv, float m)
@@ -56,24 +60,43 @@ __device__ __forceinline__ void update_element(float xv, float c, float nwf, flo
 }
 
 // Squared distance, reference order, over zero-padded rows with 128-bit loads (Standard / Median).
+// The chain s += r*r is 4 cycles per element and cannot be shortened without changing the order; the loads of
+// the next group are issued before the current group's adds so that their latency stays off the chain.
+__device__ __forceinline__ void acc4(float &s, const float4 a, const float4 b)
+{
+    float r = __fsub_rn(a.x, b.x);
+    s = __fadd_rn(s, __fmul_rn(r, r));
+    r = __fsub_rn(a.y, b.y);
+    s = __fadd_rn(s, __fmul_rn(r, r));
+    r = __fsub_rn(a.z, b.z);
+    s = __fadd_rn(s, __fmul_rn(r, r));
+    r = __fsub_rn(a.w, b.w);
+    s = __fadd_rn(s, __fmul_rn(r, r));
+}
 __device__ __forceinline__ float dist_sequential_v4(const float *m, const float *xs, int n4)
 {
     const float4 *m4 = reinterpret_cast<const float4 *>(m);
     const float4 *x4 = reinterpret_cast<const float4 *>(xs);
     float s = 0.0f;
-#pragma unroll 4
-    for (int c = 0; c < n4; ++c)
+    const int pairs = n4 >> 1;
+    if (pairs > 0)
     {
-        const float4 a = m4[c], b = x4[c];
-        float r = __fsub_rn(a.x, b.x);
-        s = __fadd_rn(s, __fmul_rn(r, r));
-        r = __fsub_rn(a.y, b.y);
-        s = __fadd_rn(s, __fmul_rn(r, r));
-        r = __fsub_rn(a.z, b.z);
-        s = __fadd_rn(s, __fmul_rn(r, r));
-        r = __fsub_rn(a.w, b.w);
-        s = __fadd_rn(s, __fmul_rn(r, r));
+        float4 a0 = m4[0], b0 = x4[0], a1 = m4[1], b1 = x4[1];
+        for (int g = 1; g < pairs; ++g)
+        {
+            const float4 c0 = m4[2 * g], d0 = x4[2 * g], c1 = m4[2 * g + 1], d1 = x4[2 * g + 1];
+            acc4(s, a0, b0);
+            acc4(s, a1, b1);
+            a0 = c0;
+            b0 = d0;
+            a1 = c1;
+            b1 = d1;
+        }
+        acc4(s, a0, b0);
+        acc4(s, a1, b1);
     }
+    if (n4 & 1)
+        acc4(s, m4[n4 - 1], x4[n4 - 1]);
     return s;
 }
 
@@ -91,10 +114,11 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 sWarpKey[kWarps];
-    __shared__ u64 sBmuKey;
+    __shared__ int sWin[8]; // bmu, bx, by, startX, endX, startY, endY of the current sample
     __shared__ int sAbort;
     __shared__ int sPendL; // local node whose post-update distance is still owed (-1: none)
     __shared__ u64 sPendT; // ... for this sample
+    __shared__ long long sClk[6], sProf[5]; // diagnostics (thread 0 only)
 
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Lmax = (p.nodeCount + G - 1) / G;
@@ -102,6 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     const int DinPad = (p.Din + 3) & ~3;
     const int DmPad = (p.Dm + 3) & ~3;
     const int n4 = DmPad >> 2;
+    const int Gp = (G + 15) & ~15; // pitch of one destination row of the exchange (whole 128-byte lines)
 
     // ---- carve shared memory (every region 16-byte aligned)
     float *xs = reinterpret_cast<float *>(smemRaw);                          // [3][DinPad] sample ring
@@ -113,6 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     const int Ppad = (p.P + 7) & ~7;
     unsigned short *pj = pi + Ppad;
     float *planes = reinterpret_cast<float *>(pj + Ppad);                    // resident rows: 2 x Lmax x smStride
+    LutEntry *lutS = reinterpret_cast<LutEntry *>(planes + (RES ? 2 * static_cast<size_t>(Lmax) * p.smStride : 0)); // optional copy of the table
 
     float *mBase, *sBase;
     size_t stride;
@@ -129,13 +155,23 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         sBase = p.S + static_cast<size_t>(b) * p.rowStride;
     }
 
-    // ---- prologue: pair tables, owned weights / positions, resident rows, first sample
+    // slices of 128 elements of the model vector (CLR: of the pair index); with one slice per node a single
+    // warp owns the node's whole update and the weight needs no double buffer.
+    const int nq = TR == VSOM_CLR ? p.P : DmPad;
+    const int nCh = (nq + 127) >> 7;
+    const bool dbl = nCh > 1;
+
+    // ---- prologue: pair tables, neighbourhood table, owned weights / positions, resident rows, first sample
     if (TR == VSOM_CLR)
         for (int q = tid; q < p.P; q += kThreads)
         {
             pi[q] = p.pairI[q];
             pj[q] = p.pairJ[q];
         }
+    if (p.lutSmem)
+        for (int i = tid; i < p.lutCount; i += kThreads)
+            lutS[i] = p.lut[i];
+    const LutEntry *lut = p.lutSmem ? lutS : p.lut;
     for (int l = tid; l < L; l += kThreads)
     {
         const unsigned node = static_cast<unsigned>(p.node0 + l * G + b);
@@ -163,32 +199,44 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         sPendT = 0;
     }
     __syncthreads();
+
+    // sample prefetch: 16-byte cp.async.cg (L2 only — a streamed sample must not evict the L1-resident table)
+    // when rows are 16-byte aligned, else 4-byte cp.async.ca
+    auto prefetch = [&](u64 t) {
+        float *dst = xs + (t % 3) * DinPad;
+        const float *src = p.x + t * static_cast<u64>(p.Din);
+        if (p.xVec)
+        {
+            for (int k = tid * 4; k < p.Din; k += kThreads * 4)
+                cp_async16(dst + k, src + k);
+        }
+        else
+        {
+            for (int k = tid; k < p.Din; k += kThreads)
+                cp_async4(dst + k, src + k);
+        }
+    };
     if (p.n > 0)
-        for (int k = tid; k < p.Din; k += kThreads)
-            cp_async4(xs + k, p.x + k);
+        prefetch(0);
 
     const double dW = static_cast<double>(p.W), dH = static_cast<double>(p.H);
-    long long prof[5] = {0, 0, 0, 0, 0};
+    if (tid == 0)
+        for (int i = 0; i < 5; ++i)
+            sProf[i] = 0;
     u64 done = 0;
 
     for (u64 t = 0; t < p.n; ++t)
     {
-        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
         if (p.prof && tid == 0)
-            c0 = clock64();
+            sClk[0] = clock64();
         const float *xt = xs + (t % 3) * DinPad;
-        float *wcur = wbuf + (t & 1) * Lpad, *wnext = wbuf + ((t + 1) & 1) * Lpad;
+        float *wcur = wbuf + (dbl ? (t & 1) * Lpad : 0), *wnext = wbuf + (dbl ? ((t + 1) & 1) * Lpad : 0);
         cp_async_wait_all();
         __syncthreads(); // sample t landed; update of sample t-1 is complete; sPend* of t-1 visible
         if (t + 1 < p.n)
-        {
-            float *xn = xs + ((t + 1) % 3) * DinPad;
-            const float *src = p.x + (t + 1) * static_cast<u64>(p.Din);
-            for (int k = tid; k < p.Din; k += kThreads)
-                cp_async4(xn + k, src + k);
-        }
+            prefetch(t + 1);
         if (p.prof && tid == 0)
-            c1 = clock64();
+            sClk[1] = clock64();
         const unsigned tag = static_cast<unsigned>((t >> 1) & 0xff);
 
         // ---- owed output of sample t-1: distance to its updated BMU (src/Som.cpp:946) + addBmu (:1189-1192)
@@ -237,32 +285,29 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
             }
         }
-        best = warp_min_u64(best);
         // REFERENCE order with at most 32 owned nodes: every key already sits in warp 0 — no CTA barrier
         const bool crossWarp = ORDER != VSOM_ORDER_REFERENCE || L > 32;
         if (crossWarp)
         {
+            best = warp_min_key(best);
             if (lane == 0)
                 sWarpKey[warp] = best;
             __syncthreads();
         }
 
-        // ---- grid-wide min-loc: publish, then read every CTA's slot of this step
+        // ---- grid-wide min-loc: push the key into every CTA's row, then poll the own row
         if (warp == 0)
         {
-            u64 k = best;
-            if (crossWarp)
-            {
-                k = lane < kWarps ? sWarpKey[lane] : ~0ull;
-                k = warp_min_u64(k);
-            }
-            u64 *slots = p.slots + static_cast<size_t>(t & 1) * G;
+            u64 k = crossWarp ? (lane < kWarps ? sWarpKey[lane] : ~0ull) : best;
+            k = warp_min_key(k);
             if (k == ~0ull) // CTA without nodes (cannot happen: G <= nodeCount) — still publish a tagged key
                 k = (~0ull << 8) | tag;
+            u64 *buf = p.slots + static_cast<size_t>(t & 1) * G * Gp;
             if (p.prof && tid == 0)
-                c2 = clock64();
-            if (lane == 0)
-                st_relaxed_gpu(slots + b, k);
+                sClk[2] = clock64();
+            for (int d = lane; d < G; d += 32)
+                st_relaxed_gpu(buf + static_cast<size_t>(d) * Gp + b, k);
+            const u64 *row = buf + static_cast<size_t>(b) * Gp;
             const long long t0 = clock64();
             u64 m;
             bool abort = false;
@@ -272,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 int ok = 1;
                 for (int i = lane; i < G; i += 32)
                 {
-                    const u64 v = ld_relaxed_gpu(slots + i);
+                    const u64 v = ld_relaxed_gpu(row + i);
                     ok &= (static_cast<unsigned>(v & 0xff) == tag);
                     m = u64_min(m, v);
                 }
@@ -284,10 +329,24 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     break;
                 }
             }
-            m = warp_min_u64(m);
+            m = warp_min_key(m);
             if (lane == 0)
             {
-                sBmuKey = m;
+                // window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric
+                const unsigned bmu = key_node(m);
+                const int bx = static_cast<int>(bmu % static_cast<unsigned>(p.W));
+                const int by = static_cast<int>(bmu / static_cast<unsigned>(p.W));
+                double lo = __dsub_rn(static_cast<double>(bx), p.radius);
+                sWin[3] = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
+                lo = __dsub_rn(static_cast<double>(by), p.radius);
+                sWin[5] = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
+                double hi = __dadd_rn(static_cast<double>(bx), p.radius);
+                sWin[4] = static_cast<int>(static_cast<u64>(hi < dW ? hi : dW));
+                hi = __dadd_rn(static_cast<double>(by), p.radius);
+                sWin[6] = static_cast<int>(static_cast<u64>(hi < dH ? hi : dH));
+                sWin[0] = static_cast<int>(bmu);
+                sWin[1] = bx;
+                sWin[2] = by;
                 sPendL = -1;
                 if (abort)
                 {
@@ -296,30 +355,18 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 }
             }
             if (p.prof && tid == 0)
-                c3 = clock64();
+                sClk[3] = clock64();
         }
         __syncthreads();
         if (sAbort)
             break;
         if (p.prof && tid == 0)
-            c4 = clock64();
+            sClk[4] = clock64();
+        const unsigned bmu = static_cast<unsigned>(sWin[0]);
+        const int bx = sWin[1], by = sWin[2], startX = sWin[3], endX = sWin[4], startY = sWin[5], endY = sWin[6];
 
-        // ---- window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric
-        const unsigned bmu = key_node(sBmuKey);
-        const int bx = static_cast<int>(bmu % static_cast<unsigned>(p.W));
-        const int by = static_cast<int>(bmu / static_cast<unsigned>(p.W));
-        double lo = __dsub_rn(static_cast<double>(bx), p.radius);
-        const int startX = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
-        lo = __dsub_rn(static_cast<double>(by), p.radius);
-        const int startY = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
-        double hi = __dadd_rn(static_cast<double>(bx), p.radius);
-        const int endX = static_cast<int>(static_cast<u64>(hi < dW ? hi : dW));
-        hi = __dadd_rn(static_cast<double>(by), p.radius);
-        const int endY = static_cast<int>(static_cast<u64>(hi < dH ? hi : dH));
-
-        // Per window node: the neighbourhood entry and the step coefficient (src/Som.cpp:915-939).  Evaluated
-        // redundantly by every warp that works on the node — reading the OLD weight from wcur — so that no
-        // barrier is needed between "weights" and "vectors".
+        // Per window node: the neighbourhood entry and the step coefficient (src/Som.cpp:915-939), from the
+        // node's OLD weight in wcur.
 #define VSOM_NODE_COEF(l_, inWin_, c_, nwf_, w1_)                                                                        \
     {                                                                                                                    \
         const int2 xy = nodeXY[l_];                                                                                      \
@@ -327,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         if (inWin_)                                                                                                      \
         {                                                                                                                \
             const int dx = xy.x > bx ? xy.x - bx : bx - xy.x, dy = xy.y > by ? xy.y - by : by - xy.y;                    \
-            const float4 raw = __ldg(reinterpret_cast<const float4 *>(p.lut + dy * p.lutW + dx));                        \
+            const float4 raw = *reinterpret_cast<const float4 *>(lut + dy * p.lutW + dx);                                \
             const float cexp = raw.z;                                                                                    \
             nwf_ = raw.w;                                                                                                \
             const float w0 = wcur[l_];                                                                                   \
@@ -346,40 +393,53 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         }                                                                                                                \
     }
 
-        // ---- phase A: one thread per owned node — the new weightMap value goes to the other weight buffer
-        for (int l = tid; l < L; l += kThreads)
-        {
-            bool inWin;
-            float c = 0.0f, nwf = 0.0f, w1 = wcur[l];
-            VSOM_NODE_COEF(l, inWin, c, nwf, w1);
-            wnext[l] = w1;
-            if (inWin)
+        // ---- phase A (only when a node's vector spans several warps): one thread per owned node writes the new
+        //      weightMap value to the other weight buffer, so that the warps of phase B all read the old one
+        if (dbl)
+            for (int l = tid; l < L; l += kThreads)
             {
-                touched[l] = 1;
-                if (static_cast<unsigned>(p.node0 + l * G + b) == bmu)
+                bool inWin;
+                float c = 0.0f, nwf = 0.0f, w1 = wcur[l];
+                VSOM_NODE_COEF(l, inWin, c, nwf, w1);
+                wnext[l] = w1;
+                if (inWin)
                 {
-                    sPendL = l;
-                    sPendT = t;
+                    touched[l] = 1;
+                    if (static_cast<unsigned>(p.node0 + l * G + b) == bmu)
+                    {
+                        sPendL = l;
+                        sPendT = t;
+                    }
                 }
+                (void)c;
+                (void)nwf;
             }
-            (void)c;
-            (void)nwf;
-        }
 
         // ---- phase B: one warp per (window node, 128-element slice) of the model vector (src/Som.cpp:912-941)
         {
-            const int nq = TR == VSOM_CLR ? p.P : DmPad;
-            const int nCh = (nq + 127) >> 7;
             const int items = L * nCh;
             for (int it = warp; it < items; it += kWarps)
             {
-                const int l = it / nCh, ch = it - l * nCh;
+                const int l = dbl ? it / nCh : it, ch = dbl ? it - l * nCh : 0;
                 bool inWin;
                 float c = 0.0f, nwf = 0.0f, w1 = 0.0f;
                 VSOM_NODE_COEF(l, inWin, c, nwf, w1);
-                (void)w1;
                 if (!inWin)
                     continue;
+                if (!dbl)
+                {
+                    __syncwarp(); // every lane has read the old weight
+                    if (lane == 0)
+                    {
+                        wcur[l] = w1;
+                        touched[l] = 1;
+                        if (static_cast<unsigned>(p.node0 + l * G + b) == bmu)
+                        {
+                            sPendL = l;
+                            sPendT = t;
+                        }
+                    }
+                }
                 float *m = mBase + l * stride, *S = sBase + l * stride;
                 if (TR != VSOM_CLR)
                 {
@@ -431,12 +491,9 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         done = t + 1;
         if (p.prof && tid == 0)
         {
-            const long long c5 = clock64();
-            prof[0] += c1 - c0;
-            prof[1] += c2 - c1;
-            prof[2] += c3 - c2;
-            prof[3] += c4 - c3;
-            prof[4] += c5 - c4;
+            sClk[5] = clock64();
+            for (int i = 0; i < 5; ++i)
+                sProf[i] += sClk[i + 1] - sClk[i];
         }
         // the __syncthreads at the top of the next iteration orders these writes before the next scan
     }
@@ -473,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             p.hits[q] += 1;
         }
     }
-    const float *wfin = wbuf + (done & 1) * Lpad;
+    const float *wfin = wbuf + (dbl ? (done & 1) * Lpad : 0);
     for (int l = tid; l < L; l += kThreads)
         p.weight[static_cast<size_t>(l) * G + b] = wfin[l];
     for (int l = warp; l < L; l += kWarps)
@@ -497,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     }
     if (p.prof && tid == 0)
         for (int i = 0; i < 5; ++i)
-            p.prof[static_cast<size_t>(b) * 5 + i] = prof[i];
+            p.prof[static_cast<size_t>(b) * 5 + i] = sProf[i];
 }
 
 // --------------------------------------------------------------------------------------------- host side
@@ -539,7 +596,7 @@ int configure_online_step(vsom_ctx *ctx)
 {
     const int G = ctx->N < ctx->numSMs ? ctx->N : ctx->numSMs;
     const int smStride = resident_stride(ctx);
-    const size_t statics = 1024; // static __shared__ of the kernel, rounded up
+    const size_t statics = kStaticSmem;
     size_t bytes = online_step_smem(ctx, G, true, smStride);
     int resident = 1;
     if (bytes + statics > static_cast<size_t>(ctx->smemOptin))
@@ -550,7 +607,7 @@ int configure_online_step(vsom_ctx *ctx)
             return set_error(ctx, VSOM_ERR_UNSUPPORTED, "online step: per-CTA bookkeeping does not fit in shared memory for this map");
     }
     StepKernel k = pick_kernel(ctx->transform, ctx->order, resident);
-    VSOM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    VSOM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smemOptin - static_cast<int>(kStaticSmem)));
     int perSm = 0;
     VSOM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k, kThreads, bytes));
     if (perSm < 1)
@@ -628,7 +685,8 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     if (rc)
         return rc;
     const int G = ctx->gridTrain;
-    VSOM_CUDA(ctx, cudaMemsetAsync(ctx->slots, 0xff, sizeof(u64) * 2 * static_cast<size_t>(G), ctx->stream));
+    const int Gp = (G + 15) & ~15;
+    VSOM_CUDA(ctx, cudaMemsetAsync(ctx->slots, 0xff, sizeof(u64) * 2 * static_cast<size_t>(G) * Gp, ctx->stream));
     VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
 
     StepParams p;
@@ -663,10 +721,16 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.timeoutCycles = 4000000000ll; // ~2 s at 1.9 GHz: a peer CTA that never publishes is a bug, not a wait
     p.prof = ctx->profDev;
     ctx->profSamples = n;
+    // the neighbourhood table rides in shared memory behind the resident rows when it fits
+    p.lutCount = ctx->lutW * ctx->lutH;
+    const size_t lutBytes = sizeof(LutEntry) * static_cast<size_t>(p.lutCount);
+    p.lutSmem = (ctx->smemTrain + lutBytes + kStaticSmem <= static_cast<size_t>(ctx->smemOptin)) ? 1 : 0;
+    const size_t smemBytes = ctx->smemTrain + (p.lutSmem ? lutBytes : 0);
+    p.xVec = (ctx->Din % 4 == 0 && (reinterpret_cast<uintptr_t>(xDev) & 15) == 0) ? 1 : 0;
 
     StepKernel k = pick_kernel(ctx->transform, ctx->order, ctx->residentTrain);
     void *args[] = {&p};
-    VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k), dim3(G), dim3(kThreads), args, ctx->smemTrain, ctx->stream));
+    VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k), dim3(G), dim3(kThreads), args, smemBytes, ctx->stream));
     ctx->launches += 1;
     return VSOM_OK;
 }
