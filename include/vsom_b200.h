@@ -106,6 +106,9 @@ VSOM_API int vsom_debug_phase_cycles(vsom_ctx *ctx, double out[5]);
 VSOM_API int vsom_upload_state(vsom_ctx *ctx, const float *mean, const float *S, const float *sigma, const float *weight, const uint64_t *hits);
 VSOM_API int vsom_download_state(vsom_ctx *ctx, float *mean, float *S, float *sigma, float *weight, uint64_t *hits);
 
+/* One node's rows: Som::getNeuron / Som::getSigmaNeuron (src/Som.cpp:194-212).  Either output may be NULL. */
+VSOM_API int vsom_get_node(vsom_ctx *ctx, size_t node, float *mean, float *sigma);
+
 /* -------------------------------------------------------------------------------- online training */
 
 /* n consecutive Som::trainSingle + Som::addBmu calls at fixed (eta, sigma): the inner loop of

@@ -1,0 +1,86 @@
+"""Drop-in check of the host C++ classes (include/SOM.hpp & co. over libvsom_b200.so): tests/cpp/api_driver.cpp is
+one program written against the REFERENCE's public API; it is compiled once against the reference's own headers and
+sources (oracle/_ref/api_driver_ref, CPU) and once against this repository's include/ + libvsom_host.so
+(tests/cpp/api_driver_b200, B200).  Same input file -> the two output files must be identical byte for byte:
+Som::train (epoch schedule, chunked DataSet protocol, metrics), getNeuron / getSigmaNeuron / getWeigthMap /
+getBmuHits, updateUMatrix + getUMatrix, evaluate, measureSimilarity, findBmu, findRestrictedBmu,
+euclidianWeightedDist, calculateNeighbourhoodWeight."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+REF_DRIVER = os.path.join(REPO, "oracle", "_ref", "api_driver_ref")
+B200_DRIVER = os.path.join(REPO, "tests", "cpp", "api_driver_b200")
+
+# W, H, Din, transform, decay, epochs, chunk, seed, n, eta0, etaDecay, sigma0, sigmaDecay   (sigma stays > 1)
+CASES = [
+    (9, 7, 12, 0, 0, 4, 50, 42, 130, 0.3, 0.2, 3.0, 0.15),
+    (8, 8, 20, 0, 1, 3, 0, 7, 90, 0.3, 0.1, 2.5, 0.2),
+    (10, 6, 33, 1, 0, 4, 64, 3, 150, 0.05, 0.1, 3.5, 0.2),
+    (7, 9, 6, 2, 0, 3, 40, 11, 100, 0.01, 0.1, 2.2, 0.1),
+    (20, 20, 784, 0, 0, 2, 30, 42, 60, 0.1, 0.01, 5.0, 0.3),
+]
+
+
+def write_case(path, case, x):
+    W, H, Din, tr, dec, epochs, chunk, seed, n, eta0, eta_d, s0, s_d = case
+    with open(path, "wb") as f:
+        f.write(struct.pack("<9i", W, H, Din, tr, dec, epochs, chunk, seed, n))
+        f.write(struct.pack("<4d", eta0, eta_d, s0, s_d))
+        f.write(np.ascontiguousarray(x, np.float32).tobytes())
+
+
+def make_x(case):
+    W, H, Din, tr, *_ = case
+    n = case[8]
+    rng = np.random.default_rng(sum(case[:9]))
+    if tr == 2:
+        z = rng.standard_normal((n, 1)).astype(np.float32)
+        return (rng.uniform(0.5, 1.5, (1, Din)).astype(np.float32) * z + 0.1 * rng.standard_normal((n, Din))).astype(np.float32)
+    return rng.standard_normal((n, Din)).astype(np.float32)
+
+
+def expected_size(case):
+    W, H, Din, tr, dec, epochs, chunk, seed, n = case[:9]
+    Dm = Din * (Din - 1) if tr == 2 else Din
+    N = W * H
+    size = 4 * epochs + N * 2 * Dm * 4 + N * 4 + N * 8 + N * 8 + 16
+    if tr != 2:
+        size += 8 + 4
+    size += min(n, 16) * 24 + 8
+    return size
+
+
+@pytest.mark.parametrize("case", CASES[:2])
+def test_reference_driver_runs_on_cpu(tmp_path, case):
+    """CPU only: the reference build of the driver produces an output of the documented layout."""
+    if not os.path.exists(REF_DRIVER):
+        pytest.skip("oracle/_ref/api_driver_ref not built (needs /root/reference)")
+    write_case(tmp_path / "case.bin", case, make_x(case))
+    subprocess.run([REF_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "ref.bin")], check=True, timeout=300)
+    assert os.path.getsize(tmp_path / "ref.bin") == expected_size(case)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("case", CASES)
+def test_host_api_is_a_drop_in(tmp_path, vsom, case):
+    if not os.path.exists(REF_DRIVER):
+        pytest.skip("oracle/_ref/api_driver_ref not built (needs /root/reference)")
+    vsom.lib()  # builds libvsom_b200.so, libvsom_host.so and the B200 driver when sources are newer
+    assert os.path.exists(B200_DRIVER)
+    write_case(tmp_path / "case.bin", case, make_x(case))
+    subprocess.run([REF_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "ref.bin")], check=True, timeout=300)
+    subprocess.run([B200_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "b200.bin")], check=True, timeout=300)
+    ref = open(tmp_path / "ref.bin", "rb").read()
+    got = open(tmp_path / "b200.bin", "rb").read()
+    assert len(ref) == expected_size(case) and len(got) == len(ref)
+    if ref != got:
+        a, b = np.frombuffer(ref, np.uint8), np.frombuffer(got, np.uint8)
+        first = int(np.nonzero(a != b)[0][0])
+        raise AssertionError(f"outputs differ in {int((a != b).sum())} bytes, first at byte {first} of {len(ref)}")

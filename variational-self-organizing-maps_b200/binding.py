@@ -34,6 +34,7 @@ _PROTOS = {
     "vsom_debug_phase_cycles": (C.c_int, [_vp, _f64p]),
     "vsom_upload_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
     "vsom_download_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
+    "vsom_get_node": (C.c_int, [_vp, C.c_size_t, _f32p, _f32p]),
     "vsom_train_chunk": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_double, C.c_double, C.c_int, _u64p, _u32p, _f32p, _f32p]),
     "vsom_train_chunk_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_double, C.c_double, C.c_int, _vp, _vp]),
     "vsom_find_bmu": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),

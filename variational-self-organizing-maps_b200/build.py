@@ -38,7 +38,7 @@ def up_to_date() -> bool:
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(REPO, "include", "*.h")) + [os.path.abspath(__file__)]
+    deps = sources() + glob.glob(os.path.join(PKG, "host", "*.cpp")) + glob.glob(os.path.join(REPO, "include", "*.hpp")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(REPO, "include", "*.h")) + [os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
@@ -71,7 +71,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
+    build_host()
     return LIB
+
+
+HOST_LIB = os.path.join(LIB_DIR, "libvsom_host.so")
+API_DRIVER = os.path.join(REPO, "tests", "cpp", "api_driver_b200")
+
+
+def build_host() -> str:
+    """The drop-in C++ classes (include/SOM.hpp, ...) on top of the C-ABI, and the API driver of tests/cpp."""
+    cxx = shutil.which("g++") or "g++"
+    eigen = "/usr/include/eigen3" if os.path.exists("/usr/include/eigen3/Eigen/Dense") else os.path.join(REPO, "include", "compat")
+    flags = ["-std=c++20", "-O2", "-fPIC", "-ffp-contract=off", "-msse2", "-I", os.path.join(REPO, "include"), "-I", eigen]
+    stdcxx = ["-nostdlib++", "-l:libstdc++.so.6"] if os.path.exists("/usr/lib/x86_64-linux-gnu/libstdc++.so.6") else []
+    srcs = sorted(glob.glob(os.path.join(PKG, "host", "*.cpp")))
+    cmd = [cxx, *flags, "-shared", "-o", HOST_LIB, *srcs, "-L", LIB_DIR, "-lvsom_b200", "-Wl,-rpath,$ORIGIN", *stdcxx]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError(f"host library failed to build:\n{out.stdout}")
+    drv = os.path.join(REPO, "tests", "cpp", "api_driver.cpp")
+    if os.path.exists(drv):
+        cmd = [cxx, *flags, drv, "-o", API_DRIVER, "-L", LIB_DIR, "-lvsom_host", "-lvsom_b200", f"-Wl,-rpath,{LIB_DIR}", *stdcxx]
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if out.returncode != 0:
+            raise RuntimeError(f"api driver failed to build:\n{out.stdout}")
+    return HOST_LIB
 
 
 if __name__ == "__main__":

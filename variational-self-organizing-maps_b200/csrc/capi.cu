@@ -284,6 +284,20 @@ int vsom_download_state(vsom_ctx *ctx, float *mean, float *S, float *sigma, floa
     return VSOM_OK;
 }
 
+int vsom_get_node(vsom_ctx *ctx, size_t node, float *mean, float *sigma)
+{
+    if (!ctx || node >= static_cast<size_t>(ctx->N))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_get_node: node out of range") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t off = node * ctx->rowStride;
+    if (mean)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(mean, ctx->mean + off, sizeof(float) * ctx->Dm, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sigma)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(sigma, ctx->sigma + off, sizeof(float) * ctx->Dm, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
 int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n, double eta, double sigma, int decay, uint32_t *out_bmu_dev,
                             float *out_dist_dev)
 {

@@ -36,6 +36,7 @@ namespace vsom
 
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
+constexpr int kMaxSlotsPerLane = 5;   // the exchange row of a CTA is read by one warp: at most 160 CTAs
 constexpr size_t kStaticSmem = 1024; // static __shared__ of the kernel, rounded up
 
 template <int TR>
@@ -44,7 +45,13 @@ __device__ __forceinline__ float stepper_scalar(float xv, float m)
     // Transformation::Stepper for Standard (src/Transformation.cpp:11-12) and Median (:49-50).
     const float d = __fsub_rn(xv, m);
     if (TR == VSOM_MEDIAN)
-        return (d != d) ? d : static_cast<float>((0.0f < d) - (d < 0.0f));
+    {
+        // sign(d) in {-1, +0, +1}; NaN stays NaN.  |d| > 0 ? 1 : |d| gives 1 / +0 / NaN, then d's sign is copied on
+        // (a zero keeps +0 like the reference's (0<d)-(d<0)).
+        const float a = fabsf(d);
+        const float mag = a > 0.0f ? 1.0f : a;
+        return __uint_as_float(__float_as_uint(mag) | (mag > 0.0f ? (__float_as_uint(d) & 0x80000000u) : 0u));
+    }
     return d;
 }
 
@@ -202,8 +209,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 
     // sample prefetch: 16-byte cp.async.cg (L2 only — a streamed sample must not evict the L1-resident table)
     // when rows are 16-byte aligned, else 4-byte cp.async.ca
-    auto prefetch = [&](u64 t) {
-        float *dst = xs + (t % 3) * DinPad;
+    auto prefetch = [&](u64 t, int slot) {
+        float *dst = xs + slot * DinPad;
         const float *src = p.x + t * static_cast<u64>(p.Din);
         if (p.xVec)
         {
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         }
     };
     if (p.n > 0)
-        prefetch(0);
+        prefetch(0, 0);
 
     const double dW = static_cast<double>(p.W), dH = static_cast<double>(p.H);
     if (tid == 0)
@@ -225,16 +232,17 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             sProf[i] = 0;
     u64 done = 0;
 
-    for (u64 t = 0; t < p.n; ++t)
+    int ring = 0; // t % 3
+    for (u64 t = 0; t < p.n; ++t, ring = ring == 2 ? 0 : ring + 1)
     {
         if (p.prof && tid == 0)
             sClk[0] = clock64();
-        const float *xt = xs + (t % 3) * DinPad;
+        const float *xt = xs + ring * DinPad;
         float *wcur = wbuf + (dbl ? (t & 1) * Lpad : 0), *wnext = wbuf + (dbl ? ((t + 1) & 1) * Lpad : 0);
         cp_async_wait_all();
         __syncthreads(); // sample t landed; update of sample t-1 is complete; sPend* of t-1 visible
         if (t + 1 < p.n)
-            prefetch(t + 1);
+            prefetch(t + 1, ring == 2 ? 0 : ring + 1);
         if (p.prof && tid == 0)
             sClk[1] = clock64();
         const unsigned tag = static_cast<unsigned>((t >> 1) & 0xff);
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         // ---- owed output of sample t-1: distance to its updated BMU (src/Som.cpp:946) + addBmu (:1189-1192)
         const int pendL = sPendL;
         const u64 pendT = sPendT;
-        const float *xprev = xs + ((t + 2) % 3) * DinPad; // == (t-1) % 3
+        const float *xprev = xs + (ring == 0 ? 2 : ring - 1) * DinPad; // sample t-1
 
         // ---- scan: distance of sample t to every owned node, min key per thread
         u64 best = ~0ull;
@@ -311,15 +319,24 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             const long long t0 = clock64();
             u64 m;
             bool abort = false;
+            const u64 filler = (~0ull << 8) | tag;
             for (;;)
             {
+                // all loads of a round are issued before any is consumed: one L2 round trip per round, not G/32
+                u64 v[kMaxSlotsPerLane];
+#pragma unroll
+                for (int j = 0; j < kMaxSlotsPerLane; ++j)
+                {
+                    const int i = lane + 32 * j;
+                    v[j] = i < G ? ld_relaxed_gpu(row + i) : filler;
+                }
                 m = ~0ull;
                 int ok = 1;
-                for (int i = lane; i < G; i += 32)
+#pragma unroll
+                for (int j = 0; j < kMaxSlotsPerLane; ++j)
                 {
-                    const u64 v = ld_relaxed_gpu(row + i);
-                    ok &= (static_cast<unsigned>(v & 0xff) == tag);
-                    m = u64_min(m, v);
+                    ok &= (static_cast<unsigned>(v[j] & 0xff) == tag);
+                    m = u64_min(m, v[j]);
                 }
                 if (__all_sync(0xffffffffu, ok))
                     break;
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     {
         const int pendL = sPendL;
         const u64 pendT = sPendT;
-        const float *xprev = xs + (pendT % 3) * DinPad;
+        const float *xprev = xs + static_cast<int>(pendT % 3) * DinPad;
         float d = 0.0f;
         bool writer = false;
         if (ORDER == VSOM_ORDER_REFERENCE)
@@ -594,7 +611,9 @@ static StepKernel pick_kernel(int transform, int order, int resident)
 
 int configure_online_step(vsom_ctx *ctx)
 {
-    const int G = ctx->N < ctx->numSMs ? ctx->N : ctx->numSMs;
+    int G = ctx->N < ctx->numSMs ? ctx->N : ctx->numSMs;
+    if (G > 32 * kMaxSlotsPerLane)
+        G = 32 * kMaxSlotsPerLane;
     const int smStride = resident_stride(ctx);
     const size_t statics = kStaticSmem;
     size_t bytes = online_step_smem(ctx, G, true, smStride);

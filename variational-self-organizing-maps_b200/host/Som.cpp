@@ -1,0 +1,660 @@
+// Som.cpp — host side of class Som: the reference's public surface (include/SOM.hpp of the reference,
+// implementation in its src/Som.cpp) on top of the C-ABI of libvsom_b200.so.  Epoch schedules, the DataSet
+// chunk protocol, metrics and the mutex / atomic contract stay on the host exactly where the reference has
+// them (src/Som.cpp:1113-1187); everything per-sample or per-node runs in the CUDA kernels.
+#include "SOM.hpp"
+
+#include "vsom_b200.h"
+
+#include <cassert>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+struct Som::Device
+{
+    vsom_ctx *ctx{nullptr};
+    ~Device()
+    {
+        if (ctx)
+            vsom_destroy(ctx);
+    }
+};
+
+namespace
+{
+[[noreturn]] void fail(vsom_ctx *ctx, const char *what)
+{
+    throw std::runtime_error(std::string(what) + ": " + vsom_last_error(ctx));
+}
+[[noreturn]] void offPath(const char *what)
+{
+    throw std::logic_error(std::string(what) + " is not on the B200 hot path of this build (see DESIGN.md, out of scope)");
+}
+std::vector<float> flatten(const std::vector<Eigen::VectorXf> &rows, size_t depth)
+{
+    std::vector<float> out(rows.size() * depth);
+    for (size_t p = 0; p < rows.size(); ++p)
+        std::memcpy(out.data() + p * depth, rows[p].data(), depth * sizeof(float));
+    return out;
+}
+void unflatten(const std::vector<float> &flat, std::vector<Eigen::VectorXf> &rows, size_t depth)
+{
+    for (size_t p = 0; p < rows.size(); ++p)
+        std::memcpy(rows[p].data(), flat.data() + p * depth, depth * sizeof(float));
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------ construction
+
+void Som::Construct(size_t inWidth, size_t inHeight, size_t inDepth, std::vector<std::string> names)
+{
+    width = inWidth;
+    height = inHeight;
+    depth = inDepth;
+    const size_t nodes = width * height;
+    map.assign(nodes, Eigen::VectorXf::Zero(static_cast<Eigen::Index>(depth)));
+    sigmaMap = map;
+    SMap = map;
+    weightMap = Eigen::VectorXf::Zero(static_cast<Eigen::Index>(nodes));
+    bmuHits.assign(nodes, 0u);
+    uMatrix.assign(nodes, 0.0);
+    transform.names = names;
+    _isTraining = false;
+    hostIsStale = false;
+    deviceIsStale = true;
+}
+
+Som::Som(const char *) : transform{} { offPath("Som(const char *filename) [Octave-text persistence]"); }
+
+Som::Som(const Som &som)
+    : transform{som.transform}, metrics{}, _isTraining{}, height{som.height}, width{som.width}, depth{som.depth}, metricsMutex{}
+{
+    som.pull();
+    map = som.map;
+    sigmaMap = som.sigmaMap;
+    SMap = som.SMap;
+    weightMap = som.weightMap;
+    bmuHits = som.bmuHits;
+    uMatrix = som.uMatrix;
+    reductionOrderLanes = som.reductionOrderLanes;
+    _isTraining.store(som._isTraining.load());
+    hostIsStale = false;
+    deviceIsStale = true; // the copy gets its own context on first use
+}
+
+Som &Som::operator=(const Som &other)
+{
+    if (this == &other)
+        return *this;
+    other.pull();
+    transform = other.transform;
+    map = other.map;
+    sigmaMap = other.sigmaMap;
+    SMap = other.SMap;
+    weightMap = other.weightMap;
+    bmuHits = other.bmuHits;
+    uMatrix = other.uMatrix;
+    height = other.height;
+    width = other.width;
+    depth = other.depth;
+    reductionOrderLanes = other.reductionOrderLanes;
+    _isTraining.store(other._isTraining.load());
+    device.reset();
+    hostIsStale = false;
+    deviceIsStale = true;
+    return *this;
+}
+
+Som::~Som() = default;
+
+size_t Som::inputLength() const
+{
+    if (transform.deviceKind() != Transformation::DeviceKind::LinearRegression)
+        return depth;
+    // depth = J (J - 1)  (Transformation::Length of CLR, reference src/Transformation.cpp:162-165)
+    size_t j = static_cast<size_t>((1.0 + std::sqrt(1.0 + 4.0 * static_cast<double>(depth))) / 2.0 + 0.5);
+    while (j * (j - 1) > depth)
+        --j;
+    while (j * (j - 1) < depth)
+        ++j;
+    if (j * (j - 1) != depth)
+        throw std::invalid_argument("Som: depth is not J*(J-1) for a linear-regression transformation");
+    return j;
+}
+
+vsom_ctx *Som::context() const
+{
+    if (!device)
+        device = std::make_shared<Device>();
+    if (!device->ctx)
+    {
+        const auto kind = transform.deviceKind();
+        if (kind == Transformation::DeviceKind::Custom)
+            throw std::runtime_error("Som: this Transformation is not one of the shipped factories (Standard, StandardMedianEstimator, "
+                                     "CombinatorialLinearRegression); std::function strategies cannot run on the device and there is no CPU fallback");
+        const int rc = vsom_create(&device->ctx, 0, static_cast<int>(width), static_cast<int>(height), static_cast<int>(inputLength()),
+                                   static_cast<int>(kind), reductionOrderLanes ? VSOM_ORDER_LANES : VSOM_ORDER_REFERENCE);
+        if (rc != VSOM_OK)
+            throw std::runtime_error(std::string("Som: vsom_create failed: ") + vsom_last_error(nullptr));
+        deviceIsStale = true;
+    }
+    if (deviceIsStale)
+    {
+        const auto m = flatten(map, depth), s = flatten(SMap, depth), g = flatten(sigmaMap, depth);
+        std::vector<uint64_t> hits(bmuHits.begin(), bmuHits.end());
+        if (vsom_upload_state(device->ctx, m.data(), s.data(), g.data(), weightMap.data(), hits.data()) != VSOM_OK)
+            fail(device->ctx, "Som: upload");
+        deviceIsStale = false;
+        hostIsStale = false;
+    }
+    return device->ctx;
+}
+
+void Som::pull() const
+{
+    if (!hostIsStale || !device || !device->ctx)
+        return;
+    const size_t nodes = width * height;
+    std::vector<float> m(nodes * depth), s(nodes * depth), g(nodes * depth);
+    std::vector<uint64_t> hits(nodes);
+    if (vsom_download_state(device->ctx, m.data(), s.data(), g.data(), weightMap.data(), hits.data()) != VSOM_OK)
+        fail(device->ctx, "Som: download");
+    unflatten(m, map, depth);
+    unflatten(s, SMap, depth);
+    unflatten(g, sigmaMap, depth);
+    for (size_t p = 0; p < nodes; ++p)
+        bmuHits[p] = static_cast<size_t>(hits[p]);
+    hostIsStale = false;
+}
+
+void Som::setFastReductionOrder(bool lanes)
+{
+    if (lanes == reductionOrderLanes)
+        return;
+    pull();
+    device.reset();
+    deviceIsStale = true;
+    reductionOrderLanes = lanes;
+}
+
+// Som::randomInitialize of the reference (src/Som.cpp:977-997): host-side, glibc rand() in node-major order,
+// so that the initial planes are the reference's for the same seed.
+void Som::randomInitialize(int seed, float sigma)
+{
+    std::srand(static_cast<unsigned>(seed));
+    metrics = Metrics{depth};
+    const int span = static_cast<int>(2000 * sigma);
+    for (size_t p = 0; p < width * height; ++p)
+    {
+        for (Eigen::Index k = 0; k < map[p].size(); ++k)
+        {
+            map[p](k) = (static_cast<float>(std::rand() % span) - (1000.f * sigma)) / 1000.f;
+            sigmaMap[p](k) = 0.0f;
+            SMap[p](k) = 0.0f;
+        }
+        weightMap[static_cast<Eigen::Index>(p)] = 0.0f;
+        bmuHits[p] = 0u;
+        uMatrix[p] = 0.0;
+    }
+    hostIsStale = false;
+    deviceIsStale = true;
+}
+
+// ------------------------------------------------------------------------------------------------ training
+
+void Som::train(DataSet &data, size_t numberOfEpochs, double eta0, double etaDecay, double sigma0, double sigmaDecay,
+                WeigthDecayFunction weightDecayFunction, bool updateUMatrixAfterEpoch)
+{
+    // same contract as the reference (src/Som.cpp:1113-1132): exceptions end the run with a message on
+    // std::cerr and the flag is cleared either way, so a polling thread never hangs on isTraining()
+    _isTraining = true;
+    try
+    {
+        if (weightDecayFunction == WeigthDecayFunction::BatchMap)
+            trainBatchSom(data, numberOfEpochs, sigma0, sigmaDecay, updateUMatrixAfterEpoch);
+        else
+            trainBasicSom(data, numberOfEpochs, eta0, etaDecay, sigma0, sigmaDecay, weightDecayFunction, updateUMatrixAfterEpoch);
+    }
+    catch (const std::exception &e)
+    {
+        std::cerr << e.what() << '\n';
+    }
+    _isTraining = false;
+}
+
+void Som::trainBasicSom(DataSet &data, size_t numberOfEpochs, double eta0, double etaDecay, double sigma0, double sigmaDecay,
+                        WeigthDecayFunction weightDecayFunction, bool updateUMatrixAfterEpoch)
+{
+    if (weightDecayFunction == WeigthDecayFunction::BatchMap)
+        offPath("trainBasicSom(BatchMap)");
+    vsom_ctx *ctx = context();
+    metrics = Metrics(numberOfEpochs);
+    const int decay = weightDecayFunction == WeigthDecayFunction::Exponential ? VSOM_EXPONENTIAL : VSOM_INVERSE_PROPORTIONAL;
+    std::vector<float> resid2;
+    std::vector<uint64_t> last;
+    for (size_t epoch = 0; epoch < numberOfEpochs; ++epoch)
+    {
+        // schedules of src/Som.cpp:1145-1149 (sigma is clamped UP to 1)
+        const double eta = eta0 * std::exp(-etaDecay * static_cast<double>(epoch));
+        double sigma = sigma0 * std::exp(-sigmaDecay * static_cast<double>(epoch));
+        if (sigma < 1.0)
+            sigma = 1.0;
+        float meanSquareError{0.0};
+        size_t chunks{0};
+        while (!data.hasReadWholeDataStream())
+        {
+            data.loadNextDataFromStream();
+            const size_t rows = data.size();
+            resid2.resize(rows);
+            auto &lastColumn = data.lastBmuColumn();
+            last.assign(lastColumn.begin(), lastColumn.end());
+            // one persistent kernel runs the whole chunk: trainSingle + addBmu for every row, in row order
+            if (vsom_train_chunk(ctx, data.contiguousRows(), rows, eta, sigma, decay, last.data(), nullptr, nullptr, resid2.data()) != VSOM_OK)
+                fail(ctx, "Som::trainBasicSom");
+            hostIsStale = true;
+            for (size_t j = 0; j < rows; ++j)
+            {
+                lastColumn[j] = static_cast<size_t>(last[j]);
+                meanSquareError += resid2[j] / static_cast<float>(rows); // src/Som.cpp:1167, f32, row order
+            }
+            ++chunks;
+        }
+        meanSquareError /= static_cast<float>(chunks);
+        {
+            const std::lock_guard<std::mutex> lock(metricsMutex);
+            metrics.MeanSquaredError[epoch] = meanSquareError;
+        }
+        data.resetStreamLoadPosition();
+        if (updateUMatrixAfterEpoch)
+            updateUMatrix(data.getWeights());
+    }
+}
+
+void Som::trainBatchSom(DataSet &, size_t, double, double, bool) { offPath("trainBatchSom"); }
+float Som::trainBatchSomEpoch(DataSet &, double, bool) { offPath("trainBatchSomEpoch"); }
+
+Som::TrainingReturnValue Som::trainSingle(const Eigen::VectorXf &v, const Eigen::VectorXf &valid, const Eigen::VectorXf &weights, const double eta,
+                                          const double sigma, size_t &lastBMU, const WeigthDecayFunction weightDecayFunction)
+{
+    if (weightDecayFunction == WeigthDecayFunction::BatchMap)
+        offPath("trainSingle(BatchMap)");
+    vsom_ctx *ctx = context();
+    uint64_t last = lastBMU;
+    uint32_t bmu = 0;
+    float dist = 0;
+    const int decay = weightDecayFunction == WeigthDecayFunction::Exponential ? VSOM_EXPONENTIAL : VSOM_INVERSE_PROPORTIONAL;
+    // NB: unlike trainBasicSom this does NOT count the hit: the reference's caller does that with addBmu()
+    if (vsom_train_chunk(ctx, v.data(), 1, eta, sigma, decay, &last, &bmu, &dist, nullptr) != VSOM_OK)
+        fail(ctx, "Som::trainSingle");
+    hostIsStale = true;
+    lastBMU = static_cast<size_t>(last);
+    Eigen::VectorXf neuron(static_cast<Eigen::Index>(depth)), spread(static_cast<Eigen::Index>(depth));
+    if (vsom_get_node(ctx, bmu, neuron.data(), spread.data()) != VSOM_OK)
+        fail(ctx, "Som::trainSingle");
+    // the kernel's chunk entry point already did addBmu for its row; undo it so that trainSingle + addBmu
+    // by the caller counts once, like in the reference (src/Som.cpp:1163-1165)
+    pull();
+    bmuHits[bmu] -= 1;
+    deviceIsStale = true;
+    Eigen::VectorXf mask = (valid.array() * weights.array()).matrix();
+    return TrainingReturnValue{SomIndex(bmu % width, bmu / width), transform.Comparer(v, neuron, spread, mask), dist};
+}
+
+void Som::addBmu(SomIndex position)
+{
+    pull();
+    bmuHits[getIndex(position)] += 1;
+    deviceIsStale = true;
+}
+
+// ------------------------------------------------------------------------------------------------ scoring
+
+void Som::mapDataSet(const DataSet &dataset, std::vector<size_t> &bmuOut, std::vector<float> &distOut, size_t minBmuHits) const
+{
+    vsom_ctx *ctx = context();
+    const size_t rows = dataset.size();
+    std::vector<uint32_t> bmu(rows);
+    distOut.resize(rows);
+    if (vsom_find_bmu(ctx, dataset.contiguousRows(), rows, minBmuHits, bmu.data(), distOut.data()) != VSOM_OK)
+        fail(ctx, "Som::mapDataSet");
+    bmuOut.assign(bmu.begin(), bmu.end());
+}
+
+void Som::buildIndex(const std::vector<size_t> &bmu, std::vector<size_t> &counts, std::vector<size_t> &offsets, std::vector<unsigned> &rowIds) const
+{
+    vsom_ctx *ctx = context();
+    std::vector<uint32_t> b(bmu.begin(), bmu.end());
+    std::vector<uint64_t> c(width * height), o(width * height + 1);
+    rowIds.resize(bmu.size());
+    if (vsom_build_index(ctx, b.data(), b.size(), c.data(), o.data(), rowIds.data()) != VSOM_OK)
+        fail(ctx, "Som::buildIndex");
+    counts.assign(c.begin(), c.end());
+    offsets.assign(o.begin(), o.end());
+}
+
+SomIndex Som::findBmu(const Eigen::VectorXf &v) const
+{
+    const Eigen::VectorXf ones = Eigen::VectorXf::Ones(v.size());
+    return findBmu(v, ones, ones);
+}
+
+SomIndex Som::findBmu(const Eigen::VectorXf &v, const Eigen::VectorXf &, const Eigen::VectorXf &) const
+{
+    // validity and weights are built and then ignored by every shipped Comparer
+    vsom_ctx *ctx = context();
+    uint32_t bmu = 0;
+    if (vsom_find_bmu(ctx, v.data(), 1, 0, &bmu, nullptr) != VSOM_OK)
+        fail(ctx, "Som::findBmu");
+    return SomIndex(bmu % width, bmu / width);
+}
+
+SomIndex Som::findRestrictedBmu(const Eigen::VectorXf &v, const Eigen::VectorXf &, const size_t minBmuHits, const Eigen::VectorXf &) const
+{
+    vsom_ctx *ctx = context();
+    uint32_t bmu = 0;
+    if (vsom_find_bmu(ctx, v.data(), 1, minBmuHits, &bmu, nullptr) != VSOM_OK)
+        fail(ctx, "Som::findRestrictedBmu");
+    return SomIndex(bmu % width, bmu / width);
+}
+
+// findLocalBmu (reference src/Som.cpp:335-454): the greedy walk itself is a handful of comparisons; the
+// distances it compares come from the device (one pass over all nodes), so they are the device's bits.
+SomIndex Som::findLocalBmu(const Eigen::VectorXf &v, const Eigen::VectorXf &, const size_t &lastBMUref, const Eigen::VectorXf &) const
+{
+    vsom_ctx *ctx = context();
+    std::vector<double> dist(width * height);
+    if (vsom_all_dists(ctx, v.data(), dist.data()) != VSOM_OK)
+        fail(ctx, "Som::findLocalBmu");
+    const size_t W = width, H = height, M1 = static_cast<size_t>(-1);
+    // size_t arithmetic on purpose: "-1" is 2^64-1, so min(x + off, W-1) wraps the left/up neighbour of
+    // column/row 0 to the last column/row
+    auto clampX = [&](size_t x) { return std::max<size_t>(std::min<size_t>(x, W - 1), 0); };
+    auto clampY = [&](size_t y) { return std::max<size_t>(std::min<size_t>(y, H - 1), 0); };
+    const size_t offX[8] = {M1, 0, 1, 1, 1, 0, M1, M1}, offY[8] = {1, 1, 1, 0, M1, M1, M1, 0};
+    size_t from = lastBMUref, best = from, probe = from;
+    double bestDist = dist[from];
+    auto consider = [&](size_t cx, size_t cy) {
+        const size_t at = cy * W + cx;
+        if (dist[at] < bestDist)
+        {
+            bestDist = dist[at];
+            best = at;
+        }
+    };
+    for (;;)
+    {
+        const size_t px = probe % W, py = probe / W, fx = from % W, fy = from / W;
+        if (probe == from)
+        {
+            for (int k = 0; k < 8; ++k)
+                consider(clampX(px + offX[k]), clampY(py + offY[k]));
+            if (best == from)
+                break;
+            probe = best;
+        }
+        else
+        {
+            if (px - fx) // continue in the X direction: three cells one step further
+                for (int k = -1; k < 2; ++k)
+                    consider(clampX(px + px - fx), clampY(py + static_cast<size_t>(static_cast<long long>(k))));
+            // the reference's Y-direction continuation starts its column loop at size_t(-1) and therefore never
+            // runs (src/Som.cpp:411-426); nothing to do here
+            if (best == probe)
+                break;
+            from = probe;
+            probe = best;
+        }
+    }
+    return SomIndex(best % W, best / W);
+}
+
+std::vector<double> Som::findRestrictedBmd(const Eigen::VectorXf &v, const Eigen::VectorXf &, size_t minBmuHits, const Eigen::VectorXf &) const
+{
+    vsom_ctx *ctx = context();
+    std::vector<double> out(width * height);
+    if (vsom_all_dists(ctx, v.data(), out.data()) != VSOM_OK)
+        fail(ctx, "Som::findRestrictedBmd");
+    pull();
+    // reference src/Som.cpp:457-487: exp(-d*d/2) of the (already squared) distance, normalised by the sum
+    double total = 0;
+    for (size_t p = 0; p < out.size(); ++p)
+    {
+        out[p] = bmuHits[p] >= minBmuHits ? std::exp(-out[p] * out[p] / 2) : 0.0;
+        total += out[p];
+    }
+    for (double &d : out)
+        d /= total;
+    return out;
+}
+
+double Som::euclidianWeightedDist(const SomIndex &pos, const Eigen::VectorXf &v, const Eigen::VectorXf &valid, const Eigen::VectorXf &weights) const
+{
+    const size_t at = getIndex(pos);
+    return euclidianWeightedDist(at, v, valid, weights);
+}
+
+double Som::euclidianWeightedDist(const size_t &pos, const Eigen::VectorXf &v, const Eigen::VectorXf &, const Eigen::VectorXf &) const
+{
+    vsom_ctx *ctx = context();
+    std::vector<double> dist(width * height);
+    if (vsom_all_dists(ctx, v.data(), dist.data()) != VSOM_OK)
+        fail(ctx, "Som::euclidianWeightedDist");
+    return dist[pos];
+}
+
+// reference src/Som.cpp:143-157 — only updateUMatrix uses it there; single calls are evaluated on the mirror
+double Som::euclidianWeightedDistRaw(const size_t &pos, const Eigen::VectorXf &v, const Eigen::VectorXf &valid, const Eigen::VectorXf &weights) const
+{
+    pull();
+    float sum = 0.0f;
+    for (Eigen::Index k = 0; k < map[pos].size(); ++k)
+    {
+        const float s = sigmaMap[pos][k] < 0.00001f ? 0.00001f : sigmaMap[pos][k];
+        const float d = map[pos][k] - v[k];
+        const float a = d / s;
+        const float b = (d * (valid[k] * weights[k])) / s;
+        sum = sum + a * b;
+    }
+    return static_cast<double>(sum);
+}
+
+double Som::evaluate(const DataSet &dataset) const
+{
+    vsom_ctx *ctx = context();
+    const Eigen::ArrayXi binary = dataset.getBinary();
+    bool anyBinary = false;
+    for (Eigen::Index k = 0; k < binary.size(); ++k)
+        anyBinary = anyBinary || binary[k] != 0;
+    const size_t rows = dataset.size();
+    if (!anyBinary)
+    {
+        double error = 0;
+        if (vsom_evaluate(ctx, dataset.contiguousRows(), rows, &error) != VSOM_OK)
+            fail(ctx, "Som::evaluate");
+        return error;
+    }
+    // binary columns: BMUs and distances from the device, the cross-entropy term of src/Som.cpp:509-519 here
+    // (the reference reads an uninitialised `ones` array at :495; the evident intent, 1.0, is used)
+    std::vector<uint32_t> bmu(rows);
+    std::vector<float> dist(rows);
+    if (vsom_find_bmu(ctx, dataset.contiguousRows(), rows, 0, bmu.data(), dist.data()) != VSOM_OK)
+        fail(ctx, "Som::evaluate");
+    pull();
+    double error = 0;
+    for (size_t i = 0; i < rows; ++i)
+    {
+        const Eigen::VectorXf x = dataset.getData(i);
+        const Eigen::VectorXi ok = dataset.getValidity(i);
+        const Eigen::ArrayXi cont = dataset.getContinuous();
+        float ce2 = 0.0f;
+        for (Eigen::Index k = 0; k < x.size(); ++k)
+        {
+            const float m = map[bmu[i]][k];
+            float e = std::log(m) * x[k] + std::log(1.0f - m) * (1.0f - x[k]);
+            if (std::isnan(e) || std::isinf(e))
+                e = -99999;
+            e = e * static_cast<float>(binary[k]) * static_cast<float>(ok[k] * cont[k]);
+            ce2 = ce2 + e * e;
+        }
+        error += 1. / (static_cast<double>(i) + 1.0) * (static_cast<double>(dist[i]) + std::sqrt(ce2) - error);
+    }
+    return error;
+}
+
+// reference src/Som.cpp:631-714 with its quirks (reversed sigma clamp :658, signed delta against a stored
+// |delta| :686-688, re-visit of the arg-max row :643-647); the per-row BMU search is one device pass.
+int Som::measureSimilarity(const DataSet *dataset, int numberOfSigmas, size_t minBmuHits) const
+{
+    vsom_ctx *ctx = context();
+    const size_t rows = dataset->size();
+    if (rows == 0)
+        return 1;
+    std::vector<uint32_t> bmu(rows);
+    if (vsom_find_bmu(ctx, dataset->contiguousRows(), rows, minBmuHits, bmu.data(), nullptr) != VSOM_OK)
+        fail(ctx, "Som::measureSimilarity");
+    pull();
+    const size_t D = dataset->vectorLength();
+    const float k = static_cast<float>(numberOfSigmas);
+    float largest = -99999999.f;
+    size_t largestRow = 0;
+    int success = 1;
+    auto visit = [&](size_t i, bool judge) {
+        const float *v = dataset->contiguousRows() + i * D;
+        const Eigen::VectorXf &m = map[bmu[i]], &sg = sigmaMap[bmu[i]];
+        for (size_t d = 0; d < D; ++d)
+        {
+            const float sM = sg[d] > 0.00001f ? 0.00001f : sg[d];
+            const float delta = ((v[d] - m[d]) / sM) / k;
+            if (delta > largest)
+            {
+                largest = static_cast<float>(std::fabs(static_cast<double>(delta)));
+                largestRow = i;
+            }
+            if (judge && (v[d] < m[d] - sM * k || v[d] > m[d] + sM * k))
+                success = 0;
+        }
+    };
+    for (size_t i = 0; i < rows; ++i)
+        visit(i, false);
+    visit(largestRow, true);
+    return success;
+}
+
+int Som::autoEncoder(const DataSet *, size_t) const { offPath("autoEncoder"); }
+size_t Som::variationalAutoEncoder(const DataSet *, size_t) const { offPath("variationalAutoEncoder"); }
+
+// ------------------------------------------------------------------------------------------------ U-matrix
+
+void Som::updateUMatrix(const Eigen::VectorXf &)
+{
+    // the argument is ignored by the reference too (it overwrites it with ones, src/Som.cpp:1002-1003)
+    vsom_ctx *ctx = context();
+    if (vsom_update_umatrix(ctx, uMatrix.data()) != VSOM_OK)
+        fail(ctx, "Som::updateUMatrix");
+}
+
+UMatrix Som::getUMatrix() const noexcept { return UMatrix{uMatrix, width, height}; }
+
+// ------------------------------------------------------------------------------------------------ accessors
+
+Eigen::VectorXf Som::getWeigthMap() const noexcept
+{
+    pull();
+    return weightMap;
+}
+std::vector<size_t> Som::getBmuHits() const noexcept
+{
+    pull();
+    return bmuHits;
+}
+size_t Som::getHeight() const noexcept { return height; }
+size_t Som::getWidth() const noexcept { return width; }
+size_t Som::getDepth() const noexcept { return depth; }
+size_t Som::getIndex(SomIndex index) const noexcept { return index.getY() * width + index.getX(); }
+Eigen::VectorXf Som::getNeuron(SomIndex index) const noexcept { return getNeuron(getIndex(index)); }
+Eigen::VectorXf Som::getNeuron(size_t index) const noexcept
+{
+    pull();
+    return map[index];
+}
+Eigen::VectorXf Som::getSigmaNeuron(SomIndex index) const noexcept { return getSigmaNeuron(getIndex(index)); }
+Eigen::VectorXf Som::getSigmaNeuron(size_t index) const noexcept
+{
+    pull();
+    return sigmaMap[index];
+}
+std::vector<std::string> Som::getNeuronStrings(SomIndex index) const noexcept { return transform.Displayer(getNeuron(index)); }
+std::vector<std::string> Som::getSigmaNeuronStrings(SomIndex index) const noexcept { return transform.Displayer(getSigmaNeuron(index)); }
+
+namespace
+{
+template <typename Pick> float extreme(const std::vector<Eigen::VectorXf> &plane, size_t feature, Pick better)
+{
+    assert(feature < static_cast<size_t>(plane.at(0).size()));
+    float best = plane[0][static_cast<Eigen::Index>(feature)];
+    for (const auto &row : plane)
+        if (better(row[static_cast<Eigen::Index>(feature)], best))
+            best = row[static_cast<Eigen::Index>(feature)];
+    return best;
+}
+} // namespace
+
+float Som::getMaxValueOfFeature(size_t f) const
+{
+    pull();
+    return extreme(map, f, [](float a, float b) { return a > b; });
+}
+float Som::getMinValueOfFeature(size_t f) const
+{
+    pull();
+    return extreme(map, f, [](float a, float b) { return a < b; });
+}
+float Som::getMaxSigmaOfFeature(size_t f) const
+{
+    pull();
+    return extreme(sigmaMap, f, [](float a, float b) { return a > b; });
+}
+float Som::getMinSigmaOfFeature(size_t f) const
+{
+    pull();
+    return extreme(sigmaMap, f, [](float a, float b) { return a < b; });
+}
+
+Som::Metrics Som::getMetrics() const noexcept { return metrics; }
+bool Som::isTraining() const noexcept { return _isTraining; }
+bool Som::isCompatibleWithData(DataSet &data) const noexcept { return transform.Length(data.vectorLength()) == depth; }
+
+void Som::display() const
+{
+    pull();
+    for (size_t p = 0; p < map.size(); ++p)
+        std::cout << "node " << p << ": " << map[p].transpose() << "\n";
+}
+void Som::displayUMatrix() const
+{
+    for (size_t y = 0; y < height; ++y)
+    {
+        for (size_t x = 0; x < width; ++x)
+            std::cout << uMatrix[y * width + x] << (x + 1 < width ? " " : "");
+        std::cout << "\n";
+    }
+}
+
+void Som::save(const char *) const { offPath("save [Octave-text persistence]"); }
+void Som::load(const char *) { offPath("load [Octave-text persistence]"); }
+Eigen::VectorXf Som::getSizeFromFile(const char *) { offPath("getSizeFromFile [Octave-text persistence]"); }
+
+// reference src/Som.cpp:949-975, same division order; host libm exp() like the kernel's table builder
+double Som::calculateNeighbourhoodWeight(const size_t &currentX, const size_t &currentY, const size_t &bmuX, const size_t &bmuY,
+                                         const double &currentSigma)
+{
+    if (currentSigma > 1.0)
+    {
+        const double dx = static_cast<double>(currentX) - static_cast<double>(bmuX), dy = static_cast<double>(currentY) - static_cast<double>(bmuY);
+        return std::exp(-(dx * dx / 2.0 / currentSigma / currentSigma + dy * dy / 2.0 / currentSigma / currentSigma));
+    }
+    return (currentX == bmuX && currentY == bmuY) ? 1.0 : 0.0;
+}
