@@ -131,6 +131,15 @@ VSOM_API int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n
  * and out_dist = (float)euclidianWeightedDist(bmu, row) (src/Som.cpp:124-141).  Outputs may be NULL. */
 VSOM_API int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist);
 VSOM_API int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev);
+/* Same contract and same results as vsom_find_bmu, for large batches: the candidate search runs on the tensor cores
+ * (K2: tcgen05 + TMA, bf16 operands), the 8 best candidates per row are re-evaluated in the reference's f32 arithmetic,
+ * and rows whose candidate set cannot be proven complete are re-scored by the exact scan.  Falls back to the exact
+ * scan entirely for shapes K2 does not cover (CLR, Dm > 256) or small batches.  fallback_rows (may be NULL) receives the
+ * number of rows that took the exact full scan. */
+VSOM_API int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, uint64_t *fallback_rows);
+VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev,
+                                        uint64_t *fallback_rows);
+
 /* Som::evaluate for all-continuous columns (src/Som.cpp:490-523): f64 running mean of the BMU distance in row
  * order.  (With binary columns the reference adds a cross-entropy term; that is host work on top of the
  * BMU indices this call family returns.) */

@@ -215,3 +215,49 @@ def test_full_size_properties_config2(vsom):
     c, o, rows = ctx.build_index(bmu)
     assert np.array_equal(c, st["hits"]) and np.all(np.diff(bmu[rows].astype(np.int64)) >= 0)
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ K2 (tensor cores)
+def _tc_case(rng, W, H, D, n, near_nodes):
+    m = rng.standard_normal((W * H, D)).astype(np.float32)
+    if near_nodes:  # rows close to (several) nodes: small gaps between candidates, exercises the guard / fallback
+        x = (m[rng.integers(0, W * H, n)] * 0.5 + m[rng.integers(0, W * H, n)] * 0.5 + 0.05 * rng.standard_normal((n, D))).astype(np.float32)
+    else:
+        x = rng.standard_normal((n, D)).astype(np.float32)
+    return m, x
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 128, 5000, False), (128, 128, 256, 3001, False), (30, 21, 100, 4097, True), (128, 128, 256, 2048, True),
+                                   (16, 16, 7, 1500, False)])
+def test_tensor_core_scoring_equals_exact_scan(vsom, shape):
+    """K2 (tcgen05 candidate search + exact rescore + guarded fallback) must return exactly what K3 returns:
+    same BMU ids (bit-exact) and same f32 distances (bit-exact) — the tensor cores only select candidates."""
+    W, H, D, n, near = shape
+    rng = np.random.default_rng(W * H + D + n)
+    m, x = _tc_case(rng, W, H, D, n, near)
+    ctx = vsom.VsomContext(W, H, D, vsom.STANDARD)
+    hits = rng.integers(0, 4, W * H).astype(np.uint64)
+    ctx.upload_state(mean=m, hits=hits)
+    eb, ed = ctx.find_bmu(x)
+    tb, td, fb = ctx.find_bmu_batch(x)
+    print(f"K2 {W}x{H}x{D}, {n} rows, near={near}: {fb} rows ({100.0 * fb / n:.2f}%) took the exact-scan fallback")
+    assert_bit_equal(tb, eb, "bmu")
+    assert_bit_equal(td, ed, "dist")
+    assert fb < n  # the tensor-core path did the selection for at least some rows
+    eb2, _ = ctx.find_bmu(x[:2000], min_hits=2)
+    tb2, _, _ = ctx.find_bmu_batch(x[:2000], min_hits=2)
+    assert_bit_equal(tb2, eb2, "restricted bmu")
+    ctx.close()
+
+
+def test_tensor_core_scoring_unsupported_shapes_use_exact(vsom):
+    ctx = vsom.VsomContext(20, 20, 784, vsom.STANDARD)  # Dm > 256: exact scan
+    rng = np.random.default_rng(1)
+    ctx.upload_state(mean=rng.standard_normal((400, 784)).astype(np.float32))
+    x = rng.standard_normal((1500, 784)).astype(np.float32)
+    eb, ed = ctx.find_bmu(x)
+    tb, td, fb = ctx.find_bmu_batch(x)
+    assert fb == 1500
+    assert_bit_equal(tb, eb, "bmu")
+    assert_bit_equal(td, ed, "dist")
+    ctx.close()

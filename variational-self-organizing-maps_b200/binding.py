@@ -39,6 +39,8 @@ _PROTOS = {
     "vsom_train_chunk_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_double, C.c_double, C.c_int, _vp, _vp]),
     "vsom_find_bmu": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
     "vsom_find_bmu_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
+    "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
+    "vsom_find_bmu_batch_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, _u64p]),
     "vsom_evaluate": (C.c_int, [_vp, _f32p, C.c_size_t, _f64p]),
     "vsom_all_dists": (C.c_int, [_vp, _f32p, _f64p]),
     "vsom_update_umatrix": (C.c_int, [_vp, _f64p]),
@@ -172,6 +174,23 @@ class VsomContext:
         self._check(lib().vsom_find_bmu_device(self._h, x_dev.data_ptr(), n, min_hits,
                                                out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
                                                out_dist_dev.data_ptr() if out_dist_dev is not None else None))
+
+    def find_bmu_batch(self, x, min_hits=0):
+        """Tensor-core candidate search + exact rescore; returns (bmu, dist, rows that took the exact full scan)."""
+        x = _f32(x).reshape(-1, self.Din)
+        n = x.shape[0]
+        bmu = np.empty(n, np.uint32)
+        dist = np.empty(n, np.float32)
+        fb = C.c_uint64(0)
+        self._check(lib().vsom_find_bmu_batch(self._h, _p(x, _f32p), n, min_hits, _p(bmu, _u32p), _p(dist, _f32p), C.byref(fb)))
+        return bmu, dist, int(fb.value)
+
+    def find_bmu_batch_device(self, x_dev, n, out_bmu_dev=None, out_dist_dev=None, min_hits=0):
+        fb = C.c_uint64(0)
+        self._check(lib().vsom_find_bmu_batch_device(self._h, x_dev.data_ptr(), n, min_hits,
+                                                     out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
+                                                     out_dist_dev.data_ptr() if out_dist_dev is not None else None, C.byref(fb)))
+        return int(fb.value)
 
     def evaluate(self, x):
         x = _f32(x).reshape(-1, self.Din)

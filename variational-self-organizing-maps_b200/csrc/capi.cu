@@ -393,6 +393,60 @@ int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, ui
     return VSOM_OK;
 }
 
+int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev,
+                               uint64_t *fallback_rows)
+{
+    if (!ctx || (!x_dev && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_batch_device: x is NULL") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (fallback_rows)
+        *fallback_rows = 0;
+    if (!score_tc_supported(ctx) || n < 1024)
+    {
+        if (fallback_rows)
+            *fallback_rows = n;
+        return launch_find_bmu(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev);
+    }
+    unsigned long long fb = 0;
+    const int rc = launch_find_bmu_tc(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev, &fb);
+    if (fallback_rows)
+        *fallback_rows = fb;
+    return rc;
+}
+
+int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, uint64_t *fallback_rows)
+{
+    if (!ctx || (!x && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_batch: x is NULL") : VSOM_ERR_INVALID;
+    if (fallback_rows)
+        *fallback_rows = 0;
+    if (n == 0)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 2, sizeof(float) * n);
+    if (rc)
+        return rc;
+    float *xDev = static_cast<float *>(ctx->stage[0]);
+    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
+    float *distDev = static_cast<float *>(ctx->stage[2]);
+    VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    rc = vsom_find_bmu_batch_device(ctx, xDev, n, min_hits, bmuDev, distDev, fallback_rows);
+    if (rc)
+        return rc;
+    if (out_bmu)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_bmu, bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_dist)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_dist, distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
 int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)
 {
     if (!ctx || !mean_error)

@@ -79,8 +79,9 @@ struct vsom_ctx
     double lutEta = -1, lutSigma = -1;
     int lutW = 0, lutH = 0;
     // grow-only device staging for the host entry points
-    void *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t stageCap[6] = {0, 0, 0, 0, 0, 0};
+    void *stage[10] = {};
+    size_t stageCap[10] = {};
+    unsigned long long lastFallbackRows = 0; // rows of the last tensor-core scoring call that needed the exact full scan
     int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;
     size_t smemTrain = 0;
     uint64_t launches = 0;
@@ -109,6 +110,8 @@ int stage_reserve(vsom_ctx *ctx, int slot, size_t bytes);
 int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev);
 int configure_online_step(vsom_ctx *ctx);
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev);
+bool score_tc_supported(const vsom_ctx *ctx);
+int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut);
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
 int launch_umatrix(vsom_ctx *ctx);
 int launch_build_index(vsom_ctx *ctx, const unsigned *bmuDev, size_t n, u64 *countsDev, u64 *offsetsDev, unsigned *rowIdsDev);

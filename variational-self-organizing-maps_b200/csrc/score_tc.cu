@@ -1,0 +1,577 @@
+// score_tc.cu — K2: batch BMU search as a dense contraction on the 5th-generation tensor cores, + exact rescore.
+//
+// Replaces the same row loops as score_exact.cu (Som::evaluate src/Som.cpp:503-520, findBmu :291-309,
+// findRestrictedBmu :313-332 over a loaded DataSet) when the batch is large:
+//     d(r,p) = |x_r|^2 - 2 x_r . m_p + |m_p|^2            (Standard / Median Comparer, src/Transformation.cpp:7-8)
+// The cross term X[R x K] . M^T[K x N] runs as tcgen05.mma (bf16 operands, fp32 accumulators in TMEM), operands
+// staged by TMA (128-byte swizzle).  The tensor cores only SELECT: each row keeps the 8 smallest approximate
+// scores c_p - 2 x.m over all nodes; the exact pass then re-evaluates those 8 candidates in the reference's own
+// f32 arithmetic and order (bit-identical distances) and applies findBmu's lowest-index rule among them.
+// A per-row guard proves that no other node can win: with tau = the 8th approximate score and
+// E = 2^-7 |x| max_p|m_p| (bf16 operand rounding, Cauchy-Schwarz) every non-candidate has
+// d >= (tau + |x|^2 - E)(1 - 1e-4); rows where that does not exceed the best exact candidate distance are
+// re-scored by the exact full scan (score_exact.cu), so the result is ALWAYS the reference's argmin.
+//
+// Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
+//   warp 0   TMA producer : A tile (128 rows x K, resident for the row tile) + B tiles (256 nodes x 64) through a
+//                           4-stage mbarrier ring
+//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) into one
+//                           of two 256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes
+//                           the accumulator
+//   warp 2   TMEM allocator (512 columns)
+//   warps 4-7 epilogue    : thread = one row (TMEM lane); tcgen05.ld 32 columns at a time, score = c_p - 2 acc,
+//                           branch-free threshold test, rare sorted insertion into the row's top-8
+// Limits of this version: Standard / Median transformation, Dm <= 256 (A tile resident); other shapes use K3.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+
+namespace vsom
+{
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_TOPK = 8, TC_THREADS = 256;
+constexpr int TC_MAXK = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per k-block
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB per stage
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(void *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// bounded wait: a pipeline bug must end the kernel (error flag), not hang the GPU
+__device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity, int *err)
+{
+    for (long long spin = 0; spin < (1ll << 26); ++spin)
+        if (mbar_try_wait(bar, parity))
+            return true;
+    *err = 2;
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, void *bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(void *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(unsigned tmemC, u64 descA, u64 descB, unsigned idesc, unsigned accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemC), "l"(descA),
+                 "l"(descB), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned addr, unsigned (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), LBO (ignored for swizzled K-major, set 1) in [16,30), SBO = 1024 B (8 rows x 128 B)
+// in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64)
+__device__ __forceinline__ u64 umma_desc_sw128(unsigned smemAddr)
+{
+    return static_cast<u64>((smemAddr & 0x3ffff) >> 4) | (1ull << 16) | (static_cast<u64>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10), both K-major, N>>3 at 17, M>>4 at 24
+constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<unsigned>(TC_BN >> 3) << 17) | (static_cast<unsigned>(TC_BM >> 4) << 24);
+
+struct TcShared
+{
+    // offsets inside the dynamic shared buffer (1024-byte aligned base)
+    static constexpr int A_OFF = 0;                                   // up to 4 k-blocks x 16 KB
+    static constexpr int B_OFF = A_OFF + (TC_MAXK / TC_BK) * TC_A_BYTES; // 4 stages x 32 KB
+    static constexpr int CN_OFF = B_OFF + TC_STAGES * TC_B_BYTES;      // 2 x 256 floats
+    static constexpr int BAR_OFF = CN_OFF + 2 * TC_BN * 4;             // mbarriers
+    static constexpr int TOTAL = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, const float *__restrict__ cnorm, int rowsTotal,
+                int numRowTiles, int numNodeTiles, int kBlocks, unsigned *__restrict__ candOut, float *__restrict__ tauOut, int *err)
+{
+    extern __shared__ unsigned char rawSmem[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(rawSmem) + 1023) & ~static_cast<uintptr_t>(1023));
+    unsigned char *sA = smem + TcShared::A_OFF;
+    unsigned char *sB = smem + TcShared::B_OFF;
+    float *sCn = reinterpret_cast<float *>(smem + TcShared::CN_OFF);
+    u64 *bars = reinterpret_cast<u64 *>(smem + TcShared::BAR_OFF);
+    u64 *bFull = bars, *bEmpty = bars + TC_STAGES, *aFull = bars + 2 * TC_STAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
+    unsigned *tmemBaseSlot = reinterpret_cast<unsigned *>(tEmpty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 1 && lane == 0)
+    {
+        for (int s = 0; s < TC_STAGES; ++s)
+        {
+            mbar_init(&bFull[s], 1);
+            mbar_init(&bEmpty[s], 1);
+        }
+        mbar_init(aFull, 1);
+        mbar_init(aEmpty, 1);
+        for (int a = 0; a < 2; ++a)
+        {
+            mbar_init(&tFull[a], 1);
+            mbar_init(&tEmpty[a], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2)
+    {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemBaseSlot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmemBase = *tmemBaseSlot;
+
+    if (warp == 0)
+    {
+        // ===================================================== TMA producer
+        if (lane == 0)
+        {
+            unsigned stage = 0, phase = 0, aPhase = 0;
+            bool ok = true;
+            for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
+            {
+                ok = mbar_wait(aEmpty, aPhase ^ 1, err); // previous row tile's MMAs are done with A
+                aPhase ^= 1;
+                mbar_expect_tx(aFull, static_cast<unsigned>(kBlocks) * TC_A_BYTES);
+                for (int kb = 0; kb < kBlocks; ++kb)
+                    tma_load_2d(sA + kb * TC_A_BYTES, &mapX, aFull, kb * TC_BK, rt * TC_BM);
+                for (int nt = 0; nt < numNodeTiles && ok; ++nt)
+                    for (int kb = 0; kb < kBlocks && ok; ++kb)
+                    {
+                        ok = mbar_wait(&bEmpty[stage], phase ^ 1, err);
+                        mbar_expect_tx(&bFull[stage], TC_B_BYTES);
+                        tma_load_2d(sB + stage * TC_B_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
+                        if (++stage == TC_STAGES)
+                        {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        // ===================================================== MMA issuer (one lane)
+        if (lane == 0)
+        {
+            unsigned stage = 0, phase = 0, aPhase = 0, acc = 0, accPhase = 0;
+            bool ok = true;
+            for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
+            {
+                ok = mbar_wait(aFull, aPhase, err);
+                aPhase ^= 1;
+                for (int nt = 0; nt < numNodeTiles && ok; ++nt)
+                {
+                    ok = mbar_wait(&tEmpty[acc], accPhase ^ 1, err); // epilogue drained this accumulator
+                    tc_fence_after();
+                    const unsigned tmemC = tmemBase + acc * TC_BN;
+                    for (int kb = 0; kb < kBlocks && ok; ++kb)
+                    {
+                        ok = mbar_wait(&bFull[stage], phase, err);
+                        tc_fence_after();
+                        const unsigned aAddr = smem_u32(sA + kb * TC_A_BYTES), bAddr = smem_u32(sB + stage * TC_B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                        {
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row
+                            const u64 da = umma_desc_sw128(aAddr + k * 32), db = umma_desc_sw128(bAddr + k * 32);
+                            umma_f16(tmemC, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&bEmpty[stage]); // frees the B stage when the MMAs above have read it
+                        if (++stage == TC_STAGES)
+                        {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tFull[acc]); // accumulator complete
+                    if (++acc == 2)
+                    {
+                        acc = 0;
+                        accPhase ^= 1;
+                    }
+                }
+                umma_commit(aEmpty); // all MMAs of this row tile are done reading A
+            }
+        }
+    }
+    else if (warp >= 4)
+    {
+        // ===================================================== epilogue: thread = one row of the tile
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int rowInTile = q * 32 + lane;
+        const int et = threadIdx.x - 128;  // 0..127
+        unsigned acc = 0, accPhase = 0;
+        bool ok = true;
+        for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
+        {
+            float sc[TC_TOPK];
+            unsigned id[TC_TOPK];
+#pragma unroll
+            for (int i = 0; i < TC_TOPK; ++i)
+            {
+                sc[i] = __int_as_float(0x7f800000);
+                id[i] = 0;
+            }
+            for (int nt = 0; nt < numNodeTiles && ok; ++nt)
+            {
+                // per-node constants of this tile
+                float *cn = sCn + acc * TC_BN;
+                cn[et] = cnorm[nt * TC_BN + et];
+                cn[et + 128] = cnorm[nt * TC_BN + et + 128];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                ok = mbar_wait(&tFull[acc], accPhase, err);
+                tc_fence_after();
+                const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN;
+#pragma unroll 1
+                for (int c = 0; c < TC_BN / 32; ++c)
+                {
+                    unsigned v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_wait_ld();
+                    float thr = sc[TC_TOPK - 1];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                    {
+                        const float s = fmaf(-2.0f, __uint_as_float(v[j]), cn[c * 32 + j]);
+                        if (s < thr)
+                        {
+                            sc[TC_TOPK - 1] = s;
+                            id[TC_TOPK - 1] = static_cast<unsigned>(nt * TC_BN + c * 32 + j);
+#pragma unroll
+                            for (int i = TC_TOPK - 1; i > 0; --i)
+                                if (sc[i] < sc[i - 1])
+                                {
+                                    const float ts = sc[i];
+                                    sc[i] = sc[i - 1];
+                                    sc[i - 1] = ts;
+                                    const unsigned ti = id[i];
+                                    id[i] = id[i - 1];
+                                    id[i - 1] = ti;
+                                }
+                            thr = sc[TC_TOPK - 1];
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tEmpty[acc]);
+                if (++acc == 2)
+                {
+                    acc = 0;
+                    accPhase ^= 1;
+                }
+            }
+            const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
+            if (row < rowsTotal)
+            {
+#pragma unroll
+                for (int i = 0; i < TC_TOPK; ++i)
+                    candOut[row * TC_TOPK + i] = id[i];
+                tauOut[row] = sc[TC_TOPK - 1];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+
+// rows of f32 -> bf16 (zero padded to Kpad), optional |row|^2 (f32, any order: only used by the guard)
+__global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long rows, int D, int srcStride, __nv_bfloat16 *__restrict__ dst, int Kpad,
+                                    float *__restrict__ norm2)
+{
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows)
+        return;
+    float s = 0.0f;
+    for (int k = lane; k < Kpad; k += 32)
+    {
+        const float v = k < D ? src[row * srcStride + k] : 0.0f;
+        dst[row * Kpad + k] = __float2bfloat16_rn(v);
+        s += v * v;
+    }
+    for (int o = 16; o; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && norm2)
+        norm2[row] = s;
+}
+
+// per-node constant of the score: |m_p|^2 for nodes that may win, +inf for padding and for nodes below min_hits
+// (node 0 always competes: it seeds findRestrictedBmu regardless of its hit count, src/Som.cpp:316-322)
+__global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__restrict__ hits, u64 minHits, int N, int Npad, float *__restrict__ cnorm,
+                                  float *__restrict__ maxNorm2)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Npad)
+        return;
+    float c = __int_as_float(0x7f800000);
+    if (p < N && (p == 0 || minHits == 0 || hits[p] >= minHits))
+        c = norm2[p];
+    cnorm[p] = c;
+    if (p < N)
+        atomicMax(reinterpret_cast<int *>(maxNorm2), __float_as_int(norm2[p])); // non-negative floats order like ints
+}
+
+// ------------------------------------------------------------------------------------------------ exact rescore + guard
+
+// 8 threads per row: each re-evaluates one candidate with the reference's sequential f32 chain.
+__global__ void rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
+                               const unsigned *__restrict__ cand, const float *__restrict__ tau, const float *__restrict__ xnorm2,
+                               const float *__restrict__ maxNorm2, unsigned *__restrict__ outBmu, float *__restrict__ outDist,
+                               unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
+{
+    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long row = gid >> 3;
+    const int j = static_cast<int>(gid & 7);
+    const bool live = row < rows;
+    u64 key = ~0ull;
+    if (live)
+    {
+        const unsigned node = cand[row * TC_TOPK + j];
+        const float *m = mean + static_cast<size_t>(node) * rowStride, *xr = x + row * D;
+        float s = 0.0f;
+        for (int k = 0; k < D; ++k)
+        {
+            const float r = __fsub_rn(m[k], xr[k]);
+            s = __fadd_rn(s, __fmul_rn(r, r));
+        }
+        key = make_key(s, node, (s != s) ? 1u : 0u);
+    }
+#pragma unroll
+    for (int o = 4; o; o >>= 1)
+        key = u64_min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (live && j == 0)
+    {
+        float d = __uint_as_float(static_cast<unsigned>(key >> 32));
+        if (key & 1ull)
+            d = __uint_as_float(0x7fc00000u);
+        if (outBmu)
+            outBmu[row] = key_node(key);
+        if (outDist)
+            outDist[row] = d;
+        // guard: can a node outside the candidate set beat (or tie) the best candidate?
+        const float xn = xnorm2[row];
+        const float E = 0.0079f * sqrtf(xn * maxNorm2[0]) + 1e-5f * (xn + maxNorm2[0]);
+        const float lower = (tau[row] + xn - E) * (1.0f - 1e-4f);
+        if (!(lower > d)) // also catches NaN
+            fallbackRows[atomicAdd(fallbackCount, 1u)] = static_cast<unsigned>(row);
+    }
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows, unsigned count, float *__restrict__ out)
+{
+    const unsigned i = blockIdx.x;
+    if (i >= count)
+        return;
+    const size_t r = rows[i];
+    for (int k = threadIdx.x; k < D; k += blockDim.x)
+        out[static_cast<size_t>(i) * D + k] = x[r * D + k];
+}
+__global__ void scatter_results_kernel(const unsigned *__restrict__ rows, unsigned count, const unsigned *__restrict__ bmuIn, const float *__restrict__ distIn,
+                                       unsigned *__restrict__ outBmu, float *__restrict__ outDist)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    if (outBmu)
+        outBmu[rows[i]] = bmuIn[i];
+    if (outDist)
+        outDist[rows[i]] = distIn[i];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn)
+    {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int make_map(vsom_ctx *ctx, CUtensorMap *map, void *base, unsigned long long rows, int Kpad, int boxRows)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc)
+        return set_error(ctx, VSOM_ERR_CUDA, "score_tc: cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kpad), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kpad) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK), static_cast<cuuint32_t>(boxRows)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(ctx, VSOM_ERR_CUDA, "score_tc: cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
+    return VSOM_OK;
+}
+
+bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR && ctx->Dm <= TC_MAXK; }
+
+// stage slots used here: 6 = bf16 map + node constants, 7 = bf16 rows of the current slab, 8 = per-row scratch
+int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut)
+{
+    if (!score_tc_supported(ctx))
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 256");
+    if (fallbackRowsOut)
+        *fallbackRowsOut = 0;
+    if (n == 0)
+        return VSOM_OK;
+    const int D = ctx->Dm, N = ctx->N;
+    const int Kpad = (D + TC_BK - 1) / TC_BK * TC_BK, kBlocks = Kpad / TC_BK;
+    const int Npad = (N + TC_BN - 1) / TC_BN * TC_BN, nodeTiles = Npad / TC_BN;
+
+    // ---- map side: bf16 copy, |m|^2, node constants, max |m|^2
+    const size_t mbBytes = sizeof(__nv_bfloat16) * static_cast<size_t>(Npad) * Kpad;
+    int rc = stage_reserve(ctx, 6, mbBytes + sizeof(float) * (2 * static_cast<size_t>(Npad) + 64));
+    if (rc)
+        return rc;
+    __nv_bfloat16 *Mb = static_cast<__nv_bfloat16 *>(ctx->stage[6]);
+    float *mnorm = reinterpret_cast<float *>(static_cast<unsigned char *>(ctx->stage[6]) + mbBytes);
+    float *cnorm = mnorm + Npad;
+    float *maxNorm2 = cnorm + Npad;
+    VSOM_CUDA(ctx, cudaMemsetAsync(Mb, 0, mbBytes, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemsetAsync(maxNorm2, 0, sizeof(float), ctx->stream));
+    to_bf16_rows_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, Mb, Kpad, mnorm);
+    node_const_kernel<<<(Npad + 255) / 256, 256, 0, ctx->stream>>>(mnorm, ctx->hits, minHits, N, Npad, cnorm, maxNorm2);
+    ctx->launches += 2;
+    CUtensorMap mapM;
+    rc = make_map(ctx, &mapM, Mb, static_cast<unsigned long long>(Npad), Kpad, TC_BN);
+    if (rc)
+        return rc;
+
+    static bool attrSet = false;
+    const int smemBytes = TcShared::TOTAL + 1024;
+    if (!attrSet)
+    {
+        VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+        attrSet = true;
+    }
+
+    // ---- rows, in slabs that bound the bf16 staging buffer
+    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << 22); // 4M rows: 2 GB of bf16 at K=256
+    rc = stage_reserve(ctx, 7, sizeof(__nv_bfloat16) * slabRows * Kpad);
+    if (rc)
+        return rc;
+    // per-row scratch: candidates, tau, |x|^2, fallback list + count, fallback results
+    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(float) * 2 + sizeof(unsigned) * 2 + sizeof(float);
+    rc = stage_reserve(ctx, 8, perRow * slabRows + 256);
+    if (rc)
+        return rc;
+    __nv_bfloat16 *Xb = static_cast<__nv_bfloat16 *>(ctx->stage[7]);
+    unsigned *cand = static_cast<unsigned *>(ctx->stage[8]);
+    float *tau = reinterpret_cast<float *>(cand + slabRows * TC_TOPK);
+    float *xnorm = tau + slabRows;
+    unsigned *fbRows = reinterpret_cast<unsigned *>(xnorm + slabRows);
+    unsigned *fbBmu = fbRows + slabRows;
+    float *fbDist = reinterpret_cast<float *>(fbBmu + slabRows);
+    unsigned *fbCount = reinterpret_cast<unsigned *>(fbDist + slabRows);
+
+    unsigned long long totalFallback = 0;
+    for (size_t r0 = 0; r0 < n; r0 += slabRows)
+    {
+        const size_t rows = std::min(slabRows, n - r0);
+        const float *xs = xDev + r0 * D;
+        to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), D, D, Xb, Kpad, xnorm);
+        CUtensorMap mapX;
+        rc = make_map(ctx, &mapX, Xb, rows, Kpad, TC_BM);
+        if (rc)
+            return rc;
+        const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
+        const int grid = std::min(rowTiles, ctx->numSMs);
+        VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
+        VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
+        score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, cand, tau,
+                                                                      ctx->errFlag);
+        rescore_kernel<<<static_cast<unsigned>((rows * 8 + 255) / 256), 256, 0, ctx->stream>>>(
+            xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, tau, xnorm, maxNorm2, outBmuDev ? outBmuDev + r0 : nullptr,
+            outDistDev ? outDistDev + r0 : nullptr, fbRows, fbCount);
+        ctx->launches += 3;
+        VSOM_CUDA(ctx, cudaGetLastError());
+        // rows the guard could not certify: exact full scan
+        unsigned count = 0;
+        int flag = 0;
+        VSOM_CUDA(ctx, cudaMemcpyAsync(&count, fbCount, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag)
+            return set_error(ctx, VSOM_ERR_TIMEOUT, "score_tc: pipeline barrier timed out (kernel bug)");
+        if (count)
+        {
+            rc = stage_reserve(ctx, 9, sizeof(float) * static_cast<size_t>(count) * D);
+            if (rc)
+                return rc;
+            float *gx = static_cast<float *>(ctx->stage[9]);
+            gather_rows_kernel<<<count, 128, 0, ctx->stream>>>(xs, D, fbRows, count, gx);
+            ctx->launches += 1;
+            rc = launch_find_bmu(ctx, gx, count, minHits, fbBmu, fbDist);
+            if (rc)
+                return rc;
+            scatter_results_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fbRows, count, fbBmu, fbDist, outBmuDev ? outBmuDev + r0 : nullptr,
+                                                                                 outDistDev ? outDistDev + r0 : nullptr);
+            ctx->launches += 1;
+            totalFallback += count;
+        }
+    }
+    VSOM_CUDA(ctx, cudaGetLastError());
+    if (fallbackRowsOut)
+        *fallbackRowsOut = totalFallback;
+    ctx->lastFallbackRows = totalFallback;
+    return VSOM_OK;
+}
+
+} // namespace vsom
