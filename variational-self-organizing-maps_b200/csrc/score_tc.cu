@@ -265,33 +265,57 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 ok = mbar_wait(&tFull[acc], accPhase, err);
                 tc_fence_after();
                 const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN;
-#pragma unroll 1
+                // TMEM -> registers 32 columns at a time; the load of chunk c+1 is in flight while chunk c is scored.
+                // Fast path per column: one FFMA (score) + one FMNMX (chunk minimum), no branch; the sorted
+                // insertion runs only when the chunk minimum beats the row's current 8th best (rare after warm-up).
+                unsigned v[2][32];
+                tmem_ld32(taddr, v[0]);
+#pragma unroll
                 for (int c = 0; c < TC_BN / 32; ++c)
                 {
-                    unsigned v[32];
-                    tmem_ld32(taddr + c * 32, v);
                     tmem_wait_ld();
-                    float thr = sc[TC_TOPK - 1];
+                    if (c + 1 < TC_BN / 32)
+                        tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    unsigned(&w)[32] = v[c & 1];
+                    float mn = __int_as_float(0x7f800000);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
+                    for (int j4 = 0; j4 < 8; ++j4)
                     {
-                        const float s = fmaf(-2.0f, __uint_as_float(v[j]), cn[c * 32 + j]);
-                        if (s < thr)
-                        {
-                            sc[TC_TOPK - 1] = s;
-                            id[TC_TOPK - 1] = static_cast<unsigned>(nt * TC_BN + c * 32 + j);
+                        const float4 k4 = *reinterpret_cast<const float4 *>(cn + c * 32 + j4 * 4);
+                        const float s0 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 0]), k4.x);
+                        const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
+                        const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
+                        const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
+                        w[j4 * 4 + 0] = __float_as_uint(s0);
+                        w[j4 * 4 + 1] = __float_as_uint(s1);
+                        w[j4 * 4 + 2] = __float_as_uint(s2);
+                        w[j4 * 4 + 3] = __float_as_uint(s3);
+                        mn = fminf(mn, fminf(fminf(s0, s1), fminf(s2, s3)));
+                    }
+                    if (mn < sc[TC_TOPK - 1])
+                    {
+                        float thr = sc[TC_TOPK - 1];
 #pragma unroll
-                            for (int i = TC_TOPK - 1; i > 0; --i)
-                                if (sc[i] < sc[i - 1])
-                                {
-                                    const float ts = sc[i];
-                                    sc[i] = sc[i - 1];
-                                    sc[i - 1] = ts;
-                                    const unsigned ti = id[i];
-                                    id[i] = id[i - 1];
-                                    id[i - 1] = ti;
-                                }
-                            thr = sc[TC_TOPK - 1];
+                        for (int j = 0; j < 32; ++j)
+                        {
+                            const float s = __uint_as_float(w[j]);
+                            if (s < thr)
+                            {
+                                sc[TC_TOPK - 1] = s;
+                                id[TC_TOPK - 1] = static_cast<unsigned>(nt * TC_BN + c * 32 + j);
+#pragma unroll
+                                for (int i = TC_TOPK - 1; i > 0; --i)
+                                    if (sc[i] < sc[i - 1])
+                                    {
+                                        const float ts = sc[i];
+                                        sc[i] = sc[i - 1];
+                                        sc[i - 1] = ts;
+                                        const unsigned ti = id[i];
+                                        id[i] = id[i - 1];
+                                        id[i - 1] = ti;
+                                    }
+                                thr = sc[TC_TOPK - 1];
+                            }
                         }
                     }
                 }
@@ -377,7 +401,26 @@ __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int 
         const unsigned node = cand[row * TC_TOPK + j];
         const float *m = mean + static_cast<size_t>(node) * rowStride, *xr = x + row * D;
         float s = 0.0f;
-        for (int k = 0; k < D; ++k)
+        int k = 0;
+        if ((D & 3) == 0) // rows of x are 16-byte aligned: 128-bit loads, same sequential order of the adds
+        {
+            const float4 *m4 = reinterpret_cast<const float4 *>(m), *x4 = reinterpret_cast<const float4 *>(xr);
+#pragma unroll 4
+            for (int c = 0; c < (D >> 2); ++c)
+            {
+                const float4 a = m4[c], b = x4[c];
+                float r = __fsub_rn(a.x, b.x);
+                s = __fadd_rn(s, __fmul_rn(r, r));
+                r = __fsub_rn(a.y, b.y);
+                s = __fadd_rn(s, __fmul_rn(r, r));
+                r = __fsub_rn(a.z, b.z);
+                s = __fadd_rn(s, __fmul_rn(r, r));
+                r = __fsub_rn(a.w, b.w);
+                s = __fadd_rn(s, __fmul_rn(r, r));
+            }
+            k = D;
+        }
+        for (; k < D; ++k)
         {
             const float r = __fsub_rn(m[k], xr[k]);
             s = __fadd_rn(s, __fmul_rn(r, r));
