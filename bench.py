@@ -179,6 +179,7 @@ def cpu_baseline_leg():
 
 
 def main():
+    global SCORE_ROWS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -187,7 +188,9 @@ def main():
     ap.add_argument("--order", default="reference", choices=["reference", "lanes"], help="reduction order of the online step's distances")
     ap.add_argument("--rows", type=int, default=ROWS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--score-rows", type=int, default=SCORE_ROWS)
     args = ap.parse_args()
+    SCORE_ROWS = args.score_rows
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

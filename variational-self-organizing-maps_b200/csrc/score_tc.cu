@@ -118,7 +118,8 @@ struct TcShared
     static constexpr int B_OFF = A_OFF + (TC_MAXK / TC_BK) * TC_A_BYTES; // 4 stages x 32 KB
     static constexpr int CN_OFF = B_OFF + TC_STAGES * TC_B_BYTES;      // 2 x 256 floats
     static constexpr int BAR_OFF = CN_OFF + 2 * TC_BN * 4;             // mbarriers
-    static constexpr int TOTAL = BAR_OFF + 256;
+    static constexpr int SCR_OFF = BAR_OFF + 256;                      // 32 x 128 floats: slow-path scratch of the epilogue
+    static constexpr int TOTAL = SCR_OFF + 32 * 128 * 4;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -133,6 +134,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     u64 *bars = reinterpret_cast<u64 *>(smem + TcShared::BAR_OFF);
     u64 *bFull = bars, *bEmpty = bars + TC_STAGES, *aFull = bars + 2 * TC_STAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
     unsigned *tmemBaseSlot = reinterpret_cast<unsigned *>(tEmpty + 2);
+    float *scratch = reinterpret_cast<float *>(smem + TcShared::SCR_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -294,11 +296,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     }
                     if (mn < sc[TC_TOPK - 1])
                     {
-                        float thr = sc[TC_TOPK - 1];
+                        // slow path, kept SMALL in code size: the 32 scores go through a per-thread column of shared
+                        // memory so that one non-unrolled loop can index them (an unrolled copy of the insertion per
+                        // column made the kernel 290 KB of SASS and the fast path instruction-cache bound)
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
+                            scratch[j * 128 + et] = __uint_as_float(w[j]);
+                        float thr = sc[TC_TOPK - 1];
+#pragma unroll 1
+                        for (int j = 0; j < 32; ++j)
                         {
-                            const float s = __uint_as_float(w[j]);
+                            const float s = scratch[j * 128 + et];
                             if (s < thr)
                             {
                                 sc[TC_TOPK - 1] = s;
