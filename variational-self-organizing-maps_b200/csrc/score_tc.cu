@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace vsom
 {
@@ -124,7 +125,7 @@ struct TcShared
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, const float *__restrict__ cnorm, int rowsTotal,
-                int numRowTiles, int numNodeTiles, int kBlocks, unsigned *__restrict__ candOut, float *__restrict__ tauOut, int *err)
+                int numRowTiles, int numNodeTiles, int kBlocks, int stagger, unsigned *__restrict__ candOut, float *__restrict__ tauOut, int *err)
 {
     extern __shared__ unsigned char rawSmem[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(rawSmem) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -137,6 +138,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     float *scratch = reinterpret_cast<float *>(smem + TcShared::SCR_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTAs walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
+    // of L2 (all starting at tile 0 makes 148 SMs ask the same lines at once)
+    const int ntStart = stagger ? static_cast<int>((static_cast<unsigned>(blockIdx.x) * 7u) % static_cast<unsigned>(numNodeTiles)) : 0;
 
     if (warp == 1 && lane == 0)
     {
@@ -178,9 +182,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 mbar_expect_tx(aFull, static_cast<unsigned>(kBlocks) * TC_A_BYTES);
                 for (int kb = 0; kb < kBlocks; ++kb)
                     tma_load_2d(sA + kb * TC_A_BYTES, &mapX, aFull, kb * TC_BK, rt * TC_BM);
-                for (int nt = 0; nt < numNodeTiles && ok; ++nt)
+                for (int i = 0; i < numNodeTiles && ok; ++i)
                     for (int kb = 0; kb < kBlocks && ok; ++kb)
                     {
+                        const int nt = (i + ntStart) % numNodeTiles;
                         ok = mbar_wait(&bEmpty[stage], phase ^ 1, err);
                         mbar_expect_tx(&bFull[stage], TC_B_BYTES);
                         tma_load_2d(sB + stage * TC_B_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
@@ -257,8 +262,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 sc[i] = __int_as_float(0x7f800000);
                 id[i] = 0;
             }
-            for (int nt = 0; nt < numNodeTiles && ok; ++nt)
+            for (int i = 0; i < numNodeTiles && ok; ++i)
             {
+                const int nt = (i + ntStart) % numNodeTiles;
                 // per-node constants of this tile
                 float *cn = sCn + acc * TC_BN;
                 cn[et] = cnorm[nt * TC_BN + et];
@@ -573,6 +579,8 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
     unsigned *fbCount = reinterpret_cast<unsigned *>(fbDist + slabRows);
 
     unsigned long long totalFallback = 0;
+    const char *stg = getenv("VSOM_TC_STAGGER");
+    const int stagger = stg ? atoi(stg) : 1;
     for (size_t r0 = 0; r0 < n; r0 += slabRows)
     {
         const size_t rows = std::min(slabRows, n - r0);
@@ -586,7 +594,7 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         const int grid = std::min(rowTiles, ctx->numSMs);
         VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
         VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-        score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, cand, tau,
+        score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, stagger, cand, tau,
                                                                       ctx->errFlag);
         rescore_kernel<<<static_cast<unsigned>((rows * 8 + 255) / 256), 256, 0, ctx->stream>>>(
             xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, tau, xnorm, maxNorm2, outBmuDev ? outBmuDev + r0 : nullptr,
