@@ -4,23 +4,27 @@
 // findRestrictedBmu :313-332 over a loaded DataSet) when the batch is large:
 //     d(r,p) = |x_r|^2 - 2 x_r . m_p + |m_p|^2            (Standard / Median Comparer, src/Transformation.cpp:7-8)
 // The cross term X[R x K] . M^T[K x N] runs as tcgen05.mma (bf16 operands, fp32 accumulators in TMEM), operands
-// staged by TMA (128-byte swizzle).  The tensor cores only SELECT: each row keeps the 8 smallest approximate
-// scores c_p - 2 x.m over all nodes; the exact pass then re-evaluates those 8 candidates in the reference's own
-// f32 arithmetic and order (bit-identical distances) and applies findBmu's lowest-index rule among them.
-// A per-row guard proves that no other node can win: with tau = the 8th approximate score and
-// E = 2^-7 |x| max_p|m_p| (bf16 operand rounding, Cauchy-Schwarz) every non-candidate has
-// d >= (tau + |x|^2 - E)(1 - 1e-4); rows where that does not exceed the best exact candidate distance are
-// re-scored by the exact full scan (score_exact.cu), so the result is ALWAYS the reference's argmin.
+// staged by TMA (128-byte swizzle).  The tensor cores only SELECT candidates; the exact pass re-evaluates them in
+// the reference's own f32 arithmetic and order (bit-identical distances) and applies findBmu's lowest-index rule.
+//
+// Candidate rule (margin list).  With approximate score a_p = c_p - 2 acc_p, E = 2^-7 |x| max_p|m_p| bounds
+// |a_p + |x|^2 - d_p| (bf16 rounding of both operands, Cauchy-Schwarz; f32 effects are covered by a relative slack).
+// While streaming over the node tiles each row keeps its running best score and appends every node with
+// a_p < best + Delta, Delta = 2.2 E + slack, to a small per-row list.  Any node NOT appended had a_p >= best_final +
+// Delta, hence d_p >= best_final + |x|^2 + Delta - E > d(best node): it cannot be the BMU, nor tie with it.  So the
+// BMU is always in the list — by construction, no statistical recall argument.  At the end of the row tile the list
+// is filtered against the final threshold; up to 8 survivors go to the exact rescore, rows with more (or whose list
+// overflowed) are re-scored by the exact full scan (score_exact.cu).
 //
 // Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
 //   warp 0   TMA producer : A tile (128 rows x K, resident for the row tile) + B tiles (256 nodes x 64) through a
-//                           4-stage mbarrier ring
+//                           3-stage mbarrier ring
 //   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) into one
 //                           of two 256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes
 //                           the accumulator
 //   warp 2   TMEM allocator (512 columns)
-//   warps 4-7 epilogue    : thread = one row (TMEM lane); tcgen05.ld 32 columns at a time, score = c_p - 2 acc,
-//                           branch-free threshold test, rare sorted insertion into the row's top-8
+//   warps 4-7 epilogue    : thread = one row (TMEM lane); tcgen05.ld 32 columns at a time (next chunk in flight),
+//                           per column: FFMA (score), compare, predicated append; running best via FMNMX
 // Limits of this version: Standard / Median transformation, Dm <= 256 (A tile resident); other shapes use K3.
 #include "common.cuh"
 
@@ -34,7 +38,10 @@
 namespace vsom
 {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_TOPK = 8, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 8, TC_THREADS = 256;
+constexpr int TC_LIST = 48;    // per-row candidate list (shared memory), compacted when it passes TC_LIST_HI
+constexpr int TC_LIST_HI = 16; // a 32-column chunk can append at most 32 entries: 16 + 32 <= 48
+constexpr unsigned TC_OVERFLOW = 255;
 constexpr int TC_MAXK = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per k-block
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB per stage
@@ -119,13 +126,14 @@ struct TcShared
     static constexpr int B_OFF = A_OFF + (TC_MAXK / TC_BK) * TC_A_BYTES; // 4 stages x 32 KB
     static constexpr int CN_OFF = B_OFF + TC_STAGES * TC_B_BYTES;      // 2 x 256 floats
     static constexpr int BAR_OFF = CN_OFF + 2 * TC_BN * 4;             // mbarriers
-    static constexpr int SCR_OFF = BAR_OFF + 256;                      // 32 x 128 floats: slow-path scratch of the epilogue
-    static constexpr int TOTAL = SCR_OFF + 32 * 128 * 4;
+    static constexpr int LIST_OFF = BAR_OFF + 256;                     // TC_LIST x 128 x {score, node}: per-row candidate lists
+    static constexpr int TOTAL = LIST_OFF + TC_LIST * 128 * 8;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, const float *__restrict__ cnorm, int rowsTotal,
-                int numRowTiles, int numNodeTiles, int kBlocks, int stagger, unsigned *__restrict__ candOut, float *__restrict__ tauOut, int *err)
+                int numRowTiles, int numNodeTiles, int kBlocks, int stagger, const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, unsigned *__restrict__ candOut,
+                unsigned *__restrict__ countOut, int *err)
 {
     extern __shared__ unsigned char rawSmem[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(rawSmem) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -135,7 +143,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     u64 *bars = reinterpret_cast<u64 *>(smem + TcShared::BAR_OFF);
     u64 *bFull = bars, *bEmpty = bars + TC_STAGES, *aFull = bars + 2 * TC_STAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
     unsigned *tmemBaseSlot = reinterpret_cast<unsigned *>(tEmpty + 2);
-    float *scratch = reinterpret_cast<float *>(smem + TcShared::SCR_OFF);
+    uint2 *lists = reinterpret_cast<uint2 *>(smem + TcShared::LIST_OFF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTAs walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
@@ -250,18 +258,44 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const int q = warp & 3;            // TMEM lane quarter this warp may access
         const int rowInTile = q * 32 + lane;
         const int et = threadIdx.x - 128;  // 0..127
+        uint2 *mine = lists + et;          // entry e of this row at mine[e * 128]
         unsigned acc = 0, accPhase = 0;
         bool ok = true;
+        const float mx = maxNorm2[0];
+        const float inf = __int_as_float(0x7f800000);
+
+        // drop list entries that are no longer below the (tightened) threshold; warp-uniform control flow
+        auto compact = [&](int &cnt, float thr, bool &ovf) {
+            const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+            int k = 0;
+#pragma unroll 1
+            for (int e = 0; e < maxc; ++e)
+                if (e < cnt)
+                {
+                    const uint2 v = mine[e * 128];
+                    if (__uint_as_float(v.x) < thr)
+                    {
+                        mine[k * 128] = v;
+                        ++k;
+                    }
+                }
+            cnt = k;
+            if (cnt > TC_LIST_HI)
+            {
+                ovf = true; // too many nodes within the margin of the best: this row takes the exact scan
+                cnt = 0;
+            }
+        };
+
         for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
         {
-            float sc[TC_TOPK];
-            unsigned id[TC_TOPK];
-#pragma unroll
-            for (int i = 0; i < TC_TOPK; ++i)
-            {
-                sc[i] = __int_as_float(0x7f800000);
-                id[i] = 0;
-            }
+            const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
+            const float xn = row < rowsTotal ? xnorm2[row] : 0.0f;
+            const float E = 0.0079f * sqrtf(xn * mx) + 1e-5f * (xn + mx);
+            const float delta = 2.2f * E + 2e-4f * (xn + mx);
+            float best = inf, thr = inf;
+            int cnt = 0;
+            bool ovf = false;
             for (int i = 0; i < numNodeTiles && ok; ++i)
             {
                 const int nt = (i + ntStart) % numNodeTiles;
@@ -273,9 +307,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 ok = mbar_wait(&tFull[acc], accPhase, err);
                 tc_fence_after();
                 const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN;
-                // TMEM -> registers 32 columns at a time; the load of chunk c+1 is in flight while chunk c is scored.
-                // Fast path per column: one FFMA (score) + one FMNMX (chunk minimum), no branch; the sorted
-                // insertion runs only when the chunk minimum beats the row's current 8th best (rare after warm-up).
                 unsigned v[2][32];
                 tmem_ld32(taddr, v[0]);
 #pragma unroll
@@ -284,8 +315,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     tmem_wait_ld();
                     if (c + 1 < TC_BN / 32)
                         tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (__any_sync(0xffffffffu, cnt > TC_LIST_HI))
+                        compact(cnt, thr, ovf);
                     unsigned(&w)[32] = v[c & 1];
-                    float mn = __int_as_float(0x7f800000);
+                    const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + c * 32);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
                     {
@@ -294,43 +327,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
                         const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
                         const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
-                        w[j4 * 4 + 0] = __float_as_uint(s0);
-                        w[j4 * 4 + 1] = __float_as_uint(s1);
-                        w[j4 * 4 + 2] = __float_as_uint(s2);
-                        w[j4 * 4 + 3] = __float_as_uint(s3);
-                        mn = fminf(mn, fminf(fminf(s0, s1), fminf(s2, s3)));
-                    }
-                    if (mn < sc[TC_TOPK - 1])
-                    {
-                        // slow path, kept SMALL in code size: the 32 scores go through a per-thread column of shared
-                        // memory so that one non-unrolled loop can index them (an unrolled copy of the insertion per
-                        // column made the kernel 290 KB of SASS and the fast path instruction-cache bound)
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            scratch[j * 128 + et] = __uint_as_float(w[j]);
-                        float thr = sc[TC_TOPK - 1];
-#pragma unroll 1
-                        for (int j = 0; j < 32; ++j)
-                        {
-                            const float s = scratch[j * 128 + et];
-                            if (s < thr)
-                            {
-                                sc[TC_TOPK - 1] = s;
-                                id[TC_TOPK - 1] = static_cast<unsigned>(nt * TC_BN + c * 32 + j);
-#pragma unroll
-                                for (int i = TC_TOPK - 1; i > 0; --i)
-                                    if (sc[i] < sc[i - 1])
-                                    {
-                                        const float ts = sc[i];
-                                        sc[i] = sc[i - 1];
-                                        sc[i - 1] = ts;
-                                        const unsigned ti = id[i];
-                                        id[i] = id[i - 1];
-                                        id[i - 1] = ti;
-                                    }
-                                thr = sc[TC_TOPK - 1];
-                            }
-                        }
+                        // a threshold that is a few columns stale is still valid (it only ever decreases)
+                        if (s0 < thr)
+                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s0), nodeBase + j4 * 4 + 0);
+                        if (s1 < thr)
+                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s1), nodeBase + j4 * 4 + 1);
+                        if (s2 < thr)
+                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s2), nodeBase + j4 * 4 + 2);
+                        if (s3 < thr)
+                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s3), nodeBase + j4 * 4 + 3);
+                        best = fminf(best, fminf(fminf(s0, s1), fminf(s2, s3)));
+                        thr = best + delta;
                     }
                 }
                 tc_fence_before();
@@ -341,13 +348,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     accPhase ^= 1;
                 }
             }
-            const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
+            // final filter against the final threshold; at most TC_TOPK survivors go to the exact rescore
+            compact(cnt, thr, ovf);
             if (row < rowsTotal)
             {
-#pragma unroll
-                for (int i = 0; i < TC_TOPK; ++i)
-                    candOut[row * TC_TOPK + i] = id[i];
-                tauOut[row] = sc[TC_TOPK - 1];
+                unsigned count = (ovf || cnt > TC_TOPK || cnt == 0) ? TC_OVERFLOW : static_cast<unsigned>(cnt);
+                if (count != TC_OVERFLOW)
+                    for (int e = 0; e < cnt; ++e)
+                        candOut[row * TC_TOPK + e] = mine[e * 128].y;
+                countOut[row] = count;
             }
         }
     }
@@ -399,18 +408,19 @@ __global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__
 
 // ------------------------------------------------------------------------------------------------ exact rescore + guard
 
-// 8 threads per row: each re-evaluates one candidate with the reference's sequential f32 chain.
+// 8 threads per row: thread j re-evaluates candidate j (if the row has that many) with the reference's sequential
+// f32 chain.  Rows whose list overflowed go to the fallback list (exact full scan).
 __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
-                               const unsigned *__restrict__ cand, const float *__restrict__ tau, const float *__restrict__ xnorm2,
-                               const float *__restrict__ maxNorm2, unsigned *__restrict__ outBmu, float *__restrict__ outDist,
-                               unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
+                               const unsigned *__restrict__ cand, const unsigned *__restrict__ count, unsigned *__restrict__ outBmu,
+                               float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
 {
     const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long row = gid >> 3;
     const int j = static_cast<int>(gid & 7);
     const bool live = row < rows;
+    const unsigned cnt = live ? count[row] : 0u;
     u64 key = ~0ull;
-    if (live)
+    if (live && cnt != TC_OVERFLOW && static_cast<unsigned>(j) < cnt)
     {
         const unsigned node = cand[row * TC_TOPK + j];
         const float *m = mean + static_cast<size_t>(node) * rowStride, *xr = x + row * D;
@@ -447,18 +457,16 @@ __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int 
     if (live && j == 0)
     {
         float d = __uint_as_float(static_cast<unsigned>(key >> 32));
-        if (key & 1ull)
-            d = __uint_as_float(0x7fc00000u);
-        if (outBmu)
-            outBmu[row] = key_node(key);
-        if (outDist)
-            outDist[row] = d;
-        // guard: can a node outside the candidate set beat (or tie) the best candidate?
-        const float xn = xnorm2[row];
-        const float E = 0.0079f * sqrtf(xn * maxNorm2[0]) + 1e-5f * (xn + maxNorm2[0]);
-        const float lower = (tau[row] + xn - E) * (1.0f - 1e-4f);
-        if (!(lower > d)) // also catches NaN
+        const bool nan = (key & 1ull) != 0;
+        if (cnt == TC_OVERFLOW || nan)
             fallbackRows[atomicAdd(fallbackCount, 1u)] = static_cast<unsigned>(row);
+        else
+        {
+            if (outBmu)
+                outBmu[row] = key_node(key);
+            if (outDist)
+                outDist[row] = d;
+        }
     }
 }
 
@@ -564,15 +572,15 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
     rc = stage_reserve(ctx, 7, sizeof(__nv_bfloat16) * slabRows * Kpad);
     if (rc)
         return rc;
-    // per-row scratch: candidates, tau, |x|^2, fallback list + count, fallback results
+    // per-row scratch: candidates, their count, |x|^2, fallback list + count, fallback results
     const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(float) * 2 + sizeof(unsigned) * 2 + sizeof(float);
     rc = stage_reserve(ctx, 8, perRow * slabRows + 256);
     if (rc)
         return rc;
     __nv_bfloat16 *Xb = static_cast<__nv_bfloat16 *>(ctx->stage[7]);
     unsigned *cand = static_cast<unsigned *>(ctx->stage[8]);
-    float *tau = reinterpret_cast<float *>(cand + slabRows * TC_TOPK);
-    float *xnorm = tau + slabRows;
+    unsigned *candCount = cand + slabRows * TC_TOPK;
+    float *xnorm = reinterpret_cast<float *>(candCount + slabRows);
     unsigned *fbRows = reinterpret_cast<unsigned *>(xnorm + slabRows);
     unsigned *fbBmu = fbRows + slabRows;
     float *fbDist = reinterpret_cast<float *>(fbBmu + slabRows);
@@ -594,10 +602,10 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         const int grid = std::min(rowTiles, ctx->numSMs);
         VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
         VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-        score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, stagger, cand, tau,
+        score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, stagger, xnorm, maxNorm2, cand, candCount,
                                                                       ctx->errFlag);
         rescore_kernel<<<static_cast<unsigned>((rows * 8 + 255) / 256), 256, 0, ctx->stream>>>(
-            xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, tau, xnorm, maxNorm2, outBmuDev ? outBmuDev + r0 : nullptr,
+            xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, candCount, outBmuDev ? outBmuDev + r0 : nullptr,
             outDistDev ? outDistDev + r0 : nullptr, fbRows, fbCount);
         ctx->launches += 3;
         VSOM_CUDA(ctx, cudaGetLastError());
