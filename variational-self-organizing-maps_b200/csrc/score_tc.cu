@@ -135,8 +135,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 int numRowTiles, int numNodeTiles, int kBlocks, int stagger, const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, unsigned *__restrict__ candOut,
                 unsigned *__restrict__ countOut, int *err)
 {
-    extern __shared__ unsigned char rawSmem[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(rawSmem) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 128-byte-swizzled TMA / UMMA tiles need a 1024-byte aligned base; declaring the alignment (instead of rounding
+    // a pointer up by hand) also lets the compiler keep every derived pointer in the shared address space (LDS/STS)
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem + TcShared::A_OFF;
     unsigned char *sB = smem + TcShared::B_OFF;
     float *sCn = reinterpret_cast<float *>(smem + TcShared::CN_OFF);
@@ -296,6 +297,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
+            uint2 *wp = mine; // next free entry of this row's list (cnt == (wp - mine) / 128)
             for (int i = 0; i < numNodeTiles && ok; ++i)
             {
                 const int nt = (i + ntStart) % numNodeTiles;
@@ -315,8 +317,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     tmem_wait_ld();
                     if (c + 1 < TC_BN / 32)
                         tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    cnt = static_cast<int>(wp - mine) >> 7;
                     if (__any_sync(0xffffffffu, cnt > TC_LIST_HI))
+                    {
                         compact(cnt, thr, ovf);
+                        wp = mine + cnt * 128;
+                    }
                     unsigned(&w)[32] = v[c & 1];
                     const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + c * 32);
 #pragma unroll
@@ -329,13 +335,25 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
                         // a threshold that is a few columns stale is still valid (it only ever decreases)
                         if (s0 < thr)
-                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s0), nodeBase + j4 * 4 + 0);
+                        {
+                            *wp = make_uint2(__float_as_uint(s0), nodeBase + j4 * 4 + 0);
+                            wp += 128;
+                        }
                         if (s1 < thr)
-                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s1), nodeBase + j4 * 4 + 1);
+                        {
+                            *wp = make_uint2(__float_as_uint(s1), nodeBase + j4 * 4 + 1);
+                            wp += 128;
+                        }
                         if (s2 < thr)
-                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s2), nodeBase + j4 * 4 + 2);
+                        {
+                            *wp = make_uint2(__float_as_uint(s2), nodeBase + j4 * 4 + 2);
+                            wp += 128;
+                        }
                         if (s3 < thr)
-                            mine[(cnt++) * 128] = make_uint2(__float_as_uint(s3), nodeBase + j4 * 4 + 3);
+                        {
+                            *wp = make_uint2(__float_as_uint(s3), nodeBase + j4 * 4 + 3);
+                            wp += 128;
+                        }
                         best = fminf(best, fminf(fminf(s0, s1), fminf(s2, s3)));
                         thr = best + delta;
                     }
@@ -349,6 +367,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 }
             }
             // final filter against the final threshold; at most TC_TOPK survivors go to the exact rescore
+            cnt = static_cast<int>(wp - mine) >> 7;
             compact(cnt, thr, ovf);
             if (row < rowsTotal)
             {
@@ -560,7 +579,7 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         return rc;
 
     static bool attrSet = false;
-    const int smemBytes = TcShared::TOTAL + 1024;
+    const int smemBytes = TcShared::TOTAL;
     if (!attrSet)
     {
         VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
