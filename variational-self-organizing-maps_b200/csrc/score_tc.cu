@@ -105,6 +105,10 @@ __device__ __forceinline__ void tmem_ld32(unsigned addr, unsigned (&v)[32])
                  : "r"(addr)
                  : "memory");
 }
+__device__ __forceinline__ void sts64(unsigned addr, unsigned lo, unsigned hi)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -260,6 +264,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const int rowInTile = q * 32 + lane;
         const int et = threadIdx.x - 128;  // 0..127
         uint2 *mine = lists + et;          // entry e of this row at mine[e * 128]
+        const unsigned mineAddr = smem_u32(mine);
         unsigned acc = 0, accPhase = 0;
         bool ok = true;
         const float mx = maxNorm2[0];
@@ -297,7 +302,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
-            uint2 *wp = mine; // next free entry of this row's list (cnt == (wp - mine) / 128)
+            unsigned wp = mineAddr; // shared address of the next free entry of this row's list (1024 bytes apart)
             for (int i = 0; i < numNodeTiles && ok; ++i)
             {
                 const int nt = (i + ntStart) % numNodeTiles;
@@ -317,11 +322,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     tmem_wait_ld();
                     if (c + 1 < TC_BN / 32)
                         tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-                    cnt = static_cast<int>(wp - mine) >> 7;
+                    cnt = static_cast<int>((wp - mineAddr) >> 10);
                     if (__any_sync(0xffffffffu, cnt > TC_LIST_HI))
                     {
                         compact(cnt, thr, ovf);
-                        wp = mine + cnt * 128;
+                        wp = mineAddr + (static_cast<unsigned>(cnt) << 10);
                     }
                     unsigned(&w)[32] = v[c & 1];
                     const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + c * 32);
@@ -333,28 +338,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
                         const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
                         const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
-                        // a threshold that is a few columns stale is still valid (it only ever decreases)
-                        if (s0 < thr)
+                        // Four columns are tested at once: only when some row of the warp has a column below its
+                        // threshold (about one group in five) do the four predicated appends run.  A threshold
+                        // that is a few columns stale is still valid (it only ever decreases).
+                        const float m4 = fminf(fminf(s0, s1), fminf(s2, s3));
+                        if (__any_sync(0xffffffffu, m4 < thr))
                         {
-                            *wp = make_uint2(__float_as_uint(s0), nodeBase + j4 * 4 + 0);
-                            wp += 128;
+                            if (s0 < thr)
+                            {
+                                sts64(wp, __float_as_uint(s0), nodeBase + j4 * 4 + 0);
+                                wp += 1024;
+                            }
+                            if (s1 < thr)
+                            {
+                                sts64(wp, __float_as_uint(s1), nodeBase + j4 * 4 + 1);
+                                wp += 1024;
+                            }
+                            if (s2 < thr)
+                            {
+                                sts64(wp, __float_as_uint(s2), nodeBase + j4 * 4 + 2);
+                                wp += 1024;
+                            }
+                            if (s3 < thr)
+                            {
+                                sts64(wp, __float_as_uint(s3), nodeBase + j4 * 4 + 3);
+                                wp += 1024;
+                            }
                         }
-                        if (s1 < thr)
-                        {
-                            *wp = make_uint2(__float_as_uint(s1), nodeBase + j4 * 4 + 1);
-                            wp += 128;
-                        }
-                        if (s2 < thr)
-                        {
-                            *wp = make_uint2(__float_as_uint(s2), nodeBase + j4 * 4 + 2);
-                            wp += 128;
-                        }
-                        if (s3 < thr)
-                        {
-                            *wp = make_uint2(__float_as_uint(s3), nodeBase + j4 * 4 + 3);
-                            wp += 128;
-                        }
-                        best = fminf(best, fminf(fminf(s0, s1), fminf(s2, s3)));
+                        best = fminf(best, m4);
                         thr = best + delta;
                     }
                 }
@@ -367,7 +378,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 }
             }
             // final filter against the final threshold; at most TC_TOPK survivors go to the exact rescore
-            cnt = static_cast<int>(wp - mine) >> 7;
+            cnt = static_cast<int>((wp - mineAddr) >> 10);
             compact(cnt, thr, ovf);
             if (row < rowsTotal)
             {
