@@ -153,7 +153,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTAs walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
     // of L2 (all starting at tile 0 makes 148 SMs ask the same lines at once)
-    const int ntStart = stagger ? static_cast<int>((static_cast<unsigned>(blockIdx.x) * 7u) % static_cast<unsigned>(numNodeTiles)) : 0;
+    const int ntStart = (stagger & 1) ? static_cast<int>((static_cast<unsigned>(blockIdx.x) * 7u) % static_cast<unsigned>(numNodeTiles)) : 0;
 
     if (warp == 1 && lane == 0)
     {
@@ -315,6 +315,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 tc_fence_after();
                 const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN;
                 unsigned v[2][32];
+                if ((stagger & 2) == 0) // bit 1 of the debug word: skip the column work (pipeline-only timing)
+                {
                 tmem_ld32(taddr, v[0]);
 #pragma unroll
                 for (int c = 0; c < TC_BN / 32; ++c)
@@ -330,6 +332,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     }
                     unsigned(&w)[32] = v[c & 1];
                     const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + c * 32);
+                    // All 32 scores of the chunk and the per-group minima first (independent instructions, no
+                    // branch): the threshold is only refreshed once per chunk — a stale threshold is still valid, it
+                    // only ever decreases.  gm = groups of four columns in which this row has something to append.
+                    unsigned gm = 0;
+                    float cm = inf;
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4)
                     {
@@ -338,36 +345,38 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
                         const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
                         const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
-                        // Four columns are tested at once: only when some row of the warp has a column below its
-                        // threshold (about one group in five) do the four predicated appends run.  A threshold
-                        // that is a few columns stale is still valid (it only ever decreases).
+                        w[j4 * 4 + 0] = __float_as_uint(s0);
+                        w[j4 * 4 + 1] = __float_as_uint(s1);
+                        w[j4 * 4 + 2] = __float_as_uint(s2);
+                        w[j4 * 4 + 3] = __float_as_uint(s3);
                         const float m4 = fminf(fminf(s0, s1), fminf(s2, s3));
-                        if (__any_sync(0xffffffffu, m4 < thr))
-                        {
-                            if (s0 < thr)
-                            {
-                                sts64(wp, __float_as_uint(s0), nodeBase + j4 * 4 + 0);
-                                wp += 1024;
-                            }
-                            if (s1 < thr)
-                            {
-                                sts64(wp, __float_as_uint(s1), nodeBase + j4 * 4 + 1);
-                                wp += 1024;
-                            }
-                            if (s2 < thr)
-                            {
-                                sts64(wp, __float_as_uint(s2), nodeBase + j4 * 4 + 2);
-                                wp += 1024;
-                            }
-                            if (s3 < thr)
-                            {
-                                sts64(wp, __float_as_uint(s3), nodeBase + j4 * 4 + 3);
-                                wp += 1024;
-                            }
-                        }
-                        best = fminf(best, m4);
-                        thr = best + delta;
+                        gm |= (m4 < thr) ? (1u << j4) : 0u;
+                        cm = fminf(cm, m4);
                     }
+                    // one REDUX tells the whole warp which groups need the (predicated) appends; the branches below
+                    // are on a warp-uniform value
+                    const unsigned any = __reduce_or_sync(0xffffffffu, gm);
+                    if (any)
+                    {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            if (any & (1u << j4))
+                            {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                {
+                                    const float sk = __uint_as_float(w[j4 * 4 + k]);
+                                    if (sk < thr)
+                                    {
+                                        sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
+                                        wp += 1024;
+                                    }
+                                }
+                            }
+                    }
+                    best = fminf(best, cm);
+                    thr = best + delta;
+                }
                 }
                 tc_fence_before();
                 mbar_arrive(&tEmpty[acc]);
