@@ -38,9 +38,9 @@
 namespace vsom
 {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 8, TC_THREADS = 256;
-constexpr int TC_LIST = 48;    // per-row candidate list (shared memory), compacted when it passes TC_LIST_HI
-constexpr int TC_LIST_HI = 16; // a 32-column chunk can append at most 32 entries: 16 + 32 <= 48
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 16, TC_THREADS = 384;
+constexpr int TC_LIST = 24;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
+constexpr int TC_LIST_HI = 12; // lists are compacted against the current threshold when one passes this length
 constexpr unsigned TC_OVERFLOW = 255;
 constexpr int TC_MAXK = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per k-block
@@ -130,8 +130,9 @@ struct TcShared
     static constexpr int B_OFF = A_OFF + (TC_MAXK / TC_BK) * TC_A_BYTES; // 4 stages x 32 KB
     static constexpr int CN_OFF = B_OFF + TC_STAGES * TC_B_BYTES;      // 2 x 256 floats
     static constexpr int BAR_OFF = CN_OFF + 2 * TC_BN * 4;             // mbarriers
-    static constexpr int LIST_OFF = BAR_OFF + 256;                     // TC_LIST x 128 x {score, node}: per-row candidate lists
-    static constexpr int TOTAL = LIST_OFF + TC_LIST * 128 * 8;
+    static constexpr int LIST_OFF = BAR_OFF + 256;                     // TC_LIST x 256 x {score, node}: per-thread candidate lists
+    static constexpr int MERGE_OFF = LIST_OFF + TC_LIST * 256 * 8;     // 256 floats + 256 ints: merge of the two half rows
+    static constexpr int TOTAL = MERGE_OFF + 256 * 8;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -149,6 +150,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     u64 *bFull = bars, *bEmpty = bars + TC_STAGES, *aFull = bars + 2 * TC_STAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
     unsigned *tmemBaseSlot = reinterpret_cast<unsigned *>(tEmpty + 2);
     uint2 *lists = reinterpret_cast<uint2 *>(smem + TcShared::LIST_OFF);
+    float *sBest = reinterpret_cast<float *>(smem + TcShared::MERGE_OFF);
+    int *sCnt = reinterpret_cast<int *>(sBest + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTAs walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
@@ -167,7 +170,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         for (int a = 0; a < 2; ++a)
         {
             mbar_init(&tFull[a], 1);
-            mbar_init(&tEmpty[a], 128);
+            mbar_init(&tEmpty[a], 256);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -259,38 +262,39 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     }
     else if (warp >= 4)
     {
-        // ===================================================== epilogue: thread = one row of the tile
+        // ===================================================== epilogue: 8 warps, two threads per row of the tile
+        // Warps 4-7 score columns 0..127 of every accumulator, warps 8-11 columns 128..255 (warp w may only touch the
+        // TMEM lane quarter w % 4, so both halves cover all 128 rows).  Two resident warps per scheduler hide each
+        // other's LDS / ALU latencies; each thread keeps its own running best and its own short list, merged per row
+        // at the end of the row tile.
         const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;  // 0: columns 0..127, 1: columns 128..255
         const int rowInTile = q * 32 + lane;
-        const int et = threadIdx.x - 128;  // 0..127
-        uint2 *mine = lists + et;          // entry e of this row at mine[e * 128]
+        const int et = threadIdx.x - 128;  // 0..255 ; partner thread of the same row: et ^ 128
+        uint2 *mine = lists + et;          // entry e of this thread at mine[e * 256]
         const unsigned mineAddr = smem_u32(mine);
+        const unsigned mineEnd = mineAddr + TC_LIST * 2048u;
         unsigned acc = 0, accPhase = 0;
         bool ok = true;
         const float mx = maxNorm2[0];
         const float inf = __int_as_float(0x7f800000);
 
         // drop list entries that are no longer below the (tightened) threshold; warp-uniform control flow
-        auto compact = [&](int &cnt, float thr, bool &ovf) {
+        auto compact = [&](int &cnt, float thr) {
             const int maxc = __reduce_max_sync(0xffffffffu, cnt);
             int k = 0;
 #pragma unroll 1
             for (int e = 0; e < maxc; ++e)
                 if (e < cnt)
                 {
-                    const uint2 v = mine[e * 128];
+                    const uint2 v = mine[e * 256];
                     if (__uint_as_float(v.x) < thr)
                     {
-                        mine[k * 128] = v;
+                        mine[k * 256] = v;
                         ++k;
                     }
                 }
             cnt = k;
-            if (cnt > TC_LIST_HI)
-            {
-                ovf = true; // too many nodes within the margin of the best: this row takes the exact scan
-                cnt = 0;
-            }
         };
 
         for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
@@ -302,81 +306,83 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
-            unsigned wp = mineAddr; // shared address of the next free entry of this row's list (1024 bytes apart)
+            unsigned wp = mineAddr; // shared address of the next free entry of this thread's list (2048 bytes apart)
             for (int i = 0; i < numNodeTiles && ok; ++i)
             {
                 const int nt = (i + ntStart) % numNodeTiles;
                 // per-node constants of this tile
                 float *cn = sCn + acc * TC_BN;
                 cn[et] = cnorm[nt * TC_BN + et];
-                cn[et + 128] = cnorm[nt * TC_BN + et + 128];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 ok = mbar_wait(&tFull[acc], accPhase, err);
                 tc_fence_after();
-                const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN;
+                const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
+                const float *cnh = cn + half * (TC_BN / 2);
                 unsigned v[2][32];
                 if ((stagger & 2) == 0) // bit 1 of the debug word: skip the column work (pipeline-only timing)
                 {
-                tmem_ld32(taddr, v[0]);
+                    tmem_ld32(taddr, v[0]);
 #pragma unroll
-                for (int c = 0; c < TC_BN / 32; ++c)
-                {
-                    tmem_wait_ld();
-                    if (c + 1 < TC_BN / 32)
-                        tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-                    cnt = static_cast<int>((wp - mineAddr) >> 10);
-                    if (__any_sync(0xffffffffu, cnt > TC_LIST_HI))
+                    for (int c = 0; c < TC_BN / 64; ++c)
                     {
-                        compact(cnt, thr, ovf);
-                        wp = mineAddr + (static_cast<unsigned>(cnt) << 10);
-                    }
-                    unsigned(&w)[32] = v[c & 1];
-                    const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + c * 32);
-                    // All 32 scores of the chunk and the per-group minima first (independent instructions, no
-                    // branch): the threshold is only refreshed once per chunk — a stale threshold is still valid, it
-                    // only ever decreases.  gm = groups of four columns in which this row has something to append.
-                    unsigned gm = 0;
-                    float cm = inf;
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4)
-                    {
-                        const float4 k4 = *reinterpret_cast<const float4 *>(cn + c * 32 + j4 * 4);
-                        const float s0 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 0]), k4.x);
-                        const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
-                        const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
-                        const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
-                        w[j4 * 4 + 0] = __float_as_uint(s0);
-                        w[j4 * 4 + 1] = __float_as_uint(s1);
-                        w[j4 * 4 + 2] = __float_as_uint(s2);
-                        w[j4 * 4 + 3] = __float_as_uint(s3);
-                        const float m4 = fminf(fminf(s0, s1), fminf(s2, s3));
-                        gm |= (m4 < thr) ? (1u << j4) : 0u;
-                        cm = fminf(cm, m4);
-                    }
-                    // one REDUX tells the whole warp which groups need the (predicated) appends; the branches below
-                    // are on a warp-uniform value
-                    const unsigned any = __reduce_or_sync(0xffffffffu, gm);
-                    if (any)
-                    {
+                        tmem_wait_ld();
+                        if (c + 1 < TC_BN / 64)
+                            tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                        cnt = static_cast<int>((wp - mineAddr) >> 11);
+                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI))
+                        {
+                            compact(cnt, thr);
+                            wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
+                        }
+                        unsigned(&w)[32] = v[c & 1];
+                        const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
+                        // All 32 scores of the chunk and the per-group minima first (independent instructions, no
+                        // branch).  gm = groups of four columns in which this row may have something to append.
+                        unsigned gm = 0;
+                        float cm = inf;
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
-                            if (any & (1u << j4))
-                            {
+                        {
+                            const float4 k4 = *reinterpret_cast<const float4 *>(cnh + c * 32 + j4 * 4);
+                            const float s0 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 0]), k4.x);
+                            const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
+                            const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
+                            const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
+                            w[j4 * 4 + 0] = __float_as_uint(s0);
+                            w[j4 * 4 + 1] = __float_as_uint(s1);
+                            w[j4 * 4 + 2] = __float_as_uint(s2);
+                            w[j4 * 4 + 3] = __float_as_uint(s3);
+                            const float m4 = fminf(fminf(s0, s1), fminf(s2, s3));
+                            gm |= (m4 < thr) ? (1u << j4) : 0u; // against the (valid, possibly stale) old threshold
+                            cm = fminf(cm, m4);
+                        }
+                        // the chunk's own minimum tightens the threshold BEFORE anything is appended
+                        best = fminf(best, cm);
+                        thr = best + delta;
+                        // one REDUX tells the whole warp which groups need the (predicated) appends; the branches
+                        // below are on a warp-uniform value
+                        const unsigned any = __reduce_or_sync(0xffffffffu, gm);
+                        if (any)
+                        {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
+                            for (int j4 = 0; j4 < 8; ++j4)
+                                if (any & (1u << j4))
                                 {
-                                    const float sk = __uint_as_float(w[j4 * 4 + k]);
-                                    if (sk < thr)
-                                    {
-                                        sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
-                                        wp += 1024;
-                                    }
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (__uint_as_float(w[j4 * 4 + k]) < thr)
+                                        {
+                                            if (wp < mineEnd)
+                                            {
+                                                sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
+                                                wp += 2048;
+                                            }
+                                            else
+                                                ovf = true; // list full: this row takes the exact scan
+                                        }
                                 }
-                            }
+                        }
                     }
-                    best = fminf(best, cm);
-                    thr = best + delta;
-                }
                 }
                 tc_fence_before();
                 mbar_arrive(&tEmpty[acc]);
@@ -386,17 +392,28 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     accPhase ^= 1;
                 }
             }
-            // final filter against the final threshold; at most TC_TOPK survivors go to the exact rescore
-            cnt = static_cast<int>((wp - mineAddr) >> 10);
-            compact(cnt, thr, ovf);
+            // merge the two halves of the row: common best -> final threshold -> filter both lists -> candidates
+            cnt = static_cast<int>((wp - mineAddr) >> 11);
+            sBest[et] = best;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float thrF = fminf(best, sBest[et ^ 128]) + delta;
+            compact(cnt, thrF);
+            sCnt[et] = ovf ? 1000 : cnt;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int other = sCnt[et ^ 128], total = sCnt[et] + other;
             if (row < rowsTotal)
             {
-                unsigned count = (ovf || cnt > TC_TOPK || cnt == 0) ? TC_OVERFLOW : static_cast<unsigned>(cnt);
-                if (count != TC_OVERFLOW)
+                const bool bad = total > TC_TOPK || total == 0;
+                if (!bad)
+                {
+                    const int off = half ? other : 0;
                     for (int e = 0; e < cnt; ++e)
-                        candOut[row * TC_TOPK + e] = mine[e * 128].y;
-                countOut[row] = count;
+                        candOut[row * TC_TOPK + off + e] = mine[e * 256].y;
+                }
+                if (half == 0)
+                    countOut[row] = bad ? TC_OVERFLOW : static_cast<unsigned>(total);
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory"); // sBest / sCnt are reused by the next row tile
         }
     }
 
@@ -447,15 +464,15 @@ __global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__
 
 // ------------------------------------------------------------------------------------------------ exact rescore + guard
 
-// 8 threads per row: thread j re-evaluates candidate j (if the row has that many) with the reference's sequential
+// TC_TOPK (16) threads per row: thread j re-evaluates candidate j (if the row has that many) with the reference's sequential
 // f32 chain.  Rows whose list overflowed go to the fallback list (exact full scan).
 __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
                                const unsigned *__restrict__ cand, const unsigned *__restrict__ count, unsigned *__restrict__ outBmu,
                                float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
 {
     const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long row = gid >> 3;
-    const int j = static_cast<int>(gid & 7);
+    const long long row = gid >> 4;
+    const int j = static_cast<int>(gid & 15);
     const bool live = row < rows;
     const unsigned cnt = live ? count[row] : 0u;
     u64 key = ~0ull;
@@ -491,7 +508,7 @@ __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int 
         key = make_key(s, node, (s != s) ? 1u : 0u);
     }
 #pragma unroll
-    for (int o = 4; o; o >>= 1)
+    for (int o = 8; o; o >>= 1)
         key = u64_min(key, __shfl_xor_sync(0xffffffffu, key, o));
     if (live && j == 0)
     {
@@ -643,7 +660,7 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
         score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, stagger, xnorm, maxNorm2, cand, candCount,
                                                                       ctx->errFlag);
-        rescore_kernel<<<static_cast<unsigned>((rows * 8 + 255) / 256), 256, 0, ctx->stream>>>(
+        rescore_kernel<<<static_cast<unsigned>((rows * TC_TOPK + 255) / 256), 256, 0, ctx->stream>>>(
             xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, candCount, outBmuDev ? outBmuDev + r0 : nullptr,
             outDistDev ? outDistDev + r0 : nullptr, fbRows, fbCount);
         ctx->launches += 3;
