@@ -261,3 +261,23 @@ def test_tensor_core_scoring_unsupported_shapes_use_exact(vsom):
     assert_bit_equal(tb, eb, "bmu")
     assert_bit_equal(td, ed, "dist")
     ctx.close()
+
+
+def test_tensor_core_scoring_ties_and_overflow_take_the_exact_scan(vsom):
+    """A map made of 40 distinct rows repeated many times: every row has dozens of EXACT ties at its best distance.
+    The candidate lists overflow, those rows go through the exact scan, and the reference's lowest-index rule must
+    hold (the BMU is the first copy)."""
+    rng = np.random.default_rng(9)
+    W, H, D, n = 48, 48, 64, 3000
+    base = rng.standard_normal((40, D)).astype(np.float32)
+    m = base[np.arange(W * H) % 40]
+    x = (base[rng.integers(0, 40, n)] + 0.01 * rng.standard_normal((n, D))).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, vsom.MEDIAN)
+    ctx.upload_state(mean=m)
+    eb, ed = ctx.find_bmu(x)
+    tb, td, fb = ctx.find_bmu_batch(x)
+    assert eb.max() < 40  # lowest index among the copies
+    assert_bit_equal(tb, eb, "bmu")
+    assert_bit_equal(td, ed, "dist")
+    assert fb > 0
+    ctx.close()

@@ -526,6 +526,63 @@ __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int 
     }
 }
 
+// Exact full scan for a FEW rows (the rows the candidate lists could not certify): one CTA per row, threads over
+// nodes, every (row, node) distance summed sequentially in f32 like the reference.  Same key rule as K3.
+__global__ void __launch_bounds__(256) find_bmu_rowwise_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows, unsigned count,
+                                                               const float *__restrict__ mean, int rowStride, int N, const u64 *__restrict__ hits,
+                                                               u64 minHits, unsigned *__restrict__ outBmu, float *__restrict__ outDist)
+{
+    extern __shared__ float xrow[];
+    __shared__ u64 wkey[8];
+    const unsigned i = blockIdx.x;
+    if (i >= count)
+        return;
+    const size_t r = rows[i];
+    for (int k = threadIdx.x; k < D; k += blockDim.x)
+        xrow[k] = x[r * D + k];
+    __syncthreads();
+    u64 best = ~0ull;
+    for (int node = threadIdx.x; node < N; node += blockDim.x)
+    {
+        if (!(node == 0 || minHits == 0 || hits[node] >= minHits))
+            continue;
+        const float *m = mean + static_cast<size_t>(node) * rowStride;
+        float s = 0.0f;
+        int k = 0;
+        for (; k + 4 <= D; k += 4)
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(m + k);
+            float q = __fsub_rn(a.x, xrow[k]);
+            s = __fadd_rn(s, __fmul_rn(q, q));
+            q = __fsub_rn(a.y, xrow[k + 1]);
+            s = __fadd_rn(s, __fmul_rn(q, q));
+            q = __fsub_rn(a.z, xrow[k + 2]);
+            s = __fadd_rn(s, __fmul_rn(q, q));
+            q = __fsub_rn(a.w, xrow[k + 3]);
+            s = __fadd_rn(s, __fmul_rn(q, q));
+        }
+        for (; k < D; ++k)
+        {
+            const float q = __fsub_rn(m[k], xrow[k]);
+            s = __fadd_rn(s, __fmul_rn(q, q));
+        }
+        best = u64_min(best, make_key(s, static_cast<unsigned>(node), (s != s) ? 1u : 0u));
+    }
+    best = warp_min_u64(best);
+    if ((threadIdx.x & 31) == 0)
+        wkey[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < 8; ++w)
+            best = u64_min(best, wkey[w]);
+        if (outBmu)
+            outBmu[r] = key_node(best);
+        if (outDist)
+            outDist[r] = (best & 1ull) ? __uint_as_float(0x7fc00000u) : __uint_as_float(static_cast<unsigned>(best >> 32));
+    }
+}
+
 __global__ void gather_rows_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows, unsigned count, float *__restrict__ out)
 {
     const unsigned i = blockIdx.x;
@@ -673,7 +730,16 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (flag)
             return set_error(ctx, VSOM_ERR_TIMEOUT, "score_tc: pipeline barrier timed out (kernel bug)");
-        if (count)
+        if (count && count <= 8192)
+        {
+            // few rows: one CTA per row, results written in place
+            find_bmu_rowwise_kernel<<<count, 256, sizeof(float) * D, ctx->stream>>>(xs, D, fbRows, count, ctx->mean, ctx->rowStride, N, ctx->hits, minHits,
+                                                                                   outBmuDev ? outBmuDev + r0 : nullptr,
+                                                                                   outDistDev ? outDistDev + r0 : nullptr);
+            ctx->launches += 1;
+            totalFallback += count;
+        }
+        else if (count)
         {
             rc = stage_reserve(ctx, 9, sizeof(float) * static_cast<size_t>(count) * D);
             if (rc)
