@@ -80,6 +80,18 @@ typedef enum vsom_reduction_order
  * all planes zero.  `device` is a CUDA ordinal. */
 VSOM_API int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order);
 VSOM_API void vsom_destroy(vsom_ctx *ctx);
+/* Node-sharded training of a large map across the GPUs of one NVLink box (BASELINE config 5): rank r of `world` holds the
+ * contiguous band of grid rows [H*r/world, H*(r+1)/world).  Every rank calls vsom_train_chunk[_device] with the SAME
+ * samples; inside the persistent kernel each GPU scans its band, CTA 0 pushes the GPU-local (distance,node) key into every
+ * rank's memory over NVLink (peer-mapped pointers, system-scope stores) and every CTA takes the min of the `world` keys —
+ * one 8-byte exchange per sample, no host round trip, no NCCL call on the data path.  Setup: each rank exports the handle of
+ * its slot buffer (vsom_peer_export), the handles are all-gathered by the caller (e.g. torch.distributed) and imported
+ * (vsom_peer_import) before the first chunk.  upload / download take FULL-map arrays and touch only the rank's band.
+ * Scoring, U-matrix and index entry points need an unsharded context. */
+VSOM_API int vsom_create_sharded(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order, int rank, int world);
+VSOM_API int vsom_peer_export(vsom_ctx *ctx, unsigned char handle[64]);
+VSOM_API int vsom_peer_import(vsom_ctx *ctx, int rank, const unsigned char handle[64]);
+VSOM_API int vsom_shard_range(const vsom_ctx *ctx, int *first_node, int *node_count);
 /* Text of the last error on ctx (or of the last failed vsom_create when ctx is NULL). */
 VSOM_API const char *vsom_last_error(const vsom_ctx *ctx);
 /* Transformation::Length (src/Transformation.cpp:31-35, :69-73, :162-165). */

@@ -22,6 +22,10 @@ _vp = C.c_void_p
 _PROTOS = {
     "vsom_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vsom_destroy": (None, [_vp]),
+    "vsom_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vsom_peer_export": (C.c_int, [_vp, C.c_char_p]),
+    "vsom_peer_import": (C.c_int, [_vp, C.c_int, C.c_char_p]),
+    "vsom_shard_range": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vsom_last_error": (C.c_char_p, [_vp]),
     "vsom_model_length": (C.c_int, [C.c_int, C.c_int]),
     "vsom_depth": (C.c_int, [_vp]),
@@ -101,15 +105,19 @@ class VsomContext:
     """One map on one B200.  Method names follow the C-ABI; arrays are numpy (host entry points) or anything
     with a ``data_ptr()`` (torch CUDA tensors; ``*_device`` entry points)."""
 
-    def __init__(self, width, height, d_in, transform=STANDARD, order=ORDER_REFERENCE, device=0):
+    def __init__(self, width, height, d_in, transform=STANDARD, order=ORDER_REFERENCE, device=0, rank=0, world=1):
         L = lib()
         h = _vp()
-        rc = L.vsom_create(C.byref(h), device, width, height, d_in, transform, order)
+        if world > 1:
+            rc = L.vsom_create_sharded(C.byref(h), device, width, height, d_in, transform, order, rank, world)
+        else:
+            rc = L.vsom_create(C.byref(h), device, width, height, d_in, transform, order)
         if rc != 0:
             raise VsomError(rc, (L.vsom_last_error(None) or b"").decode())
         self._h = h
         self.W, self.H, self.N, self.Din = width, height, width * height, d_in
         self.transform, self.order, self.device = transform, order, device
+        self.rank, self.world = rank, world
         self.Dm = L.vsom_depth(h)
 
     def close(self):
@@ -141,6 +149,16 @@ class VsomContext:
         sigma = np.empty_like(mean)
         weight = np.empty(self.N, np.float32)
         hits = np.empty(self.N, np.uint64)
+        self._check(lib().vsom_download_state(self._h, _p(mean, _f32p), _p(S, _f32p), _p(sigma, _f32p), _p(weight, _f32p), _p(hits, _u64p)))
+        return dict(mean=mean, S=S, sigma=sigma, weight=weight, hits=hits)
+
+    def download_state_zero_filled(self):
+        """Sharded contexts: full-size arrays with this rank's band filled in and zeros elsewhere."""
+        mean = np.zeros((self.N, self.Dm), np.float32)
+        S = np.zeros_like(mean)
+        sigma = np.zeros_like(mean)
+        weight = np.zeros(self.N, np.float32)
+        hits = np.zeros(self.N, np.uint64)
         self._check(lib().vsom_download_state(self._h, _p(mean, _f32p), _p(S, _f32p), _p(sigma, _f32p), _p(weight, _f32p), _p(hits, _u64p)))
         return dict(mean=mean, S=S, sigma=sigma, weight=weight, hits=hits)
 
@@ -218,6 +236,20 @@ class VsomContext:
         rows = np.empty(n, np.uint32)
         self._check(lib().vsom_build_index(self._h, _p(bmu, _u32p), n, _p(counts, _u64p), _p(offsets, _u64p), _p(rows, _u32p)))
         return counts, offsets, rows
+
+    # ---- node sharding across GPUs
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(lib().vsom_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_import(self, rank: int, handle: bytes):
+        self._check(lib().vsom_peer_import(self._h, rank, handle))
+
+    def shard_range(self):
+        a, b = C.c_int(0), C.c_int(0)
+        self._check(lib().vsom_shard_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # ---- diagnostics
     def debug_profile(self, enable=True):

@@ -63,7 +63,7 @@ extern "C"
 
 int vsom_model_length(int d_in, int transform) { return transform == VSOM_CLR ? d_in * (d_in - 1) : d_in; }
 
-int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order)
+static int create_impl(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order, int rank, int world)
 {
     if (!out)
         return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: out is NULL");
@@ -75,6 +75,8 @@ int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int
         return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: at most 2^24 - 1 nodes");
     if (transform == VSOM_CLR && d_in > 65535)
         return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: CLR pair tables are 16-bit");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || world > height)
+        return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create_sharded: need 1 <= world <= 8, 0 <= rank < world, world <= height");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count < 1 || device < 0 || device >= count)
@@ -96,6 +98,15 @@ int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int
     ctx->P = transform == VSOM_CLR ? ctx->Dm / 2 : 0;
     ctx->Dr = transform == VSOM_CLR ? ctx->P : ctx->Dm;
     ctx->rowStride = (ctx->Dm + 3) & ~3;
+    ctx->rank = rank;
+    ctx->world = world;
+    {
+        // contiguous bands of grid rows per rank
+        const int y0 = static_cast<int>(static_cast<long long>(height) * rank / world);
+        const int y1 = static_cast<int>(static_cast<long long>(height) * (rank + 1) / world);
+        ctx->node0 = y0 * width;
+        ctx->localN = (y1 - y0) * width;
+    }
 
     auto fail = [&](int rc) {
         g_createError = ctx->err;
@@ -121,20 +132,23 @@ int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int
     ctx->numSMs = prop.multiProcessorCount;
     ctx->smemOptin = static_cast<int>(prop.sharedMemPerBlockOptin);
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    const size_t plane = sizeof(float) * static_cast<size_t>(ctx->N) * ctx->rowStride;
+    const size_t plane = sizeof(float) * static_cast<size_t>(ctx->localN) * ctx->rowStride;
     CREATE_CUDA(cudaMalloc(&ctx->mean, plane));
     CREATE_CUDA(cudaMalloc(&ctx->S, plane));
     CREATE_CUDA(cudaMalloc(&ctx->sigma, plane));
-    CREATE_CUDA(cudaMalloc(&ctx->weight, sizeof(float) * ctx->N));
-    CREATE_CUDA(cudaMalloc(&ctx->hits, sizeof(u64) * ctx->N));
+    CREATE_CUDA(cudaMalloc(&ctx->weight, sizeof(float) * ctx->localN));
+    CREATE_CUDA(cudaMalloc(&ctx->hits, sizeof(u64) * ctx->localN));
+    CREATE_CUDA(cudaMalloc(&ctx->rankSlots, sizeof(u64) * 2 * 8));
+    CREATE_CUDA(cudaMemsetAsync(ctx->rankSlots, 0xff, sizeof(u64) * 2 * 8, ctx->stream));
+    ctx->peerSlots[rank] = ctx->rankSlots;
     CREATE_CUDA(cudaMalloc(&ctx->umatrix, sizeof(double) * ctx->N));
     CREATE_CUDA(cudaMalloc(&ctx->slots, sizeof(u64) * 2 * static_cast<size_t>(ctx->numSMs) * ((ctx->numSMs + 15) & ~15)));
     CREATE_CUDA(cudaMalloc(&ctx->errFlag, sizeof(int)));
     CREATE_CUDA(cudaMemsetAsync(ctx->mean, 0, plane, ctx->stream));
     CREATE_CUDA(cudaMemsetAsync(ctx->S, 0, plane, ctx->stream));
     CREATE_CUDA(cudaMemsetAsync(ctx->sigma, 0, plane, ctx->stream));
-    CREATE_CUDA(cudaMemsetAsync(ctx->weight, 0, sizeof(float) * ctx->N, ctx->stream));
-    CREATE_CUDA(cudaMemsetAsync(ctx->hits, 0, sizeof(u64) * ctx->N, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->weight, 0, sizeof(float) * ctx->localN, ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->hits, 0, sizeof(u64) * ctx->localN, ctx->stream));
     CREATE_CUDA(cudaMemsetAsync(ctx->umatrix, 0, sizeof(double) * ctx->N, ctx->stream));
     CREATE_CUDA(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
     if (transform == VSOM_CLR)
@@ -163,6 +177,55 @@ int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int
     return VSOM_OK;
 }
 
+int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order)
+{
+    return create_impl(out, device, width, height, d_in, transform, order, 0, 1);
+}
+
+int vsom_create_sharded(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order, int rank, int world)
+{
+    return create_impl(out, device, width, height, d_in, transform, order, rank, world);
+}
+
+int vsom_peer_export(vsom_ctx *ctx, unsigned char handle[64])
+{
+    if (!ctx || !handle)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    VSOM_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->rankSlots));
+    std::memcpy(handle, &h, 64);
+    return VSOM_OK;
+}
+
+int vsom_peer_import(vsom_ctx *ctx, int rank, const unsigned char handle[64])
+{
+    if (!ctx || !handle || rank < 0 || rank >= ctx->world)
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_peer_import: bad rank") : VSOM_ERR_INVALID;
+    if (rank == ctx->rank)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void *ptr = nullptr;
+    VSOM_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peerSlots[rank] = static_cast<u64 *>(ptr);
+    ctx->peerOpened[rank] = true;
+    return VSOM_OK;
+}
+
+int vsom_shard_range(const vsom_ctx *ctx, int *first_node, int *node_count)
+{
+    if (!ctx)
+        return VSOM_ERR_INVALID;
+    if (first_node)
+        *first_node = ctx->node0;
+    if (node_count)
+        *node_count = ctx->localN;
+    return VSOM_OK;
+}
+
 void vsom_destroy(vsom_ctx *ctx)
 {
     if (!ctx)
@@ -179,6 +242,10 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->pairI);
     cudaFree(ctx->pairJ);
     cudaFree(ctx->slots);
+    for (int r = 0; r < 8; ++r)
+        if (ctx->peerOpened[r])
+            cudaIpcCloseMemHandle(ctx->peerSlots[r]);
+    cudaFree(ctx->rankSlots);
     cudaFree(ctx->errFlag);
     cudaFree(ctx->lut);
     cudaFree(ctx->profDev);
@@ -251,15 +318,15 @@ int vsom_upload_state(vsom_ctx *ctx, const float *mean, const float *S, const fl
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
     if (mean)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->mean, pitch, mean, w, w, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->mean, pitch, mean + static_cast<size_t>(ctx->node0) * ctx->Dm, w, w, ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
     if (S)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->S, pitch, S, w, w, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->S, pitch, S + static_cast<size_t>(ctx->node0) * ctx->Dm, w, w, ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
     if (sigma)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->sigma, pitch, sigma, w, w, ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->sigma, pitch, sigma + static_cast<size_t>(ctx->node0) * ctx->Dm, w, w, ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
     if (weight)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->weight, weight, sizeof(float) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->weight, weight + ctx->node0, sizeof(float) * ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
     if (hits)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->hits, hits, sizeof(u64) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->hits, hits + ctx->node0, sizeof(u64) * ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VSOM_OK;
 }
@@ -271,21 +338,23 @@ int vsom_download_state(vsom_ctx *ctx, float *mean, float *S, float *sigma, floa
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
     if (mean)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(mean, w, ctx->mean, pitch, w, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(mean + static_cast<size_t>(ctx->node0) * ctx->Dm, w, ctx->mean, pitch, w, ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
     if (S)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(S, w, ctx->S, pitch, w, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(S + static_cast<size_t>(ctx->node0) * ctx->Dm, w, ctx->S, pitch, w, ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
     if (sigma)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(sigma, w, ctx->sigma, pitch, w, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpy2DAsync(sigma + static_cast<size_t>(ctx->node0) * ctx->Dm, w, ctx->sigma, pitch, w, ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
     if (weight)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(weight, ctx->weight, sizeof(float) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpyAsync(weight + ctx->node0, ctx->weight, sizeof(float) * ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
     if (hits)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(hits, ctx->hits, sizeof(u64) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpyAsync(hits + ctx->node0, ctx->hits, sizeof(u64) * ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VSOM_OK;
 }
 
 int vsom_get_node(vsom_ctx *ctx, size_t node, float *mean, float *sigma)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || node >= static_cast<size_t>(ctx->N))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_get_node: node out of range") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -328,6 +397,8 @@ int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double
     unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
     float *distDev = static_cast<float *>(ctx->stage[2]);
     VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->world > 1) // only the rank that owns a sample's BMU reports its distance; the others keep NaN
+        VSOM_CUDA(ctx, cudaMemsetAsync(distDev, 0xff, sizeof(float) * n, ctx->stream));
     rc = launch_online_step(ctx, xDev, n, eta, sigma, decay, bmuDev, distDev);
     if (rc)
         return rc;
@@ -356,6 +427,8 @@ int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double
 
 int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || (!x_dev && n))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_device: x is NULL") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -364,6 +437,8 @@ int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t m
 
 int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || (!x && n))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu: x is NULL") : VSOM_ERR_INVALID;
     if (n == 0)
@@ -396,6 +471,8 @@ int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, ui
 int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev,
                                uint64_t *fallback_rows)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || (!x_dev && n))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_batch_device: x is NULL") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -416,6 +493,8 @@ int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint
 
 int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, uint64_t *fallback_rows)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || (!x && n))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_batch: x is NULL") : VSOM_ERR_INVALID;
     if (fallback_rows)
@@ -466,6 +545,8 @@ int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)
 
 int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || !v || !out)
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_all_dists: NULL argument") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -486,6 +567,8 @@ int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out)
 
 int vsom_update_umatrix(vsom_ctx *ctx, double *out)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx)
         return VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -500,6 +583,8 @@ int vsom_update_umatrix(vsom_ctx *ctx, double *out)
 
 int vsom_build_index(vsom_ctx *ctx, const uint32_t *bmu, size_t n, uint64_t *counts, uint64_t *offsets, uint32_t *row_ids)
 {
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx || (!bmu && n))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_build_index: bmu is NULL") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));

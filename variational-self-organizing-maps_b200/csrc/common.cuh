@@ -53,6 +53,10 @@ struct StepParams
     long long timeoutCycles;
     int lutSmem, lutCount;    // copy the table into shared memory (it fits behind the resident rows)
     int xVec;                 // sample rows are 16-byte aligned: 16-byte cp.async
+    int world, rank;          // node-sharded training across GPUs (world == 1: single GPU)
+    u64 *rankSlots;           // [2][world] keys pushed into THIS GPU's memory by every rank (peer stores over NVLink)
+    u64 *peerSlots[8];        // rankSlots of every rank (index = rank), peer-mapped; peerSlots[rank] == rankSlots
+    u64 stepBase;             // samples trained before this launch: the cross-GPU exchange is indexed by the global step
     long long *prof;          // optional [gridDim.x][5] per-phase cycle sums of thread 0 (diagnostics), else null
 };
 
@@ -62,6 +66,12 @@ struct vsom_ctx
 {
     int device = 0;
     int W = 0, H = 0, N = 0, Din = 0, Dm = 0, Dr = 0, P = 0;
+    int rank = 0, world = 1;      // node sharding: this context holds grid rows [y0, y1) = nodes [node0, node0 + localN)
+    int node0 = 0, localN = 0;
+    vsom::u64 *rankSlots = nullptr;
+    vsom::u64 *peerSlots[8] = {};
+    bool peerOpened[8] = {};
+    vsom::u64 stepBase = 0;
     int transform = 0, order = 0;
     int rowStride = 0;
     int numSMs = 0, smemOptin = 0;
@@ -128,6 +138,16 @@ __device__ __forceinline__ u64 ld_relaxed_gpu(const u64 *p)
 __device__ __forceinline__ void st_relaxed_gpu(u64 *p, u64 v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_sys(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void *smemDst, const void *gmemSrc)
 {

@@ -347,6 +347,36 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 }
             }
             m = warp_min_key(m);
+            if (p.world > 1 && !abort)
+            {
+                // ---- node-sharded map: the GPU-local winner is pushed into every rank's memory over NVLink by CTA 0
+                // (system-scope stores to peer-mapped pointers); every CTA then polls ITS OWN GPU's row of `world`
+                // tagged keys.  Indexed by the global step, so it needs neither a reset nor a host barrier between
+                // launches; ranks can never be more than one step apart.
+                const u64 gs = p.stepBase + t;
+                const unsigned gtag = static_cast<unsigned>((gs >> 1) & 0xff);
+                const int gbuf = static_cast<int>(gs & 1);
+                const u64 mine = (m & ~0xffull) | gtag;
+                if (b == 0 && lane < p.world)
+                    st_relaxed_sys(p.peerSlots[lane] + gbuf * p.world + p.rank, mine);
+                const u64 *grow = p.rankSlots + gbuf * p.world;
+                const long long g0 = clock64();
+                u64 gv;
+                for (;;)
+                {
+                    gv = lane < p.world ? ld_relaxed_sys(grow + lane) : ((~0ull << 8) | gtag);
+                    if (__all_sync(0xffffffffu, static_cast<unsigned>(gv & 0xff) == gtag))
+                        break;
+                    if (__any_sync(0xffffffffu, clock64() - g0 > p.timeoutCycles))
+                    {
+                        abort = true;
+                        break;
+                    }
+                }
+                m = warp_min_key(gv);
+                if (b == 0 && lane == 0 && p.outBmu && !abort)
+                    p.outBmu[t] = key_node(m); // every rank records the global BMU of every sample
+            }
             if (lane == 0)
             {
                 // window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric
@@ -586,7 +616,7 @@ static int resident_stride(const vsom_ctx *ctx)
 
 static size_t online_step_smem(const vsom_ctx *ctx, int G, bool resident, int smStride)
 {
-    const int Lmax = (ctx->N + G - 1) / G;
+    const int Lmax = (ctx->localN + G - 1) / G;
     const int Lpad = (Lmax + 3) & ~3;
     const int DinPad = (ctx->Din + 3) & ~3;
     const int Ppad = (ctx->P + 7) & ~7;
@@ -611,7 +641,7 @@ static StepKernel pick_kernel(int transform, int order, int resident)
 
 int configure_online_step(vsom_ctx *ctx)
 {
-    int G = ctx->N < ctx->numSMs ? ctx->N : ctx->numSMs;
+    int G = ctx->localN < ctx->numSMs ? ctx->localN : ctx->numSMs;
     if (G > 32 * kMaxSlotsPerLane)
         G = 32 * kMaxSlotsPerLane;
     const int smStride = resident_stride(ctx);
@@ -711,8 +741,18 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     StepParams p;
     p.W = ctx->W;
     p.H = ctx->H;
-    p.node0 = 0;
-    p.nodeCount = ctx->N;
+    p.node0 = ctx->node0;
+    p.nodeCount = ctx->localN;
+    p.world = ctx->world;
+    p.rank = ctx->rank;
+    p.rankSlots = ctx->rankSlots;
+    for (int r = 0; r < 8; ++r)
+        p.peerSlots[r] = ctx->peerSlots[r];
+    p.stepBase = ctx->stepBase;
+    if (ctx->world > 1)
+        for (int r = 0; r < ctx->world; ++r)
+            if (!ctx->peerSlots[r])
+                return set_error(ctx, VSOM_ERR_INVALID, "online step: sharded context without vsom_peer_import for every rank");
     p.Din = ctx->Din;
     p.Dm = ctx->Dm;
     p.Dr = ctx->Dr;
@@ -751,6 +791,7 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     void *args[] = {&p};
     VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k), dim3(G), dim3(kThreads), args, smemBytes, ctx->stream));
     ctx->launches += 1;
+    ctx->stepBase += n;
     return VSOM_OK;
 }
 
