@@ -62,7 +62,7 @@ def synth_chunk(n, d, seed):
 def init_map(n_nodes, dm, seed):
     """Same distribution as Som::randomInitialize(seed, 1.0f) (src/Som.cpp:977-997): multiples of 1/1000 in [-1, 1)."""
     rng = np.random.default_rng(seed)
-    return (rng.integers(-1000, 1000, (n_nodes, dm)).astype(np.float32) / np.float32(1000.0)).astype(np.float32)
+    return (rng.integers(-1000, 1000, (n_nodes, dm), dtype=np.int16).astype(np.float32) / np.float32(1000.0)).astype(np.float32)
 
 
 def window_nodes(w, h, sigma):
@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-rows", type=int, default=SCORE_ROWS)
+    ap.add_argument("--no-large-map", action="store_true")
+    ap.add_argument("--large-rows", type=int, default=1024)
     args = ap.parse_args()
     SCORE_ROWS = args.score_rows
 
@@ -311,6 +313,63 @@ def main():
     exact_ms, _ = timed(lambda: sctx.find_bmu_device(q_dev, exact_rows, s_bmu, s_dist))
     exact_rows_s = world * exact_rows / (exact_ms / 1e3)
 
+    # ---------------- large map (BASELINE configs[4] shape): 512x512 grid x 784-dim, online training with the grid rows
+    #   node-sharded over the `world` GPUs (in-kernel NVLink min-loc exchange per sample); at N=1 the same map on one GPU,
+    #   plus the full U-matrix.  Reported honestly either way.
+    large = None
+    if not args.no_large_map:
+        LW, LH, LD, LROWS, LSIG = 512, 512, 784, args.large_rows, 16.0
+        lctx = vsom.VsomContext(LW, LH, LD, vsom.STANDARD, order, device=local_rank, rank=rank, world=world)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, lctx.peer_export())
+            for r, hdl in enumerate(handles):
+                lctx.peer_import(r, hdl)
+        n0, ncnt = lctx.shard_range()
+        full = np.zeros((LW * LH, LD), np.float32)
+        full[n0:n0 + ncnt] = init_map(ncnt, LD, 4242 + rank)
+        lctx.upload_state(mean=full)
+        del full
+        lx = torch.from_numpy(synth_chunk(LROWS, LD, 777)).to(x_dev.device)  # the same samples on every rank
+        lb = torch.empty(LROWS, dtype=torch.int32, device=x_dev.device)
+        ld_ = torch.empty(LROWS, dtype=torch.float32, device=x_dev.device)
+        lstream = torch.cuda.ExternalStream(lctx.stream, device=local_rank)
+        lctx.train_chunk_device(lx, min(LROWS, 64), 0.05, LSIG, vsom.EXPONENTIAL, lb, ld_)
+        lctx.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(lstream):
+            e0.record(lstream)
+            lctx.train_chunk_device(lx, LROWS, 0.05, LSIG, vsom.EXPONENTIAL, lb, ld_)
+            e1.record(lstream)
+        lctx.synchronize()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=x_dev.device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        lms = float(tt.item())
+        kwin = min(int(np.ceil(2.5 * LSIG)) + int(np.floor(2.5 * LSIG)), LW) ** 2
+        lbytes = algorithmic_bytes_per_sample(LW * LH, LD, LD, kwin)
+        large = {"workload": "512x512 grid x 784-dim online training (BASELINE configs[4] shape), sigma=16, Standard, Exponential",
+                 "layout": "single GPU" if world == 1 else f"grid rows node-sharded over {world} GPUs, per-sample 8-byte min-loc exchange inside the persistent kernel over NVLink peer memory",
+                 "samples": LROWS, "ms": lms, "value": LROWS / (lms / 1e3), "unit": "samples/s", "us_per_sample": 1e3 * lms / LROWS,
+                 "roofline": {"bound": "hbm", "algorithmic_bytes_per_sample": lbytes, "achieved": lbytes * LROWS / (lms / 1e3) / 1e9 / world,
+                              "unit": "GB/s per GPU", "window_nodes": kwin},
+                 "planes_resident_in_smem": lctx.planes_resident, "reduction_order": args.order}
+        if world == 1:
+            lctx.update_umatrix()
+            lctx.synchronize()
+            with torch.cuda.stream(lstream):
+                e0.record(lstream)
+                lib_rc = vsom.lib().vsom_update_umatrix(lctx._h, None)
+                e1.record(lstream)
+            lctx.synchronize()
+            ums = e0.elapsed_time(e1)
+            ubytes = 8 * LW * LH * LD + 8 * LW * LH
+            large["umatrix"] = {"ms": ums, "algorithmic_bytes": ubytes, "achieved_gbs": ubytes / (ums / 1e3) / 1e9}
+        lctx.close()
+        del lx
+
     if rank == 0:
         hbm_gbs, bf16_tf, peak_src = peaks()
         k = window_nodes(W_, H_, SIGMA)
@@ -347,6 +406,10 @@ def main():
                         "exact_scan_rows_per_s": exact_rows_s, "exact_scan_rows": exact_rows * world,
                         "scaling": "row-sharded, no communication"},
         }
+        if large is not None:
+            large["roofline"]["peak"] = hbm_gbs
+            large["roofline"]["frac"] = large["roofline"]["achieved"] / hbm_gbs
+            line["large_map"] = large
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(line))

@@ -22,7 +22,7 @@ def main():
 
     ok = True
     # (W, H, Din, transform, rows, eta, sigma, decay): resident and global-memory planes, all transformations
-    cases = [(24, 16, 20, 0, 200, 0.2, 4.0, 0), (31, 9, 7, 1, 150, 0.05, 2.5, 1), (12, 10, 6, 2, 80, 0.002, 3.0, 0), (90, 80, 784, 0, 10, 0.1, 6.0, 0)]
+    cases = [(24, 16, 20, 0, 200, 0.2, 4.0, 0), (31, 9, 7, 1, 150, 0.05, 2.5, 1), (12, 10, 6, 2, 80, 0.002, 3.0, 0), (160, 100, 784, 0, 6, 0.1, 6.0, 0)]
     for ci, (W, H, D, tr, n, eta, sigma, decay) in enumerate(cases):
         rng = np.random.default_rng(100 + ci)
         o = po.Oracle(W, H, D, tr)
