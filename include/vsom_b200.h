@@ -133,7 +133,8 @@ VSOM_API int vsom_get_node(vsom_ctx *ctx, size_t node, float *mean, float *sigma
  *   out_resid2 = residual.squaredNorm() (the term of src/Som.cpp:1167).  Each may be NULL. */
 VSOM_API int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double sigma, int decay, uint64_t *last_bmu,
                      uint32_t *out_bmu, float *out_dist, float *out_resid2);
-/* Same with x / outputs in device memory; enqueue only.  sigma must be > 1 (global-BMU regime). */
+/* Same with x / outputs in device memory; enqueue only.  With sigma <= 1 every row's local walk starts at node 0, which is
+ * what DataSet gives the reference too (lastBMU is zeroed at every chunk load, src/DataSet.cpp:136-137). */
 VSOM_API int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n, double eta, double sigma, int decay,
                             uint32_t *out_bmu_dev, float *out_dist_dev);
 

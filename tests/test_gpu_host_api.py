@@ -17,13 +17,17 @@ from conftest import REPO
 REF_DRIVER = os.path.join(REPO, "oracle", "_ref", "api_driver_ref")
 B200_DRIVER = os.path.join(REPO, "tests", "cpp", "api_driver_b200")
 
-# W, H, Din, transform, decay, epochs, chunk, seed, n, eta0, etaDecay, sigma0, sigmaDecay   (sigma stays > 1)
+# W, H, Din, transform, decay, epochs, chunk, seed, n, eta0, etaDecay, sigma0, sigmaDecay
+# (the last three schedules decay into the sigma == 1 findLocalBmu regime)
 CASES = [
     (9, 7, 12, 0, 0, 4, 50, 42, 130, 0.3, 0.2, 3.0, 0.15),
     (8, 8, 20, 0, 1, 3, 0, 7, 90, 0.3, 0.1, 2.5, 0.2),
     (10, 6, 33, 1, 0, 4, 64, 3, 150, 0.05, 0.1, 3.5, 0.2),
     (7, 9, 6, 2, 0, 3, 40, 11, 100, 0.01, 0.1, 2.2, 0.1),
     (20, 20, 784, 0, 0, 2, 30, 42, 60, 0.1, 0.01, 5.0, 0.3),
+    (9, 7, 12, 0, 0, 7, 50, 42, 130, 0.3, 0.2, 2.5, 0.4),
+    (11, 8, 16, 1, 1, 6, 33, 5, 100, 0.05, 0.1, 1.8, 0.5),
+    (6, 7, 5, 2, 0, 5, 0, 2, 90, 0.01, 0.1, 1.5, 0.6),
 ]
 
 

@@ -36,11 +36,6 @@ def test_online_step_matches_reference_fixture(vsom, name):
     rows = int(g["rows"])
     for si, sg in enumerate(g["sigmas"]):
         seg = g["x"][si * rows:(si + 1) * rows]
-        if not sg > 1.0:
-            with pytest.raises(vsom.VsomError) as e:  # findLocalBmu regime: refused, never emulated on the CPU
-                ctx.train_chunk(seg, float(g["eta"]), float(sg), dec)
-            assert e.value.code == -3
-            break
         bmu, dist, resid2, last = ctx.train_chunk(seg, float(g["eta"]), float(sg), dec)
         assert_bit_equal(bmu, g[f"bmu{si}"], f"bmu seg {si}")
         assert_bit_equal(dist, g[f"dist{si}"], f"dist seg {si}")
@@ -101,13 +96,17 @@ def test_online_step_matches_oracle_bit_exact(vsom, po, shape, decay):
     ctx = vsom.VsomContext(W, H, Din, tr, vsom.ORDER_REFERENCE)
     upload_like(ctx, o.get_state())
     x = synth(rng, 2 * n, Din, tr)
-    for seg, sg in ((x[:n], sigma), (x[n:], max(1.0001, sigma * 0.6))):  # second chunk: smaller window, carried state
-        ob, od, orr, _ = o.train_rows(seg, eta, sg, decay)
-        gb, gd, gr, gl = ctx.train_chunk(seg, eta, sg, decay)
-        assert_bit_equal(gb, ob, "bmu")
-        assert_bit_equal(gd, od, "dist")
-        assert_bit_equal(gr, orr, "resid2")
-        assert np.array_equal(gl, ob.astype(np.uint64))
+    # second chunk: smaller window, carried state; third and fourth: the findLocalBmu regime (sigma <= 1), once from node
+    # 0 like DataSet gives it, once from arbitrary start nodes
+    m = max(8, n // 3)
+    starts = rng.integers(0, W * H, m).astype(np.uint64)
+    for seg, sg, last in ((x[:n], sigma, None), (x[n:], max(1.0001, sigma * 0.6), None), (x[:m], 1.0, None), (x[m:2 * m], 0.75, starts)):
+        ob, od, orr, ol = o.train_rows(seg, eta, sg, decay, last_bmu=None if last is None else last.copy())
+        gb, gd, gr, gl = ctx.train_chunk(seg, eta, sg, decay, last_bmu=None if last is None else last.copy())
+        assert_bit_equal(gb, ob, f"bmu sigma={sg}")
+        assert_bit_equal(gd, od, f"dist sigma={sg}")
+        assert_bit_equal(gr, orr, f"resid2 sigma={sg}")
+        assert np.array_equal(gl, ol)
         assert_state_equal(ctx, o.get_state(), f"sigma={sg}")
     # scoring / U-matrix on the trained state
     q = x[:40]

@@ -248,6 +248,7 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->rankSlots);
     cudaFree(ctx->errFlag);
     cudaFree(ctx->lut);
+    cudaFree(ctx->distBuf);
     cudaFree(ctx->profDev);
     for (void *p : ctx->stage)
         cudaFree(p);
@@ -399,7 +400,19 @@ int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double
     VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->world > 1) // only the rank that owns a sample's BMU reports its distance; the others keep NaN
         VSOM_CUDA(ctx, cudaMemsetAsync(distDev, 0xff, sizeof(float) * n, ctx->stream));
-    rc = launch_online_step(ctx, xDev, n, eta, sigma, decay, bmuDev, distDev);
+    const u64 *lastDev = nullptr;
+    if (!(sigma > 1.0) && last_bmu) // findLocalBmu starts its walk at the row's lastBMU (src/Som.cpp:891)
+    {
+        rc = stage_reserve(ctx, 3, sizeof(u64) * n);
+        if (rc)
+            return rc;
+        for (size_t r = 0; r < n; ++r)
+            if (last_bmu[r] >= static_cast<uint64_t>(ctx->N))
+                return set_error(ctx, VSOM_ERR_INVALID, "vsom_train_chunk: last_bmu out of range");
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->stage[3], last_bmu, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+        lastDev = static_cast<const u64 *>(ctx->stage[3]);
+    }
+    rc = launch_online_step(ctx, xDev, n, eta, sigma, decay, bmuDev, distDev, lastDev);
     if (rc)
         return rc;
     std::vector<unsigned> tmp;

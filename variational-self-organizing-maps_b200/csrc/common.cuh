@@ -57,6 +57,9 @@ struct StepParams
     u64 *rankSlots;           // [2][world] keys pushed into THIS GPU's memory by every rank (peer stores over NVLink)
     u64 *peerSlots[8];        // rankSlots of every rank (index = rank), peer-mapped; peerSlots[rank] == rankSlots
     u64 stepBase;             // samples trained before this launch: the cross-GPU exchange is indexed by the global step
+    int localSearch;          // sigma <= 1: BMU by the reference's greedy local walk (findLocalBmu) instead of the global argmin
+    float *distBuf;           // [2][nodeCount] per-step distances of every node (local search only)
+    const u64 *lastIn;        // per-sample start node of the walk (DataSet::lastBMU), null = 0
     long long *prof;          // optional [gridDim.x][5] per-phase cycle sums of thread 0 (diagnostics), else null
 };
 
@@ -72,6 +75,7 @@ struct vsom_ctx
     vsom::u64 *peerSlots[8] = {};
     bool peerOpened[8] = {};
     vsom::u64 stepBase = 0;
+    float *distBuf = nullptr; // local-search regime scratch
     int transform = 0, order = 0;
     int rowStride = 0;
     int numSMs = 0, smemOptin = 0;
@@ -117,7 +121,8 @@ int stage_reserve(vsom_ctx *ctx, int slot, size_t bytes);
     } while (0)
 
 // kernels' host launchers (each returns a vsom_status)
-int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev);
+int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev,
+                       const u64 *lastInDev = nullptr);
 int configure_online_step(vsom_ctx *ctx);
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev);
 bool score_tc_supported(const vsom_ctx *ctx);
@@ -133,6 +138,12 @@ __device__ __forceinline__ u64 ld_relaxed_gpu(const u64 *p)
 {
     u64 v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_gpu_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_relaxed_gpu(u64 *p, u64 v)

@@ -116,6 +116,74 @@ __device__ __forceinline__ float node_dist_reference(const float *m, const float
     return dist_sequential<TR>(m, xs, p.Dr, p.P, pi, pj);
 }
 
+// Som::findLocalBmu (src/Som.cpp:335-454) on the per-step distance array: greedy walk from `start` over the
+// 8-neighbourhood, then three cells one step further in the X direction of travel, until the best node stops moving.
+// The reference's size_t arithmetic is kept: the "-1" offsets are 2^64-1, min(x + off, W-1) therefore wraps the left / up
+// neighbour of column / row 0 to the last column / row, and its Y-direction continuation loop never runs (it starts at
+// size_t(-1)).  Distances are compared as the reference does (strict '<', first candidate in its order wins).
+__device__ __forceinline__ unsigned local_bmu_walk(const float *dist, u64 W, u64 H, u64 start)
+{
+    const u64 M1 = ~0ull;
+    const u64 fx[8] = {M1, 0, 1, 1, 1, 0, M1, M1};
+    const u64 fy[8] = {1, 1, 1, 0, M1, M1, M1, 0};
+    u64 lastBMU = start, minIndex = start, lastMeasured = start;
+    float minDist = ld_relaxed_gpu_f32(dist + start);
+    for (;;)
+    {
+        const u64 lmX = lastMeasured % W, lmY = lastMeasured / W, lbX = lastBMU % W, lbY = lastBMU / W;
+        if (lastMeasured == lastBMU)
+        {
+            u64 idx[8];
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                const u64 cx = lmX + fx[i] < W - 1 ? lmX + fx[i] : W - 1; // min(x + off, W-1) in size_t
+                const u64 cy = lmY + fy[i] < H - 1 ? lmY + fy[i] : H - 1;
+                idx[i] = cy * W + cx;
+                v[i] = ld_relaxed_gpu_f32(dist + idx[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (v[i] < minDist)
+                {
+                    minDist = v[i];
+                    minIndex = idx[i];
+                }
+            if (minIndex == lastBMU)
+                return static_cast<unsigned>(minIndex);
+            lastMeasured = minIndex;
+        }
+        else
+        {
+            if (lmX - lbX) // moving in X
+            {
+                u64 idx[3];
+                float v[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                {
+                    const u64 ox = lmX + lmX - lbX, oy = lmY + static_cast<u64>(static_cast<long long>(i - 1));
+                    const u64 cx = ox < W - 1 ? ox : W - 1, cy = oy < H - 1 ? oy : H - 1;
+                    idx[i] = cy * W + cx;
+                    v[i] = ld_relaxed_gpu_f32(dist + idx[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (v[i] < minDist)
+                    {
+                        minDist = v[i];
+                        minIndex = idx[i];
+                    }
+            }
+            if (minIndex == lastMeasured)
+                return static_cast<unsigned>(minIndex);
+            lastBMU = lastMeasured;
+            lastMeasured = minIndex;
+        }
+    }
+}
+
 template <int TR, int ORDER, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepParams p)
 {
@@ -269,6 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             for (int l = tid; l < L; l += kThreads)
             {
                 const float d = node_dist_reference<TR>(mBase + l * stride, xt, p, n4, pi, pj);
+                if (p.localSearch)
+                    p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
                 best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
             }
         }
@@ -290,9 +360,13 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             for (int l = warp; l < L; l += kWarps)
             {
                 const float d = dist_lanes<TR>(mBase + l * stride, xt, p.Dr, p.P, pi, pj, lane);
+                if (p.localSearch && lane == 0)
+                    p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
                 best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
             }
         }
+        if (p.localSearch)
+            __threadfence(); // the distances written above must be visible before this CTA's key is
         // REFERENCE order with at most 32 owned nodes: every key already sits in warp 0 — no CTA barrier
         const bool crossWarp = ORDER != VSOM_ORDER_REFERENCE || L > 32;
         if (crossWarp)
@@ -377,10 +451,23 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 if (b == 0 && lane == 0 && p.outBmu && !abort)
                     p.outBmu[t] = key_node(m); // every rank records the global BMU of every sample
             }
+            if (p.localSearch && !abort)
+            {
+                // every CTA has seen every CTA's key of this step, hence (fence above) every distance of this step
+                __threadfence();
+                __syncwarp();
+            }
             if (lane == 0)
             {
                 // window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric
-                const unsigned bmu = key_node(m);
+                unsigned bmu = key_node(m);
+                if (p.localSearch && !abort)
+                {
+                    bmu = local_bmu_walk(p.distBuf + (t & 1) * static_cast<u64>(p.nodeCount), static_cast<u64>(p.W), static_cast<u64>(p.H),
+                                         p.lastIn ? p.lastIn[t] : 0ull);
+                    if (b == 0 && p.outBmu)
+                        p.outBmu[t] = bmu;
+                }
                 const int bx = static_cast<int>(bmu % static_cast<unsigned>(p.W));
                 const int by = static_cast<int>(bmu / static_cast<unsigned>(p.W));
                 double lo = __dsub_rn(static_cast<double>(bx), p.radius);
@@ -715,11 +802,14 @@ static int build_lut(vsom_ctx *ctx, double eta, double sigma)
     return VSOM_OK;
 }
 
-int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev)
+int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev,
+                       const u64 *lastInDev)
 {
-    if (!(sigma > 1.0))
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED,
-                         "online step: sigma <= 1 selects the reference's findLocalBmu regime (src/Som.cpp:335-454), not built on the device yet");
+    const bool localSearch = !(sigma > 1.0); // SIGMA_SWITCH_TO_LOCAL (include/SOM.hpp:37, src/Som.cpp:889-892)
+    if (localSearch && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "online step: the findLocalBmu regime (sigma <= 1) is not available on node-sharded contexts");
+    if (localSearch && !ctx->distBuf)
+        VSOM_CUDA(ctx, cudaMalloc(&ctx->distBuf, sizeof(float) * 2 * static_cast<size_t>(ctx->N)));
     if (decay != VSOM_EXPONENTIAL && decay != VSOM_INVERSE_PROPORTIONAL)
         return set_error(ctx, VSOM_ERR_INVALID, "online step: decay must be Exponential or InverseProportional");
     if (n == 0)
@@ -778,6 +868,9 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.resident = ctx->residentTrain;
     p.smStride = ctx->smStrideTrain;
     p.timeoutCycles = 4000000000ll; // ~2 s at 1.9 GHz: a peer CTA that never publishes is a bug, not a wait
+    p.localSearch = localSearch ? 1 : 0;
+    p.distBuf = ctx->distBuf;
+    p.lastIn = lastInDev;
     p.prof = ctx->profDev;
     ctx->profSamples = n;
     // the neighbourhood table rides in shared memory behind the resident rows when it fits
