@@ -46,11 +46,11 @@ __device__ __forceinline__ float stepper_scalar(float xv, float m)
     const float d = __fsub_rn(xv, m);
     if (TR == VSOM_MEDIAN)
     {
-        // sign(d) in {-1, +0, +1}; NaN stays NaN.  |d| > 0 ? 1 : |d| gives 1 / +0 / NaN, then d's sign is copied on
-        // (a zero keeps +0 like the reference's (0<d)-(d<0)).
+        // sign(d) in {-1, +0, +1}; NaN stays NaN: |d| > 0 ? copysign(1, d) : |d|   (a zero gives +0 like the reference's
+        // (0<d)-(d<0); NaN fails the comparison and |NaN| is NaN)
         const float a = fabsf(d);
-        const float mag = a > 0.0f ? 1.0f : a;
-        return __uint_as_float(__float_as_uint(mag) | (mag > 0.0f ? (__float_as_uint(d) & 0x80000000u) : 0u));
+        const float one = __uint_as_float((__float_as_uint(d) & 0x80000000u) | 0x3f800000u); // copysign(1, d)
+        return a > 0.0f ? one : a;
     }
     return d;
 }
@@ -130,7 +130,7 @@ __device__ __forceinline__ unsigned local_bmu_walk(const float *dist, u64 W, u64
     float minDist = ld_relaxed_gpu_f32(dist + start);
     for (;;)
     {
-        const u64 lmX = lastMeasured % W, lmY = lastMeasured / W, lbX = lastBMU % W, lbY = lastBMU / W;
+        const u64 lmX = lastMeasured % W, lmY = lastMeasured / W, lbX = lastBMU % W;
         if (lastMeasured == lastBMU)
         {
             u64 idx[8];
@@ -189,7 +189,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 sWarpKey[kWarps];
-    __shared__ int sWin[8]; // bmu, bx, by, startX, endX, startY, endY of the current sample
     __shared__ int sAbort;
     __shared__ int sPendL; // local node whose post-update distance is still owed (-1: none)
     __shared__ u64 sPendT; // ... for this sample
@@ -205,11 +204,13 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 
     // ---- carve shared memory (every region 16-byte aligned)
     float *xs = reinterpret_cast<float *>(smemRaw);                          // [3][DinPad] sample ring
-    float *wbuf = xs + 3 * DinPad;                                           // [2][Lpad] weightMap of the owned nodes
+    float *wbuf = xs + 3 * DinPad;                                           // [Lpad] weightMap of the owned nodes
     const int Lpad = (Lmax + 3) & ~3;
-    int2 *nodeXY = reinterpret_cast<int2 *>(wbuf + 2 * Lpad);                // [Lpad] grid position of the owned nodes
+    float2 *coef = reinterpret_cast<float2 *>(wbuf + Lpad);                  // [Lpad] per owned node in the window: {step coefficient, (float)nw}
+    int2 *nodeXY = reinterpret_cast<int2 *>(coef + Lpad);                    // [Lpad] grid position of the owned nodes
     unsigned *touched = reinterpret_cast<unsigned *>(nodeXY + Lpad);         // [Lpad] visited in this chunk
-    unsigned short *pi = reinterpret_cast<unsigned short *>(touched + Lpad); // [Ppad] CLR pair tables
+    unsigned *inWin = touched + Lpad;                                        // [Lpad] inside the window of the current sample
+    unsigned short *pi = reinterpret_cast<unsigned short *>(inWin + Lpad);   // [Ppad] CLR pair tables
     const int Ppad = (p.P + 7) & ~7;
     unsigned short *pj = pi + Ppad;
     float *planes = reinterpret_cast<float *>(pj + Ppad);                    // resident rows: 2 x Lmax x smStride
@@ -230,11 +231,9 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         sBase = p.S + static_cast<size_t>(b) * p.rowStride;
     }
 
-    // slices of 128 elements of the model vector (CLR: of the pair index); with one slice per node a single
-    // warp owns the node's whole update and the weight needs no double buffer.
+    // slices of 128 elements of the model vector (CLR: of the pair index): one warp per (window node, slice)
     const int nq = TR == VSOM_CLR ? p.P : DmPad;
     const int nCh = (nq + 127) >> 7;
-    const bool dbl = nCh > 1;
 
     // ---- prologue: pair tables, neighbourhood table, owned weights / positions, resident rows, first sample
     if (TR == VSOM_CLR)
@@ -246,7 +245,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     if (p.lutSmem)
         for (int i = tid; i < p.lutCount; i += kThreads)
             lutS[i] = p.lut[i];
-    const LutEntry *lut = p.lutSmem ? lutS : p.lut;
     for (int l = tid; l < L; l += kThreads)
     {
         const unsigned node = static_cast<unsigned>(p.node0 + l * G + b);
@@ -306,7 +304,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         if (p.prof && tid == 0)
             sClk[0] = clock64();
         const float *xt = xs + ring * DinPad;
-        float *wcur = wbuf + (dbl ? (t & 1) * Lpad : 0), *wnext = wbuf + (dbl ? ((t + 1) & 1) * Lpad : 0);
         cp_async_wait_all();
         __syncthreads(); // sample t landed; update of sample t-1 is complete; sPend* of t-1 visible
         if (t + 1 < p.n)
@@ -457,9 +454,11 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 __threadfence();
                 __syncwarp();
             }
+            // window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric.  Lane 0 computes it
+            // (f64, exactly the reference's expressions) and broadcasts it to the warp.
+            int wbmu = 0, wbx = 0, wby = 0, wsx = 0, wex = 0, wsy = 0, wey = 0;
             if (lane == 0)
             {
-                // window of the update (src/Som.cpp:899-903): [startX,endX) x [startY,endY), asymmetric
                 unsigned bmu = key_node(m);
                 if (p.localSearch && !abort)
                 {
@@ -468,25 +467,73 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     if (b == 0 && p.outBmu)
                         p.outBmu[t] = bmu;
                 }
-                const int bx = static_cast<int>(bmu % static_cast<unsigned>(p.W));
-                const int by = static_cast<int>(bmu / static_cast<unsigned>(p.W));
-                double lo = __dsub_rn(static_cast<double>(bx), p.radius);
-                sWin[3] = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
-                lo = __dsub_rn(static_cast<double>(by), p.radius);
-                sWin[5] = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
-                double hi = __dadd_rn(static_cast<double>(bx), p.radius);
-                sWin[4] = static_cast<int>(static_cast<u64>(hi < dW ? hi : dW));
-                hi = __dadd_rn(static_cast<double>(by), p.radius);
-                sWin[6] = static_cast<int>(static_cast<u64>(hi < dH ? hi : dH));
-                sWin[0] = static_cast<int>(bmu);
-                sWin[1] = bx;
-                sWin[2] = by;
+                wbmu = static_cast<int>(bmu);
+                wbx = static_cast<int>(bmu % static_cast<unsigned>(p.W));
+                wby = static_cast<int>(bmu / static_cast<unsigned>(p.W));
+                double lo = __dsub_rn(static_cast<double>(wbx), p.radius);
+                wsx = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
+                lo = __dsub_rn(static_cast<double>(wby), p.radius);
+                wsy = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
+                double hi = __dadd_rn(static_cast<double>(wbx), p.radius);
+                wex = static_cast<int>(static_cast<u64>(hi < dW ? hi : dW));
+                hi = __dadd_rn(static_cast<double>(wby), p.radius);
+                wey = static_cast<int>(static_cast<u64>(hi < dH ? hi : dH));
                 sPendL = -1;
                 if (abort)
                 {
                     sAbort = 1;
                     *p.err = 1;
                 }
+            }
+            wbmu = __shfl_sync(0xffffffffu, wbmu, 0);
+            wbx = __shfl_sync(0xffffffffu, wbx, 0);
+            wby = __shfl_sync(0xffffffffu, wby, 0);
+            wsx = __shfl_sync(0xffffffffu, wsx, 0);
+            wex = __shfl_sync(0xffffffffu, wex, 0);
+            wsy = __shfl_sync(0xffffffffu, wsy, 0);
+            wey = __shfl_sync(0xffffffffu, wey, 0);
+            // ---- per owned node (lanes = nodes): neighbourhood entry, weightMap update and the step coefficient
+            //      (src/Som.cpp:915-939).  Done once here instead of redundantly by every warp of the update.
+            for (int l = lane; l < L; l += 32)
+            {
+                const int2 xy = nodeXY[l];
+                float2 cf = make_float2(-1.0f, 0.0f);
+                if (xy.x >= wsx && xy.x < wex && xy.y >= wsy && xy.y < wey)
+                {
+                    const int dx = xy.x > wbx ? xy.x - wbx : wbx - xy.x, dy = xy.y > wby ? xy.y - wby : wby - xy.y;
+                    const int li = dy * p.lutW + dx;
+                    float4 raw;
+                    if (p.lutSmem)
+                        raw = *reinterpret_cast<const float4 *>(lutS + li);
+                    else
+                        raw = __ldg(reinterpret_cast<const float4 *>(p.lut + li));
+                    const float cexp = raw.z, nwf = raw.w;
+                    float w = wbuf[l], c;
+                    if (p.decay == VSOM_EXPONENTIAL)
+                    {
+                        w = __fadd_rn(w, cexp); // :924
+                        c = cexp;               // :925
+                    }
+                    else
+                    {
+                        w = __fadd_rn(w, nwf); // :930
+                        const double nw = __hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x));
+                        const double tw = (w == 0.0f) ? 1.0 : __ddiv_rn(nw, static_cast<double>(w)); // :933
+                        c = static_cast<float>(tw);                                                    // :935
+                    }
+                    wbuf[l] = w;
+                    touched[l] = 1;
+                    cf = make_float2(c, nwf);
+                    if (static_cast<unsigned>(p.node0 + l * G + b) == static_cast<unsigned>(wbmu))
+                    {
+                        sPendL = l;
+                        sPendT = t;
+                    }
+                    inWin[l] = 1;
+                }
+                else
+                    inWin[l] = 0;
+                coef[l] = cf;
             }
             if (p.prof && tid == 0)
                 sClk[3] = clock64();
@@ -496,84 +543,16 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             break;
         if (p.prof && tid == 0)
             sClk[4] = clock64();
-        const unsigned bmu = static_cast<unsigned>(sWin[0]);
-        const int bx = sWin[1], by = sWin[2], startX = sWin[3], endX = sWin[4], startY = sWin[5], endY = sWin[6];
-
-        // Per window node: the neighbourhood entry and the step coefficient (src/Som.cpp:915-939), from the
-        // node's OLD weight in wcur.
-#define VSOM_NODE_COEF(l_, inWin_, c_, nwf_, w1_)                                                                        \
-    {                                                                                                                    \
-        const int2 xy = nodeXY[l_];                                                                                      \
-        inWin_ = xy.x >= startX && xy.x < endX && xy.y >= startY && xy.y < endY;                                         \
-        if (inWin_)                                                                                                      \
-        {                                                                                                                \
-            const int dx = xy.x > bx ? xy.x - bx : bx - xy.x, dy = xy.y > by ? xy.y - by : by - xy.y;                    \
-            const float4 raw = *reinterpret_cast<const float4 *>(lut + dy * p.lutW + dx);                                \
-            const float cexp = raw.z;                                                                                    \
-            nwf_ = raw.w;                                                                                                \
-            const float w0 = wcur[l_];                                                                                   \
-            if (p.decay == VSOM_EXPONENTIAL)                                                                             \
-            {                                                                                                            \
-                w1_ = __fadd_rn(w0, cexp); /* :924 */                                                                    \
-                c_ = cexp;                 /* :925 */                                                                    \
-            }                                                                                                            \
-            else                                                                                                         \
-            {                                                                                                            \
-                w1_ = __fadd_rn(w0, nwf_); /* :930 */                                                                    \
-                const double nw = __hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x));                        \
-                const double tw = (w1_ == 0.0f) ? 1.0 : __ddiv_rn(nw, static_cast<double>(w1_)); /* :933 */              \
-                c_ = static_cast<float>(tw);                                                     /* :935 */              \
-            }                                                                                                            \
-        }                                                                                                                \
-    }
-
-        // ---- phase A (only when a node's vector spans several warps): one thread per owned node writes the new
-        //      weightMap value to the other weight buffer, so that the warps of phase B all read the old one
-        if (dbl)
-            for (int l = tid; l < L; l += kThreads)
-            {
-                bool inWin;
-                float c = 0.0f, nwf = 0.0f, w1 = wcur[l];
-                VSOM_NODE_COEF(l, inWin, c, nwf, w1);
-                wnext[l] = w1;
-                if (inWin)
-                {
-                    touched[l] = 1;
-                    if (static_cast<unsigned>(p.node0 + l * G + b) == bmu)
-                    {
-                        sPendL = l;
-                        sPendT = t;
-                    }
-                }
-                (void)c;
-                (void)nwf;
-            }
-
-        // ---- phase B: one warp per (window node, 128-element slice) of the model vector (src/Som.cpp:912-941)
+        // ---- update: one warp per (window node, 128-element slice) of the model vector (src/Som.cpp:912-941)
         {
             const int items = L * nCh;
             for (int it = warp; it < items; it += kWarps)
             {
-                const int l = dbl ? it / nCh : it, ch = dbl ? it - l * nCh : 0;
-                bool inWin;
-                float c = 0.0f, nwf = 0.0f, w1 = 0.0f;
-                VSOM_NODE_COEF(l, inWin, c, nwf, w1);
-                if (!inWin)
+                const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
+                if (!inWin[l])
                     continue;
-                if (!dbl)
-                {
-                    __syncwarp(); // every lane has read the old weight
-                    if (lane == 0)
-                    {
-                        wcur[l] = w1;
-                        touched[l] = 1;
-                        if (static_cast<unsigned>(p.node0 + l * G + b) == bmu)
-                        {
-                            sPendL = l;
-                            sPendT = t;
-                        }
-                    }
-                }
+                const float2 cf = coef[l];
+                const float c = cf.x, nwf = cf.y;
                 float *m = mBase + l * stride, *S = sBase + l * stride;
                 if (TR != VSOM_CLR)
                 {
@@ -621,7 +600,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 }
             }
         }
-#undef VSOM_NODE_COEF
         done = t + 1;
         if (p.prof && tid == 0)
         {
@@ -664,7 +642,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             p.hits[q] += 1;
         }
     }
-    const float *wfin = wbuf + (dbl ? (done & 1) * Lpad : 0);
+    const float *wfin = wbuf;
+    (void)done;
     for (int l = tid; l < L; l += kThreads)
         p.weight[static_cast<size_t>(l) * G + b] = wfin[l];
     for (int l = warp; l < L; l += kWarps)
@@ -707,8 +686,8 @@ static size_t online_step_smem(const vsom_ctx *ctx, int G, bool resident, int sm
     const int Lpad = (Lmax + 3) & ~3;
     const int DinPad = (ctx->Din + 3) & ~3;
     const int Ppad = (ctx->P + 7) & ~7;
-    size_t bytes = sizeof(float) * (3 * static_cast<size_t>(DinPad) + 2 * static_cast<size_t>(Lpad));
-    bytes += (sizeof(int2) + sizeof(unsigned)) * static_cast<size_t>(Lpad);
+    size_t bytes = sizeof(float) * (3 * static_cast<size_t>(DinPad) + 3 * static_cast<size_t>(Lpad));
+    bytes += (sizeof(int2) + 2 * sizeof(unsigned)) * static_cast<size_t>(Lpad);
     bytes += 2 * sizeof(unsigned short) * static_cast<size_t>(Ppad);
     if (resident)
         bytes += sizeof(float) * 2 * static_cast<size_t>(Lmax) * smStride;
