@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 sWarpKey[kWarps];
+    __shared__ int sWin[8]; // bmu, bx, by, startX, endX, startY, endY of the current sample
     __shared__ int sAbort;
     __shared__ int sPendL; // local node whose post-update distance is still owed (-1: none)
     __shared__ u64 sPendT; // ... for this sample
@@ -492,9 +493,21 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             wex = __shfl_sync(0xffffffffu, wex, 0);
             wsy = __shfl_sync(0xffffffffu, wsy, 0);
             wey = __shfl_sync(0xffffffffu, wey, 0);
+            if (lane == 0)
+            {
+                sWin[0] = wbmu;
+                sWin[1] = wbx;
+                sWin[2] = wby;
+                sWin[3] = wsx;
+                sWin[4] = wex;
+                sWin[5] = wsy;
+                sWin[6] = wey;
+            }
             // ---- per owned node (lanes = nodes): neighbourhood entry, weightMap update and the step coefficient
-            //      (src/Som.cpp:915-939).  Done once here instead of redundantly by every warp of the update.
-            for (int l = lane; l < L; l += 32)
+            //      (src/Som.cpp:915-939).  When a node's vector spans several warps (nCh > 1) this is done once here;
+            //      with one warp per node (nCh == 1) each update warp does it for its own node after the barrier,
+            //      which keeps it off this warp's critical path.
+            for (int l = lane; nCh > 1 && l < L; l += 32)
             {
                 const int2 xy = nodeXY[l];
                 float2 cf = make_float2(-1.0f, 0.0f);
@@ -549,10 +562,56 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             for (int it = warp; it < items; it += kWarps)
             {
                 const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
-                if (!inWin[l])
-                    continue;
-                const float2 cf = coef[l];
-                const float c = cf.x, nwf = cf.y;
+                float c, nwf;
+                if (nCh > 1)
+                {
+                    if (!inWin[l])
+                        continue;
+                    const float2 cf = coef[l];
+                    c = cf.x;
+                    nwf = cf.y;
+                }
+                else
+                {
+                    // one warp owns the whole node: every lane derives the coefficient (redundantly, no traffic),
+                    // lane 0 records the new weight
+                    const int2 xy = nodeXY[l];
+                    const int bx = sWin[1], by = sWin[2];
+                    if (!(xy.x >= sWin[3] && xy.x < sWin[4] && xy.y >= sWin[5] && xy.y < sWin[6]))
+                        continue;
+                    const int dx = xy.x > bx ? xy.x - bx : bx - xy.x, dy = xy.y > by ? xy.y - by : by - xy.y;
+                    const int li = dy * p.lutW + dx;
+                    float4 raw;
+                    if (p.lutSmem)
+                        raw = *reinterpret_cast<const float4 *>(lutS + li);
+                    else
+                        raw = __ldg(reinterpret_cast<const float4 *>(p.lut + li));
+                    nwf = raw.w;
+                    float w = wbuf[l];
+                    if (p.decay == VSOM_EXPONENTIAL)
+                    {
+                        w = __fadd_rn(w, raw.z); // :924
+                        c = raw.z;               // :925
+                    }
+                    else
+                    {
+                        w = __fadd_rn(w, nwf); // :930
+                        const double nw = __hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x));
+                        const double tw = (w == 0.0f) ? 1.0 : __ddiv_rn(nw, static_cast<double>(w)); // :933
+                        c = static_cast<float>(tw);                                                    // :935
+                    }
+                    __syncwarp(); // every lane has read the old weight
+                    if (lane == 0)
+                    {
+                        wbuf[l] = w;
+                        touched[l] = 1;
+                        if (static_cast<unsigned>(p.node0 + l * G + b) == static_cast<unsigned>(sWin[0]))
+                        {
+                            sPendL = l;
+                            sPendT = t;
+                        }
+                    }
+                }
                 float *m = mBase + l * stride, *S = sBase + l * stride;
                 if (TR != VSOM_CLR)
                 {
