@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *__restrict
             {
                 const float sM = sg[kk] < 0.00001f ? 0.00001f : sg[kk];  // :150
                 const float d = __fsub_rn(mc[kk], mu[kk]);
-                const float a = __fdiv_rn(d, sM);                          // (m - v) / sM
-                const float bq = __fdiv_rn(__fmul_rn(d, 1.0f), sM);        // ((m - v) * valid*weights) / sM, valid*weights == 1 (:1002-1003)
-                s = __fadd_rn(s, __fmul_rn(a, bq));                        // :156
+                // a = (m - v) / sM and b = ((m - v) * valid*weights) / sM with valid*weights == 1.0f exactly (:1002-1003):
+                // d * 1.0f == d bit for bit, so b == a and one IEEE division serves both factors of the dot product
+                const float a = __fdiv_rn(d, sM);
+                s = __fadd_rn(s, __fmul_rn(a, a));                         // :156
             }
         }
     }
