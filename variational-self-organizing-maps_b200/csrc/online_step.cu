@@ -392,19 +392,16 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             u64 m;
             bool abort = false;
             const u64 filler = (~0ull << 8) | tag;
-            // Two polling rounds are kept in flight: all loads of a round are issued before any is consumed (one L2 round
-            // trip per round, not G/32), and the next round is already on its way while the previous one is checked, so
-            // an arrival is noticed within about half a round trip.
-            u64 va[kMaxSlotsPerLane], vb[kMaxSlotsPerLane];
-            auto issue = [&](u64(&v)[kMaxSlotsPerLane]) {
+            for (;;)
+            {
+                // all loads of a round are issued before any is consumed: one L2 round trip per round, not G/32
+                u64 v[kMaxSlotsPerLane];
 #pragma unroll
                 for (int j = 0; j < kMaxSlotsPerLane; ++j)
                 {
                     const int i = lane + 32 * j;
                     v[j] = i < G ? ld_relaxed_gpu(row + i) : filler;
                 }
-            };
-            auto arrived = [&](const u64(&v)[kMaxSlotsPerLane]) {
                 m = ~0ull;
                 int ok = 1;
 #pragma unroll
@@ -413,16 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     ok &= (static_cast<unsigned>(v[j] & 0xff) == tag);
                     m = u64_min(m, v[j]);
                 }
-                return __all_sync(0xffffffffu, ok) != 0;
-            };
-            issue(va);
-            for (;;)
-            {
-                issue(vb);
-                if (arrived(va))
-                    break;
-                issue(va);
-                if (arrived(vb))
+                if (__all_sync(0xffffffffu, ok))
                     break;
                 if (__any_sync(0xffffffffu, clock64() - t0 > p.timeoutCycles))
                 {
