@@ -230,103 +230,19 @@ __device__ __forceinline__ float dist_sequential(const float *m, const float *xs
 }
 
 // Squared distance with 32 interleaved partial sums and a fixed xor butterfly (all 32 lanes call; all get the value).
-// Standard / Median: lane s owns the 128-bit chunks c = s, s+32, ... of the (zero-padded, 16-byte aligned) row and adds
-// their four squares in order; CLR: lane s owns the pairs q = s, s+32, ...  Then the butterfly 16, 8, 4, 2, 1.
 template <int TR>
 __device__ __forceinline__ float dist_lanes(const float *m, const float *xs, int Dr, int P, const unsigned short *pi, const unsigned short *pj, int lane)
 {
     float s = 0.0f;
-    if (TR != VSOM_CLR)
-    {
-        const float4 *m4 = reinterpret_cast<const float4 *>(m);
-        const float4 *x4 = reinterpret_cast<const float4 *>(xs);
-        const int n4 = (Dr + 3) >> 2;
-#pragma unroll 2
-        for (int c = lane; c < n4; c += 32)
-        {
-            const float4 a = m4[c], b = x4[c];
-            float r = __fsub_rn(a.x, b.x);
-            s = __fadd_rn(s, __fmul_rn(r, r));
-            r = __fsub_rn(a.y, b.y);
-            s = __fadd_rn(s, __fmul_rn(r, r));
-            r = __fsub_rn(a.z, b.z);
-            s = __fadd_rn(s, __fmul_rn(r, r));
-            r = __fsub_rn(a.w, b.w);
-            s = __fadd_rn(s, __fmul_rn(r, r));
-        }
-    }
-    else
-    {
 #pragma unroll 4
-        for (int k = lane; k < Dr; k += 32)
-        {
-            const float r = residual<TR>(m, xs, k, P, pi, pj);
-            s = __fadd_rn(s, __fmul_rn(r, r));
-        }
+    for (int k = lane; k < Dr; k += 32)
+    {
+        const float r = residual<TR>(m, xs, k, P, pi, pj);
+        s = __fadd_rn(s, __fmul_rn(r, r));
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1)
         s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-    return s;
-}
-
-// Squared distance in the REFERENCE order computed by a whole warp, for vectors of at most 128 residuals: the lanes form
-// the squared residuals in parallel (they are order independent), park them in a 128-float scratch row, and lane 0 adds
-// them up k = 0, 1, 2, ... exactly like the one-thread version.  Only lane 0's return value is meaningful.
-template <int TR>
-__device__ __forceinline__ float dist_reference_warp(const float *m, const float *xs, int Dr, int P, const unsigned short *pi, const unsigned short *pj,
-                                                     float *scratch, int lane)
-{
-    if (TR != VSOM_CLR)
-    {
-        const int k = lane << 2;
-        float4 r2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (k < Dr) // rows are zero padded to a multiple of four
-        {
-            const float4 a = *reinterpret_cast<const float4 *>(m + k), b = *reinterpret_cast<const float4 *>(xs + k);
-            float r = __fsub_rn(a.x, b.x);
-            r2.x = __fmul_rn(r, r);
-            r = __fsub_rn(a.y, b.y);
-            r2.y = __fmul_rn(r, r);
-            r = __fsub_rn(a.z, b.z);
-            r2.z = __fmul_rn(r, r);
-            r = __fsub_rn(a.w, b.w);
-            r2.w = __fmul_rn(r, r);
-        }
-        *reinterpret_cast<float4 *>(scratch + k) = r2;
-    }
-    else
-    {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-            const int q = lane + 32 * j;
-            float v = 0.0f;
-            if (q < Dr)
-            {
-                const float r = residual<TR>(m, xs, q, P, pi, pj);
-                v = __fmul_rn(r, r);
-            }
-            scratch[q] = v;
-        }
-    }
-    __syncwarp();
-    float s = 0.0f;
-    if (lane == 0)
-    {
-        const float4 *s4 = reinterpret_cast<const float4 *>(scratch);
-        const int n4 = (Dr + 3) >> 2; // trailing zeros add +0: s + 0 == s exactly
-#pragma unroll 4
-        for (int c = 0; c < n4; ++c)
-        {
-            const float4 v = s4[c];
-            s = __fadd_rn(s, v.x);
-            s = __fadd_rn(s, v.y);
-            s = __fadd_rn(s, v.z);
-            s = __fadd_rn(s, v.w);
-        }
-    }
-    __syncwarp();
     return s;
 }
 

@@ -189,7 +189,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 sWarpKey[kWarps];
-    __shared__ u64 sNextKey[kWarps]; // fused mode: key (tag 0) of node l = warp for the NEXT sample
     __shared__ int sWin[8]; // bmu, bx, by, startX, endX, startY, endY of the current sample
     __shared__ int sAbort;
     __shared__ int sPendL; // local node whose post-update distance is still owed (-1: none)
@@ -215,8 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     unsigned short *pi = reinterpret_cast<unsigned short *>(inWin + Lpad);   // [Ppad] CLR pair tables
     const int Ppad = (p.P + 7) & ~7;
     unsigned short *pj = pi + Ppad;
-    float *rsq = reinterpret_cast<float *>(pj + Ppad);                       // [kWarps][128] squared residuals (fused next-sample scan)
-    float *planes = rsq + kWarps * 128;                                      // resident rows: 2 x Lmax x smStride
+    float *planes = reinterpret_cast<float *>(pj + Ppad);                    // resident rows: 2 x Lmax x smStride
     LutEntry *lutS = reinterpret_cast<LutEntry *>(planes + (RES ? 2 * static_cast<size_t>(Lmax) * p.smStride : 0)); // optional copy of the table
 
     float *mBase, *sBase;
@@ -237,10 +235,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     // slices of 128 elements of the model vector (CLR: of the pair index): one warp per (window node, slice)
     const int nq = TR == VSOM_CLR ? p.P : DmPad;
     const int nCh = (nq + 127) >> 7;
-    // Fused mode: every owned node has its own warp and fits one slice, so the warp that updates a node also computes the
-    // node's distance to the NEXT sample right away (same arithmetic and order as the scan) and the separate scan phase
-    // disappears from the per-sample critical path.
-    const bool fuse = nCh == 1 && L <= kWarps && p.n > 1;
 
     // ---- prologue: pair tables, neighbourhood table, owned weights / positions, resident rows, first sample
     if (TR == VSOM_CLR)
@@ -300,30 +294,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         prefetch(0, 0);
 
     const double dW = static_cast<double>(p.W), dH = static_cast<double>(p.H);
-
-    // distance of the owned node l = warp to the sample in ring slot `slot`, in the context's reduction order
-    auto warp_node_key = [&](int slot, u64 sampleIndex) {
-        const float *xq = xs + slot * DinPad;
-        const float *mrow = mBase + warp * stride;
-        float d;
-        if (ORDER == VSOM_ORDER_REFERENCE)
-            d = dist_reference_warp<TR>(mrow, xq, p.Dr, p.P, pi, pj, rsq + warp * 128, lane);
-        else
-            d = dist_lanes<TR>(mrow, xq, p.Dr, p.P, pi, pj, lane);
-        if (lane == 0)
-        {
-            sNextKey[warp] = make_key(d, static_cast<unsigned>(p.node0 + warp * G + b), 0u);
-            if (p.localSearch)
-                p.distBuf[(sampleIndex & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(warp) * G + b] = d;
-        }
-    };
-    if (fuse)
-    {
-        cp_async_wait_all();
-        __syncthreads(); // sample 0 landed
-        if (warp < L)
-            warp_node_key(0, 0);
-    }
     if (tid == 0)
         for (int i = 0; i < 5; ++i)
             sProf[i] = 0;
@@ -350,30 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 
         // ---- scan: distance of sample t to every owned node, min key per thread
         u64 best = ~0ull;
-        if (fuse)
-        {
-            // the keys were produced by the owning warps at the end of the previous update phase
-            if (warp == 0 && lane < L)
-                best = sNextKey[lane] | tag;
-            if (warp == kWarps - 1 && pendL >= 0)
-            {
-                float d;
-                if (ORDER == VSOM_ORDER_REFERENCE)
-                    d = dist_reference_warp<TR>(mBase + pendL * stride, xprev, p.Dr, p.P, pi, pj, rsq + warp * 128, lane);
-                else
-                    d = dist_lanes<TR>(mBase + pendL * stride, xprev, p.Dr, p.P, pi, pj, lane);
-                if (lane == 0)
-                {
-                    const size_t q = static_cast<size_t>(pendL) * G + b;
-                    if (p.outBmu)
-                        p.outBmu[pendT] = static_cast<unsigned>(p.node0 + q);
-                    if (p.outDist)
-                        p.outDist[pendT] = d;
-                    p.hits[q] += 1;
-                }
-            }
-        }
-        else if (ORDER == VSOM_ORDER_REFERENCE)
+        if (ORDER == VSOM_ORDER_REFERENCE)
         {
             if (tid == kThreads - 1 && pendL >= 0)
             {
@@ -419,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         if (p.localSearch)
             __threadfence(); // the distances written above must be visible before this CTA's key is
         // REFERENCE order with at most 32 owned nodes: every key already sits in warp 0 — no CTA barrier
-        const bool crossWarp = !fuse && (ORDER != VSOM_ORDER_REFERENCE || L > 32);
+        const bool crossWarp = ORDER != VSOM_ORDER_REFERENCE || L > 32;
         if (crossWarp)
         {
             best = warp_min_key(best);
@@ -604,8 +551,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             if (p.prof && tid == 0)
                 sClk[3] = clock64();
         }
-        if (fuse)
-            cp_async_wait_all(); // sample t+1 (issued at the top of this step) is read in the update phase below
         __syncthreads();
         if (sAbort)
             break;
@@ -714,12 +659,6 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 }
             }
         }
-        // ---- fused scan of the NEXT sample by the warp that owns (and has just updated) the node
-        if (fuse && t + 1 < p.n && warp < L)
-        {
-            __syncwarp(); // the row written above by this warp's lanes
-            warp_node_key(ring == 2 ? 0 : ring + 1, t + 1);
-        }
         done = t + 1;
         if (p.prof && tid == 0)
         {
@@ -809,7 +748,6 @@ static size_t online_step_smem(const vsom_ctx *ctx, int G, bool resident, int sm
     size_t bytes = sizeof(float) * (3 * static_cast<size_t>(DinPad) + 3 * static_cast<size_t>(Lpad));
     bytes += (sizeof(int2) + 2 * sizeof(unsigned)) * static_cast<size_t>(Lpad);
     bytes += 2 * sizeof(unsigned short) * static_cast<size_t>(Ppad);
-    bytes += sizeof(float) * kWarps * 128;
     if (resident)
         bytes += sizeof(float) * 2 * static_cast<size_t>(Lmax) * smStride;
     return bytes;
