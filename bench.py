@@ -49,6 +49,17 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, units):
+    """DRAM bytes of one launch processing `units`, scaled from the committed ncu capture (profiles/r01_traffic.json)."""
+    p = os.path.join(REPO, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    k = json.load(open(p)).get(kernel)
+    if not k:
+        return None
+    return (k["dram_bytes_read"] + k["dram_bytes_write"]) / k["units"] * units
+
+
 def synth_chunk(n, d, seed):
     """Config 2 data: x ~ N(mu_c, 1) from 64 cluster centres."""
     rng = np.random.default_rng(seed)
@@ -390,8 +401,8 @@ def main():
             "gpu_launches": launches,
             "k1_phase_cycles_per_sample": phases,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": "online_step_kernel",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": measured_traffic("online_step_kernel", n),
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, scaled per sample)", "peak_source": peak_src, "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": "online_step_kernel",
                          "kernel_ms_per_launch": kern_s * 1e3,
                          "note": "planes are shared-memory resident for this map, so the HBM figure is only the contract's denominator; "
                                  "on-chip bound below", "onchip_peak_gbs": onchip_peak, "onchip_frac": (achieved / onchip_peak) if onchip_peak else None},
@@ -401,7 +412,7 @@ def main():
                         "parity": "BMU ids and distances bit-identical to the exact scan (tests/test_gpu_parity.py)",
                         "fallback_rows": fallback_rows, "fallback_frac": fallback_rows / SCORE_ROWS, "gpu_launches": score_launches,
                         "roofline": {"bound": "tensor", "achieved": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12, "peak": bf16_tf, "unit": "TFLOP/s",
-                                     "frac": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12 / bf16_tf, "traffic": None,
+                                     "frac": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12 / bf16_tf, "traffic": measured_traffic("score_tc_kernel", SCORE_ROWS),
                                      "flops_per_row": 2 * SW_ * SH_ * SD_, "peak_source": peak_src + " (sustained bf16)"},
                         "exact_scan_rows_per_s": exact_rows_s, "exact_scan_rows": exact_rows * world,
                         "scaling": "row-sharded, no communication"},

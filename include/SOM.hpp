@@ -7,8 +7,9 @@
 // forward to it.  Getters read a host mirror that is refreshed from the device on demand.  There is no CPU
 // implementation of the hot path behind this class: if the CUDA library cannot run, the methods throw.
 //
-// Not carried over (batch-map trainer, (variational) auto-encoder sampling,
-// Octave-text persistence, CLI): those members are declared for source compatibility and throw
+// save / load / getSizeFromFile / Som(const char*) keep the reference's Octave-text checkpoint format byte for byte
+// (host code over the mirror).  Not carried over (batch-map trainer, (variational)
+// auto-encoder sampling, CLI): those members are declared for source compatibility and throw
 // std::logic_error("not on the B200 hot path") when called.
 #pragma once
 

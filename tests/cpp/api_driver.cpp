@@ -16,6 +16,7 @@
 #include <cstring>
 #include <iostream>
 #include <streambuf>
+#include <string>
 #include <vector>
 
 namespace
@@ -145,6 +146,44 @@ int main(int argc, char **argv)
         put(out, &bi, 1);
         put(out, &rbi, 1);
         put(out, &d, 1);
+    }
+    // persistence: the checkpoint text itself, and a map rebuilt from it
+    {
+        const std::string ckpt = std::string(argv[2]) + ".som";
+        som.save(ckpt.c_str());
+        FILE *ck = std::fopen(ckpt.c_str(), "rb");
+        std::vector<char> text;
+        char buf[4096];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof(buf), ck)) > 0)
+            text.insert(text.end(), buf, buf + got);
+        std::fclose(ck);
+        const uint64_t bytes = text.size();
+        put(out, &bytes, 1);
+        put(out, text.data(), text.size());
+        if (transform == 0) // the file constructor always installs the default (Standard) transformation
+        {
+            Som again(ckpt.c_str());
+            const uint64_t shape[3] = {again.getWidth(), again.getHeight(), again.getDepth()};
+            put(out, shape, 3);
+            for (size_t p = 0; p < N; ++p)
+            {
+                const Eigen::VectorXf m = again.getNeuron(p), s = again.getSigmaNeuron(p);
+                put(out, m.data(), static_cast<size_t>(m.size()));
+                put(out, s.data(), static_cast<size_t>(s.size()));
+            }
+            const Eigen::VectorXf w2 = again.getWeigthMap();
+            put(out, w2.data(), static_cast<size_t>(w2.size()));
+            for (size_t v : again.getBmuHits())
+            {
+                const uint64_t u = v;
+                put(out, &u, 1);
+            }
+            const UMatrix u2 = again.getUMatrix();
+            put(out, u2.getData().data(), u2.getData().size());
+            const double e2 = again.evaluate(ds2); // scoring on the reloaded (6-decimal) map
+            put(out, &e2, 1);
+        }
     }
     const double nw = Som::calculateNeighbourhoodWeight(size_t{3}, size_t{1}, size_t{1}, size_t{2}, 2.0);
     put(out, &nw, 1);

@@ -4,7 +4,8 @@ sources (oracle/_ref/api_driver_ref, CPU) and once against this repository's inc
 (tests/cpp/api_driver_b200, B200).  Same input file -> the two output files must be identical byte for byte:
 Som::train (epoch schedule, chunked DataSet protocol, metrics), getNeuron / getSigmaNeuron / getWeigthMap /
 getBmuHits, updateUMatrix + getUMatrix, evaluate, measureSimilarity, findBmu, findRestrictedBmu,
-euclidianWeightedDist, calculateNeighbourhoodWeight."""
+euclidianWeightedDist, calculateNeighbourhoodWeight, and the Octave-text checkpoint: save() (the file's bytes),
+Som(const char*) / getSizeFromFile / load() (the reloaded map and its evaluate())."""
 import os
 import struct
 import subprocess
@@ -50,13 +51,14 @@ def make_x(case):
 
 
 def expected_size(case):
+    """Fixed part of the output; the checkpoint text (variable length) and the reloaded map follow."""
     W, H, Din, tr, dec, epochs, chunk, seed, n = case[:9]
     Dm = Din * (Din - 1) if tr == 2 else Din
     N = W * H
     size = 4 * epochs + N * 2 * Dm * 4 + N * 4 + N * 8 + N * 8 + 16
     if tr != 2:
         size += 8 + 4
-    size += min(n, 16) * 24 + 8
+    size += min(n, 16) * 24
     return size
 
 
@@ -67,7 +69,7 @@ def test_reference_driver_runs_on_cpu(tmp_path, case):
         pytest.skip("oracle/_ref/api_driver_ref not built (needs /root/reference)")
     write_case(tmp_path / "case.bin", case, make_x(case))
     subprocess.run([REF_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "ref.bin")], check=True, timeout=300)
-    assert os.path.getsize(tmp_path / "ref.bin") == expected_size(case)
+    assert os.path.getsize(tmp_path / "ref.bin") > expected_size(case)
 
 
 @pytest.mark.gpu
@@ -83,7 +85,7 @@ def test_host_api_is_a_drop_in(tmp_path, vsom, case):
     subprocess.run([B200_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "b200.bin")], check=True, timeout=300)
     ref = open(tmp_path / "ref.bin", "rb").read()
     got = open(tmp_path / "b200.bin", "rb").read()
-    assert len(ref) == expected_size(case) and len(got) == len(ref)
+    assert len(ref) > expected_size(case) and len(got) == len(ref)
     if ref != got:
         a, b = np.frombuffer(ref, np.uint8), np.frombuffer(got, np.uint8)
         first = int(np.nonzero(a != b)[0][0])

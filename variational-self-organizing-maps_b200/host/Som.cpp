@@ -9,7 +9,10 @@
 #include <cassert>
 #include <cmath>
 #include <cstdlib>
+#include <cctype>
+#include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 
@@ -67,7 +70,13 @@ void Som::Construct(size_t inWidth, size_t inHeight, size_t inDepth, std::vector
     deviceIsStale = true;
 }
 
-Som::Som(const char *) : transform{} { offPath("Som(const char *filename) [Octave-text persistence]"); }
+// Som(const char*) of the reference (src/Som.cpp:51-83): size from the file, zero planes, then load().
+Som::Som(const char *filename) : transform{}
+{
+    const Eigen::VectorXf shape = getSizeFromFile(filename);
+    Construct(width, height, static_cast<size_t>(shape.size()), std::vector<std::string>{});
+    load(filename);
+}
 
 Som::Som(const Som &som)
     : transform{som.transform}, metrics{}, _isTraining{}, height{som.height}, width{som.width}, depth{som.depth}, metricsMutex{}
@@ -643,9 +652,173 @@ void Som::displayUMatrix() const
     }
 }
 
-void Som::save(const char *) const { offPath("save [Octave-text persistence]"); }
-void Som::load(const char *) { offPath("load [Octave-text persistence]"); }
-Eigen::VectorXf Som::getSizeFromFile(const char *) { offPath("getSizeFromFile [Octave-text persistence]"); }
+// ------------------------------------------------------------------------------------------------ persistence
+// Octave-text checkpoint of the reference (src/Som.cpp:1209-1294 save, :1296-1341 getSizeFromFile, :1343-1598 load).
+// Layout: sections "som" and "sigmaSom" (ndims 3: width height depth; one " %f" per line, node index fastest, then
+// dimension), then "weightMap", "bmuHits", "U" as `width` text rows of `height` tab-separated values taken from the
+// linear arrays in order (a plain reshape: "# rows" carries the WIDTH and "# columns" the HEIGHT).  SMap is not
+// persisted, %f keeps six decimals, and the reader only accepts value lines whose first significant character is a
+// digit (or '-' in the 3-D sections) — all as in the reference; the state is pulled from the device before writing
+// and pushed again after reading.
+void Som::save(const char *filename) const
+{
+    pull();
+    FILE *fp = std::fopen(filename, "w");
+    if (!fp)
+    {
+        std::cout << "Could not open file " << filename << " for writing. Quitting...\n";
+        std::exit(EXIT_FAILURE);
+    }
+    const unsigned long W = width, H = height, D = depth;
+    std::fprintf(fp, "# This file is generated by Som.exe\n# It contains all data needed to evaluate a sample according to the SOM trained by Som.exe\n");
+    auto cube = [&](const char *name, const std::vector<Eigen::VectorXf> &plane) {
+        std::fprintf(fp, "# name: %s\n# type: matrix\n# ndims: 3\n %lu %lu %lu\n", name, W, H, D);
+        for (unsigned long k = 0; k < D; ++k)
+            for (unsigned long p = 0; p < W * H; ++p)
+                std::fprintf(fp, " %f\n", plane[p](static_cast<Eigen::Index>(k)));
+    };
+    auto sheetHeader = [&](const char *name) { std::fprintf(fp, "\n\n# name: %s\n# type: matrix\n# rows: %lu\n# columns: %lu\n", name, W, H); };
+    cube("som", map);
+    std::fprintf(fp, "\n\n");
+    cube("sigmaSom", sigmaMap);
+    sheetHeader("weightMap");
+    for (unsigned long r = 0; r < W; ++r)
+    {
+        for (unsigned long c = 0; c < H; ++c)
+            std::fprintf(fp, "%f\t", weightMap[static_cast<Eigen::Index>(r * H + c)]);
+        std::fprintf(fp, "\n");
+    }
+    sheetHeader("bmuHits");
+    for (unsigned long r = 0; r < W; ++r)
+    {
+        for (unsigned long c = 0; c < H; ++c)
+            std::fprintf(fp, "%lu\t", static_cast<unsigned long>(bmuHits[r * H + c]));
+        std::fprintf(fp, "\n");
+    }
+    sheetHeader("U");
+    for (unsigned long r = 0; r < W; ++r)
+    {
+        for (unsigned long c = 0; c < H; ++c)
+            std::fprintf(fp, "%f\t", uMatrix[r * H + c]);
+        std::fprintf(fp, "\n");
+    }
+    std::fclose(fp);
+}
+
+Eigen::VectorXf Som::getSizeFromFile(const char *filename)
+{
+    std::ifstream file(filename);
+    if (!file.is_open())
+    {
+        std::cout << "Could not open file " << filename << " for reading. Quitting...\n";
+        std::exit(EXIT_FAILURE);
+    }
+    Eigen::VectorXf shape(1);
+    std::string line;
+    while (std::getline(file, line))
+    {
+        if (line.compare(0, 9, "# ndims: ") == 0)
+        {
+            std::getline(file, line); // " W H D": the vector length is the last number
+            shape.resize(static_cast<Eigen::Index>(std::stoul(line.substr(line.find_last_of(" ") + 1))));
+        }
+        else if (line.compare(0, 8, "# rows: ") == 0)
+            height = std::stoul(line.substr(8)); // sic: swapped here, swapped back by load() (reference :1327-1336)
+        else if (line.compare(0, 11, "# columns: ") == 0)
+            width = std::stoul(line.substr(11));
+    }
+    return shape;
+}
+
+void Som::load(const char *filename)
+{
+    std::ifstream file(filename);
+    if (!file.is_open() || !file.good())
+    {
+        std::cout << "Could not open file " << filename << " for reading. Quitting...\n";
+        std::exit(EXIT_FAILURE);
+    }
+    pull();
+    enum Section { None, Mean, Sigma, Weight, Hits, U } section = None;
+    auto at = [](const std::string &s, size_t i) { return i < s.size() ? s[i] : '\0'; };
+    auto digit = [](char c) { return std::isdigit(static_cast<unsigned char>(c)) != 0; };
+    unsigned k = 0, node = 0; // 3-D sections: node index runs fastest, then the dimension
+    std::string line;
+    // text rows of a 2-D sheet: `width` lines of `height` numbers each, starting at the current line
+    auto sheet = [&](auto store) {
+        for (unsigned r = 0; r < width; ++r)
+        {
+            char *cursor = const_cast<char *>(line.c_str());
+            for (unsigned c = 0; c < height; ++c)
+                store(r * height + c, cursor);
+            std::getline(file, line);
+        }
+    };
+    while (!file.eof())
+    {
+        std::getline(file, line);
+        if (at(line, 0) == '#')
+        {
+            if (line.compare(0, 8, "# name: ") == 0)
+            {
+                const std::string name = line.substr(8, 20);
+                if (name == "som")
+                    section = Mean;
+                else if (name == "sigmaSom")
+                    section = Sigma;
+                else if (name == "weightMap")
+                    section = Weight;
+                else if (name == "bmuHits")
+                    section = Hits;
+                else if (name == "U")
+                    section = U;
+                else
+                {
+                    std::cout << "No name for vector in SOM file!\n";
+                    std::exit(EXIT_FAILURE);
+                }
+            }
+            else if (line.compare(0, 8, "# type: ") == 0)
+            {
+                if (line.compare(8, 20, "matrix") != 0)
+                {
+                    std::cout << "Incorrect type in SOM file!\n";
+                    std::exit(EXIT_FAILURE);
+                }
+            }
+            else if (line.compare(0, 9, "# ndims: ") == 0)
+                std::getline(file, line); // the shape line was consumed by getSizeFromFile
+            else if (line.compare(0, 8, "# rows: ") == 0)
+                width = std::stoul(line.substr(8));
+            else if (line.compare(0, 11, "# columns: ") == 0)
+                height = std::stoul(line.substr(11));
+            continue;
+        }
+        if ((section == Mean || section == Sigma) && (digit(at(line, 1)) || at(line, 1) == '-'))
+        {
+            auto &plane = section == Mean ? map : sigmaMap;
+            plane[node](static_cast<Eigen::Index>(k)) = static_cast<float>(std::stod(line));
+            if (++node >= height * width)
+            {
+                node = 0;
+                if (++k >= static_cast<unsigned>(plane[0].size()))
+                {
+                    k = 0;
+                    section = None;
+                }
+            }
+        }
+        else if (section == Weight && digit(at(line, 0)))
+            sheet([&](unsigned i, char *&cur) { weightMap(static_cast<Eigen::Index>(i)) = static_cast<float>(std::strtod(cur, &cur)); });
+        else if (section == Hits && digit(at(line, 0)))
+            sheet([&](unsigned i, char *&cur) { bmuHits[i] = std::strtoul(cur, &cur, 10); });
+        else if (section == U && digit(at(line, 0)))
+            sheet([&](unsigned i, char *&cur) { uMatrix[i] = std::strtod(cur, &cur); });
+    }
+    device.reset(); // the file may carry another shape: the next device call builds a fresh context from the mirror
+    hostIsStale = false;
+    deviceIsStale = true;
+}
 
 // reference src/Som.cpp:949-975, same division order; host libm exp() like the kernel's table builder
 double Som::calculateNeighbourhoodWeight(const size_t &currentX, const size_t &currentY, const size_t &bmuX, const size_t &bmuY,
