@@ -138,6 +138,12 @@ VSOM_API int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double et
 VSOM_API int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n, double eta, double sigma, int decay,
                             uint32_t *out_bmu_dev, float *out_dist_dev);
 
+/* One chunk-epoch of the batch-map trainer: Som::trainBatchSomEpoch (src/Som.cpp:756-879).  Phase A finds every row's BMU
+ * (is_first != 0: global search; else the local walk from last_bmu[row]), counts the hits and returns the mean squared
+ * residual in *out_mse; phase B replaces every neuron by the incrementally weighted mean of all rows of the chunk (and its
+ * sigma and weight).  last_bmu is in/out per row; x is n x d_in row-major on the host. */
+VSOM_API int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double sigma, int is_first, uint64_t *last_bmu, float *out_mse);
+
 /* -------------------------------------------------------------------------------- scoring */
 
 /* Per row: Som::findBmu (min_hits == 0, src/Som.cpp:291-309) or Som::findRestrictedBmu (src/Som.cpp:313-332),

@@ -98,6 +98,14 @@ class _Base:
                     C.c_double(sigma0), C.c_double(sigma_decay), int(decay), int(bool(umatrix_after_epoch)), _p(mse, _f32p))
         return mse
 
+    def train_batch(self, x, chunk_rows, epochs, sigma0, sigma_decay, umatrix_after_epoch=False):
+        """Som::train(..., BatchMap) — the batch-map trainer (src/Som.cpp:716-879)."""
+        x = _f32(x).reshape(-1, self.Din)
+        mse = np.zeros(epochs, np.float32)
+        self._train_batch(self._h, _p(x, _f32p), x.shape[0], int(chunk_rows), int(epochs), C.c_double(sigma0), C.c_double(sigma_decay),
+                          int(bool(umatrix_after_epoch)), _p(mse, _f32p))
+        return mse
+
     # -- scoring -------------------------------------------------------------------------
     def find_bmu(self, x):
         x = _f32(x).reshape(-1, self.Din)
@@ -182,6 +190,8 @@ class Oracle(_Base):
             _sig(L.oracle_find_restricted_bmd, None, [vp, _f32p, C.c_uint64, _f64p])
             _sig(L.oracle_train_rows, None, [vp, _f32p, C.c_size_t, C.c_double, C.c_double, C.c_int, _u64p, _u32p, _f32p, _f32p])
             _sig(L.oracle_train, None, [vp, _f32p, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_double] * 4 + [C.c_int, C.c_int, _f32p])
+            _sig(L.oracle_train_batch, None, [vp, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_int, _f32p])
+            _sig(L.oracle_batch_epoch, C.c_float, [vp, _f32p, C.c_size_t, C.c_double, C.c_int, _u64p])
             _sig(L.oracle_evaluate, C.c_double, [vp, _f32p, C.c_size_t])
             _sig(L.oracle_measure_similarity, C.c_int, [vp, _f32p, C.c_size_t, C.c_int, C.c_uint64])
             _sig(L.oracle_update_umatrix, None, [vp, _f64p])
@@ -197,6 +207,7 @@ class Oracle(_Base):
         self._get_state, self._set_state = L.oracle_get_state, L.oracle_set_state
         self._random_initialize = L.oracle_random_initialize
         self._train_rows, self._train = L.oracle_train_rows, L.oracle_train
+        self._train_batch = L.oracle_train_batch
         self._find_bmu, self._all_dists = L.oracle_find_bmu, L.oracle_all_dists
         self._find_local_bmu = L.oracle_find_local_bmu
         self._find_restricted_bmu, self._find_restricted_bmd = L.oracle_find_restricted_bmu, L.oracle_find_restricted_bmd
@@ -207,6 +218,12 @@ class Oracle(_Base):
         if getattr(self, "_h", None):
             self.lib().oracle_destroy(self._h)
             self._h = None
+
+    def batch_epoch(self, x, sigma, is_first, last_bmu=None):
+        x = _f32(x).reshape(-1, self.Din)
+        last = np.zeros(x.shape[0], np.uint64) if last_bmu is None else np.ascontiguousarray(last_bmu, dtype=np.uint64).copy()
+        mse = self.lib().oracle_batch_epoch(self._h, _p(x, _f32p), x.shape[0], C.c_double(sigma), int(bool(is_first)), _p(last, _u64p))
+        return float(np.float32(mse)), last
 
     def all_dists_f64(self, v):
         """Same f32 residuals, f64 accumulation — the near-tie classifier."""
@@ -260,7 +277,7 @@ class Reference(_Base):
             _sig(L.ref_update_umatrix, None, [vp, _f64p])
             _sig(L.ref_dist_raw, C.c_double, [vp, C.c_uint64, _f32p])
             _sig(L.ref_neighbourhood_weight, C.c_double, [C.c_uint64] * 4 + [C.c_double])
-            _sig(L.ref_train_batch, None, [vp, _f32p, C.c_size_t, C.c_size_t, C.c_double, C.c_double, _f32p])
+            _sig(L.ref_train_batch, None, [vp, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double, C.c_double, C.c_int, _f32p])
             _sig(L.ref_eigen_kind, C.c_char_p, [])
             cls._lib = L
         return cls._lib
@@ -273,6 +290,7 @@ class Reference(_Base):
         self._get_state, self._set_state = L.ref_get_state, L.ref_set_state
         self._random_initialize = L.ref_random_initialize
         self._train_rows, self._train = L.ref_train_rows, L.ref_train
+        self._train_batch = L.ref_train_batch
         self._find_bmu, self._all_dists = L.ref_find_bmu, L.ref_all_dists
         self._find_local_bmu = L.ref_find_local_bmu
         self._find_restricted_bmu, self._find_restricted_bmd = L.ref_find_restricted_bmu, L.ref_find_restricted_bmd

@@ -318,13 +318,14 @@ extern "C"
         return Som::calculateNeighbourhoodWeight(a, b, c, d, sigma);
     }
     // Batch-map trainer (src/Som.cpp:716-879) — a "next" row; exposed so a later round can pin it.
-    void ref_train_batch(void *h, const float *x, size_t n, size_t epochs, double sigma0, double sigmaDecay, float *outMse)
+    void ref_train_batch(void *h, const float *x, size_t n, size_t chunkRows, size_t epochs, double sigma0, double sigmaDecay, int umatrixAfterEpoch,
+                         float *outMse)
     {
         Quiet q;
         auto *s = static_cast<RefSom *>(h);
-        MemLoader loader(x, n, static_cast<size_t>(s->dIn), n);
+        MemLoader loader(x, n, static_cast<size_t>(s->dIn), chunkRows);
         DataSet ds(loader);
-        s->train(ds, epochs, 0.0, 0.0, sigma0, sigmaDecay, Som::WeigthDecayFunction::BatchMap, false);
+        s->train(ds, epochs, 0.0, 0.0, sigma0, sigmaDecay, Som::WeigthDecayFunction::BatchMap, umatrixAfterEpoch != 0);
         if (outMse)
         {
             auto m = s->mse();

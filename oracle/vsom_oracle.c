@@ -542,6 +542,123 @@ void oracle_train(vsom_oracle *o, const float *x, size_t n, size_t chunkRows, si
     free(last);
 }
 
+/* ---------------------------------------------------------------- batch-map trainer */
+
+static void quirky_xy(const vsom_oracle *o, uint64_t index, uint64_t *x, uint64_t *y)
+{
+    /* SomIndex(const Som&, index) — src/SomIndex.cpp:15-18: y divides by the map HEIGHT (only right for square maps). */
+    *x = index % (uint64_t)o->W;
+    *y = (index - index % (uint64_t)o->W) / (uint64_t)o->H;
+}
+
+float oracle_batch_epoch(vsom_oracle *o, const float *x, size_t n, double sigma, int isFirst, uint64_t *lastBMU)
+{
+    /* Som::trainBatchSomEpoch — src/Som.cpp:756-879, with the serial execution order the reference has when its
+     * parallel algorithms run on the sequential backend (no TBB): rows in order, then neurons in order. */
+    const int Dm = o->Dm;
+    float mse = 0.0f;
+    float *r = (float *)malloc(sizeof(float) * (size_t)(Dm > 0 ? Dm : 1));
+    /* phase A (:763-806): BMU per row (global on the first epoch, local walk from lastBMU afterwards), hit count,
+     * mean squared residual accumulated in f32 in row order */
+    for (size_t j = 0; j < n; ++j)
+    {
+        const float *v = x + j * (size_t)o->Din;
+        uint32_t idx = isFirst ? oracle_find_bmu_one(o, v) : oracle_find_local_bmu(o, v, lastBMU[j]);
+        lastBMU[j] = idx;
+        o->hits[idx] += 1;
+        int len = comparer(o, v, o->mean + (size_t)idx * (size_t)Dm, r);
+        float s = 0.0f;
+        for (int k = 0; k < len; ++k)
+        {
+            float sq = r[k] * r[k];
+            s = s + sq;
+        }
+        mse = mse + s / (float)n;
+    }
+    /* phase B (:809-877): every neuron re-estimates its model as the incrementally weighted mean of ALL rows
+     * (West / Finch), weights = neighbourhood of the row's BMU, and its sigma from the weighted squared steps */
+    float *cur = (float *)malloc(sizeof(float) * (size_t)(Dm > 0 ? Dm : 1));
+    float *S = (float *)malloc(sizeof(float) * (size_t)(Dm > 0 ? Dm : 1));
+    float *delta = (float *)malloc(sizeof(float) * (size_t)(Dm > 0 ? Dm : 1));
+    float *newMean = (float *)malloc(sizeof(float) * (size_t)o->N * (size_t)(Dm > 0 ? Dm : 1));
+    for (int p = 0; p < o->N; ++p)
+    {
+        uint64_t cx, cy;
+        quirky_xy(o, (uint64_t)p, &cx, &cy);
+        float sumW = 0.f;
+        for (int k = 0; k < Dm; ++k)
+        {
+            cur[k] = 0.0f;
+            S[k] = 0.0f;
+        }
+        for (size_t j = 0; j < n; ++j)
+        {
+            uint64_t bx, by;
+            quirky_xy(o, lastBMU[j], &bx, &by);
+            float w = (float)oracle_neighbourhood_weight(cx, cy, bx, by, sigma);
+            sumW = sumW + w;                                        /* Eq. 47 */
+            stepper(o, x + j * (size_t)o->Din, cur, delta);         /* Stepper(x, currentModel) == Stepper(x, lastModel) */
+            float c = w / sumW;
+            for (int k = 0; k < Dm; ++k)
+            {
+                float d = delta[k];
+                float t = c * d;
+                cur[k] = cur[k] + t;                                /* Eq. 53 */
+                float wd = w * d;
+                float wdd = wd * d;
+                S[k] = S[k] + wdd;                                  /* Eq. 68: w * Stepper(x, last) * delta, left to right */
+            }
+        }
+        for (int k = 0; k < Dm; ++k)
+        {
+            newMean[(size_t)p * (size_t)Dm + (size_t)k] = cur[k];
+            float q = S[k] / sumW;
+            o->sigma[(size_t)p * (size_t)Dm + (size_t)k] = sqrtf(q); /* Eq. 69, no abs */
+        }
+        o->weight[p] = sumW;
+    }
+    /* neurons are independent of each other's new value (they only read the rows), so writing them at the end equals
+     * the reference's in-place assignment */
+    memcpy(o->mean, newMean, sizeof(float) * (size_t)o->N * (size_t)Dm);
+    free(newMean);
+    free(delta);
+    free(S);
+    free(cur);
+    free(r);
+    return mse;
+}
+
+void oracle_train_batch(vsom_oracle *o, const float *x, size_t n, size_t chunkRows, size_t epochs, double sigma0, double sigmaDecay,
+                        int umatrixAfterEpoch, float *outMse)
+{
+    /* Som::trainBatchSom — src/Som.cpp:716-754: returns (not continues) as soon as sigma < 1; lastBMU is zeroed by
+     * every chunk load (src/DataSet.cpp:136-137). */
+    if (chunkRows == 0 || chunkRows > n)
+        chunkRows = n;
+    uint64_t *last = (uint64_t *)malloc(sizeof(uint64_t) * (chunkRows ? chunkRows : 1));
+    for (size_t e = 0; e < epochs; ++e)
+    {
+        double sigma = sigma0 * exp(-sigmaDecay * (double)e);
+        if (sigma < 1.0)
+            break;
+        float mse = 0.0f;
+        size_t chunks = 0;
+        for (size_t begin = 0; begin < n; begin += chunkRows)
+        {
+            size_t rows = n - begin < chunkRows ? n - begin : chunkRows;
+            memset(last, 0, sizeof(uint64_t) * rows);
+            mse += oracle_batch_epoch(o, x + begin * (size_t)o->Din, rows, sigma, e == 0, last);
+            ++chunks;
+        }
+        mse /= (float)chunks;
+        if (outMse)
+            outMse[e] = mse;
+        if (umatrixAfterEpoch)
+            oracle_update_umatrix(o, NULL);
+    }
+    free(last);
+}
+
 /* ---------------------------------------------------------------- scoring */
 
 double oracle_evaluate(const vsom_oracle *o, const float *x, size_t n)

@@ -60,6 +60,10 @@ void oracle_train_rows(vsom_oracle *o, const float *x, size_t n, double eta, dou
                        uint32_t *outBmu, float *outDist, float *outResid2);
 void oracle_train(vsom_oracle *o, const float *x, size_t n, size_t chunkRows, size_t epochs, double eta0, double etaDecay,
                   double sigma0, double sigmaDecay, int decay, int umatrixAfterEpoch, float *outMse);
+/* Batch-map trainer (a "next" row): one chunk-epoch, and the whole trainBatchSom schedule. */
+float oracle_batch_epoch(vsom_oracle *o, const float *x, size_t n, double sigma, int isFirst, uint64_t *lastBMU);
+void oracle_train_batch(vsom_oracle *o, const float *x, size_t n, size_t chunkRows, size_t epochs, double sigma0, double sigmaDecay,
+                        int umatrixAfterEpoch, float *outMse);
 double oracle_evaluate(const vsom_oracle *o, const float *x, size_t n);
 int oracle_measure_similarity(const vsom_oracle *o, const float *x, size_t n, int numSigmas, uint64_t minHits);
 void oracle_update_umatrix(vsom_oracle *o, double *out);

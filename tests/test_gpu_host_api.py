@@ -29,6 +29,9 @@ CASES = [
     (9, 7, 12, 0, 0, 7, 50, 42, 130, 0.3, 0.2, 2.5, 0.4),
     (11, 8, 16, 1, 1, 6, 33, 5, 100, 0.05, 0.1, 1.8, 0.5),
     (6, 7, 5, 2, 0, 5, 0, 2, 90, 0.01, 0.1, 1.5, 0.6),
+    # decay 2 = WeigthDecayFunction::BatchMap: Som::train dispatches to the batch-map trainer
+    (8, 8, 12, 0, 2, 5, 50, 42, 130, 0.0, 0.0, 3.0, 0.35),
+    (7, 5, 9, 1, 2, 4, 0, 9, 80, 0.0, 0.0, 2.0, 0.2),
 ]
 
 

@@ -280,3 +280,28 @@ def test_tensor_core_scoring_ties_and_overflow_take_the_exact_scan(vsom):
     assert_bit_equal(td, ed, "dist")
     assert fb > 0
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ K6 (batch-map trainer)
+@pytest.mark.parametrize("shape", [(6, 6, 11, 0, 90), (7, 4, 11, 1, 90), (4, 9, 5, 2, 70), (20, 20, 784, 0, 60), (33, 17, 100, 1, 300),
+                                   (12, 12, 32, 2, 150), (64, 64, 128, 0, 1500)])
+def test_batch_map_epochs_match_oracle_bit_exact(vsom, po, shape):
+    """Som::trainBatchSom's loop over chunk-epochs (global BMU on the first epoch, local walks from node 0 afterwards,
+    every neuron re-estimated from all rows) — bit-exact planes, hits, MSE and lastBMU against the oracle."""
+    W, H, Din, tr, n = shape
+    rng = np.random.default_rng(W * H + Din)
+    o = po.Oracle(W, H, Din, tr)
+    o.random_initialize(3, 1.0)
+    ctx = vsom.VsomContext(W, H, Din, tr)
+    upload_like(ctx, o.get_state())
+    x = synth(rng, n, Din, tr)
+    chunk = n // 2 + 3
+    for epoch, sigma in enumerate((3.0, 2.0, 1.2, 1.0)):
+        for lo in range(0, n, chunk):
+            seg = x[lo:lo + chunk]
+            om, ol = o.batch_epoch(seg, sigma, epoch == 0)   # lastBMU zeroed per chunk load, like DataSet
+            gm, gl = ctx.batch_epoch(seg, sigma, epoch == 0)
+            assert np.float32(gm).view(np.uint32) == np.float32(om).view(np.uint32), f"mse epoch {epoch}"
+            assert np.array_equal(gl, ol), f"lastBMU epoch {epoch}"
+            assert_state_equal(ctx, o.get_state(), f"epoch {epoch} sigma {sigma}")
+    ctx.close()

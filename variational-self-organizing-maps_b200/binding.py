@@ -41,6 +41,7 @@ _PROTOS = {
     "vsom_get_node": (C.c_int, [_vp, C.c_size_t, _f32p, _f32p]),
     "vsom_train_chunk": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_double, C.c_double, C.c_int, _u64p, _u32p, _f32p, _f32p]),
     "vsom_train_chunk_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_double, C.c_double, C.c_int, _vp, _vp]),
+    "vsom_batch_epoch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_double, C.c_int, _u64p, _f32p]),
     "vsom_find_bmu": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
     "vsom_find_bmu_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
     "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
@@ -178,6 +179,15 @@ class VsomContext:
         self._check(lib().vsom_train_chunk_device(self._h, x_dev.data_ptr(), n, eta, sigma, decay,
                                                   out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
                                                   out_dist_dev.data_ptr() if out_dist_dev is not None else None))
+
+    def batch_epoch(self, x, sigma, is_first, last_bmu=None):
+        """One chunk-epoch of the batch-map trainer; returns (mse, last_bmu)."""
+        x = _f32(x).reshape(-1, self.Din)
+        n = x.shape[0]
+        last = np.zeros(n, np.uint64) if last_bmu is None else np.ascontiguousarray(last_bmu, dtype=np.uint64).copy()
+        mse = C.c_float(0)
+        self._check(lib().vsom_batch_epoch(self._h, _p(x, _f32p), n, sigma, int(bool(is_first)), _p(last, _u64p), C.byref(mse)))
+        return float(np.float32(mse.value)), last
 
     # ---- scoring
     def find_bmu(self, x, min_hits=0):

@@ -438,6 +438,55 @@ int vsom_train_chunk(vsom_ctx *ctx, const float *x, size_t n, double eta, double
     return VSOM_OK;
 }
 
+int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double sigma, int is_first, uint64_t *last_bmu, float *out_mse)
+{
+    if (!ctx || (!x && n) || (!last_bmu && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_batch_epoch: NULL argument") : VSOM_ERR_INVALID;
+    if (out_mse)
+        *out_mse = 0.0f;
+    if (n == 0)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 2, sizeof(float) * n);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 3, sizeof(u64) * n);
+    if (rc)
+        return rc;
+    float *xDev = static_cast<float *>(ctx->stage[0]);
+    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
+    float *distDev = static_cast<float *>(ctx->stage[2]);
+    u64 *lastDev = static_cast<u64 *>(ctx->stage[3]);
+    for (size_t r = 0; r < n; ++r)
+        if (last_bmu[r] >= static_cast<uint64_t>(ctx->N))
+            return set_error(ctx, VSOM_ERR_INVALID, "vsom_batch_epoch: last_bmu out of range");
+    VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(lastDev, last_bmu, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_batch_epoch(ctx, xDev, n, sigma, is_first, lastDev, bmuDev, distDev);
+    if (rc)
+        return rc;
+    std::vector<unsigned> bmu(n);
+    std::vector<float> dist(n);
+    VSOM_CUDA(ctx, cudaMemcpyAsync(bmu.data(), bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(dist.data(), distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float mse = 0.0f;
+    for (size_t r = 0; r < n; ++r)
+    {
+        last_bmu[r] = bmu[r];                       // :777 / :800
+        mse = mse + dist[r] / static_cast<float>(n); // :781 / :804, f32, row order
+    }
+    if (out_mse)
+        *out_mse = mse;
+    return VSOM_OK;
+}
+
 int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev)
 {
     if (ctx && ctx->world > 1)

@@ -282,8 +282,50 @@ void Som::trainBasicSom(DataSet &data, size_t numberOfEpochs, double eta0, doubl
     }
 }
 
-void Som::trainBatchSom(DataSet &, size_t, double, double, bool) { offPath("trainBatchSom"); }
-float Som::trainBatchSomEpoch(DataSet &, double, bool) { offPath("trainBatchSomEpoch"); }
+// Batch-map trainer (reference src/Som.cpp:716-754): sigma schedule without clamp — the run RETURNS at the first epoch
+// whose sigma drops below 1 — one trainBatchSomEpoch per loaded chunk, MSE averaged over the chunks of the epoch.
+void Som::trainBatchSom(DataSet &data, size_t numberOfEpochs, double sigma0, double sigmaDecay, bool updateUMatrixAfterEpoch)
+{
+    metrics = Metrics(numberOfEpochs);
+    for (size_t epoch = 0; epoch < numberOfEpochs; ++epoch)
+    {
+        const double sigma = sigma0 * std::exp(-sigmaDecay * static_cast<double>(epoch));
+        if (sigma < 1.0)
+            return;
+        float meanSquareError{0.0f};
+        size_t chunks{0};
+        while (!data.hasReadWholeDataStream())
+        {
+            data.loadNextDataFromStream();
+            meanSquareError += trainBatchSomEpoch(data, sigma, epoch == 0);
+            ++chunks;
+        }
+        meanSquareError /= static_cast<float>(chunks);
+        {
+            const std::lock_guard<std::mutex> lock(metricsMutex);
+            metrics.MeanSquaredError[epoch] = meanSquareError;
+        }
+        data.resetStreamLoadPosition();
+        if (updateUMatrixAfterEpoch)
+            updateUMatrix(data.getWeights());
+    }
+}
+
+// One chunk-epoch on the device (K6, csrc/batch_map.cu): BMU per row, hits, squared residuals, then every neuron's
+// incrementally weighted mean / variance over the chunk's rows (reference src/Som.cpp:756-879).
+float Som::trainBatchSomEpoch(DataSet &data, double currentSigma, bool isFirst)
+{
+    vsom_ctx *ctx = context();
+    auto &lastColumn = data.lastBmuColumn();
+    std::vector<uint64_t> last(lastColumn.begin(), lastColumn.end());
+    float mse = 0.0f;
+    if (vsom_batch_epoch(ctx, data.contiguousRows(), data.size(), currentSigma, isFirst ? 1 : 0, last.data(), &mse) != VSOM_OK)
+        fail(ctx, "Som::trainBatchSomEpoch");
+    hostIsStale = true;
+    for (size_t j = 0; j < last.size(); ++j)
+        lastColumn[j] = static_cast<size_t>(last[j]);
+    return mse;
+}
 
 Som::TrainingReturnValue Som::trainSingle(const Eigen::VectorXf &v, const Eigen::VectorXf &valid, const Eigen::VectorXf &weights, const double eta,
                                           const double sigma, size_t &lastBMU, const WeigthDecayFunction weightDecayFunction)
