@@ -303,5 +303,15 @@ def test_batch_map_epochs_match_oracle_bit_exact(vsom, po, shape):
             gm, gl = ctx.batch_epoch(seg, sigma, epoch == 0)
             assert np.float32(gm).view(np.uint32) == np.float32(om).view(np.uint32), f"mse epoch {epoch}"
             assert np.array_equal(gl, ol), f"lastBMU epoch {epoch}"
-            assert_state_equal(ctx, o.get_state(), f"epoch {epoch} sigma {sigma}")
+            # at sigma == 1.0 the neighbourhood is a delta: a neuron that is nobody's BMU divides 0 by 0 and becomes NaN in
+            # the reference too; NaN payload / sign bits are not part of the contract (x86 gives 0xFFC00000, the GPU
+            # 0x7FFFFFFF), every other value must match bit for bit
+            got, want = ctx.download_state(), o.get_state()
+            for k in ("mean", "S", "sigma", "weight"):
+                g, w = got[k].copy(), want[k].copy()
+                assert np.array_equal(np.isnan(g), np.isnan(w)), f"{k}: NaN pattern differs (epoch {epoch})"
+                g[np.isnan(g)] = 0
+                w[np.isnan(w)] = 0
+                assert_bit_equal(g, w, f"epoch {epoch} sigma {sigma}: {k}")
+            assert_bit_equal(got["hits"], want["hits"], "hits")
     ctx.close()
