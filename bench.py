@@ -257,6 +257,7 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
     launches = ctx.launch_count - launches0
+    k1_name = "online_step_fast_kernel" if ctx.last_train_fast else "online_step_kernel"
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=x_dev.device)
@@ -270,6 +271,8 @@ def main():
     ctx.train_chunk_device(x_dev, min(n, 100_000), ETA, SIGMA, vsom.EXPONENTIAL, out_bmu, out_dist)
     ctx.synchronize()
     phases = ctx.debug_phase_cycles()
+    phases_raw = ctx.debug_phase_cycles_raw()
+    die_aware = ctx.die_aware
     ctx.debug_profile(False)
 
     # ---------------- e2e: host buffers through the reference-facing C-ABI call, copies inside the timed region
@@ -399,10 +402,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": n * D_ * 4, "d2h_bytes_per_step": n * 12, "steps": e2e_steps,
                     "result_read": "per-sample BMU, distance, residual^2 + MSE on host", "mse": mse},
             "gpu_launches": launches,
-            "k1_phase_cycles_per_sample": phases,
+            "k1_phase_cycles_per_sample": phases, "k1_phase_cycles_raw": phases_raw, "k1_exchange_rows_by_l2_die": die_aware,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": measured_traffic("online_step_kernel", n),
-                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, scaled per sample)", "peak_source": peak_src, "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": "online_step_kernel",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": measured_traffic(k1_name, n),
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, scaled per sample)", "peak_source": peak_src, "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": k1_name,
                          "kernel_ms_per_launch": kern_s * 1e3,
                          "note": "planes are shared-memory resident for this map, so the HBM figure is only the contract's denominator; "
                                  "on-chip bound below", "onchip_peak_gbs": onchip_peak, "onchip_frac": (achieved / onchip_peak) if onchip_peak else None},

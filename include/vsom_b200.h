@@ -110,7 +110,16 @@ VSOM_API int vsom_planes_resident(const vsom_ctx *ctx);
  * five phases of each sample (wait-for-sample, scan + CTA min, grid-wide min-loc exchange, broadcast barrier,
  * window update); vsom_debug_phase_cycles returns their mean over CTAs in cycles per sample for the last chunk. */
 VSOM_API int vsom_debug_profile(vsom_ctx *ctx, int enable);
+/* Which kernel the last vsom_train_chunk[_device] call ran: 1 = K1F (online_step_fast.cu: Standard / Median, reference
+ * order, planes resident in shared memory, sigma > 1, one GPU), 0 = the generic online-step kernel.  The environment
+ * variable VSOM_ONLINE_KERNEL=generic, read by vsom_create, keeps a context on the generic kernel (A/B measurements). */
+VSOM_API int vsom_debug_last_train_fast(const vsom_ctx *ctx);
 VSOM_API int vsom_debug_phase_cycles(vsom_ctx *ctx, double out[5]);
+/* The unfolded slots of the last launch.  K1F: chain, CTA min, exchange, coefficients, barrier, update, barrier, 0;
+ * generic kernel: the five phases above, then zeros. */
+VSOM_API int vsom_debug_phase_cycles_raw(vsom_ctx *ctx, double out[8]);
+/* 1 when K1F's exchange rows were placed by L2 die (the SM -> die and block -> die maps were measured and are clean). */
+VSOM_API int vsom_debug_die_aware(const vsom_ctx *ctx);
 
 /* Replace / read the model state: Som::map, SMap, sigmaMap, weightMap, bmuHits (include/SOM.hpp:56-61).
  * Any pointer may be NULL (skipped).  Initial planes come from the host (Som::randomInitialize,

@@ -35,6 +35,9 @@ _PROTOS = {
     "vsom_launch_count": (C.c_uint64, [_vp]),
     "vsom_planes_resident": (C.c_int, [_vp]),
     "vsom_debug_profile": (C.c_int, [_vp, C.c_int]),
+    "vsom_debug_last_train_fast": (C.c_int, [_vp]),
+    "vsom_debug_phase_cycles_raw": (C.c_int, [_vp, _f64p]),
+    "vsom_debug_die_aware": (C.c_int, [_vp]),
     "vsom_debug_phase_cycles": (C.c_int, [_vp, _f64p]),
     "vsom_upload_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
     "vsom_download_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
@@ -269,6 +272,24 @@ class VsomContext:
         out = np.zeros(5, np.float64)
         self._check(lib().vsom_debug_phase_cycles(self._h, _p(out, _f64p)))
         return dict(zip(("wait_sample", "scan_min", "exchange", "broadcast", "update"), out.tolist()))
+
+    def debug_phase_cycles_raw(self):
+        out = np.zeros(8, np.float64)
+        self._check(lib().vsom_debug_phase_cycles_raw(self._h, _p(out, _f64p)))
+        if self.last_train_fast:
+            names = ("chain", "cta_min", "exchange", "coefficients", "barrier1", "update", "barrier2")
+        else:
+            names = ("wait_sample", "scan_min", "exchange", "broadcast", "update")
+        return dict(zip(names, out.tolist()))
+
+    @property
+    def die_aware(self) -> bool:
+        return bool(lib().vsom_debug_die_aware(self._h))
+
+    @property
+    def last_train_fast(self) -> bool:
+        """True when the last train_chunk ran K1F (online_step_fast.cu) rather than the generic online-step kernel."""
+        return bool(lib().vsom_debug_last_train_fast(self._h))
 
     # ---- plumbing
     def synchronize(self):

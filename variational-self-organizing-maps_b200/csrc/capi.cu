@@ -2,6 +2,8 @@
 // host-buffer entry points that stage data through the context's stream around the kernel launchers.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -130,6 +132,11 @@ static int create_impl(vsom_ctx **out, int device, int width, int height, int d_
         return fail(VSOM_ERR_NO_DEVICE);
     }
     ctx->numSMs = prop.multiProcessorCount;
+    {
+        // diagnostics / A-B measurements: VSOM_ONLINE_KERNEL=generic keeps every online step on the generic kernel
+        const char *e = getenv("VSOM_ONLINE_KERNEL");
+        ctx->fastDisabled = (e && std::string(e) == "generic") ? 1 : 0;
+    }
     ctx->smemOptin = static_cast<int>(prop.sharedMemPerBlockOptin);
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     const size_t plane = sizeof(float) * static_cast<size_t>(ctx->localN) * ctx->rowStride;
@@ -249,6 +256,9 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->errFlag);
     cudaFree(ctx->lut);
     cudaFree(ctx->distBuf);
+    cudaFree(ctx->winTab);
+    cudaFree(ctx->rowPool);
+    cudaFree(ctx->rowMeta);
     cudaFree(ctx->profDev);
     for (void *p : ctx->stage)
         cudaFree(p);
@@ -264,6 +274,8 @@ void *vsom_stream(const vsom_ctx *ctx) { return ctx ? static_cast<void *>(ctx->s
 uint64_t vsom_launch_count(const vsom_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int vsom_planes_resident(const vsom_ctx *ctx) { return ctx ? ctx->residentTrain : 0; }
 
+int vsom_debug_last_train_fast(const vsom_ctx *ctx) { return ctx ? ctx->lastTrainFast : 0; }
+
 int vsom_debug_profile(vsom_ctx *ctx, int enable)
 {
     if (!ctx)
@@ -272,8 +284,8 @@ int vsom_debug_profile(vsom_ctx *ctx, int enable)
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (enable && !ctx->profDev)
     {
-        VSOM_CUDA(ctx, cudaMalloc(&ctx->profDev, sizeof(long long) * 5 * ctx->numSMs));
-        VSOM_CUDA(ctx, cudaMemset(ctx->profDev, 0, sizeof(long long) * 5 * ctx->numSMs));
+        VSOM_CUDA(ctx, cudaMalloc(&ctx->profDev, sizeof(long long) * 8 * ctx->numSMs));
+        VSOM_CUDA(ctx, cudaMemset(ctx->profDev, 0, sizeof(long long) * 8 * ctx->numSMs));
     }
     else if (!enable && ctx->profDev)
     {
@@ -283,25 +295,58 @@ int vsom_debug_profile(vsom_ctx *ctx, int enable)
     return VSOM_OK;
 }
 
+// raw per-phase cycle sums of the last online-step launch, averaged over CTAs, per sample: the generic kernel fills
+// 5 slots (stride 5), K1F 7 (stride 8)
+static int read_phase_cycles(vsom_ctx *ctx, double raw[8])
+{
+    if (!ctx->profDev || !ctx->profSamples || !ctx->gridTrain)
+        return set_error(ctx, VSOM_ERR_INVALID, "vsom_debug_phase_cycles: profiling not enabled or no chunk trained yet");
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int stride = ctx->lastTrainFast ? 8 : 5, grid = ctx->lastTrainFast ? ctx->fastGrid : ctx->gridTrain;
+    std::vector<long long> h(static_cast<size_t>(stride) * grid);
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpy(h.data(), ctx->profDev, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i)
+    {
+        double s = 0;
+        for (int b = 0; i < stride && b < grid; ++b)
+            s += static_cast<double>(h[static_cast<size_t>(b) * stride + i]);
+        raw[i] = s / grid / static_cast<double>(ctx->profSamples);
+    }
+    return VSOM_OK;
+}
+
 int vsom_debug_phase_cycles(vsom_ctx *ctx, double out[5])
 {
     if (!ctx || !out)
         return VSOM_ERR_INVALID;
-    if (!ctx->profDev || !ctx->profSamples || !ctx->gridTrain)
-        return set_error(ctx, VSOM_ERR_INVALID, "vsom_debug_phase_cycles: profiling not enabled or no chunk trained yet");
-    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<long long> h(static_cast<size_t>(5) * ctx->gridTrain);
-    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    VSOM_CUDA(ctx, cudaMemcpy(h.data(), ctx->profDev, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 5; ++i)
+    double raw[8];
+    int rc = read_phase_cycles(ctx, raw);
+    if (rc)
+        return rc;
+    if (ctx->lastTrainFast)
     {
-        double s = 0;
-        for (int b = 0; b < ctx->gridTrain; ++b)
-            s += static_cast<double>(h[static_cast<size_t>(b) * 5 + i]);
-        out[i] = s / ctx->gridTrain / static_cast<double>(ctx->profSamples);
+        // K1F has no wait-for-sample phase; fold its seven slots into the five documented ones
+        out[0] = 0.0;
+        out[1] = raw[0] + raw[1]; // FADD chain + CTA min
+        out[2] = raw[2];          // grid-wide exchange
+        out[3] = raw[3] + raw[4]; // coefficients + barrier
+        out[4] = raw[5] + raw[6]; // update (+ next sample's squared residuals) + barrier
     }
+    else
+        for (int i = 0; i < 5; ++i)
+            out[i] = raw[i];
     return VSOM_OK;
 }
+
+int vsom_debug_phase_cycles_raw(vsom_ctx *ctx, double out[8])
+{
+    if (!ctx || !out)
+        return VSOM_ERR_INVALID;
+    return read_phase_cycles(ctx, out);
+}
+
+int vsom_debug_die_aware(const vsom_ctx *ctx) { return ctx ? ctx->dieAware : 0; }
 
 int vsom_synchronize(vsom_ctx *ctx)
 {

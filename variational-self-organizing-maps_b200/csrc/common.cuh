@@ -61,6 +61,13 @@ struct StepParams
     float *distBuf;           // [2][nodeCount] per-step distances of every node (local search only)
     const u64 *lastIn;        // per-sample start node of the walk (DataSet::lastBMU), null = 0
     long long *prof;          // optional [gridDim.x][5] per-phase cycle sums of thread 0 (diagnostics), else null
+    const unsigned *winTab;   // K1F: [W + H] update window per BMU column / row, start | end << 16 (src/Som.cpp:899-903)
+    // K1F exchange rows, placed by L2 die (online_step_fast.cu, "L2 die calibration")
+    const int *dieOfSm;       // [256] die of an SM id
+    const int *rowBlocks;     // [2 dies][160 slots][2 buffers] 2 KB block of the row pool
+    int *rowOf;               // [G] row (die * 160 + slot) every CTA claimed in this launch
+    unsigned *rowCtr;         // [0..1] rows claimed per die, [2] arrivals at the one-off grid barrier
+    u64 *rowPool;
 };
 
 } // namespace vsom
@@ -99,6 +106,16 @@ struct vsom_ctx
     int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;
     size_t smemTrain = 0;
     uint64_t launches = 0;
+    // K1F (online_step_fast.cu): eligibility and launch geometry, window table of the current sigma
+    int fastTrain = 0, fastGrid = 0, fastStride = 0, fastDisabled = 0;
+    size_t fastSmem = 0;
+    unsigned *winTab = nullptr;
+    double winSigma = -1;
+    int lastTrainFast = 0;        // the last online-step launch ran K1F
+    int fastReg = 0;              // K1F keeps the rows in registers (one item per warp)
+    vsom::u64 *rowPool = nullptr; // K1F exchange rows: 1024 blocks of 2 KB
+    int *rowMeta = nullptr;       // dieOfSm[256] | rowBlocks[640] | rowOf[160] | counters[4]
+    int dieAware = 0;             // the row pool was classified by L2 die
     long long *profDev = nullptr; // diagnostics: per-phase cycle sums of the last online-step launch
     size_t profSamples = 0;
     std::string err;
@@ -124,6 +141,8 @@ int stage_reserve(vsom_ctx *ctx, int slot, size_t bytes);
 int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, double sigma, int decay, unsigned *outBmuDev, float *outDistDev,
                        const u64 *lastInDev = nullptr);
 int configure_online_step(vsom_ctx *ctx);
+int configure_online_step_fast(vsom_ctx *ctx);                               // 1: K1F eligible for this context
+int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma);      // 1: enqueued, 0: not eligible, < 0: error
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev);
 bool score_tc_supported(const vsom_ctx *ctx);
 int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut);

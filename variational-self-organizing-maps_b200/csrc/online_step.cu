@@ -790,6 +790,8 @@ int configure_online_step(vsom_ctx *ctx)
     ctx->residentTrain = resident;
     ctx->smStrideTrain = smStride;
     ctx->smemTrain = bytes;
+    if (!ctx->fastDisabled)
+        configure_online_step_fast(ctx); // K1F for the common regime, when it fits
     return VSOM_OK;
 }
 
@@ -917,6 +919,23 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.lutSmem = (ctx->smemTrain + lutBytes + kStaticSmem <= static_cast<size_t>(ctx->smemOptin)) ? 1 : 0;
     const size_t smemBytes = ctx->smemTrain + (p.lutSmem ? lutBytes : 0);
     p.xVec = (ctx->Din % 4 == 0 && (reinterpret_cast<uintptr_t>(xDev) & 15) == 0) ? 1 : 0;
+
+    p.winTab = nullptr;
+    ctx->lastTrainFast = 0;
+    if (ctx->fastTrain && !ctx->fastDisabled)
+    {
+        // common regime (Standard / Median, reference order, resident planes, sigma > 1, one GPU): K1F
+        rc = launch_online_step_fast(ctx, p, sigma);
+        if (rc < 0)
+            return rc;
+        if (rc == 1)
+        {
+            ctx->lastTrainFast = 1;
+            ctx->launches += 1;
+            ctx->stepBase += n;
+            return VSOM_OK;
+        }
+    }
 
     StepKernel k = pick_kernel(ctx->transform, ctx->order, ctx->residentTrain);
     void *args[] = {&p};

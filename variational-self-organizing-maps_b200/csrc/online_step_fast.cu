@@ -1,0 +1,1067 @@
+// online_step_fast.cu — K1F: the online VSOM training step for the common regime, one persistent sm_100a kernel
+// per sample chunk with the shortest per-sample dependency chain this library has.
+//
+// Same contract and the same bits as online_step.cu's generic kernel (Som::trainSingle src/Som.cpp:885-947 =
+// findBmu :291-309 over euclidianWeightedDist :124-141, window update :899-944, calculateNeighbourhoodWeight
+// :949-975, addBmu :1189-1192), for: Standard / Median transformation, reference summation order, planes resident
+// in shared memory, global BMU search (sigma > 1), one GPU, grid sides <= 4096.  Everything else runs the generic
+// kernel.
+//
+// Why a second kernel: the generic one measures (profiles/r01_bench_default_final_candidate.json, cycles per sample
+// at 64x64x128) wait 593 + scan 1535 + exchange 3323 + broadcast 248 + update 1643.  The strict per-sample dependency
+// makes these ADD, so each phase is rebuilt here for latency:
+//   * update and scan are fused where the work is parallel and split where it is sequential.  The warp that updates
+//     a node slice (lanes = 4 consecutive elements each, 128-bit accesses) also squares the residuals of the NEXT
+//     sample against the fresh means and leaves them in a `terms` row.  What remains of the scan is the part the
+//     reference order forces to be sequential: one lane per node adds its row's terms k = 0,1,2,... with a chain of
+//     FADDs (4 cycles each) fed by 128-bit shared-memory loads.  The f32 values added, and their order, are exactly
+//     the reference's `comparer.dot(comparer)` (src/Som.cpp:140).
+//   * the lanes of the scan warp keep their node's grid position and weightMap entry in registers for the whole
+//     chunk; after the exchange the same lanes turn the BMU into per-node update coefficients (window test against
+//     a host-built table of [start,end) per BMU column / row, neighbourhood table lookup) in ~40 instructions for
+//     32 nodes at once, instead of every update warp deriving them redundantly.
+//   * the (distance, y, x) key carries the BMU's grid position, so nobody divides by the map width.
+//   * trainSingle's return value (distance of the sample to its UPDATED BMU, :946) is produced the same way: the
+//     updating warp leaves the squared residuals in a `pend` row and an otherwise idle lane adds them up during the
+//     next sample's scan.  bmuHits are counted in shared memory and flushed once per chunk.
+//   * samples are prefetched two ahead with cp.async into a ring of four.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+namespace vsom
+{
+
+constexpr int kFThreads = 1024;
+constexpr int kFWarps = kFThreads / 32;
+constexpr int kFMaxSlotsPerLane = 5; // the exchange row of a CTA is read by one warp: at most 160 CTAs
+constexpr int kFMaxCtas = 32 * kFMaxSlotsPerLane;
+constexpr size_t kFStaticSmem = 4096;
+constexpr int kFPoolBlocks = 1024; // 2 KB blocks of the exchange row pool (2 MB per context)
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+// ---- packed f32x2 arithmetic (sm_100 FADD2 / FMUL2): two IEEE round-to-nearest operations per issue slot.
+// CAUTION: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (it never does that to the
+// scalar .rn forms).  The packed forms are therefore used only where a contraction cannot change a bit: subtractions,
+// products that are not followed by an addition in registers, and the Median update, whose products are exact
+// (one factor is -1, 0 or +1), so that fma(a, b, c) == a * b + c with separate roundings.
+__device__ __forceinline__ u64 pk(float2 v) { return (static_cast<u64>(__float_as_uint(v.y)) << 32) | __float_as_uint(v.x); }
+__device__ __forceinline__ float2 unpk(u64 v) { return make_float2(__uint_as_float(static_cast<unsigned>(v)), __uint_as_float(static_cast<unsigned>(v >> 32))); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return unpk(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return unpk(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return unpk(d);
+}
+
+// sign(d) in {-1, +0, +1}, NaN stays NaN: the Median Stepper (src/Transformation.cpp:49-50)
+__device__ __forceinline__ float sign1(float d)
+{
+    const float a = fabsf(d);
+    const float one = __uint_as_float((__float_as_uint(d) & 0x80000000u) | 0x3f800000u); // copysign(1, d)
+    return a > 0.0f ? one : a;
+}
+
+// two elements of src/Som.cpp:912-941 (sigma is evaluated lazily at the end of the chunk):
+//   d0 = Stepper(x, m); m' = m + c * d0; d1 = Stepper(x, m'); S += nwf * (d0 * d1)
+template <int TR>
+__device__ __forceinline__ void fast_update_pair(float2 x, float c, float nwf, float2 &m, float2 &S)
+{
+    if (TR == VSOM_MEDIAN)
+    {
+        float2 d0 = sub2(x, m);
+        d0 = make_float2(sign1(d0.x), sign1(d0.y));
+        const float2 m1 = add2(m, mul2(make_float2(c, c), d0)); // exact product: contraction-proof (see above)
+        float2 d1 = sub2(x, m1);
+        d1 = make_float2(sign1(d1.x), sign1(d1.y));
+        S = add2(S, mul2(make_float2(nwf, nwf), mul2(d0, d1))); // exact products again
+        m = m1;
+    }
+    else
+    {
+        const float2 d0 = sub2(x, m);
+        const float2 m1 = make_float2(__fadd_rn(m.x, __fmul_rn(c, d0.x)), __fadd_rn(m.y, __fmul_rn(c, d0.y))); // scalar: never contracted
+        const float2 d1 = sub2(x, m1);
+        const float2 q = mul2(d0, d1);
+        S = make_float2(__fadd_rn(S.x, __fmul_rn(nwf, q.x)), __fadd_rn(S.y, __fmul_rn(nwf, q.y)));
+        m = m1;
+    }
+}
+
+template <int TR>
+__device__ __forceinline__ void fast_update4(const float4 xv, float c, float nwf, float4 &mv, float4 &sv)
+{
+    float2 m0 = make_float2(mv.x, mv.y), m1 = make_float2(mv.z, mv.w), s0 = make_float2(sv.x, sv.y), s1 = make_float2(sv.z, sv.w);
+    fast_update_pair<TR>(make_float2(xv.x, xv.y), c, nwf, m0, s0);
+    fast_update_pair<TR>(make_float2(xv.z, xv.w), c, nwf, m1, s1);
+    mv = make_float4(m0.x, m0.y, m1.x, m1.y);
+    sv = make_float4(s0.x, s0.y, s1.x, s1.y);
+}
+
+// squared residuals of four elements: r = model - value (Comparer, src/Transformation.cpp:7-8, :45-46), r * r
+__device__ __forceinline__ float4 sq_res4(const float4 m, const float4 x)
+{
+    const float2 r0 = sub2(make_float2(m.x, m.y), make_float2(x.x, x.y)), r1 = sub2(make_float2(m.z, m.w), make_float2(x.z, x.w));
+    const float2 q0 = mul2(r0, r0), q1 = mul2(r1, r1);
+    return make_float4(q0.x, q0.y, q1.x, q1.y);
+}
+
+__device__ __forceinline__ void add4(float &s, const float4 a)
+{
+    s = __fadd_rn(s, a.x);
+    s = __fadd_rn(s, a.y);
+    s = __fadd_rn(s, a.z);
+    s = __fadd_rn(s, a.w);
+}
+
+// s = ((t0 + t1) + t2) + ... over a row of n16 blocks of 16 terms (zero padded; + 0 terms do not change a sum of squares).
+// 128 dependent FADDs cost 4 cycles each; the next block's four 128-bit loads are issued before the current block's adds.
+__device__ __forceinline__ float chain_terms(const float *row, int n16)
+{
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+    float s = 0.0f;
+    float4 a0 = r4[0], a1 = r4[1], a2 = r4[2], a3 = r4[3];
+#pragma unroll 2
+    for (int g = 1; g < n16; ++g)
+    {
+        r4 += 4;
+        const float4 b0 = r4[0], b1 = r4[1], b2 = r4[2], b3 = r4[3];
+        add4(s, a0);
+        add4(s, a1);
+        add4(s, a2);
+        add4(s, a3);
+        a0 = b0;
+        a1 = b1;
+        a2 = b2;
+        a3 = b3;
+    }
+    add4(s, a0);
+    add4(s, a1);
+    add4(s, a2);
+    add4(s, a3);
+    return s;
+}
+
+// key layout: [63:32] distance bits | [31:20] y | [19:8] x | [7:0] tag.  (y, x) orders like the node index y*W + x.
+__device__ __forceinline__ u64 make_key_xy(float d, unsigned x, unsigned y, unsigned tag)
+{
+    unsigned bits = __float_as_uint(d);
+    if (d != d)
+        bits = (x | y) == 0 ? 0u : 0x7fffffffu; // NaN never wins, except at node 0 which seeds findBmu (src/Som.cpp:293)
+    return (static_cast<u64>(bits) << 32) | (static_cast<u64>(y) << 20) | (static_cast<u64>(x) << 8) | tag;
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// REG: every warp owns at most one (node, 128-element slice) item, whose mean and S values then live in REGISTERS for
+// the whole chunk (configs 1 and 2); otherwise the owned rows live in shared memory and warps loop over the items.
+template <int TR, bool REG, bool PROF>
+__global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const StepParams p)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ u64 *sRowPtr[2][kFMaxCtas]; // exchange row of every CTA (two buffers), homed on that CTA's L2 die
+    __shared__ u64 sWarpKey[kFWarps];
+    __shared__ int sPend[2];  // owned node that was the BMU of sample t (slot t & 1), -1: not ours
+    __shared__ unsigned sBmu; // y << 12 | x of the current sample's BMU
+    __shared__ int sAbort;
+    __shared__ long long sProf[8];
+
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Lmax = (p.nodeCount + G - 1) / G;
+    const int L = (p.nodeCount - b + G - 1) / G; // G <= nodeCount: every CTA owns at least one node
+    const int Lpad = (Lmax + 3) & ~3;
+    const int DmPad = (p.Dm + 3) & ~3;
+    const int stride = p.smStride;     // 16 q + 4 floats, 16 q >= DmPad
+    const int n16 = (stride - 4) >> 4; // blocks of 16 terms the chain walks
+    const int nSW = (L + 31) >> 5;     // warps whose lanes own a node each
+    const int nCh = (DmPad + 127) >> 7;
+    const int items = L * nCh;
+
+    // ---- carve shared memory (every region 16-byte aligned)
+    float *xs = reinterpret_cast<float *>(smemRaw);                        // [4][DmPad] sample ring
+    float2 *coef = reinterpret_cast<float2 *>(xs + 4 * DmPad);             // [Lpad] {step coefficient, (float)nw}; nw < 0: outside the window
+    unsigned *hitsS = reinterpret_cast<unsigned *>(coef + Lpad);           // [Lpad] bmuHits of this chunk
+    unsigned *touchedS = hitsS + Lpad;                                     // [Lpad] node visited in this chunk (epilogue only)
+    float *wS = reinterpret_cast<float *>(touchedS + Lpad);                // [Lpad] final weightMap entries (epilogue only)
+    unsigned *winX = reinterpret_cast<unsigned *>(wS + Lpad);              // [Wpad] startX | endX << 16 per BMU column
+    const int Wpad = (p.W + 3) & ~3, Hpad = (p.H + 3) & ~3;
+    unsigned *winY = winX + Wpad;                                          // [Hpad]
+    float *tBase = reinterpret_cast<float *>(winY + Hpad);                 // [Lmax][stride] squared residuals of the next sample
+    float *pendRow = tBase + static_cast<size_t>(Lmax) * stride;           // [stride] squared residuals of the sample against its updated BMU
+    float *mBase = pendRow + stride;                                       // [Lmax][stride] means      (!REG only)
+    float *sBase = mBase + (REG ? 0 : static_cast<size_t>(Lmax) * stride); // [Lmax][stride] Welford S  (!REG only)
+    LutEntry *lutS = reinterpret_cast<LutEntry *>(sBase + (REG ? 0 : static_cast<size_t>(Lmax) * stride)); // optional copy of the neighbourhood table
+
+    // ---- prologue
+    // exchange rows: this CTA claims a row pair homed on the L2 die of the SM it runs on, publishes the choice, and after
+    // a one-off grid barrier (cooperative launch: all CTAs are resident) everybody knows everybody's rows.
+    if (tid == 0)
+    {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int die = p.dieOfSm[smid & 255];
+        const unsigned idx = atomicAdd(p.rowCtr + die, 1u);
+        p.rowOf[b] = die * kFMaxCtas + static_cast<int>(idx);
+        __threadfence();
+        atomicAdd(p.rowCtr + 2, 1u);
+        while (ld_relaxed_gpu_u32(p.rowCtr + 2) < static_cast<unsigned>(G))
+            ;
+        __threadfence();
+    }
+    if (p.lutSmem)
+        for (int i = tid; i < p.lutCount; i += kFThreads)
+            lutS[i] = p.lut[i];
+    for (int i = tid; i < p.W; i += kFThreads)
+        winX[i] = p.winTab[i];
+    for (int i = tid; i < p.H; i += kFThreads)
+        winY[i] = p.winTab[p.W + i];
+    for (int l = tid; l < Lpad; l += kFThreads)
+    {
+        hitsS[l] = 0;
+        touchedS[l] = 0;
+    }
+    for (int k = tid; k < 4 * DmPad; k += kFThreads)
+        xs[k] = 0.0f; // pad lanes of the 128-bit paths stay zero
+    for (int k = tid; k < stride; k += kFThreads)
+        pendRow[k] = 0.0f;
+    for (int l = warp; l < L; l += kFWarps)
+    {
+        const size_t g = (static_cast<size_t>(l) * G + b) * p.rowStride;
+        for (int k = lane; k < stride; k += 32)
+        {
+            tBase[l * stride + k] = 0.0f;
+            if (!REG)
+            {
+                const bool in = k < p.Dm;
+                mBase[l * stride + k] = in ? p.mean[g + k] : 0.0f;
+                sBase[l * stride + k] = in ? p.S[g + k] : 0.0f;
+            }
+        }
+    }
+    if (tid == 0)
+    {
+        sAbort = 0;
+        sPend[0] = sPend[1] = -1;
+        for (int i = 0; i < 8; ++i)
+            sProf[i] = 0;
+    }
+    // REG: this warp's item, its four mean / S values per lane
+    const int rl = REG ? warp / nCh : 0, rk = REG ? ((warp - rl * nCh) << 7) + (lane << 2) : 0;
+    const bool ract = REG && warp < items && rk < DmPad;
+    float4 rm = make_float4(0.f, 0.f, 0.f, 0.f), rs = rm;
+    if (ract)
+    {
+        const size_t g = (static_cast<size_t>(rl) * G + b) * p.rowStride + rk;
+        float *m = reinterpret_cast<float *>(&rm), *s = reinterpret_cast<float *>(&rs);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (rk + j < p.Dm)
+            {
+                m[j] = p.mean[g + j];
+                s[j] = p.S[g + j];
+            }
+    }
+    // per-lane state of the scan warps: lane <-> owned node l = warp * 32 + lane
+    const int myL = warp * 32 + lane;
+    const bool hasNode = warp < nSW && myL < L;
+    unsigned myX = 0, myY = 0;
+    float myW = 0.0f;
+    unsigned myTouched = 0;
+    if (hasNode)
+    {
+        const unsigned node = static_cast<unsigned>(p.node0 + myL * G + b);
+        myX = node % static_cast<unsigned>(p.W);
+        myY = node / static_cast<unsigned>(p.W);
+        myW = p.weight[static_cast<size_t>(myL) * G + b];
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * G; i += kFThreads)
+    {
+        const int d = i >> 1, buf = i & 1;
+        const int r = p.rowOf[d]; // written before the grid barrier above
+        sRowPtr[buf][d] = p.rowPool + static_cast<size_t>(p.rowBlocks[2 * r + buf]) * 256;
+    }
+
+    // sample prefetch by ONE warp that is neither the scan warp nor the pend lane's (everything the other warps execute at
+    // the top of a step competes with the scan warp's FADD chain for issue slots); loops kept rolled to stay small
+    constexpr int kPrefetchWarp = kFWarps - 2;
+    auto prefetch = [&](u64 t) {
+        if (warp != kPrefetchWarp)
+            return;
+        float *dst = xs + static_cast<int>(t & 3) * DmPad;
+        const float *src = p.x + t * static_cast<u64>(p.Din);
+        if (p.xVec)
+        {
+#pragma unroll 1
+            for (int k = lane * 4; k < p.Din; k += 128)
+                cp_async16(dst + k, src + k);
+        }
+        else
+        {
+#pragma unroll 1
+            for (int k = lane; k < p.Din; k += 32)
+                cp_async4(dst + k, src + k);
+        }
+        cp_async_commit();
+    };
+    if (p.n > 0)
+        prefetch(0);
+    if (p.n > 1)
+        prefetch(1);
+    cp_async_wait_all();
+    __syncthreads();
+    // terms of sample 0 against the initial means
+    if (REG)
+    {
+        if (ract)
+            *reinterpret_cast<float4 *>(tBase + rl * stride + rk) = sq_res4(rm, *reinterpret_cast<const float4 *>(xs + rk));
+    }
+    else
+        for (int it = warp; it < items; it += kFWarps)
+        {
+            const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
+            const int k = (ch << 7) + (lane << 2);
+            if (k < DmPad)
+                *reinterpret_cast<float4 *>(tBase + l * stride + k) =
+                    sq_res4(*reinterpret_cast<const float4 *>(mBase + l * stride + k), *reinterpret_cast<const float4 *>(xs + k));
+        }
+    __syncthreads();
+
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
+    for (u64 t = 0; t < p.n; ++t)
+    {
+        if (PROF && tid == 0)
+            c0 = clock64();
+        const unsigned tag = static_cast<unsigned>((t >> 1) & 0xff);
+        // sample t+2 on its way while this step runs (its slot held sample t-2)
+        if (t + 2 < p.n)
+            prefetch(t + 2);
+
+        // ---- owed output of sample t-1: distance to its updated BMU (src/Som.cpp:946) + addBmu (:1189-1192)
+        if (warp == kFWarps - 1 && lane == 31 && t > 0)
+        {
+            const int pl = sPend[(t - 1) & 1];
+            if (pl >= 0)
+            {
+                const float d = chain_terms(pendRow, n16);
+                if (p.outBmu)
+                    p.outBmu[t - 1] = static_cast<unsigned>(p.node0 + pl * G + b);
+                if (p.outDist)
+                    p.outDist[t - 1] = d;
+                hitsS[pl] += 1;
+            }
+        }
+
+        // ---- scan: the sequential part of the distance, one lane per owned node
+        if (warp < nSW)
+        {
+            // destinations of this step's pushes (loaded ahead of the chain)
+            u64 *dst[kFMaxSlotsPerLane];
+            if (warp == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < kFMaxSlotsPerLane; ++j)
+                    dst[j] = lane + 32 * j < G ? sRowPtr[t & 1][lane + 32 * j] : nullptr;
+            }
+            u64 key = ~0ull;
+            if (hasNode)
+                key = make_key_xy(chain_terms(tBase + myL * stride, n16), myX, myY, tag);
+            if (PROF && tid == 0)
+                c1 = clock64();
+            key = warp_min_key(key);
+            if (nSW > 1)
+            {
+                if (lane == 0)
+                    sWarpKey[warp] = key;
+                named_bar_sync(1, nSW * 32);
+            }
+            unsigned bxy = 0;
+            bool abort = false;
+            if (warp == 0)
+            {
+                if (nSW > 1)
+                    key = warp_min_key(lane < nSW ? sWarpKey[lane] : ~0ull);
+                if (PROF && tid == 0)
+                    c2 = clock64();
+                // ---- grid-wide min-loc: push the key into every CTA's row, then poll the own row
+#pragma unroll
+                for (int j = 0; j < kFMaxSlotsPerLane; ++j)
+                    if (lane + 32 * j < G)
+                        st_relaxed_gpu(dst[j] + b, key);
+                const u64 *row = sRowPtr[t & 1][b];
+                const u64 filler = (~0ull << 8) | tag;
+                u64 m;
+                long long t0 = 0;
+                for (unsigned round = 0;; ++round)
+                {
+                    u64 v[kFMaxSlotsPerLane];
+#pragma unroll
+                    for (int j = 0; j < kFMaxSlotsPerLane; ++j)
+                    {
+                        const int i = lane + 32 * j;
+                        v[j] = i < G ? ld_relaxed_gpu(row + i) : filler;
+                    }
+                    m = ~0ull;
+                    int ok = 1;
+#pragma unroll
+                    for (int j = 0; j < kFMaxSlotsPerLane; ++j)
+                    {
+                        ok &= (static_cast<unsigned>(v[j] & 0xff) == tag);
+                        m = u64_min(m, v[j]);
+                    }
+                    if (__all_sync(0xffffffffu, ok))
+                        break;
+                    if ((round & 63) == 63)
+                    {
+                        if (t0 == 0)
+                            t0 = clock64();
+                        else if (__any_sync(0xffffffffu, clock64() - t0 > p.timeoutCycles))
+                        {
+                            abort = true;
+                            break;
+                        }
+                    }
+                }
+                m = warp_min_key(m);
+                bxy = static_cast<unsigned>(m >> 8) & 0xffffffu;
+                if (lane == 0)
+                {
+                    sBmu = bxy;
+                    sPend[t & 1] = -1;
+                    if (abort)
+                    {
+                        sAbort = 1;
+                        *p.err = 1;
+                    }
+                }
+                if (PROF && tid == 0)
+                    c3 = clock64();
+                if (nSW > 1)
+                    named_bar_sync(2, nSW * 32);
+                else
+                    __syncwarp();
+            }
+            else
+            {
+                named_bar_sync(2, nSW * 32);
+                bxy = sBmu;
+                abort = sAbort != 0;
+            }
+            // ---- per owned node: window test, neighbourhood entry, weightMap and step coefficient (src/Som.cpp:899-939)
+            if (hasNode && !abort)
+            {
+                const unsigned bx = bxy & 0xfffu, by = bxy >> 12;
+                const unsigned wx = winX[bx], wy = winY[by];
+                float2 cf = make_float2(0.0f, -1.0f);
+                if (myX >= (wx & 0xffffu) && myX < (wx >> 16) && myY >= (wy & 0xffffu) && myY < (wy >> 16))
+                {
+                    const int dx = myX > bx ? myX - bx : bx - myX, dy = myY > by ? myY - by : by - myY;
+                    const int li = dy * p.lutW + dx;
+                    float4 raw;
+                    if (p.lutSmem)
+                        raw = *reinterpret_cast<const float4 *>(lutS + li);
+                    else
+                        raw = __ldg(reinterpret_cast<const float4 *>(p.lut + li));
+                    float c;
+                    if (p.decay == VSOM_EXPONENTIAL)
+                    {
+                        myW = __fadd_rn(myW, raw.z); // :924
+                        c = raw.z;                   // :925
+                    }
+                    else
+                    {
+                        myW = __fadd_rn(myW, raw.w); // :930
+                        const double nw = __hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x));
+                        const double tw = (myW == 0.0f) ? 1.0 : __ddiv_rn(nw, static_cast<double>(myW)); // :933
+                        c = static_cast<float>(tw);                                                      // :935
+                    }
+                    myTouched = 1;
+                    cf = make_float2(c, raw.w);
+                    if (dx == 0 && dy == 0)
+                        sPend[t & 1] = myL;
+                }
+                coef[myL] = cf;
+            }
+        }
+        if (warp == kPrefetchWarp)
+            cp_async_wait_all(); // samples t+1 (and t+2) have landed; the barrier publishes them
+        if (PROF && tid == 0)
+            c4 = clock64();
+        __syncthreads(); // B1: coefficients, BMU owner and sample t+1 visible
+        if (sAbort)
+            break;
+        if (PROF && tid == 0)
+            c5 = clock64();
+
+        // ---- update of the owned nodes inside the window (src/Som.cpp:912-941) fused with the squared residuals of
+        //      sample t+1 against the new means; one warp per (node, 128-element slice)
+        {
+            const float *xt = xs + static_cast<int>(t & 3) * DmPad;
+            const float *xn = xs + static_cast<int>((t + 1) & 3) * DmPad;
+            const int pl = sPend[t & 1];
+            if (REG)
+            {
+                if (ract)
+                {
+                    const float2 cf = coef[rl];
+                    const float4 nv = *reinterpret_cast<const float4 *>(xn + rk);
+                    if (cf.y >= 0.0f)
+                    {
+                        const float4 xv = *reinterpret_cast<const float4 *>(xt + rk);
+                        fast_update4<TR>(xv, cf.x, cf.y, rm, rs);
+                        if (rl == pl)
+                            *reinterpret_cast<float4 *>(pendRow + rk) = sq_res4(rm, xv);
+                    }
+                    *reinterpret_cast<float4 *>(tBase + rl * stride + rk) = sq_res4(rm, nv);
+                }
+            }
+            else
+                for (int it = warp; it < items; it += kFWarps)
+                {
+                    const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
+                    const int k = (ch << 7) + (lane << 2);
+                    if (k < DmPad)
+                    {
+                        const float2 cf = coef[l];
+                        float *mp = mBase + l * stride + k;
+                        float4 mv = *reinterpret_cast<float4 *>(mp);
+                        const float4 nv = *reinterpret_cast<const float4 *>(xn + k);
+                        if (cf.y >= 0.0f)
+                        {
+                            float *sp = sBase + l * stride + k;
+                            float4 sv = *reinterpret_cast<float4 *>(sp);
+                            const float4 xv = *reinterpret_cast<const float4 *>(xt + k);
+                            fast_update4<TR>(xv, cf.x, cf.y, mv, sv);
+                            *reinterpret_cast<float4 *>(mp) = mv;
+                            *reinterpret_cast<float4 *>(sp) = sv;
+                            if (l == pl)
+                                *reinterpret_cast<float4 *>(pendRow + k) = sq_res4(mv, xv);
+                        }
+                        *reinterpret_cast<float4 *>(tBase + l * stride + k) = sq_res4(mv, nv);
+                    }
+                }
+        }
+        if (PROF && tid == 0)
+            c6 = clock64();
+        __syncthreads(); // B2: terms of sample t+1 and the pend row are complete
+        if (PROF && tid == 0)
+        {
+            const long long c7 = clock64();
+            sProf[0] += c1 - c0; // sample prefetch issue + the FADD chain
+            sProf[1] += c2 - c1; // CTA min
+            sProf[2] += c3 - c2; // grid-wide exchange
+            sProf[3] += c4 - c3; // coefficients
+            sProf[4] += c5 - c4; // barrier B1
+            sProf[5] += c6 - c5; // update + next sample's squared residuals (this warp)
+            sProf[6] += c7 - c6; // barrier B2 (slowest warp's update)
+        }
+    }
+
+    // ---- epilogue: last owed output, lazy sigma, write the owned rows back
+    if (!sAbort && p.n > 0 && warp == kFWarps - 1 && lane == 31)
+    {
+        const int pl = sPend[(p.n - 1) & 1];
+        if (pl >= 0)
+        {
+            const float d = chain_terms(pendRow, n16);
+            if (p.outBmu)
+                p.outBmu[p.n - 1] = static_cast<unsigned>(p.node0 + pl * G + b);
+            if (p.outDist)
+                p.outDist[p.n - 1] = d;
+            hitsS[pl] += 1;
+        }
+    }
+    if (hasNode)
+    {
+        wS[myL] = myW;
+        touchedS[myL] = myTouched;
+    }
+    __syncthreads();
+    for (int l = tid; l < L; l += kFThreads)
+    {
+        const size_t q = static_cast<size_t>(l) * G + b;
+        p.weight[q] = wS[l];
+        if (hitsS[l])
+            p.hits[q] += hitsS[l];
+    }
+    // sigmaMap of a visited node: sqrt(|S / (float)(W == 0 ? 1e-6 : W)|) with its final S and W (src/Som.cpp:939-942)
+    if (REG)
+    {
+        if (ract)
+        {
+            const size_t g = (static_cast<size_t>(rl) * G + b) * p.rowStride + rk;
+            const bool vis = touchedS[rl] != 0;
+            const float w = wS[rl];
+            const float twf = static_cast<float>((w == 0.0f) ? 0.000001 : static_cast<double>(w));
+            const float *m = reinterpret_cast<const float *>(&rm), *s = reinterpret_cast<const float *>(&rs);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (rk + j < p.Dm)
+                {
+                    p.mean[g + j] = m[j];
+                    p.S[g + j] = s[j];
+                    if (vis)
+                        p.sigma[g + j] = __fsqrt_rn(fabsf(__fdiv_rn(s[j], twf)));
+                }
+        }
+    }
+    else
+        for (int l = warp; l < L; l += kFWarps)
+        {
+            const size_t g = (static_cast<size_t>(l) * G + b) * p.rowStride;
+            const bool vis = touchedS[l] != 0;
+            const float w = wS[l];
+            const float twf = static_cast<float>((w == 0.0f) ? 0.000001 : static_cast<double>(w));
+            for (int k = lane; k < p.Dm; k += 32)
+            {
+                const float sv = sBase[l * stride + k];
+                p.mean[g + k] = mBase[l * stride + k];
+                p.S[g + k] = sv;
+                if (vis)
+                    p.sigma[g + k] = __fsqrt_rn(fabsf(__fdiv_rn(sv, twf)));
+            }
+        }
+    if (PROF && p.prof && tid == 0)
+        for (int i = 0; i < 8; ++i)
+            p.prof[static_cast<size_t>(b) * 8 + i] = sProf[i];
+}
+
+// ------------------------------------------------------------------------------------ L2 die calibration
+// B200's L2 is split over two dies.  A strong (gpu-scope) store -> poll signal between two SMs costs ~480 cycles one way
+// when writer, poller and the line's home partition share a die, ~735 when only the POLLER is on the line's die, and
+// ~1000 and more when the poller is on the other die (tests/micro/die_bench2.cu, profiles/r01_exchange_micro.md).  The
+// exchange therefore gives every CTA rows homed on the die of the SM it runs on.  Neither map is documented, so both
+// are measured: (1) SM -> die, once per device and process, from the ping-pong round trip of SM pairs through one
+// flag block (two clean modes, ~950 vs ~1750 cycles); (2) 2 KB block -> die, per context, from ping-pongs of same-die
+// SM pairs on each block of the context's row pool.
+__global__ void die_pingpong_kernel(u64 *f1, u64 *f2, int ctaA, int ctaB, int iters, u64 base, long long *out, int *smids)
+{
+    if (threadIdx.x != 0)
+        return;
+    const int b = blockIdx.x;
+    if (b != ctaA && b != ctaB)
+        return;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    smids[b == ctaA ? 0 : 1] = static_cast<int>(smid);
+    const long long t0 = clock64();
+    const long long limit = 400000000ll;
+    for (int t = 1; t <= iters; ++t)
+    {
+        const u64 v = base + t;
+        if (b == ctaA)
+        {
+            st_relaxed_gpu(f1, v);
+            while (ld_relaxed_gpu(f2) != v)
+                if (clock64() - t0 > limit)
+                    return;
+        }
+        else
+        {
+            while (ld_relaxed_gpu(f1) != v)
+                if (clock64() - t0 > limit)
+                    return;
+            st_relaxed_gpu(f2, v);
+        }
+    }
+    if (b == ctaA)
+        out[0] = clock64() - t0;
+}
+
+// every pair of same-die SMs (pairOfSm / roleOfSm, indexed by %smid) ping-pongs on the blocks k = pair, pair + nPairs, ...
+__global__ void die_classify_blocks_kernel(u64 *pool, int nBlocks, const int *pairOfSm, const int *roleOfSm, int nPairs, int iters, float *rtOut)
+{
+    if (threadIdx.x != 0)
+        return;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int pr = pairOfSm[smid & 255], role = roleOfSm[smid & 255];
+    if (pr < 0)
+        return;
+    const long long start = clock64();
+    const long long limit = 2000000000ll;
+    for (int k = pr; k < nBlocks; k += nPairs)
+    {
+        u64 *f1 = pool + static_cast<size_t>(k) * 256, *f2 = f1 + 16;
+        const long long t0 = clock64();
+        for (int t = 1; t <= iters; ++t)
+        {
+            const u64 v = static_cast<u64>(t);
+            if (role == 0)
+            {
+                st_relaxed_gpu(f1, v);
+                while (ld_relaxed_gpu(f2) != v)
+                    if (clock64() - start > limit)
+                        return;
+            }
+            else
+            {
+                while (ld_relaxed_gpu(f1) != v)
+                    if (clock64() - start > limit)
+                        return;
+                st_relaxed_gpu(f2, v);
+            }
+        }
+        if (role == 0)
+            rtOut[k] = static_cast<float>(clock64() - t0) / static_cast<float>(iters);
+    }
+}
+
+// --------------------------------------------------------------------------------------------- host side
+
+static int fast_stride(const vsom_ctx *ctx)
+{
+    const int DmPad = (ctx->Dm + 3) & ~3;
+    return ((DmPad + 15) & ~15) + 4; // 16 q + 4: rows 16-byte aligned, stride / 4 odd (conflict-free 128-bit access both ways)
+}
+
+static bool fast_reg_mode(const vsom_ctx *ctx, int G)
+{
+    const int Lmax = (ctx->localN + G - 1) / G;
+    const int nCh = (((ctx->Dm + 3) & ~3) + 127) >> 7;
+    return Lmax * nCh <= kFWarps;
+}
+
+static size_t fast_smem(const vsom_ctx *ctx, int G, int stride)
+{
+    const int Lmax = (ctx->localN + G - 1) / G;
+    const int Lpad = (Lmax + 3) & ~3;
+    const int DmPad = (ctx->Dm + 3) & ~3;
+    const int Wpad = (ctx->W + 3) & ~3, Hpad = (ctx->H + 3) & ~3;
+    size_t bytes = sizeof(float) * 4 * static_cast<size_t>(DmPad);
+    bytes += (sizeof(float2) + 2 * sizeof(unsigned) + sizeof(float)) * static_cast<size_t>(Lpad);
+    bytes += sizeof(unsigned) * (static_cast<size_t>(Wpad) + Hpad);
+    const size_t rows = fast_reg_mode(ctx, G) ? static_cast<size_t>(Lmax) : 3 * static_cast<size_t>(Lmax);
+    bytes += sizeof(float) * (rows + 1) * stride;
+    return bytes;
+}
+
+typedef void (*FastKernel)(const StepParams);
+static FastKernel pick_fast(int transform, bool reg, bool prof)
+{
+#define VSOM_FK(TR) {{online_step_fast_kernel<TR, false, false>, online_step_fast_kernel<TR, false, true>}, {online_step_fast_kernel<TR, true, false>, online_step_fast_kernel<TR, true, true>}}
+    static const FastKernel table[2][2][2] = {VSOM_FK(VSOM_STANDARD), VSOM_FK(VSOM_MEDIAN)};
+#undef VSOM_FK
+    return table[transform == VSOM_MEDIAN ? 1 : 0][reg ? 1 : 0][prof ? 1 : 0];
+}
+
+// ---- SM -> die map, measured once per device and process
+struct DieMap
+{
+    bool tried = false, valid = false;
+    int dieOfSm[256] = {};
+    int count[2] = {0, 0};
+};
+static DieMap g_dieMap[64];
+
+// split sorted values at their largest gap; false when the two groups are not clearly apart
+static bool split_bimodal(std::vector<float> v, float &thr)
+{
+    if (v.size() < 4)
+        return false;
+    std::sort(v.begin(), v.end());
+    float gap = 0.f;
+    size_t at = 0;
+    for (size_t i = 1; i < v.size(); ++i)
+        if (v[i] - v[i - 1] > gap)
+        {
+            gap = v[i] - v[i - 1];
+            at = i;
+        }
+    thr = 0.5f * (v[at] + v[at - 1]);
+    const float loSpread = v[at - 1] - v[0], hiSpread = v.back() - v[at];
+    // both groups hold at least a quarter of the values and are tighter than the gap between them
+    return at >= v.size() / 4 && v.size() - at >= v.size() / 4 && gap > 1.5f * loSpread && gap > 1.5f * hiSpread;
+}
+
+static int calibrate_die_map(vsom_ctx *ctx)
+{
+    DieMap &dm = g_dieMap[ctx->device & 63];
+    if (dm.tried)
+        return VSOM_OK;
+    dm.tried = true;
+    const int n = ctx->numSMs;
+    if (n > 256)
+        return VSOM_OK;
+    u64 *flags = nullptr;
+    long long *out = nullptr;
+    int *smids = nullptr;
+    VSOM_CUDA(ctx, cudaMalloc(&flags, 2048));
+    VSOM_CUDA(ctx, cudaMalloc(&out, sizeof(long long)));
+    VSOM_CUDA(ctx, cudaMalloc(&smids, 2 * sizeof(int)));
+    VSOM_CUDA(ctx, cudaMemsetAsync(flags, 0, 2048, ctx->stream));
+    std::vector<float> rt;
+    std::vector<int> sm;
+    int sm0 = -1;
+    const int iters = 96;
+    u64 base = 0;
+    bool ok = true;
+    for (int peer = 1; peer < n && ok; ++peer)
+    {
+        u64 *f1 = flags, *f2 = flags + 16;
+        int a = 0, it = iters;
+        VSOM_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(long long), ctx->stream));
+        void *args[] = {&f1, &f2, &a, &peer, &it, &base, &out, &smids};
+        VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(die_pingpong_kernel), dim3(n), dim3(32), args, 0, ctx->stream));
+        long long cyc = 0;
+        int ids[2] = {0, 0};
+        VSOM_CUDA(ctx, cudaMemcpyAsync(&cyc, out, sizeof(cyc), cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ids, smids, sizeof(ids), cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        base += iters + 8;
+        if (cyc <= 0 || ids[1] < 0 || ids[1] > 255 || (sm0 >= 0 && ids[0] != sm0))
+            ok = false; // timed out, or CTA 0 moved between launches
+        sm0 = ids[0];
+        rt.push_back(static_cast<float>(cyc) / iters);
+        sm.push_back(ids[1]);
+    }
+    cudaFree(flags);
+    cudaFree(out);
+    cudaFree(smids);
+    float thr = 0.f;
+    const bool bimodal = ok && split_bimodal(rt, thr);
+    if (getenv("VSOM_DEBUG_DIE"))
+    {
+        std::vector<float> srt = rt;
+        std::sort(srt.begin(), srt.end());
+        fprintf(stderr, "[vsom] SM die calibration: ok=%d bimodal=%d thr=%.0f n=%zu min=%.0f median=%.0f max=%.0f\n", ok ? 1 : 0, bimodal ? 1 : 0, thr, srt.size(),
+                srt.empty() ? 0.f : srt.front(), srt.empty() ? 0.f : srt[srt.size() / 2], srt.empty() ? 0.f : srt.back());
+    }
+    if (!bimodal)
+        return VSOM_OK; // leave the map invalid: rows are then taken in pool order (still correct, only slower)
+    dm.dieOfSm[sm0 & 255] = 0;
+    dm.count[0] = 1;
+    for (size_t i = 0; i < rt.size(); ++i)
+    {
+        const int d = rt[i] > thr ? 1 : 0;
+        dm.dieOfSm[sm[i] & 255] = d;
+        dm.count[d] += 1;
+    }
+    dm.valid = true;
+    return VSOM_OK;
+}
+
+// row pool of the context + the home die of each of its 2 KB blocks -> rowBlocks[die][slot][buffer]
+static int build_row_pool(vsom_ctx *ctx)
+{
+    if (ctx->rowPool)
+        return VSOM_OK;
+    int rc = calibrate_die_map(ctx);
+    if (rc)
+        return rc;
+    const DieMap &dm = g_dieMap[ctx->device & 63];
+    VSOM_CUDA(ctx, cudaMalloc(&ctx->rowPool, static_cast<size_t>(kFPoolBlocks) * 2048));
+    VSOM_CUDA(ctx, cudaMalloc(&ctx->rowMeta, sizeof(int) * (256 + 2 * 2 * kFMaxCtas + kFMaxCtas) + sizeof(unsigned) * 4));
+    std::vector<int> home(kFPoolBlocks, -1);
+    bool haveHomes = false;
+    if (dm.valid)
+    {
+        // pairs of die-0 SMs, by SM id
+        std::vector<int> pairOf(256, -1), roleOf(256, 0), die0;
+        for (int s = 0; s < 256; ++s)
+            if (dm.dieOfSm[s] == 0 && s < 256)
+                die0.push_back(s);
+        // dieOfSm defaults to 0 for ids that were never seen; keep only SM ids below the SM count
+        die0.erase(std::remove_if(die0.begin(), die0.end(), [&](int s) { return s >= ctx->numSMs; }), die0.end());
+        const int nPairs = static_cast<int>(die0.size()) / 2;
+        for (int i = 0; i < nPairs; ++i)
+        {
+            pairOf[die0[2 * i]] = i;
+            roleOf[die0[2 * i]] = 0;
+            pairOf[die0[2 * i + 1]] = i;
+            roleOf[die0[2 * i + 1]] = 1;
+        }
+        if (nPairs >= 4)
+        {
+            int *tab = nullptr;
+            float *rtDev = nullptr;
+            VSOM_CUDA(ctx, cudaMalloc(&tab, sizeof(int) * 512));
+            VSOM_CUDA(ctx, cudaMalloc(&rtDev, sizeof(float) * kFPoolBlocks));
+            VSOM_CUDA(ctx, cudaMemcpyAsync(tab, pairOf.data(), sizeof(int) * 256, cudaMemcpyHostToDevice, ctx->stream));
+            VSOM_CUDA(ctx, cudaMemcpyAsync(tab + 256, roleOf.data(), sizeof(int) * 256, cudaMemcpyHostToDevice, ctx->stream));
+            VSOM_CUDA(ctx, cudaMemsetAsync(rtDev, 0, sizeof(float) * kFPoolBlocks, ctx->stream));
+            VSOM_CUDA(ctx, cudaMemsetAsync(ctx->rowPool, 0, static_cast<size_t>(kFPoolBlocks) * 2048, ctx->stream));
+            u64 *pool = ctx->rowPool;
+            int nb = kFPoolBlocks, np = nPairs, iters = 48;
+            const int *pairDev = tab, *roleDev = tab + 256;
+            void *args[] = {&pool, &nb, &pairDev, &roleDev, &np, &iters, &rtDev};
+            VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(die_classify_blocks_kernel), dim3(ctx->numSMs), dim3(32), args, 0, ctx->stream));
+            std::vector<float> rt(kFPoolBlocks);
+            VSOM_CUDA(ctx, cudaMemcpyAsync(rt.data(), rtDev, sizeof(float) * kFPoolBlocks, cudaMemcpyDeviceToHost, ctx->stream));
+            VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(tab);
+            cudaFree(rtDev);
+            float thr = 0.f;
+            bool complete = true;
+            for (float v : rt)
+                complete = complete && v > 0.f;
+            const bool bimodal = complete && split_bimodal(rt, thr);
+            if (getenv("VSOM_DEBUG_DIE"))
+            {
+                std::vector<float> srt = rt;
+                std::sort(srt.begin(), srt.end());
+                fprintf(stderr, "[vsom] block die calibration: pairs=%d complete=%d bimodal=%d thr=%.0f min=%.0f median=%.0f max=%.0f\n", nPairs, complete ? 1 : 0,
+                        bimodal ? 1 : 0, thr, srt.front(), srt[srt.size() / 2], srt.back());
+            }
+            if (bimodal)
+            {
+                for (int k = 0; k < kFPoolBlocks; ++k)
+                    home[k] = rt[k] > thr ? 1 : 0; // measured by die-0 pairs: fast = homed on die 0
+                haveHomes = true;
+            }
+        }
+    }
+    // rowBlocks[(die * kFMaxCtas + slot) * 2 + buffer] = block index; every (die, slot, buffer) gets its own block
+    std::vector<int> rowBlocks(2 * 2 * kFMaxCtas, 0), dieOfSm(256, 0);
+    int next = 0;
+    std::vector<int> byDie[2];
+    for (int k = 0; k < kFPoolBlocks; ++k)
+        byDie[haveHomes ? home[k] : (k & 1)].push_back(k);
+    ctx->dieAware = haveHomes ? 1 : 0;
+    if (haveHomes)
+        for (int s = 0; s < 256; ++s)
+            dieOfSm[s] = dm.dieOfSm[s];
+    bool enough = byDie[0].size() >= 2 * 100 && byDie[1].size() >= 2 * 100; // a die has at most ~80 SMs
+    if (!enough)
+    {
+        ctx->dieAware = 0;
+        byDie[0].clear();
+        byDie[1].clear();
+        for (int k = 0; k < kFPoolBlocks; ++k)
+            byDie[k & 1].push_back(k);
+        std::fill(dieOfSm.begin(), dieOfSm.end(), 0);
+    }
+    (void)next;
+    for (int d = 0; d < 2; ++d)
+        for (int slot = 0; slot < kFMaxCtas; ++slot)
+            for (int buf = 0; buf < 2; ++buf)
+            {
+                const size_t i = static_cast<size_t>(slot) * 2 + buf;
+                // past the die's own blocks (more CTAs on one die than any B200 has SMs there) borrow from the other list
+                const std::vector<int> &own = byDie[d], &other = byDie[1 - d];
+                rowBlocks[(d * kFMaxCtas + slot) * 2 + buf] = i < own.size() ? own[i] : other[other.size() - 1 - (i - own.size())];
+            }
+    int *meta = ctx->rowMeta;
+    VSOM_CUDA(ctx, cudaMemcpyAsync(meta, dieOfSm.data(), sizeof(int) * 256, cudaMemcpyHostToDevice, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(meta + 256, rowBlocks.data(), sizeof(int) * rowBlocks.size(), cudaMemcpyHostToDevice, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
+// 0: not eligible (the caller runs the generic kernel), 1: configured
+int configure_online_step_fast(vsom_ctx *ctx)
+{
+    ctx->fastTrain = 0;
+    if (ctx->transform == VSOM_CLR || ctx->order != VSOM_ORDER_REFERENCE || ctx->world > 1 || ctx->W > 4096 || ctx->H > 4096)
+        return 0;
+    int G = ctx->localN < ctx->numSMs ? ctx->localN : ctx->numSMs;
+    if (G > kFMaxCtas)
+        G = kFMaxCtas;
+    const int stride = fast_stride(ctx);
+    const size_t bytes = fast_smem(ctx, G, stride);
+    if (bytes + kFStaticSmem > static_cast<size_t>(ctx->smemOptin))
+        return 0;
+    const bool reg = fast_reg_mode(ctx, G);
+    for (int prof = 0; prof < 2; ++prof)
+    {
+        FastKernel k = pick_fast(ctx->transform, reg, prof != 0);
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smemOptin - static_cast<int>(kFStaticSmem)) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k, kFThreads, bytes) != cudaSuccess || perSm < 1)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+    }
+    ctx->fastTrain = 1;
+    ctx->fastGrid = G;
+    ctx->fastStride = stride;
+    ctx->fastSmem = bytes;
+    ctx->fastReg = reg ? 1 : 0;
+    return 1;
+}
+
+// [start,end) of the update window per BMU column and row: the f64 expressions of src/Som.cpp:899-903
+static int build_window_table(vsom_ctx *ctx, double sigma)
+{
+    if (ctx->winTab && ctx->winSigma == sigma)
+        return VSOM_OK;
+    if (!ctx->winTab)
+        VSOM_CUDA(ctx, cudaMalloc(&ctx->winTab, sizeof(unsigned) * (static_cast<size_t>(ctx->W) + ctx->H)));
+    std::vector<unsigned> h(static_cast<size_t>(ctx->W) + ctx->H);
+    const double dW = static_cast<double>(ctx->W), dH = static_cast<double>(ctx->H);
+    for (int i = 0; i < ctx->W + ctx->H; ++i)
+    {
+        const bool isX = i < ctx->W;
+        const double c = static_cast<double>(isX ? i : i - ctx->W), lim = isX ? dW : dH;
+        const double lo = c - 2.5 * sigma, hi = c + 2.5 * sigma;
+        const size_t start = static_cast<size_t>(lo > 0. ? lo : 0.);
+        const size_t end = static_cast<size_t>(hi < lim ? hi : lim);
+        h[i] = static_cast<unsigned>(start > 0xffff ? 0xffff : start) | (static_cast<unsigned>(end) << 16);
+    }
+    VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->winTab, h.data(), sizeof(unsigned) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->winSigma = sigma;
+    return VSOM_OK;
+}
+
+// Called by launch_online_step after the neighbourhood table is in place.  Returns 1 when the chunk was enqueued,
+// 0 when this launch is not eligible (sigma <= 1, ...), < 0 on error.
+int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma)
+{
+    if (!ctx->fastTrain || p.localSearch || p.world > 1)
+        return 0;
+    int rc = build_row_pool(ctx);
+    if (rc)
+        return rc;
+    rc = build_window_table(ctx, sigma);
+    if (rc)
+        return rc;
+    const int G = ctx->fastGrid;
+    VSOM_CUDA(ctx, cudaMemsetAsync(ctx->rowPool, 0xff, static_cast<size_t>(kFPoolBlocks) * 2048, ctx->stream));
+    unsigned *ctr = reinterpret_cast<unsigned *>(ctx->rowMeta + 256 + 2 * 2 * kFMaxCtas + kFMaxCtas);
+    VSOM_CUDA(ctx, cudaMemsetAsync(ctr, 0, sizeof(unsigned) * 4, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
+    p.winTab = ctx->winTab;
+    p.dieOfSm = ctx->rowMeta;
+    p.rowBlocks = ctx->rowMeta + 256;
+    p.rowOf = ctx->rowMeta + 256 + 2 * 2 * kFMaxCtas;
+    p.rowCtr = ctr;
+    p.rowPool = ctx->rowPool;
+    p.resident = 1;
+    p.smStride = ctx->fastStride;
+    const size_t lutBytes = sizeof(LutEntry) * static_cast<size_t>(p.lutCount);
+    p.lutSmem = (ctx->fastSmem + lutBytes + kFStaticSmem <= static_cast<size_t>(ctx->smemOptin)) ? 1 : 0;
+    const size_t smemBytes = ctx->fastSmem + (p.lutSmem ? lutBytes : 0);
+    FastKernel k = pick_fast(ctx->transform, ctx->fastReg != 0, p.prof != nullptr);
+    void *args[] = {&p};
+    VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k), dim3(G), dim3(kFThreads), args, smemBytes, ctx->stream));
+    return 1;
+}
+
+} // namespace vsom
