@@ -776,24 +776,25 @@ struct DieMap
 };
 static DieMap g_dieMap[64];
 
-// split sorted values at their largest gap; false when the two groups are not clearly apart
+// Two-mode split of round-trip times: threshold halfway between the lower and the upper quartile (both maps are close
+// to half / half), accepted when the quartiles are clearly apart and few values sit near the threshold.
 static bool split_bimodal(std::vector<float> v, float &thr)
 {
-    if (v.size() < 4)
+    if (v.size() < 8)
         return false;
     std::sort(v.begin(), v.end());
-    float gap = 0.f;
-    size_t at = 0;
-    for (size_t i = 1; i < v.size(); ++i)
-        if (v[i] - v[i - 1] > gap)
-        {
-            gap = v[i] - v[i - 1];
-            at = i;
-        }
-    thr = 0.5f * (v[at] + v[at - 1]);
-    const float loSpread = v[at - 1] - v[0], hiSpread = v.back() - v[at];
-    // both groups hold at least a quarter of the values and are tighter than the gap between them
-    return at >= v.size() / 4 && v.size() - at >= v.size() / 4 && gap > 1.5f * loSpread && gap > 1.5f * hiSpread;
+    const float q1 = v[v.size() / 4], q3 = v[(3 * v.size()) / 4];
+    thr = 0.5f * (q1 + q3);
+    if (q3 < 1.3f * q1)
+        return false;
+    const float band = 0.15f * (q3 - q1);
+    size_t near = 0, low = 0;
+    for (float x : v)
+    {
+        near += (x > thr - band && x < thr + band) ? 1 : 0;
+        low += x <= thr ? 1 : 0;
+    }
+    return near * 20 <= v.size() && low * 10 >= 3 * v.size() && low * 10 <= 7 * v.size();
 }
 
 static int calibrate_die_map(vsom_ctx *ctx)
