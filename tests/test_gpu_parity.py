@@ -94,6 +94,7 @@ SHAPES = [
     (37, 29, 33, 0, 64, 0.1, 4.0),
     (31, 1, 5, 1, 40, 0.2, 2.0),
     (1, 200, 130, 0, 40, 0.2, 3.0),
+    (40, 40, 64, 1, 48, 0.1, 6.0),     # 11 nodes per CTA: two register-resident items per warp
 ]
 
 

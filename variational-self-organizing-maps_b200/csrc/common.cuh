@@ -112,7 +112,7 @@ struct vsom_ctx
     unsigned *winTab = nullptr;
     double winSigma = -1;
     int lastTrainFast = 0;        // the last online-step launch ran K1F
-    int fastReg = 0;              // K1F keeps the rows in registers (one item per warp)
+    int fastReg = 0;              // K1F: items per warp whose rows live in registers (0: rows in shared memory)
     vsom::u64 *rowPool = nullptr; // K1F exchange rows: 1024 blocks of 2 KB
     int *rowMeta = nullptr;       // dieOfSm[256] | rowBlocks[640] | rowOf[160] | counters[4]
     int dieAware = 0;             // the row pool was classified by L2 die

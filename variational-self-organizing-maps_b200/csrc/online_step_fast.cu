@@ -35,7 +35,7 @@
 namespace vsom
 {
 
-constexpr int kFThreads = 1024;
+constexpr int kFThreads = 256;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kFMaxSlotsPerLane = 5; // the exchange row of a CTA is read by one warp: at most 160 CTAs
 constexpr int kFMaxCtas = 32 * kFMaxSlotsPerLane;
@@ -175,11 +175,14 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned *p)
     return v;
 }
 
-// REG: every warp owns at most one (node, 128-element slice) item, whose mean and S values then live in REGISTERS for
-// the whole chunk (configs 1 and 2); otherwise the owned rows live in shared memory and warps loop over the items.
-template <int TR, bool REG, bool PROF>
+// IPW > 0: every warp owns at most IPW (node, 128-element slice) items, whose mean and S values then live in REGISTERS
+// for the whole chunk (configs 1 and 2); IPW == 0: the owned rows live in shared memory and the warps loop over the items.
+// 256 threads: the per-sample critical path is one warp's serial code, so registers (no rematerialised addresses) matter
+// more than warps; the update phase is issue-bound either way.
+template <int TR, int IPW, bool PROF>
 __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const StepParams p)
 {
+    constexpr int NI = IPW > 0 ? IPW : 1;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 *sRowPtr[2][kFMaxCtas]; // exchange row of every CTA (two buffers), homed on that CTA's L2 die
     __shared__ u64 sWarpKey[kFWarps];
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
 
     const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Lmax = (p.nodeCount + G - 1) / G;
-    const int L = (p.nodeCount - b + G - 1) / G; // G <= nodeCount: every CTA owns at least one node
+    const int L = (p.nodeCount - b + G - 1) / G; // G <= nodeCount: every CTA owns at least one node; L <= kFThreads
     const int Lpad = (Lmax + 3) & ~3;
     const int DmPad = (p.Dm + 3) & ~3;
     const int stride = p.smStride;     // 16 q + 4 floats, 16 q >= DmPad
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     const int nSW = (L + 31) >> 5;     // warps whose lanes own a node each
     const int nCh = (DmPad + 127) >> 7;
     const int items = L * nCh;
+    const unsigned n = static_cast<unsigned>(p.n); // the host keeps chunks below 2^32 samples on this path
 
     // ---- carve shared memory (every region 16-byte aligned)
     float *xs = reinterpret_cast<float *>(smemRaw);                        // [4][DmPad] sample ring
@@ -210,9 +214,9 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     unsigned *winY = winX + Wpad;                                          // [Hpad]
     float *tBase = reinterpret_cast<float *>(winY + Hpad);                 // [Lmax][stride] squared residuals of the next sample
     float *pendRow = tBase + static_cast<size_t>(Lmax) * stride;           // [stride] squared residuals of the sample against its updated BMU
-    float *mBase = pendRow + stride;                                       // [Lmax][stride] means      (!REG only)
-    float *sBase = mBase + (REG ? 0 : static_cast<size_t>(Lmax) * stride); // [Lmax][stride] Welford S  (!REG only)
-    LutEntry *lutS = reinterpret_cast<LutEntry *>(sBase + (REG ? 0 : static_cast<size_t>(Lmax) * stride)); // optional copy of the neighbourhood table
+    float *mBase = pendRow + stride;                                       // [Lmax][stride] means      (IPW == 0 only)
+    float *sBase = mBase + (IPW > 0 ? 0 : static_cast<size_t>(Lmax) * stride); // [Lmax][stride] Welford S  (IPW == 0 only)
+    LutEntry *lutS = reinterpret_cast<LutEntry *>(sBase + (IPW > 0 ? 0 : static_cast<size_t>(Lmax) * stride)); // optional copy of the neighbourhood table
 
     // ---- prologue
     // exchange rows: this CTA claims a row pair homed on the L2 die of the SM it runs on, publishes the choice, and after
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         for (int k = lane; k < stride; k += 32)
         {
             tBase[l * stride + k] = 0.0f;
-            if (!REG)
+            if (IPW == 0)
             {
                 const bool in = k < p.Dm;
                 mBase[l * stride + k] = in ? p.mean[g + k] : 0.0f;
@@ -267,25 +271,35 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         for (int i = 0; i < 8; ++i)
             sProf[i] = 0;
     }
-    // REG: this warp's item, its four mean / S values per lane
-    const int rl = REG ? warp / nCh : 0, rk = REG ? ((warp - rl * nCh) << 7) + (lane << 2) : 0;
-    const bool ract = REG && warp < items && rk < DmPad;
-    float4 rm = make_float4(0.f, 0.f, 0.f, 0.f), rs = rm;
-    if (ract)
-    {
-        const size_t g = (static_cast<size_t>(rl) * G + b) * p.rowStride + rk;
-        float *m = reinterpret_cast<float *>(&rm), *s = reinterpret_cast<float *>(&rs);
+    // IPW > 0: this warp's items it = warp + kFWarps * j, four mean / S values per lane and item
+    int rl[NI], rk[NI];
+    bool ract[NI];
+    float4 rm[NI], rs[NI];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (rk + j < p.Dm)
-            {
-                m[j] = p.mean[g + j];
-                s[j] = p.S[g + j];
-            }
+    for (int j = 0; j < NI; ++j)
+    {
+        const int it = warp + kFWarps * j;
+        rl[j] = it / nCh;
+        rk[j] = ((it - rl[j] * nCh) << 7) + (lane << 2);
+        ract[j] = IPW > 0 && it < items && rk[j] < DmPad;
+        rm[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rs[j] = rm[j];
+        if (ract[j])
+        {
+            const size_t g = (static_cast<size_t>(rl[j]) * G + b) * p.rowStride + rk[j];
+            float *m = reinterpret_cast<float *>(&rm[j]), *s = reinterpret_cast<float *>(&rs[j]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (rk[j] + e < p.Dm)
+                {
+                    m[e] = p.mean[g + e];
+                    s[e] = p.S[g + e];
+                }
+        }
     }
-    // per-lane state of the scan warps: lane <-> owned node l = warp * 32 + lane
-    const int myL = warp * 32 + lane;
-    const bool hasNode = warp < nSW && myL < L;
+    // per-lane state of the scan warps: thread <-> owned node
+    const int myL = tid;
+    const bool hasNode = myL < L;
     unsigned myX = 0, myY = 0;
     float myW = 0.0f;
     unsigned myTouched = 0;
@@ -296,6 +310,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         myY = node / static_cast<unsigned>(p.W);
         myW = p.weight[static_cast<size_t>(myL) * G + b];
     }
+    const float *myTerms = tBase + myL * stride;
     __syncthreads();
     for (int i = tid; i < 2 * G; i += kFThreads)
     {
@@ -304,39 +319,45 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         sRowPtr[buf][d] = p.rowPool + static_cast<size_t>(p.rowBlocks[2 * r + buf]) * 256;
     }
 
-    // sample prefetch by ONE warp that is neither the scan warp nor the pend lane's (everything the other warps execute at
-    // the top of a step competes with the scan warp's FADD chain for issue slots); loops kept rolled to stay small
+    // sample prefetch by ONE warp that is not the first scan warp (everything the other warps execute at the top of a
+    // step competes with the scan warp's FADD chain for issue slots); loops kept rolled to stay small
     constexpr int kPrefetchWarp = kFWarps - 2;
-    auto prefetch = [&](u64 t) {
-        if (warp != kPrefetchWarp)
-            return;
-        float *dst = xs + static_cast<int>(t & 3) * DmPad;
-        const float *src = p.x + t * static_cast<u64>(p.Din);
+    const float *xsrc = p.x; // next sample to fetch (prefetch warp only)
+    int xdst = 0;            // its ring slot offset
+    auto prefetch = [&]() {
+        float *dst = xs + xdst;
         if (p.xVec)
         {
 #pragma unroll 1
             for (int k = lane * 4; k < p.Din; k += 128)
-                cp_async16(dst + k, src + k);
+                cp_async16(dst + k, xsrc + k);
         }
         else
         {
 #pragma unroll 1
             for (int k = lane; k < p.Din; k += 32)
-                cp_async4(dst + k, src + k);
+                cp_async4(dst + k, xsrc + k);
         }
         cp_async_commit();
+        xsrc += p.Din;
+        xdst = xdst + DmPad == 4 * DmPad ? 0 : xdst + DmPad;
     };
-    if (p.n > 0)
-        prefetch(0);
-    if (p.n > 1)
-        prefetch(1);
-    cp_async_wait_all();
+    if (warp == kPrefetchWarp)
+    {
+        if (n > 0)
+            prefetch();
+        if (n > 1)
+            prefetch();
+        cp_async_wait_all();
+    }
     __syncthreads();
     // terms of sample 0 against the initial means
-    if (REG)
+    if (IPW > 0)
     {
-        if (ract)
-            *reinterpret_cast<float4 *>(tBase + rl * stride + rk) = sq_res4(rm, *reinterpret_cast<const float4 *>(xs + rk));
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+            if (ract[j])
+                *reinterpret_cast<float4 *>(tBase + rl[j] * stride + rk[j]) = sq_res4(rm[j], *reinterpret_cast<const float4 *>(xs + rk[j]));
     }
     else
         for (int it = warp; it < items; it += kFWarps)
@@ -350,19 +371,21 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     __syncthreads();
 
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
-    for (u64 t = 0; t < p.n; ++t)
+    int curOff = 0, nextOff = DmPad; // ring offsets of samples t and t+1
+    for (unsigned t = 0; t < n; ++t)
     {
         if (PROF && tid == 0)
             c0 = clock64();
-        const unsigned tag = static_cast<unsigned>((t >> 1) & 0xff);
-        // sample t+2 on its way while this step runs (its slot held sample t-2)
-        if (t + 2 < p.n)
-            prefetch(t + 2);
+        const unsigned tag = (t >> 1) & 0xffu;
+        const int par = static_cast<int>(t & 1u);
+
+        if (warp == kPrefetchWarp && t + 2 < n)
+            prefetch(); // sample t+2 on its way while this step runs (its slot held sample t-2)
 
         // ---- owed output of sample t-1: distance to its updated BMU (src/Som.cpp:946) + addBmu (:1189-1192)
-        if (warp == kFWarps - 1 && lane == 31 && t > 0)
+        if (tid == kFThreads - 1 && t > 0)
         {
-            const int pl = sPend[(t - 1) & 1];
+            const int pl = sPend[par ^ 1];
             if (pl >= 0)
             {
                 const float d = chain_terms(pendRow, n16);
@@ -377,17 +400,9 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         // ---- scan: the sequential part of the distance, one lane per owned node
         if (warp < nSW)
         {
-            // destinations of this step's pushes (loaded ahead of the chain)
-            u64 *dst[kFMaxSlotsPerLane];
-            if (warp == 0)
-            {
-#pragma unroll
-                for (int j = 0; j < kFMaxSlotsPerLane; ++j)
-                    dst[j] = lane + 32 * j < G ? sRowPtr[t & 1][lane + 32 * j] : nullptr;
-            }
             u64 key = ~0ull;
             if (hasNode)
-                key = make_key_xy(chain_terms(tBase + myL * stride, n16), myX, myY, tag);
+                key = make_key_xy(chain_terms(myTerms, n16), myX, myY, tag);
             if (PROF && tid == 0)
                 c1 = clock64();
             key = warp_min_key(key);
@@ -406,11 +421,12 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 if (PROF && tid == 0)
                     c2 = clock64();
                 // ---- grid-wide min-loc: push the key into every CTA's row, then poll the own row
+                u64 *const *rp = sRowPtr[par];
 #pragma unroll
                 for (int j = 0; j < kFMaxSlotsPerLane; ++j)
                     if (lane + 32 * j < G)
-                        st_relaxed_gpu(dst[j] + b, key);
-                const u64 *row = sRowPtr[t & 1][b];
+                        st_relaxed_gpu(rp[lane + 32 * j] + b, key);
+                const u64 *row = rp[b];
                 const u64 filler = (~0ull << 8) | tag;
                 u64 m;
                 long long t0 = 0;
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 if (lane == 0)
                 {
                     sBmu = bxy;
-                    sPend[t & 1] = -1;
+                    sPend[par] = -1;
                     if (abort)
                     {
                         sAbort = 1;
@@ -500,7 +516,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                     myTouched = 1;
                     cf = make_float2(c, raw.w);
                     if (dx == 0 && dy == 0)
-                        sPend[t & 1] = myL;
+                        sPend[par] = myL;
                 }
                 coef[myL] = cf;
             }
@@ -518,24 +534,26 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         // ---- update of the owned nodes inside the window (src/Som.cpp:912-941) fused with the squared residuals of
         //      sample t+1 against the new means; one warp per (node, 128-element slice)
         {
-            const float *xt = xs + static_cast<int>(t & 3) * DmPad;
-            const float *xn = xs + static_cast<int>((t + 1) & 3) * DmPad;
-            const int pl = sPend[t & 1];
-            if (REG)
+            const float *xt = xs + curOff;
+            const float *xn = xs + nextOff;
+            const int pl = sPend[par];
+            if (IPW > 0)
             {
-                if (ract)
-                {
-                    const float2 cf = coef[rl];
-                    const float4 nv = *reinterpret_cast<const float4 *>(xn + rk);
-                    if (cf.y >= 0.0f)
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+                    if (ract[j])
                     {
-                        const float4 xv = *reinterpret_cast<const float4 *>(xt + rk);
-                        fast_update4<TR>(xv, cf.x, cf.y, rm, rs);
-                        if (rl == pl)
-                            *reinterpret_cast<float4 *>(pendRow + rk) = sq_res4(rm, xv);
+                        const float2 cf = coef[rl[j]];
+                        const float4 nv = *reinterpret_cast<const float4 *>(xn + rk[j]);
+                        if (cf.y >= 0.0f)
+                        {
+                            const float4 xv = *reinterpret_cast<const float4 *>(xt + rk[j]);
+                            fast_update4<TR>(xv, cf.x, cf.y, rm[j], rs[j]);
+                            if (rl[j] == pl)
+                                *reinterpret_cast<float4 *>(pendRow + rk[j]) = sq_res4(rm[j], xv);
+                        }
+                        *reinterpret_cast<float4 *>(tBase + rl[j] * stride + rk[j]) = sq_res4(rm[j], nv);
                     }
-                    *reinterpret_cast<float4 *>(tBase + rl * stride + rk) = sq_res4(rm, nv);
-                }
             }
             else
                 for (int it = warp; it < items; it += kFWarps)
@@ -563,13 +581,15 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                     }
                 }
         }
+        curOff = nextOff;
+        nextOff = nextOff + DmPad == 4 * DmPad ? 0 : nextOff + DmPad;
         if (PROF && tid == 0)
             c6 = clock64();
         __syncthreads(); // B2: terms of sample t+1 and the pend row are complete
         if (PROF && tid == 0)
         {
             const long long c7 = clock64();
-            sProf[0] += c1 - c0; // sample prefetch issue + the FADD chain
+            sProf[0] += c1 - c0; // the FADD chain
             sProf[1] += c2 - c1; // CTA min
             sProf[2] += c3 - c2; // grid-wide exchange
             sProf[3] += c4 - c3; // coefficients
@@ -580,16 +600,16 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     }
 
     // ---- epilogue: last owed output, lazy sigma, write the owned rows back
-    if (!sAbort && p.n > 0 && warp == kFWarps - 1 && lane == 31)
+    if (!sAbort && n > 0 && tid == kFThreads - 1)
     {
-        const int pl = sPend[(p.n - 1) & 1];
+        const int pl = sPend[(n - 1) & 1];
         if (pl >= 0)
         {
             const float d = chain_terms(pendRow, n16);
             if (p.outBmu)
-                p.outBmu[p.n - 1] = static_cast<unsigned>(p.node0 + pl * G + b);
+                p.outBmu[n - 1] = static_cast<unsigned>(p.node0 + pl * G + b);
             if (p.outDist)
-                p.outDist[p.n - 1] = d;
+                p.outDist[n - 1] = d;
             hitsS[pl] += 1;
         }
     }
@@ -607,25 +627,27 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             p.hits[q] += hitsS[l];
     }
     // sigmaMap of a visited node: sqrt(|S / (float)(W == 0 ? 1e-6 : W)|) with its final S and W (src/Som.cpp:939-942)
-    if (REG)
+    if (IPW > 0)
     {
-        if (ract)
-        {
-            const size_t g = (static_cast<size_t>(rl) * G + b) * p.rowStride + rk;
-            const bool vis = touchedS[rl] != 0;
-            const float w = wS[rl];
-            const float twf = static_cast<float>((w == 0.0f) ? 0.000001 : static_cast<double>(w));
-            const float *m = reinterpret_cast<const float *>(&rm), *s = reinterpret_cast<const float *>(&rs);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (rk + j < p.Dm)
-                {
-                    p.mean[g + j] = m[j];
-                    p.S[g + j] = s[j];
-                    if (vis)
-                        p.sigma[g + j] = __fsqrt_rn(fabsf(__fdiv_rn(s[j], twf)));
-                }
-        }
+        for (int j = 0; j < NI; ++j)
+            if (ract[j])
+            {
+                const size_t g = (static_cast<size_t>(rl[j]) * G + b) * p.rowStride + rk[j];
+                const bool vis = touchedS[rl[j]] != 0;
+                const float w = wS[rl[j]];
+                const float twf = static_cast<float>((w == 0.0f) ? 0.000001 : static_cast<double>(w));
+                const float *m = reinterpret_cast<const float *>(&rm[j]), *s = reinterpret_cast<const float *>(&rs[j]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (rk[j] + e < p.Dm)
+                    {
+                        p.mean[g + e] = m[e];
+                        p.S[g + e] = s[e];
+                        if (vis)
+                            p.sigma[g + e] = __fsqrt_rn(fabsf(__fdiv_rn(s[e], twf)));
+                    }
+            }
     }
     else
         for (int l = warp; l < L; l += kFWarps)
@@ -737,11 +759,16 @@ static int fast_stride(const vsom_ctx *ctx)
     return ((DmPad + 15) & ~15) + 4; // 16 q + 4: rows 16-byte aligned, stride / 4 odd (conflict-free 128-bit access both ways)
 }
 
-static bool fast_reg_mode(const vsom_ctx *ctx, int G)
+// items per warp kept in registers (1, 2 or 4), 0 when the CTA owns more items than that: rows in shared memory
+static int fast_ipw(const vsom_ctx *ctx, int G)
 {
     const int Lmax = (ctx->localN + G - 1) / G;
     const int nCh = (((ctx->Dm + 3) & ~3) + 127) >> 7;
-    return Lmax * nCh <= kFWarps;
+    const int items = Lmax * nCh;
+    for (int ipw = 1; ipw <= 4; ipw *= 2)
+        if (items <= kFWarps * ipw)
+            return ipw;
+    return 0;
 }
 
 static size_t fast_smem(const vsom_ctx *ctx, int G, int stride)
@@ -753,18 +780,21 @@ static size_t fast_smem(const vsom_ctx *ctx, int G, int stride)
     size_t bytes = sizeof(float) * 4 * static_cast<size_t>(DmPad);
     bytes += (sizeof(float2) + 2 * sizeof(unsigned) + sizeof(float)) * static_cast<size_t>(Lpad);
     bytes += sizeof(unsigned) * (static_cast<size_t>(Wpad) + Hpad);
-    const size_t rows = fast_reg_mode(ctx, G) ? static_cast<size_t>(Lmax) : 3 * static_cast<size_t>(Lmax);
+    const size_t rows = fast_ipw(ctx, G) > 0 ? static_cast<size_t>(Lmax) : 3 * static_cast<size_t>(Lmax);
     bytes += sizeof(float) * (rows + 1) * stride;
     return bytes;
 }
 
 typedef void (*FastKernel)(const StepParams);
-static FastKernel pick_fast(int transform, bool reg, bool prof)
+static FastKernel pick_fast(int transform, int ipw, bool prof)
 {
-#define VSOM_FK(TR) {{online_step_fast_kernel<TR, false, false>, online_step_fast_kernel<TR, false, true>}, {online_step_fast_kernel<TR, true, false>, online_step_fast_kernel<TR, true, true>}}
-    static const FastKernel table[2][2][2] = {VSOM_FK(VSOM_STANDARD), VSOM_FK(VSOM_MEDIAN)};
+#define VSOM_FK(TR, I) {online_step_fast_kernel<TR, I, false>, online_step_fast_kernel<TR, I, true>}
+#define VSOM_FKS(TR) {VSOM_FK(TR, 0), VSOM_FK(TR, 1), VSOM_FK(TR, 2), VSOM_FK(TR, 4)}
+    static const FastKernel table[2][4][2] = {VSOM_FKS(VSOM_STANDARD), VSOM_FKS(VSOM_MEDIAN)};
+#undef VSOM_FKS
 #undef VSOM_FK
-    return table[transform == VSOM_MEDIAN ? 1 : 0][reg ? 1 : 0][prof ? 1 : 0];
+    const int slot = ipw == 4 ? 3 : ipw;
+    return table[transform == VSOM_MEDIAN ? 1 : 0][slot][prof ? 1 : 0];
 }
 
 // ---- SM -> die map, measured once per device and process
@@ -809,19 +839,17 @@ static int calibrate_die_map(vsom_ctx *ctx)
     u64 *flags = nullptr;
     long long *out = nullptr;
     int *smids = nullptr;
-    VSOM_CUDA(ctx, cudaMalloc(&flags, 2048));
+    const int kCand = 16; // candidate flag blocks (2 KB apart)
+    VSOM_CUDA(ctx, cudaMalloc(&flags, 2048 * kCand));
     VSOM_CUDA(ctx, cudaMalloc(&out, sizeof(long long)));
     VSOM_CUDA(ctx, cudaMalloc(&smids, 2 * sizeof(int)));
-    VSOM_CUDA(ctx, cudaMemsetAsync(flags, 0, 2048, ctx->stream));
-    std::vector<float> rt;
-    std::vector<int> sm;
-    int sm0 = -1;
+    VSOM_CUDA(ctx, cudaMemsetAsync(flags, 0, 2048 * kCand, ctx->stream));
     const int iters = 96;
     u64 base = 0;
     bool ok = true;
-    for (int peer = 1; peer < n && ok; ++peer)
-    {
-        u64 *f1 = flags, *f2 = flags + 16;
+    int sm0 = -1;
+    auto pingpong = [&](int blk, int peer, float &cycles, int &peerSm) -> int {
+        u64 *f1 = flags + static_cast<size_t>(blk) * 256, *f2 = f1 + 16;
         int a = 0, it = iters;
         VSOM_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(long long), ctx->stream));
         void *args[] = {&f1, &f2, &a, &peer, &it, &base, &out, &smids};
@@ -835,20 +863,51 @@ static int calibrate_die_map(vsom_ctx *ctx)
         if (cyc <= 0 || ids[1] < 0 || ids[1] > 255 || (sm0 >= 0 && ids[0] != sm0))
             ok = false; // timed out, or CTA 0 moved between launches
         sm0 = ids[0];
-        rt.push_back(static_cast<float>(cyc) / iters);
-        sm.push_back(ids[1]);
+        cycles = static_cast<float>(cyc) / iters;
+        peerSm = ids[1];
+        return VSOM_OK;
+    };
+    // the flag block must be homed on CTA 0's own die, or the two modes of the scan below are hard to tell apart (a far
+    // home adds its latency to every pair): take the candidate with the shortest round trip to the neighbouring CTA
+    int flagBlk = 0;
+    float bestRt = 0.f;
+    for (int k = 0; k < kCand && ok; ++k)
+    {
+        float c = 0.f;
+        int psm = 0;
+        int rc = pingpong(k, 1, c, psm);
+        if (rc)
+            return rc;
+        if (k == 0 || c < bestRt)
+        {
+            bestRt = c;
+            flagBlk = k;
+        }
+    }
+    std::vector<float> rt;
+    std::vector<int> sm;
+    for (int peer = 1; peer < n && ok; ++peer)
+    {
+        float c = 0.f;
+        int psm = 0;
+        int rc = pingpong(flagBlk, peer, c, psm);
+        if (rc)
+            return rc;
+        rt.push_back(c);
+        sm.push_back(psm);
     }
     cudaFree(flags);
     cudaFree(out);
     cudaFree(smids);
     float thr = 0.f;
     const bool bimodal = ok && split_bimodal(rt, thr);
-    if (getenv("VSOM_DEBUG_DIE"))
+    if (getenv("VSOM_DEBUG_DIE") || !bimodal)
     {
         std::vector<float> srt = rt;
         std::sort(srt.begin(), srt.end());
-        fprintf(stderr, "[vsom] SM die calibration: ok=%d bimodal=%d thr=%.0f n=%zu min=%.0f median=%.0f max=%.0f\n", ok ? 1 : 0, bimodal ? 1 : 0, thr, srt.size(),
-                srt.empty() ? 0.f : srt.front(), srt.empty() ? 0.f : srt[srt.size() / 2], srt.empty() ? 0.f : srt.back());
+        fprintf(stderr, "[vsom] SM die calibration: ok=%d bimodal=%d thr=%.0f n=%zu min=%.0f q1=%.0f median=%.0f q3=%.0f max=%.0f\n", ok ? 1 : 0, bimodal ? 1 : 0, thr,
+                srt.size(), srt.empty() ? 0.f : srt.front(), srt.empty() ? 0.f : srt[srt.size() / 4], srt.empty() ? 0.f : srt[srt.size() / 2],
+                srt.empty() ? 0.f : srt[3 * srt.size() / 4], srt.empty() ? 0.f : srt.back());
     }
     if (!bimodal)
         return VSOM_OK; // leave the map invalid: rows are then taken in pool order (still correct, only slower)
@@ -919,12 +978,15 @@ static int build_row_pool(vsom_ctx *ctx)
             for (float v : rt)
                 complete = complete && v > 0.f;
             const bool bimodal = complete && split_bimodal(rt, thr);
-            if (getenv("VSOM_DEBUG_DIE"))
+            if (getenv("VSOM_DEBUG_DIE") || !bimodal)
             {
                 std::vector<float> srt = rt;
                 std::sort(srt.begin(), srt.end());
-                fprintf(stderr, "[vsom] block die calibration: pairs=%d complete=%d bimodal=%d thr=%.0f min=%.0f median=%.0f max=%.0f\n", nPairs, complete ? 1 : 0,
-                        bimodal ? 1 : 0, thr, srt.front(), srt[srt.size() / 2], srt.back());
+                size_t near = 0;
+                for (float x : srt)
+                    near += (x > thr - 0.15f * (srt[3 * srt.size() / 4] - srt[srt.size() / 4]) && x < thr + 0.15f * (srt[3 * srt.size() / 4] - srt[srt.size() / 4])) ? 1 : 0;
+                fprintf(stderr, "[vsom] block die calibration: pairs=%d complete=%d bimodal=%d thr=%.0f min=%.0f q1=%.0f median=%.0f q3=%.0f max=%.0f near=%zu\n", nPairs,
+                        complete ? 1 : 0, bimodal ? 1 : 0, thr, srt.front(), srt[srt.size() / 4], srt[srt.size() / 2], srt[3 * srt.size() / 4], srt.back(), near);
             }
             if (bimodal)
             {
@@ -984,10 +1046,13 @@ int configure_online_step_fast(vsom_ctx *ctx)
     const size_t bytes = fast_smem(ctx, G, stride);
     if (bytes + kFStaticSmem > static_cast<size_t>(ctx->smemOptin))
         return 0;
-    const bool reg = fast_reg_mode(ctx, G);
+    const int Lmax = (ctx->localN + G - 1) / G;
+    if (Lmax > kFThreads)
+        return 0; // one scan lane per owned node
+    const int ipw = fast_ipw(ctx, G);
     for (int prof = 0; prof < 2; ++prof)
     {
-        FastKernel k = pick_fast(ctx->transform, reg, prof != 0);
+        FastKernel k = pick_fast(ctx->transform, ipw, prof != 0);
         if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smemOptin - static_cast<int>(kFStaticSmem)) != cudaSuccess)
         {
             cudaGetLastError();
@@ -1004,7 +1069,7 @@ int configure_online_step_fast(vsom_ctx *ctx)
     ctx->fastGrid = G;
     ctx->fastStride = stride;
     ctx->fastSmem = bytes;
-    ctx->fastReg = reg ? 1 : 0;
+    ctx->fastReg = ipw;
     return 1;
 }
 
@@ -1035,7 +1100,7 @@ static int build_window_table(vsom_ctx *ctx, double sigma)
 // 0 when this launch is not eligible (sigma <= 1, ...), < 0 on error.
 int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma)
 {
-    if (!ctx->fastTrain || p.localSearch || p.world > 1)
+    if (!ctx->fastTrain || p.localSearch || p.world > 1 || p.n >= (1ull << 32))
         return 0;
     int rc = build_row_pool(ctx);
     if (rc)
@@ -1059,7 +1124,7 @@ int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma)
     const size_t lutBytes = sizeof(LutEntry) * static_cast<size_t>(p.lutCount);
     p.lutSmem = (ctx->fastSmem + lutBytes + kFStaticSmem <= static_cast<size_t>(ctx->smemOptin)) ? 1 : 0;
     const size_t smemBytes = ctx->fastSmem + (p.lutSmem ? lutBytes : 0);
-    FastKernel k = pick_fast(ctx->transform, ctx->fastReg != 0, p.prof != nullptr);
+    FastKernel k = pick_fast(ctx->transform, ctx->fastReg, p.prof != nullptr);
     void *args[] = {&p};
     VSOM_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k), dim3(G), dim3(kFThreads), args, smemBytes, ctx->stream));
     return 1;
