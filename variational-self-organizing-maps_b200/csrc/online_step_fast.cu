@@ -35,7 +35,7 @@
 namespace vsom
 {
 
-constexpr int kFThreads = 256;
+constexpr int kFThreads = 512;
 constexpr int kFWarps = kFThreads / 32;
 constexpr int kFMaxSlotsPerLane = 5; // the exchange row of a CTA is read by one warp: at most 160 CTAs
 constexpr int kFMaxCtas = 32 * kFMaxSlotsPerLane;
