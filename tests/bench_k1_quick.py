@@ -1,0 +1,26 @@
+"""Quick A/B timing of the online step at config 2 (not a test, not the bench): samples/s and phase cycles of a 200k chunk."""
+import importlib, sys, time
+import numpy as np
+sys.path.insert(0, ".")
+v = importlib.import_module("variational-self-organizing-maps_b200")
+import torch
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+rng = np.random.default_rng(0)
+W, H, D = 64, 64, 128
+ctx = v.VsomContext(W, H, D, v.MEDIAN)
+ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * H, D)) / 1000).astype(np.float32))
+x = (rng.standard_normal((n, D)) + 3 * rng.standard_normal((64, D))[rng.integers(0, 64, n)]).astype(np.float32)
+xd = torch.from_numpy(x).cuda(); ob = torch.empty(n, dtype=torch.int32, device="cuda"); od = torch.empty(n, dtype=torch.float32, device="cuda")
+for _ in range(2):
+    ctx.train_chunk_device(xd, n, 0.05, 32.0, v.EXPONENTIAL, ob, od)
+ctx.synchronize()
+t0 = time.perf_counter()
+for _ in range(3):
+    ctx.train_chunk_device(xd, n, 0.05, 32.0, v.EXPONENTIAL, ob, od)
+ctx.synchronize()
+dt = time.perf_counter() - t0
+ctx.debug_profile(True)
+ctx.train_chunk_device(xd, n, 0.05, 32.0, v.EXPONENTIAL, ob, od)
+ctx.synchronize()
+ph = ctx.debug_phase_cycles_raw()
+print(f"{3 * n / dt:10.0f} samples/s  fast={ctx.last_train_fast} die={ctx.die_aware} ", {k: round(val) for k, val in ph.items()})

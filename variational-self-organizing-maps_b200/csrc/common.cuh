@@ -68,6 +68,7 @@ struct StepParams
     int *rowOf;               // [G] row (die * 160 + slot) every CTA claimed in this launch
     unsigned *rowCtr;         // [0..1] rows claimed per die, [2] arrivals at the one-off grid barrier
     u64 *rowPool;
+    int pollDelay;            // cycles between the pushes and the first poll
 };
 
 } // namespace vsom

@@ -921,6 +921,7 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.xVec = (ctx->Din % 4 == 0 && (reinterpret_cast<uintptr_t>(xDev) & 15) == 0) ? 1 : 0;
 
     p.winTab = nullptr;
+    p.pollDelay = 0;
     ctx->lastTrainFast = 0;
     if (ctx->fastTrain && !ctx->fastDisabled)
     {

@@ -282,6 +282,11 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         rl[j] = it / nCh;
         rk[j] = ((it - rl[j] * nCh) << 7) + (lane << 2);
         ract[j] = IPW > 0 && it < items && rk[j] < DmPad;
+        if (!ract[j])
+        {
+            rl[j] = 0; // inactive: loads of the update phase stay in bounds, nothing is stored
+            rk[j] = 0;
+        }
         rm[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         rs[j] = rm[j];
         if (ract[j])
@@ -372,6 +377,9 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
 
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
     int curOff = 0, nextOff = DmPad; // ring offsets of samples t and t+1
+    // the scan warp's serial code is the critical path: keep what it reads from the parameter block in registers
+    int lutW = p.lutW, lutInSmem = p.lutSmem, expDecay = p.decay == VSOM_EXPONENTIAL ? 1 : 0;
+    asm volatile("" : "+r"(lutW), "+r"(lutInSmem), "+r"(expDecay));
     for (unsigned t = 0; t < n; ++t)
     {
         if (PROF && tid == 0)
@@ -430,6 +438,14 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 const u64 filler = (~0ull << 8) | tag;
                 u64 m;
                 long long t0 = 0;
+                // one batch of loads per round, all in flight together.  (Two batches in flight were measured twice and
+                // lose: exchange 1529 -> 1855 cycles; more polling traffic on the lines the keys arrive in delays them.)
+                if (p.pollDelay > 0)
+                {
+                    const long long w0 = clock64();
+                    while (clock64() - w0 < p.pollDelay)
+                        ;
+                }
                 for (unsigned round = 0;; ++round)
                 {
                     u64 v[kFMaxSlotsPerLane];
@@ -494,14 +510,14 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 if (myX >= (wx & 0xffffu) && myX < (wx >> 16) && myY >= (wy & 0xffffu) && myY < (wy >> 16))
                 {
                     const int dx = myX > bx ? myX - bx : bx - myX, dy = myY > by ? myY - by : by - myY;
-                    const int li = dy * p.lutW + dx;
+                    const int li = dy * lutW + dx;
                     float4 raw;
-                    if (p.lutSmem)
+                    if (lutInSmem)
                         raw = *reinterpret_cast<const float4 *>(lutS + li);
                     else
                         raw = __ldg(reinterpret_cast<const float4 *>(p.lut + li));
                     float c;
-                    if (p.decay == VSOM_EXPONENTIAL)
+                    if (expDecay)
                     {
                         myW = __fadd_rn(myW, raw.z); // :924
                         c = raw.z;                   // :925
@@ -539,21 +555,48 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             const int pl = sPend[par];
             if (IPW > 0)
             {
+                // all loads first; when every item of the warp is inside the window (warp-uniform, the usual case while the
+                // neighbourhood is wide) the items are updated in one straight-line block so that their dependency chains
+                // interleave; otherwise item by item
+                float2 cf[NI];
+                float4 nv[NI], xv[NI];
+                bool allIn = true;
 #pragma unroll
                 for (int j = 0; j < NI; ++j)
-                    if (ract[j])
+                {
+                    cf[j] = coef[rl[j]];
+                    nv[j] = *reinterpret_cast<const float4 *>(xn + rk[j]);
+                    xv[j] = *reinterpret_cast<const float4 *>(xt + rk[j]);
+                    allIn = allIn && ract[j] && cf[j].y >= 0.0f;
+                }
+                if (allIn)
+                {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j)
+                        fast_update4<TR>(xv[j], cf[j].x, cf[j].y, rm[j], rs[j]);
+#pragma unroll
+                    for (int j = 0; j < NI; ++j)
                     {
-                        const float2 cf = coef[rl[j]];
-                        const float4 nv = *reinterpret_cast<const float4 *>(xn + rk[j]);
-                        if (cf.y >= 0.0f)
-                        {
-                            const float4 xv = *reinterpret_cast<const float4 *>(xt + rk[j]);
-                            fast_update4<TR>(xv, cf.x, cf.y, rm[j], rs[j]);
-                            if (rl[j] == pl)
-                                *reinterpret_cast<float4 *>(pendRow + rk[j]) = sq_res4(rm[j], xv);
-                        }
-                        *reinterpret_cast<float4 *>(tBase + rl[j] * stride + rk[j]) = sq_res4(rm[j], nv);
+                        if (rl[j] == pl)
+                            *reinterpret_cast<float4 *>(pendRow + rk[j]) = sq_res4(rm[j], xv[j]);
+                        *reinterpret_cast<float4 *>(tBase + rl[j] * stride + rk[j]) = sq_res4(rm[j], nv[j]);
                     }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < NI; ++j)
+                        if (ract[j])
+                        {
+                            if (cf[j].y >= 0.0f)
+                            {
+                                fast_update4<TR>(xv[j], cf[j].x, cf[j].y, rm[j], rs[j]);
+                                if (rl[j] == pl)
+                                    *reinterpret_cast<float4 *>(pendRow + rk[j]) = sq_res4(rm[j], xv[j]);
+                            }
+                            *reinterpret_cast<float4 *>(tBase + rl[j] * stride + rk[j]) = sq_res4(rm[j], nv[j]);
+                        }
+                }
             }
             else
                 for (int it = warp; it < items; it += kFWarps)
@@ -1114,6 +1157,10 @@ int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma)
     VSOM_CUDA(ctx, cudaMemsetAsync(ctr, 0, sizeof(unsigned) * 4, ctx->stream));
     VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
     p.winTab = ctx->winTab;
+    {
+        const char *e = getenv("VSOM_POLL_DELAY"); // experiment knob: cycles to wait between the pushes and the first poll
+        p.pollDelay = e ? atoi(e) : 0;
+    }
     p.dieOfSm = ctx->rowMeta;
     p.rowBlocks = ctx->rowMeta + 256;
     p.rowOf = ctx->rowMeta + 256 + 2 * 2 * kFMaxCtas;
