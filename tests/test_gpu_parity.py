@@ -95,6 +95,10 @@ SHAPES = [
     (31, 1, 5, 1, 40, 0.2, 2.0),
     (1, 200, 130, 0, 40, 0.2, 3.0),
     (40, 40, 64, 1, 48, 0.1, 6.0),     # 11 nodes per CTA: two register-resident items per warp
+    # generic kernel with many owned nodes per CTA: window-cell enumeration instead of a test of every owned node, on an
+    # HBM-resident map (warp-tiled scan) and on a shared-memory-resident CLR map
+    (150, 150, 784, 0, 10, 0.1, 6.0),
+    (130, 130, 8, 2, 24, 0.001, 5.0),
 ]
 
 
@@ -110,7 +114,7 @@ def synth(rng, n, Din, tr):
 @pytest.mark.parametrize("decay", [0, 1])
 def test_online_step_matches_oracle_bit_exact(vsom, po, shape, decay, online_kernel):
     W, H, Din, tr, n, eta, sigma = shape
-    if online_kernel == "generic" and (W, H, Din) in ((100, 100, 784), (64, 64, 784)):
+    if online_kernel == "generic" and (W, H, Din) in ((100, 100, 784), (64, 64, 784), (150, 150, 784), (130, 130, 8)):
         pytest.skip("the generic kernel is what runs these shapes in the fast variant too (K1F does not fit)")
     rng = np.random.default_rng(hash((W, H, Din, tr, decay)) % (2 ** 32))
     o = po.Oracle(W, H, Din, tr)

@@ -140,7 +140,11 @@ static int create_impl(vsom_ctx **out, int device, int width, int height, int d_
     ctx->smemOptin = static_cast<int>(prop.sharedMemPerBlockOptin);
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     const size_t plane = sizeof(float) * static_cast<size_t>(ctx->localN) * ctx->rowStride;
-    CREATE_CUDA(cudaMalloc(&ctx->mean, plane));
+    // the mean plane carries a tail of zero rows: the streamed scan's TMA descriptor (online_step.cu) addresses rows as
+    // (owner CTA, owned-row index) and its last index may reach up to one grid of rows past the map
+    const size_t meanTail = sizeof(float) * 160 * static_cast<size_t>(ctx->rowStride);
+    CREATE_CUDA(cudaMalloc(&ctx->mean, plane + meanTail));
+    CREATE_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(ctx->mean) + plane, 0, meanTail, ctx->stream));
     CREATE_CUDA(cudaMalloc(&ctx->S, plane));
     CREATE_CUDA(cudaMalloc(&ctx->sigma, plane));
     CREATE_CUDA(cudaMalloc(&ctx->weight, sizeof(float) * ctx->localN));
@@ -257,6 +261,7 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->lut);
     cudaFree(ctx->distBuf);
     cudaFree(ctx->winTab);
+    cudaFree(ctx->scanMapDev);
     cudaFree(ctx->rowPool);
     cudaFree(ctx->rowMeta);
     cudaFree(ctx->profDev);

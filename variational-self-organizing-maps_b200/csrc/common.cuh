@@ -69,6 +69,8 @@ struct StepParams
     unsigned *rowCtr;         // [0..1] rows claimed per die, [2] arrivals at the one-off grid barrier
     u64 *rowPool;
     int pollDelay;            // cycles between the pushes and the first poll
+    int scanBufs, scanSeg, scanNSeg; // K1 on HBM-resident rows: streamed scan (ring of scanBufs buffers of 32 row segments of scanSeg floats)
+    const void *scanMap;      // ... its TMA descriptor of the mean plane (device memory)
 };
 
 } // namespace vsom
@@ -117,6 +119,8 @@ struct vsom_ctx
     vsom::u64 *rowPool = nullptr; // K1F exchange rows: 1024 blocks of 2 KB
     int *rowMeta = nullptr;       // dieOfSm[256] | rowBlocks[640] | rowOf[160] | counters[4]
     int dieAware = 0;             // the row pool was classified by L2 die
+    int scanBufs = 0, scanSeg = 0, scanNSeg = 0; // K1: HBM-resident rows are streamed through a ring of segment buffers
+    void *scanMapDev = nullptr;                   // TMA descriptor of the mean plane for that scan
     long long *profDev = nullptr; // diagnostics: per-phase cycle sums of the last online-step launch
     size_t profSamples = 0;
     std::string err;

@@ -29,7 +29,10 @@
 //     otherwise idle thread / warp of the owner CTA during the next sample's scan, off the critical path.
 #include "common.cuh"
 
+#include <cuda.h>
+
 #include <cmath>
+#include <string>
 
 namespace vsom
 {
@@ -114,6 +117,33 @@ __device__ __forceinline__ float node_dist_reference(const float *m, const float
     if (TR != VSOM_CLR)
         return dist_sequential_v4(m, xs, n4); // the zero padding adds +0 terms: s + 0 == s exactly
     return dist_sequential<TR>(m, xs, p.Dr, p.P, pi, pj);
+}
+
+constexpr int kScanSegMax = 132; // floats of a row per streamed segment at most; a segment is (odd number) x 4 floats long
+constexpr int kScanMaxBufs = 6;  // buffers per scan warp
+constexpr int kListThreshold = 96; // owned nodes per CTA above which the update window is enumerated cell by cell
+constexpr int kScanWarps = 4;    // warps that stream and scan (each its own ring)
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void scan_bar_init(u64 *bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void scan_bar_expect(u64 *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool scan_bar_try_wait(u64 *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// one TMA box of the mean plane -> shared memory, completion counted in bytes on an mbarrier.  The plane is described as
+// the 3-D tensor (column, owner CTA, owned-row index): row = index * G + cta, so a box {scanSeg, 1, 32} is a segment of 32
+// consecutive OWNED rows of one CTA although they lie G rows apart in memory.
+__device__ __forceinline__ void scan_tma_load(void *dst, const void *map, u64 *bar, int col, int cta, int row)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_addr(dst)), "l"(map),
+                 "r"(smem_addr(bar)), "r"(col), "r"(cta), "r"(row)
+                 : "memory");
 }
 
 // Som::findLocalBmu (src/Som.cpp:335-454) on the per-step distance array: greedy walk from `start` over the
@@ -208,14 +238,21 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     float *wbuf = xs + 3 * DinPad;                                           // [Lpad] weightMap of the owned nodes
     const int Lpad = (Lmax + 3) & ~3;
     float2 *coef = reinterpret_cast<float2 *>(wbuf + Lpad);                  // [Lpad] per owned node in the window: {step coefficient, (float)nw}
-    int2 *nodeXY = reinterpret_cast<int2 *>(coef + Lpad);                    // [Lpad] grid position of the owned nodes
-    unsigned *touched = reinterpret_cast<unsigned *>(nodeXY + Lpad);         // [Lpad] visited in this chunk
+    const bool useList = Lmax > kListThreshold; // many owned nodes: enumerate the window's cells instead of testing every owned node
+    int2 *nodeXY = reinterpret_cast<int2 *>(coef + Lpad);                    // [Lpad] grid position of the owned nodes (not with the list)
+    unsigned *touched = reinterpret_cast<unsigned *>(nodeXY + (useList ? 0 : Lpad)); // [Lpad] visited in this chunk
     unsigned *inWin = touched + Lpad;                                        // [Lpad] inside the window of the current sample
     unsigned short *pi = reinterpret_cast<unsigned short *>(inWin + Lpad);   // [Ppad] CLR pair tables
     const int Ppad = (p.P + 7) & ~7;
     unsigned short *pj = pi + Ppad;
     float *planes = reinterpret_cast<float *>(pj + Ppad);                    // resident rows: 2 x Lmax x smStride
-    LutEntry *lutS = reinterpret_cast<LutEntry *>(planes + (RES ? 2 * static_cast<size_t>(Lmax) * p.smStride : 0)); // optional copy of the table
+    // !RES with p.scanBufs: ring of streamed row segments [warps][bufs][32][scanSeg], 128-byte aligned for the TMA engine
+    // (pointer arithmetic on a shared-memory pointer, not an integer round trip: the loads must stay LDS, not generic LD)
+    float *sbuf = planes + (((128u - (smem_addr(planes) & 127u)) & 127u) >> 2);
+    LutEntry *lutS = reinterpret_cast<LutEntry *>(RES ? planes + 2 * static_cast<size_t>(Lmax) * p.smStride
+                                                      : (p.scanBufs > 0 ? sbuf + static_cast<size_t>(kScanWarps) * p.scanBufs * 32 * p.scanSeg : planes)); // optional copy of the table
+    __shared__ __align__(8) u64 sScanBar[kScanWarps * kScanMaxBufs];
+    __shared__ int sListN;                                                   // owned nodes inside the window of the current sample
 
     float *mBase, *sBase;
     size_t stride;
@@ -250,7 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
     {
         const unsigned node = static_cast<unsigned>(p.node0 + l * G + b);
         wbuf[l] = p.weight[static_cast<size_t>(l) * G + b];
-        nodeXY[l] = make_int2(static_cast<int>(node % static_cast<unsigned>(p.W)), static_cast<int>(node / static_cast<unsigned>(p.W)));
+        if (!useList)
+            nodeXY[l] = make_int2(static_cast<int>(node % static_cast<unsigned>(p.W)), static_cast<int>(node / static_cast<unsigned>(p.W)));
         touched[l] = 0;
     }
     for (int k = tid; k < 3 * DinPad; k += kThreads)
@@ -271,7 +309,13 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         sAbort = 0;
         sPendL = -1;
         sPendT = 0;
+        for (int i = 0; i < kScanWarps * kScanMaxBufs; ++i)
+            scan_bar_init(&sScanBar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    int scanBuf = 0;      // streamed scan: next buffer of this warp's ring to consume ...
+    unsigned scanPar = 0; // ... and the phase its mbarrier completes next
     __syncthreads();
 
     // sample prefetch: 16-byte cp.async.cg (L2 only — a streamed sample must not evict the L1-resident table)
@@ -332,13 +376,116 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     p.outDist[pendT] = d;
                 p.hits[q] += 1;
             }
-            for (int l = tid; l < L; l += kThreads)
+            if (!RES && TR != VSOM_CLR && p.scanBufs > 0)
             {
-                const float d = node_dist_reference<TR>(mBase + l * stride, xt, p, n4, pi, pj);
-                if (p.localSearch)
-                    p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
-                best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                // HBM-resident map.  A thread-per-node scan reads 16 bytes per row and instruction and reaches 49 % of the HBM
+                // roofline; coalescing through warp tiles of 128-byte row chunks was slower still (many small scattered
+                // requests, little in flight).  Here the rows are STREAMED: each of the first kScanWarps warps keeps its own
+                // ring of buffers in flight, a buffer being filled by 32 bulk copies (cp.async.bulk: one contiguous row
+                // segment of ~0.5 KB per lane, completion counted in bytes on an mbarrier); lane r then walks row r's
+                // segment in order — the reference's sequential sum, one row per lane, fed by contiguous DRAM bursts with
+                // ~100 KB in flight per SM.  The other warps wait at the barrier below.
+                if (warp < kScanWarps)
+                {
+                    const int nSeg = p.scanNSeg, Kseg = p.scanSeg, segStride = Kseg, NB = p.scanBufs;
+                    const int nGroups = (L + 31) >> 5;
+                    const int myGroups = nGroups > warp ? (nGroups - warp + kScanWarps - 1) / kScanWarps : 0, steps = myGroups * nSeg;
+                    float *ring = sbuf + static_cast<size_t>(warp) * NB * 32 * segStride;
+                    u64 *bars = sScanBar + warp * kScanMaxBufs;
+                    // issue and consume cursors advance incrementally (no divisions on this path): segment within the group,
+                    // group, buffer of the ring; the ring position and the mbarrier phase carry over from sample to sample
+                    int sgI = 0, gI = warp, bufI = scanBuf;
+                    auto issue = [&]() {
+                        if (lane == 0)
+                        {
+                            scan_bar_expect(&bars[bufI], static_cast<unsigned>(32 * Kseg * 4)); // a box always delivers all its bytes (zero fill outside)
+                            scan_tma_load(ring + static_cast<size_t>(bufI) * 32 * segStride, p.scanMap, &bars[bufI], sgI * Kseg, b, 32 * gI);
+                        }
+                        if (++sgI == nSeg)
+                        {
+                            sgI = 0;
+                            gI += kScanWarps;
+                        }
+                        if (++bufI == NB)
+                            bufI = 0;
+                    };
+                    int issued = 0;
+                    for (; issued < NB && issued < steps; ++issued)
+                        issue();
+                    float sacc = 0.0f;
+                    int sg = 0, g = warp;
+                    for (int i = 0; i < steps; ++i)
+                    {
+                        unsigned spins = 0;
+                        while (!scan_bar_try_wait(&bars[scanBuf], scanPar))
+                            if (++spins > (1u << 24))
+                            {
+                                sAbort = 1; // a box that never lands is a bug, not a wait
+                                *p.err = 1;
+                                break;
+                            }
+                        const int n4s = min(Kseg, DmPad - sg * Kseg) >> 2;
+                        if (sg == 0)
+                            sacc = 0.0f;
+                        const int l = 32 * g + lane;
+                        if (l < L)
+                        {
+                            // s += (m_k - x_k)^2 in order, loads a pair of 128-bit words ahead of the adds
+                            const float4 *m4 = reinterpret_cast<const float4 *>(ring + (static_cast<size_t>(scanBuf) * 32 + lane) * segStride);
+                            const float4 *x4 = reinterpret_cast<const float4 *>(xt + sg * Kseg);
+                            const int pairs = n4s >> 1;
+                            if (pairs > 0)
+                            {
+                                float4 a0 = m4[0], b0 = x4[0], a1 = m4[1], b1 = x4[1];
+                                for (int k = 1; k < pairs; ++k)
+                                {
+                                    const float4 c0 = m4[2 * k], d0 = x4[2 * k], c1 = m4[2 * k + 1], d1 = x4[2 * k + 1];
+                                    acc4(sacc, a0, b0);
+                                    acc4(sacc, a1, b1);
+                                    a0 = c0;
+                                    b0 = d0;
+                                    a1 = c1;
+                                    b1 = d1;
+                                }
+                                acc4(sacc, a0, b0);
+                                acc4(sacc, a1, b1);
+                            }
+                            if (n4s & 1)
+                                acc4(sacc, m4[n4s - 1], x4[n4s - 1]);
+                            if (sg == nSeg - 1)
+                            {
+                                if (p.localSearch)
+                                    p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = sacc;
+                                best = u64_min(best, make_key(sacc, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                            }
+                        }
+                        __syncwarp(); // every lane is done with this buffer before it is refilled
+                        if (issued < steps)
+                        {
+                            issue();
+                            ++issued;
+                        }
+                        if (++sg == nSeg)
+                        {
+                            sg = 0;
+                            g += kScanWarps;
+                        }
+                        if (++scanBuf == NB)
+                        {
+                            scanBuf = 0;
+                            scanPar ^= 1u;
+                        }
+                    }
+                }
             }
+            else
+                for (int l = tid; l < L; l += kThreads)
+                {
+                    const float d = node_dist_reference<TR>(mBase + l * stride, xt, p, n4, pi, pj);
+                    if (p.localSearch)
+                        p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
+                    best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                }
         }
         else
         {
@@ -507,7 +654,9 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             //      (src/Som.cpp:915-939).  When a node's vector spans several warps (nCh > 1) this is done once here;
             //      with one warp per node (nCh == 1) each update warp does it for its own node after the barrier,
             //      which keeps it off this warp's critical path.
-            for (int l = lane; nCh > 1 && l < L; l += 32)
+            if (lane == 0)
+                sListN = 0;
+            for (int l = lane; nCh > 1 && !useList && l < L; l += 32)
             {
                 const int2 xy = nodeXY[l];
                 float2 cf = make_float2(-1.0f, 0.0f);
@@ -554,16 +703,74 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         __syncthreads();
         if (sAbort)
             break;
+        if (useList)
+        {
+            // every thread walks cells of the window; an owned node is appended to the list (kept in inWin[]) together with
+            // its neighbourhood entry, new weightMap value and step coefficient (src/Som.cpp:915-939).  Nodes are
+            // independent, so the order of the list does not matter.
+            const int wbmu = sWin[0], wbx = sWin[1], wby = sWin[2], wsx = sWin[3], wex = sWin[4], wsy = sWin[5], wey = sWin[6];
+            const int ww = wex - wsx, cells = ww * (wey - wsy);
+            for (int cidx = tid; cidx < cells; cidx += kThreads)
+            {
+                const int cy = cidx / ww, cx = cidx - cy * ww;
+                const int x = wsx + cx, y = wsy + cy;
+                const int rel = y * p.W + x - p.node0;
+                if (rel < 0 || rel >= p.nodeCount)
+                    continue;
+                const int l = rel / G;
+                if (rel - l * G != b)
+                    continue;
+                const int dx = x > wbx ? x - wbx : wbx - x, dy = y > wby ? y - wby : wby - y;
+                const int li = dy * p.lutW + dx;
+                float4 raw;
+                if (p.lutSmem)
+                    raw = *reinterpret_cast<const float4 *>(lutS + li);
+                else
+                    raw = __ldg(reinterpret_cast<const float4 *>(p.lut + li));
+                const float cexp = raw.z, nwf = raw.w;
+                float w = wbuf[l], c;
+                if (p.decay == VSOM_EXPONENTIAL)
+                {
+                    w = __fadd_rn(w, cexp); // :924
+                    c = cexp;               // :925
+                }
+                else
+                {
+                    w = __fadd_rn(w, nwf); // :930
+                    const double nw = __hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x));
+                    const double tw = (w == 0.0f) ? 1.0 : __ddiv_rn(nw, static_cast<double>(w)); // :933
+                    c = static_cast<float>(tw);                                                    // :935
+                }
+                wbuf[l] = w;
+                touched[l] = 1;
+                coef[l] = make_float2(c, nwf);
+                if (rel + p.node0 == wbmu)
+                {
+                    sPendL = l;
+                    sPendT = t;
+                }
+                inWin[atomicAdd(&sListN, 1)] = static_cast<unsigned>(l);
+            }
+            __syncthreads();
+        }
         if (p.prof && tid == 0)
             sClk[4] = clock64();
         // ---- update: one warp per (window node, 128-element slice) of the model vector (src/Som.cpp:912-941)
         {
-            const int items = L * nCh;
+            const int items = (useList ? sListN : L) * nCh;
             for (int it = warp; it < items; it += kWarps)
             {
-                const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
+                int l = nCh > 1 ? it / nCh : it;
+                const int ch = nCh > 1 ? it - l * nCh : 0;
                 float c, nwf;
-                if (nCh > 1)
+                if (useList)
+                {
+                    l = static_cast<int>(inWin[l]);
+                    const float2 cf = coef[l];
+                    c = cf.x;
+                    nwf = cf.y;
+                }
+                else if (nCh > 1)
                 {
                     if (!inWin[l])
                         continue;
@@ -659,6 +866,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 }
             }
         }
+        if (!RES && p.scanBufs > 0)
+            asm volatile("fence.proxy.async.global;" ::: "memory"); // this sample's stores to the mean plane before the next scan's TMA reads
         done = t + 1;
         if (p.prof && tid == 0)
         {
@@ -746,7 +955,7 @@ static size_t online_step_smem(const vsom_ctx *ctx, int G, bool resident, int sm
     const int DinPad = (ctx->Din + 3) & ~3;
     const int Ppad = (ctx->P + 7) & ~7;
     size_t bytes = sizeof(float) * (3 * static_cast<size_t>(DinPad) + 3 * static_cast<size_t>(Lpad));
-    bytes += (sizeof(int2) + 2 * sizeof(unsigned)) * static_cast<size_t>(Lpad);
+    bytes += ((Lmax > kListThreshold ? 0 : sizeof(int2)) + 2 * sizeof(unsigned)) * static_cast<size_t>(Lpad);
     bytes += 2 * sizeof(unsigned short) * static_cast<size_t>(Ppad);
     if (resident)
         bytes += sizeof(float) * 2 * static_cast<size_t>(Lmax) * smStride;
@@ -764,6 +973,39 @@ static StepKernel pick_kernel(int transform, int order, int resident)
     return table[transform][order][resident ? 1 : 0];
 }
 
+typedef CUresult (*ScanEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                 const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// mean plane as (column, owner CTA, owned-row index), box {seg, 1, 32}; the descriptor lives in device memory
+static int make_scan_map(vsom_ctx *ctx, int G, int seg)
+{
+    static ScanEncodeFn enc = nullptr;
+    if (!enc)
+    {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<ScanEncodeFn>(fp);
+    }
+    if (!enc)
+        return set_error(ctx, VSOM_ERR_CUDA, "online step: cuTensorMapEncodeTiled entry point not available");
+    const int Lmax = (ctx->localN + G - 1) / G;
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(ctx->rowStride), static_cast<cuuint64_t>(G), static_cast<cuuint64_t>(Lmax)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(ctx->rowStride) * 4, static_cast<cuuint64_t>(ctx->rowStride) * 4 * G};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(seg), 1, 32};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ctx->mean, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(ctx, VSOM_ERR_CUDA, "online step: cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
+    if (!ctx->scanMapDev)
+        VSOM_CUDA(ctx, cudaMalloc(&ctx->scanMapDev, 256));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->scanMapDev, &map, sizeof(map), cudaMemcpyHostToDevice, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
 int configure_online_step(vsom_ctx *ctx)
 {
     int G = ctx->localN < ctx->numSMs ? ctx->localN : ctx->numSMs;
@@ -773,12 +1015,37 @@ int configure_online_step(vsom_ctx *ctx)
     const size_t statics = kStaticSmem;
     size_t bytes = online_step_smem(ctx, G, true, smStride);
     int resident = 1;
+    ctx->scanBufs = 0;
     if (bytes + statics > static_cast<size_t>(ctx->smemOptin))
     {
         resident = 0;
         bytes = online_step_smem(ctx, G, false, smStride);
         if (bytes + statics > static_cast<size_t>(ctx->smemOptin))
             return set_error(ctx, VSOM_ERR_UNSUPPORTED, "online step: per-CTA bookkeeping does not fit in shared memory for this map");
+        // streamed scan of the HBM-resident rows (Standard / Median, reference order): as many segment buffers as fit
+        if (ctx->transform != VSOM_CLR && ctx->order == VSOM_ORDER_REFERENCE)
+        {
+            const int DmPad = (ctx->Dm + 3) & ~3;
+            int seg = DmPad < kScanSegMax ? DmPad : kScanSegMax;
+            if (((seg >> 2) & 1) == 0)
+                seg -= 4; // (seg / 4) odd: lanes = rows read the dense box without bank conflicts
+            if (seg >= 4)
+                for (int bufs = kScanMaxBufs; bufs >= 2; --bufs)
+                {
+                    const size_t ring = sizeof(float) * kScanWarps * bufs * 32 * seg;
+                    if (bytes + ring + statics + 1024 <= static_cast<size_t>(ctx->smemOptin))
+                    {
+                        int rc = make_scan_map(ctx, G, seg);
+                        if (rc)
+                            return rc;
+                        ctx->scanBufs = bufs;
+                        ctx->scanSeg = seg;
+                        ctx->scanNSeg = (DmPad + seg - 1) / seg;
+                        bytes += ring + 1024; // room to start the ring on a 1 KB boundary
+                        break;
+                    }
+                }
+        }
     }
     StepKernel k = pick_kernel(ctx->transform, ctx->order, resident);
     VSOM_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smemOptin - static_cast<int>(kStaticSmem)));
@@ -922,6 +1189,10 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
 
     p.winTab = nullptr;
     p.pollDelay = 0;
+    p.scanBufs = ctx->scanBufs;
+    p.scanSeg = ctx->scanSeg;
+    p.scanNSeg = ctx->scanNSeg;
+    p.scanMap = ctx->scanMapDev;
     ctx->lastTrainFast = 0;
     if (ctx->fastTrain && !ctx->fastDisabled)
     {
