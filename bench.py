@@ -189,7 +189,17 @@ def cpu_baseline_leg():
     return out
 
 
+def _claim_stdout():
+    """Libraries under us (NCCL's version banner) write to the C-level stdout; the contract is ONE JSON line there.  Point fd 1 at
+    stderr for the run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    sys.stdout = _claim_stdout()  # Python-level prints (the result line) keep going to the real stdout
     global SCORE_ROWS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -426,7 +436,7 @@ def main():
             line["large_map"] = large
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     ctx.close()
     sctx.close()
     if world > 1:
