@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-rows", type=int, default=SCORE_ROWS)
     ap.add_argument("--no-large-map", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--large-rows", type=int, default=1024)
     args = ap.parse_args()
     SCORE_ROWS = args.score_rows
@@ -394,6 +395,43 @@ def main():
         lctx.close()
         del lx
 
+    # ---------------- the other named training shapes, short runs (resident chunk, CUDA events): BASELINE configs[0]
+    #   (20x20, Standard, 784-dim — K1F) and configs[2] (50x50, combinatorial linear regression at J = 32 — generic K1)
+    others = []
+    if not args.no_other_configs:
+        def clr_chunk(n, j, seed):
+            rng = np.random.default_rng(seed)
+            z = rng.standard_normal((n, 1)).astype(np.float32)
+            a = rng.uniform(0.5, 1.5, (1, j)).astype(np.float32)
+            bb = rng.uniform(-1, 1, (1, j)).astype(np.float32)
+            return (a * z + bb + 0.1 * rng.standard_normal((n, j))).astype(np.float32)
+
+        for name, (ow, oh, od, otr, oeta, osig, orows) in (("configs[0]: 20x20 grid, Standard, 784-dim", (20, 20, 784, vsom.STANDARD, 0.1, 10.0, 60000)),
+                                                            ("configs[2]: 50x50 grid, combinatorial linear regression J=32 (992 parameters / node)", (50, 50, 32, vsom.CLR, 0.001, 25.0, 60000))):
+            octx = vsom.VsomContext(ow, oh, od, otr, order, device=local_rank)
+            odm = vsom.model_length(od, otr)
+            octx.upload_state(mean=init_map(ow * oh, odm, 99 + rank))
+            ox_np = clr_chunk(orows, od, 31 + rank) if otr == vsom.CLR else np.floor(256 * np.random.default_rng(5 + rank).random((orows, od), dtype=np.float32) ** 2).astype(np.float32)
+            ox = torch.from_numpy(ox_np).to(x_dev.device)
+            ob_ = torch.empty(orows, dtype=torch.int32, device=x_dev.device)
+            od_ = torch.empty(orows, dtype=torch.float32, device=x_dev.device)
+            ostream = torch.cuda.ExternalStream(octx.stream, device=local_rank)
+            octx.train_chunk_device(ox, orows // 10, oeta, osig, vsom.EXPONENTIAL, ob_, od_)
+            octx.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ostream):
+                e0.record(ostream)
+                octx.train_chunk_device(ox, orows, oeta, osig, vsom.EXPONENTIAL, ob_, od_)
+                e1.record(ostream)
+            octx.synchronize()
+            oms = e0.elapsed_time(e1)
+            kw = window_nodes(ow, oh, osig)
+            obytes = algorithmic_bytes_per_sample(ow * oh, odm, od, kw)
+            others.append({"workload": name, "samples": orows, "ms": oms, "value": orows / (oms / 1e3), "unit": "samples/s (per GPU)",
+                           "kernel": "online_step_fast_kernel" if octx.last_train_fast else "online_step_kernel", "eta": oeta, "sigma": osig,
+                           "algorithmic_bytes_per_sample": obytes, "achieved_gbs_vs_hbm": obytes * orows / (oms / 1e3) / 1e9})
+            octx.close()
+
     if rank == 0:
         hbm_gbs, bf16_tf, peak_src = peaks()
         k = window_nodes(W_, H_, SIGMA)
@@ -430,6 +468,8 @@ def main():
                         "exact_scan_rows_per_s": exact_rows_s, "exact_scan_rows": exact_rows * world,
                         "scaling": "row-sharded, no communication"},
         }
+        if others:
+            line["other_training_shapes"] = others
         if large is not None:
             large["roofline"]["peak"] = hbm_gbs
             large["roofline"]["frac"] = large["roofline"]["achieved"] / hbm_gbs
