@@ -159,6 +159,43 @@ __device__ __forceinline__ float chain_terms(const float *row, int n16)
     return s;
 }
 
+// ---- CLR (src/Transformation.cpp:79-167), scalar round-to-nearest operations only: a * x + b must never contract
+// residual of a pair: (A x' + B) - y'  (:104)
+__device__ __forceinline__ float clr_res(float a, float b, float xi, float xj) { return __fsub_rn(__fadd_rn(__fmul_rn(a, xi), b), xj); }
+// xi / xj: the sample's elements already gathered per pair (x' = x[pi_q], y' = x[pj_q] are the same for every node)
+__device__ __forceinline__ float4 clr_terms4(const float4 a, const float4 b, const float4 xi, const float4 xj)
+{
+    float4 t;
+    float r = clr_res(a.x, b.x, xi.x, xj.x);
+    t.x = __fmul_rn(r, r);
+    r = clr_res(a.y, b.y, xi.y, xj.y);
+    t.y = __fmul_rn(r, r);
+    r = clr_res(a.z, b.z, xi.z, xj.z);
+    t.z = __fmul_rn(r, r);
+    r = clr_res(a.w, b.w, xi.w, xj.w);
+    t.w = __fmul_rn(r, r);
+    return t;
+}
+// one pair of the window update (src/Som.cpp:912-941 with the CLR Stepper, src/Transformation.cpp:107-142):
+//   inner = (A x' + B) - y';  delta = [(-2 inner) x' || -2 inner];  model += c * delta;  S += nwf * (delta0 * delta1)
+// pend = squared residual of this sample against the UPDATED model (trainSingle's return value, :946)
+__device__ __forceinline__ void clr_update_pair(float xi, float xj, float c, float nwf, float &a, float &b, float &sa, float &sb, float &pend)
+{
+    const float in0 = clr_res(a, b, xi, xj);
+    const float db0 = __fmul_rn(-2.0f, in0);
+    const float da0 = __fmul_rn(db0, xi);
+    const float a1 = __fadd_rn(a, __fmul_rn(c, da0));
+    const float b1 = __fadd_rn(b, __fmul_rn(c, db0));
+    const float in1 = clr_res(a1, b1, xi, xj);
+    const float db1 = __fmul_rn(-2.0f, in1);
+    const float da1 = __fmul_rn(db1, xi);
+    sa = __fadd_rn(sa, __fmul_rn(nwf, __fmul_rn(da0, da1)));
+    sb = __fadd_rn(sb, __fmul_rn(nwf, __fmul_rn(db0, db1)));
+    a = a1;
+    b = b1;
+    pend = __fmul_rn(in1, in1);
+}
+
 // key layout: [63:32] distance bits | [31:20] y | [19:8] x | [7:0] tag.  (y, x) orders like the node index y*W + x.
 __device__ __forceinline__ u64 make_key_xy(float d, unsigned x, unsigned y, unsigned tag)
 {
@@ -195,8 +232,15 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     const int Lmax = (p.nodeCount + G - 1) / G;
     const int L = (p.nodeCount - b + G - 1) / G; // G <= nodeCount: every CTA owns at least one node; L <= kFThreads
     const int Lpad = (Lmax + 3) & ~3;
-    const int DmPad = (p.Dm + 3) & ~3;
-    const int stride = p.smStride;     // 16 q + 4 floats, 16 q >= DmPad
+    // CLR (combinatorial linear regression, src/Transformation.cpp:79-167): the model of a node is [A(P) || B(P)], the
+    // residual has one element per pair q: r_q = (A_q x[pi_q] + B_q) - x[pj_q].  Items, terms rows and the chain run over
+    // the P pairs; the shared-memory rows hold [A(Ppad) || B(Ppad)].  CLR always takes the shared-memory-row mode.
+    constexpr bool kClr = TR == VSOM_CLR;
+    const int Ppad = (p.P + 3) & ~3;
+    const int DmPad = kClr ? Ppad : (p.Dm + 3) & ~3; // length of the residual / terms row (padded)
+    const int XS = kClr ? ((p.Din + 3) & ~3) + 4 : DmPad; // ring slot of a sample; CLR keeps four zeros behind it for the pad pairs
+    const int stride = p.smStride;     // terms rows: 16 q + 4 floats, 16 q >= DmPad
+    const int rstride = kClr ? 2 * Ppad : stride; // mean / S rows (shared-memory-row mode)
     const int n16 = (stride - 4) >> 4; // blocks of 16 terms the chain walks
     const int nSW = (L + 31) >> 5;     // warps whose lanes own a node each
     const int nCh = (DmPad + 127) >> 7;
@@ -204,8 +248,8 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     const unsigned n = static_cast<unsigned>(p.n); // the host keeps chunks below 2^32 samples on this path
 
     // ---- carve shared memory (every region 16-byte aligned)
-    float *xs = reinterpret_cast<float *>(smemRaw);                        // [4][DmPad] sample ring
-    float2 *coef = reinterpret_cast<float2 *>(xs + 4 * DmPad);             // [Lpad] {step coefficient, (float)nw}; nw < 0: outside the window
+    float *xs = reinterpret_cast<float *>(smemRaw);                        // [4][XS] sample ring
+    float2 *coef = reinterpret_cast<float2 *>(xs + 4 * XS);                // [Lpad] {step coefficient, (float)nw}; nw < 0: outside the window
     unsigned *hitsS = reinterpret_cast<unsigned *>(coef + Lpad);           // [Lpad] bmuHits of this chunk
     unsigned *touchedS = hitsS + Lpad;                                     // [Lpad] node visited in this chunk (epilogue only)
     float *wS = reinterpret_cast<float *>(touchedS + Lpad);                // [Lpad] final weightMap entries (epilogue only)
@@ -214,9 +258,21 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     unsigned *winY = winX + Wpad;                                          // [Hpad]
     float *tBase = reinterpret_cast<float *>(winY + Hpad);                 // [Lmax][stride] squared residuals of the next sample
     float *pendRow = tBase + static_cast<size_t>(Lmax) * stride;           // [stride] squared residuals of the sample against its updated BMU
-    float *mBase = pendRow + stride;                                       // [Lmax][stride] means      (IPW == 0 only)
-    float *sBase = mBase + (IPW > 0 ? 0 : static_cast<size_t>(Lmax) * stride); // [Lmax][stride] Welford S  (IPW == 0 only)
-    LutEntry *lutS = reinterpret_cast<LutEntry *>(sBase + (IPW > 0 ? 0 : static_cast<size_t>(Lmax) * stride)); // optional copy of the neighbourhood table
+    float *mBase = pendRow + stride;                                       // [Lmax][rstride] means      (IPW == 0 only)
+    float *sBase = mBase + (IPW > 0 ? 0 : static_cast<size_t>(Lmax) * rstride); // [Lmax][rstride] Welford S  (IPW == 0 only)
+    ushort4 *pairS = reinterpret_cast<ushort4 *>(sBase + (IPW > 0 ? 0 : static_cast<size_t>(Lmax) * rstride)); // CLR: [2][Ppad / 4] pair tables pi, pj
+    float *gS = reinterpret_cast<float *>(pairS + (kClr ? 2 * (Ppad >> 2) : 0));   // CLR: [3][2][Ppad] x' = x[pi], y' = x[pj] of samples t, t+1, t+2
+    LutEntry *lutS = reinterpret_cast<LutEntry *>(gS + (kClr ? 6 * Ppad : 0));     // optional copy of the neighbourhood table
+    if (kClr)
+    {
+        unsigned short *pt = reinterpret_cast<unsigned short *>(pairS);
+        const unsigned short zeroAt = static_cast<unsigned short>(XS - 4); // pad pairs read the zeros behind the sample
+        for (int q = tid; q < Ppad; q += kFThreads)
+        {
+            pt[q] = q < p.P ? p.pairI[q] : zeroAt;
+            pt[Ppad + q] = q < p.P ? p.pairJ[q] : zeroAt;
+        }
+    }
 
     // ---- prologue
     // exchange rows: this CTA claims a row pair homed on the L2 die of the SM it runs on, publishes the choice, and after
@@ -246,7 +302,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         hitsS[l] = 0;
         touchedS[l] = 0;
     }
-    for (int k = tid; k < 4 * DmPad; k += kFThreads)
+    for (int k = tid; k < 4 * XS; k += kFThreads)
         xs[k] = 0.0f; // pad lanes of the 128-bit paths stay zero
     for (int k = tid; k < stride; k += kFThreads)
         pendRow[k] = 0.0f;
@@ -256,13 +312,21 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         for (int k = lane; k < stride; k += 32)
         {
             tBase[l * stride + k] = 0.0f;
-            if (IPW == 0)
+            if (IPW == 0 && !kClr)
             {
                 const bool in = k < p.Dm;
                 mBase[l * stride + k] = in ? p.mean[g + k] : 0.0f;
                 sBase[l * stride + k] = in ? p.S[g + k] : 0.0f;
             }
         }
+        if (kClr)
+            for (int k = lane; k < rstride; k += 32)
+            {
+                const int half = k >= Ppad ? 1 : 0, q = k - half * Ppad;
+                const bool in = q < p.P;
+                mBase[l * rstride + k] = in ? p.mean[g + half * p.P + q] : 0.0f;
+                sBase[l * rstride + k] = in ? p.S[g + half * p.P + q] : 0.0f;
+            }
     }
     if (tid == 0)
     {
@@ -345,7 +409,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         }
         cp_async_commit();
         xsrc += p.Din;
-        xdst = xdst + DmPad == 4 * DmPad ? 0 : xdst + DmPad;
+        xdst = xdst + XS == 4 * XS ? 0 : xdst + XS;
     };
     if (warp == kPrefetchWarp)
     {
@@ -356,6 +420,30 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         cp_async_wait_all();
     }
     __syncthreads();
+    // CLR: every thread below Ppad owns one pair for the gathers
+    int gpi = 0, gpj = 0;
+    if (kClr && tid < Ppad)
+    {
+        const unsigned short *pt = reinterpret_cast<const unsigned short *>(pairS);
+        gpi = pt[tid];
+        gpj = pt[Ppad + tid];
+    }
+    auto gather = [&](int slot, const float *x) { // x' and y' of one sample for every pair
+        for (int q = tid; q < Ppad; q += kFThreads)
+        {
+            const unsigned short *pt = reinterpret_cast<const unsigned short *>(pairS);
+            const int qi = q == tid ? gpi : pt[q], qj = q == tid ? gpj : pt[Ppad + q];
+            gS[(slot * 2) * Ppad + q] = x[qi];
+            gS[(slot * 2 + 1) * Ppad + q] = x[qj];
+        }
+    };
+    if (kClr)
+    {
+        gather(0, xs);
+        if (n > 1)
+            gather(1, xs + XS);
+        __syncthreads();
+    }
     // terms of sample 0 against the initial means
     if (IPW > 0)
     {
@@ -370,13 +458,23 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
             const int k = (ch << 7) + (lane << 2);
             if (k < DmPad)
-                *reinterpret_cast<float4 *>(tBase + l * stride + k) =
-                    sq_res4(*reinterpret_cast<const float4 *>(mBase + l * stride + k), *reinterpret_cast<const float4 *>(xs + k));
+            {
+                if (kClr)
+                {
+                    const float4 av = *reinterpret_cast<const float4 *>(mBase + l * rstride + k), bv = *reinterpret_cast<const float4 *>(mBase + l * rstride + Ppad + k);
+                    *reinterpret_cast<float4 *>(tBase + l * stride + k) =
+                        clr_terms4(av, bv, *reinterpret_cast<const float4 *>(gS + k), *reinterpret_cast<const float4 *>(gS + Ppad + k));
+                }
+                else
+                    *reinterpret_cast<float4 *>(tBase + l * stride + k) =
+                        sq_res4(*reinterpret_cast<const float4 *>(mBase + l * stride + k), *reinterpret_cast<const float4 *>(xs + k));
+            }
         }
     __syncthreads();
 
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
-    int curOff = 0, nextOff = DmPad; // ring offsets of samples t and t+1
+    int curOff = 0, nextOff = XS; // ring offsets of samples t and t+1
+    int gSlot = 0;                // CLR: gather slot of sample t (t mod 3)
     // the scan warp's serial code is the critical path: keep what it reads from the parameter block in registers
     int lutW = p.lutW, lutInSmem = p.lutSmem, expDecay = p.decay == VSOM_EXPONENTIAL ? 1 : 0;
     asm volatile("" : "+r"(lutW), "+r"(lutInSmem), "+r"(expDecay));
@@ -553,6 +651,9 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             const float *xt = xs + curOff;
             const float *xn = xs + nextOff;
             const int pl = sPend[par];
+            const float *gCur = gS + gSlot * 2 * Ppad, *gNext = gS + (gSlot == 2 ? 0 : gSlot + 1) * 2 * Ppad;
+            if (kClr && t + 2 < n) // sample t+2 landed with barrier B1: its x', y' are needed from the next step on
+                gather(gSlot == 0 ? 2 : gSlot - 1, xs + (nextOff + XS == 4 * XS ? 0 : nextOff + XS));
             if (IPW > 0)
             {
                 // all loads first; when every item of the warp is inside the window (warp-uniform, the usual case while the
@@ -603,7 +704,35 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 {
                     const int l = nCh > 1 ? it / nCh : it, ch = nCh > 1 ? it - l * nCh : 0;
                     const int k = (ch << 7) + (lane << 2);
-                    if (k < DmPad)
+                    if (kClr)
+                    {
+                        if (k < DmPad)
+                        {
+                            const float2 cf = coef[l];
+                            float *ap = mBase + l * rstride + k, *bp = ap + Ppad;
+                            float4 av = *reinterpret_cast<float4 *>(ap), bv = *reinterpret_cast<float4 *>(bp);
+                            if (cf.y >= 0.0f)
+                            {
+                                float *sap = sBase + l * rstride + k, *sbp = sap + Ppad;
+                                float4 sav = *reinterpret_cast<float4 *>(sap), sbv = *reinterpret_cast<float4 *>(sbp);
+                                const float4 xi = *reinterpret_cast<const float4 *>(gCur + k), xj = *reinterpret_cast<const float4 *>(gCur + Ppad + k);
+                                float4 pendv;
+                                clr_update_pair(xi.x, xj.x, cf.x, cf.y, av.x, bv.x, sav.x, sbv.x, pendv.x);
+                                clr_update_pair(xi.y, xj.y, cf.x, cf.y, av.y, bv.y, sav.y, sbv.y, pendv.y);
+                                clr_update_pair(xi.z, xj.z, cf.x, cf.y, av.z, bv.z, sav.z, sbv.z, pendv.z);
+                                clr_update_pair(xi.w, xj.w, cf.x, cf.y, av.w, bv.w, sav.w, sbv.w, pendv.w);
+                                *reinterpret_cast<float4 *>(ap) = av;
+                                *reinterpret_cast<float4 *>(bp) = bv;
+                                *reinterpret_cast<float4 *>(sap) = sav;
+                                *reinterpret_cast<float4 *>(sbp) = sbv;
+                                if (l == pl)
+                                    *reinterpret_cast<float4 *>(pendRow + k) = pendv;
+                            }
+                            *reinterpret_cast<float4 *>(tBase + l * stride + k) =
+                                clr_terms4(av, bv, *reinterpret_cast<const float4 *>(gNext + k), *reinterpret_cast<const float4 *>(gNext + Ppad + k));
+                        }
+                    }
+                    else if (k < DmPad)
                     {
                         const float2 cf = coef[l];
                         float *mp = mBase + l * stride + k;
@@ -625,7 +754,8 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 }
         }
         curOff = nextOff;
-        nextOff = nextOff + DmPad == 4 * DmPad ? 0 : nextOff + DmPad;
+        nextOff = nextOff + XS == 4 * XS ? 0 : nextOff + XS;
+        gSlot = gSlot == 2 ? 0 : gSlot + 1;
         if (PROF && tid == 0)
             c6 = clock64();
         __syncthreads(); // B2: terms of sample t+1 and the pend row are complete
@@ -701,8 +831,10 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             const float twf = static_cast<float>((w == 0.0f) ? 0.000001 : static_cast<double>(w));
             for (int k = lane; k < p.Dm; k += 32)
             {
-                const float sv = sBase[l * stride + k];
-                p.mean[g + k] = mBase[l * stride + k];
+                // CLR rows are [A(Ppad) || B(Ppad)] in shared memory, [A(P) || B(P)] in the plane
+                const int ks = kClr ? (k < p.P ? k : Ppad + (k - p.P)) : k;
+                const float sv = sBase[l * rstride + ks];
+                p.mean[g + k] = mBase[l * rstride + ks];
                 p.S[g + k] = sv;
                 if (vis)
                     p.sigma[g + k] = __fsqrt_rn(fabsf(__fdiv_rn(sv, twf)));
@@ -798,13 +930,15 @@ __global__ void die_classify_blocks_kernel(u64 *pool, int nBlocks, const int *pa
 
 static int fast_stride(const vsom_ctx *ctx)
 {
-    const int DmPad = (ctx->Dm + 3) & ~3;
+    const int DmPad = ctx->transform == VSOM_CLR ? (ctx->P + 3) & ~3 : (ctx->Dm + 3) & ~3; // residual length
     return ((DmPad + 15) & ~15) + 4; // 16 q + 4: rows 16-byte aligned, stride / 4 odd (conflict-free 128-bit access both ways)
 }
 
 // items per warp kept in registers (1, 2 or 4), 0 when the CTA owns more items than that: rows in shared memory
 static int fast_ipw(const vsom_ctx *ctx, int G)
 {
+    if (ctx->transform == VSOM_CLR)
+        return 0; // [A || B] rows stay in shared memory
     const int Lmax = (ctx->localN + G - 1) / G;
     const int nCh = (((ctx->Dm + 3) & ~3) + 127) >> 7;
     const int items = Lmax * nCh;
@@ -818,19 +952,26 @@ static size_t fast_smem(const vsom_ctx *ctx, int G, int stride)
 {
     const int Lmax = (ctx->localN + G - 1) / G;
     const int Lpad = (Lmax + 3) & ~3;
-    const int DmPad = (ctx->Dm + 3) & ~3;
+    const bool clr = ctx->transform == VSOM_CLR;
+    const int Ppad = (ctx->P + 3) & ~3;
+    const int XS = clr ? ((ctx->Din + 3) & ~3) + 4 : (ctx->Dm + 3) & ~3;
     const int Wpad = (ctx->W + 3) & ~3, Hpad = (ctx->H + 3) & ~3;
-    size_t bytes = sizeof(float) * 4 * static_cast<size_t>(DmPad);
+    size_t bytes = sizeof(float) * 4 * static_cast<size_t>(XS);
     bytes += (sizeof(float2) + 2 * sizeof(unsigned) + sizeof(float)) * static_cast<size_t>(Lpad);
     bytes += sizeof(unsigned) * (static_cast<size_t>(Wpad) + Hpad);
-    const size_t rows = fast_ipw(ctx, G) > 0 ? static_cast<size_t>(Lmax) : 3 * static_cast<size_t>(Lmax);
-    bytes += sizeof(float) * (rows + 1) * stride;
+    bytes += sizeof(float) * (static_cast<size_t>(Lmax) + 1) * stride; // terms rows + pend row
+    if (fast_ipw(ctx, G) == 0)
+        bytes += sizeof(float) * 2 * static_cast<size_t>(Lmax) * (clr ? 2 * Ppad : stride); // mean and S rows
+    if (clr)
+        bytes += sizeof(unsigned short) * 2 * static_cast<size_t>(Ppad) + sizeof(float) * 6 * static_cast<size_t>(Ppad);
     return bytes;
 }
 
 typedef void (*FastKernel)(const StepParams);
 static FastKernel pick_fast(int transform, int ipw, bool prof)
 {
+    if (transform == VSOM_CLR)
+        return prof ? online_step_fast_kernel<VSOM_CLR, 0, true> : online_step_fast_kernel<VSOM_CLR, 0, false>;
 #define VSOM_FK(TR, I) {online_step_fast_kernel<TR, I, false>, online_step_fast_kernel<TR, I, true>}
 #define VSOM_FKS(TR) {VSOM_FK(TR, 0), VSOM_FK(TR, 1), VSOM_FK(TR, 2), VSOM_FK(TR, 4)}
     static const FastKernel table[2][4][2] = {VSOM_FKS(VSOM_STANDARD), VSOM_FKS(VSOM_MEDIAN)};
@@ -1080,8 +1221,10 @@ static int build_row_pool(vsom_ctx *ctx)
 int configure_online_step_fast(vsom_ctx *ctx)
 {
     ctx->fastTrain = 0;
-    if (ctx->transform == VSOM_CLR || ctx->order != VSOM_ORDER_REFERENCE || ctx->world > 1 || ctx->W > 4096 || ctx->H > 4096)
+    if (ctx->order != VSOM_ORDER_REFERENCE || ctx->world > 1 || ctx->W > 4096 || ctx->H > 4096)
         return 0;
+    if (ctx->transform == VSOM_CLR && ((ctx->Din + 3) & ~3) + 4 > 65535)
+        return 0; // pair tables are 16-bit
     int G = ctx->localN < ctx->numSMs ? ctx->localN : ctx->numSMs;
     if (G > kFMaxCtas)
         G = kFMaxCtas;
