@@ -309,6 +309,32 @@ def test_tensor_core_scoring_ties_and_overflow_take_the_exact_scan(vsom):
     ctx.close()
 
 
+def test_tc_scoring_pipelines_slabs(vsom, monkeypatch):
+    monkeypatch.setenv("VSOM_TC_SLAB_LOG2", "20")  # 1M-row slabs instead of 4M, so that three of them fit a test
+    _tc_scoring_pipelines_slabs(vsom)
+
+
+def _tc_scoring_pipelines_slabs(vsom):
+    """More than two 1M-row slabs: the search of slab i+1 overlaps the re-scoring of slab i on a second stream and the
+    candidate scratch is reused by parity — results must still equal the exact scan row for row (some duplicated nodes so
+    that every slab also has rows for the exact-scan fallback)."""
+    rng = np.random.default_rng(11)
+    W, H, D, n = 16, 16, 32, (1 << 21) + 300_001
+    m = rng.standard_normal((W * H, D)).astype(np.float32)
+    m[216:] = m[0]  # 41 copies of node 0: more exact ties than the candidate list holds
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    hot = rng.integers(0, n, 3000)
+    x[hot] = m[0] + 0.001 * rng.standard_normal((3000, D)).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, vsom.STANDARD)
+    ctx.upload_state(mean=m)
+    eb, ed = ctx.find_bmu(x)
+    tb, td, fb = ctx.find_bmu_batch(x)
+    assert_bit_equal(tb, eb, "bmu")
+    assert_bit_equal(td, ed, "dist")
+    assert fb > 0
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ K6 (batch-map trainer)
 @pytest.mark.parametrize("shape", [(6, 6, 11, 0, 90), (7, 4, 11, 1, 90), (4, 9, 5, 2, 70), (20, 20, 784, 0, 60), (33, 17, 100, 1, 300),
                                    (12, 12, 32, 2, 150), (64, 64, 128, 0, 1500)])

@@ -267,6 +267,15 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->profDev);
     for (void *p : ctx->stage)
         cudaFree(p);
+    if (ctx->auxStream)
+    {
+        cudaStreamDestroy(ctx->auxStream);
+        for (int i = 0; i < 2; ++i)
+        {
+            cudaEventDestroy(ctx->evScore[i]);
+            cudaEventDestroy(ctx->evDone[i]);
+        }
+    }
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -90,6 +90,8 @@ struct vsom_ctx
     int rowStride = 0;
     int numSMs = 0, smemOptin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t auxStream = nullptr;           // K2: re-scoring of slab i overlaps the search of slab i + 1
+    cudaEvent_t evScore[2] = {}, evDone[2] = {};
     float *mean = nullptr, *S = nullptr, *sigma = nullptr, *weight = nullptr;
     vsom::u64 *hits = nullptr;
     double *umatrix = nullptr;

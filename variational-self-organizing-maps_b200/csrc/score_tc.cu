@@ -464,20 +464,61 @@ __global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__
 
 // ------------------------------------------------------------------------------------------------ exact rescore + guard
 
-// TC_TOPK (16) threads per row: thread j re-evaluates candidate j (if the row has that many) with the reference's sequential
-// f32 chain.  Rows whose list overflowed go to the fallback list (exact full scan).
-__global__ void rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
-                               const unsigned *__restrict__ cand, const unsigned *__restrict__ count, unsigned *__restrict__ outBmu,
-                               float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
+// Re-evaluation of the candidates with the reference's sequential f32 chain.  Rows keep 1-3 candidates on average, so a
+// thread per (row, slot) would leave nine lanes in ten idle: a CTA takes 128 rows, compacts their (row, candidate) items into
+// a list (block scan of the counts) and its 256 threads walk the list, all lanes busy; the per-row winner is an atomic min of
+// the (distance, node) key in shared memory — lowest index on ties, like the reference.  Rows whose list overflowed, or whose
+// winner is NaN, go to the fallback list (exact full scan).
+constexpr int RS_ROWS = 128;
+constexpr int RS_THREADS = 256;
+__global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
+                                                             const unsigned *__restrict__ cand, const unsigned *__restrict__ count, unsigned *__restrict__ outBmu,
+                                                             float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
 {
-    const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long row = gid >> 4;
-    const int j = static_cast<int>(gid & 15);
-    const bool live = row < rows;
-    const unsigned cnt = live ? count[row] : 0u;
-    u64 key = ~0ull;
-    if (live && cnt != TC_OVERFLOW && static_cast<unsigned>(j) < cnt)
+    __shared__ unsigned sOff[RS_ROWS + 1];
+    __shared__ unsigned sWarpTot[RS_ROWS / 32];
+    __shared__ u64 sKey[RS_ROWS];
+    __shared__ unsigned short sItem[RS_ROWS * TC_TOPK];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row0 = static_cast<long long>(blockIdx.x) * RS_ROWS;
+    unsigned cnt = 0, c = 0;
+    if (tid < RS_ROWS)
     {
+        const long long row = row0 + tid;
+        cnt = row < rows ? count[row] : 0u;
+        c = cnt == TC_OVERFLOW ? 0u : cnt;
+        sKey[tid] = ~0ull;
+        unsigned inc = c; // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += v;
+        }
+        if (lane == 31)
+            sWarpTot[warp] = inc;
+        sOff[tid] = inc - c; // exclusive, warp-local for now
+    }
+    __syncthreads();
+    if (tid < RS_ROWS)
+    {
+        unsigned base = 0;
+        for (int w = 0; w < warp; ++w)
+            base += sWarpTot[w];
+        const unsigned off = sOff[tid] + base;
+        for (unsigned j = 0; j < c; ++j)
+            sItem[off + j] = static_cast<unsigned short>((tid << 4) | j);
+        if (tid == RS_ROWS - 1)
+            sOff[RS_ROWS] = off + c;
+    }
+    __syncthreads();
+    const unsigned total = sOff[RS_ROWS];
+    for (unsigned i = tid; i < total; i += RS_THREADS)
+    {
+        const unsigned it = sItem[i];
+        const int r = static_cast<int>(it >> 4), j = static_cast<int>(it & 15u);
+        const long long row = row0 + r;
         const unsigned node = cand[row * TC_TOPK + j];
         const float *m = mean + static_cast<size_t>(node) * rowStride, *xr = x + row * D;
         float s = 0.0f;
@@ -486,122 +527,107 @@ __global__ void rescore_kernel(const float *__restrict__ x, long long rows, int 
         {
             const float4 *m4 = reinterpret_cast<const float4 *>(m), *x4 = reinterpret_cast<const float4 *>(xr);
 #pragma unroll 4
-            for (int c = 0; c < (D >> 2); ++c)
+            for (int q = 0; q < (D >> 2); ++q)
             {
-                const float4 a = m4[c], b = x4[c];
-                float r = __fsub_rn(a.x, b.x);
-                s = __fadd_rn(s, __fmul_rn(r, r));
-                r = __fsub_rn(a.y, b.y);
-                s = __fadd_rn(s, __fmul_rn(r, r));
-                r = __fsub_rn(a.z, b.z);
-                s = __fadd_rn(s, __fmul_rn(r, r));
-                r = __fsub_rn(a.w, b.w);
-                s = __fadd_rn(s, __fmul_rn(r, r));
+                const float4 a = m4[q], b = x4[q];
+                float d = __fsub_rn(a.x, b.x);
+                s = __fadd_rn(s, __fmul_rn(d, d));
+                d = __fsub_rn(a.y, b.y);
+                s = __fadd_rn(s, __fmul_rn(d, d));
+                d = __fsub_rn(a.z, b.z);
+                s = __fadd_rn(s, __fmul_rn(d, d));
+                d = __fsub_rn(a.w, b.w);
+                s = __fadd_rn(s, __fmul_rn(d, d));
             }
             k = D;
         }
         for (; k < D; ++k)
         {
-            const float r = __fsub_rn(m[k], xr[k]);
-            s = __fadd_rn(s, __fmul_rn(r, r));
+            const float d = __fsub_rn(m[k], xr[k]);
+            s = __fadd_rn(s, __fmul_rn(d, d));
         }
-        key = make_key(s, node, (s != s) ? 1u : 0u);
+        atomicMin(&sKey[r], make_key(s, node, (s != s) ? 1u : 0u));
     }
-#pragma unroll
-    for (int o = 8; o; o >>= 1)
-        key = u64_min(key, __shfl_xor_sync(0xffffffffu, key, o));
-    if (live && j == 0)
+    __syncthreads();
+    if (tid < RS_ROWS && row0 + tid < rows)
     {
-        float d = __uint_as_float(static_cast<unsigned>(key >> 32));
+        const long long row = row0 + tid;
+        const u64 key = sKey[tid];
         const bool nan = (key & 1ull) != 0;
-        if (cnt == TC_OVERFLOW || nan)
+        if (cnt == TC_OVERFLOW || nan || key == ~0ull)
             fallbackRows[atomicAdd(fallbackCount, 1u)] = static_cast<unsigned>(row);
         else
         {
             if (outBmu)
                 outBmu[row] = key_node(key);
             if (outDist)
-                outDist[row] = d;
+                outDist[row] = __uint_as_float(static_cast<unsigned>(key >> 32));
         }
     }
 }
 
 // Exact full scan for a FEW rows (the rows the candidate lists could not certify): one CTA per row, threads over
 // nodes, every (row, node) distance summed sequentially in f32 like the reference.  Same key rule as K3.
-__global__ void __launch_bounds__(256) find_bmu_rowwise_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows, unsigned count,
-                                                               const float *__restrict__ mean, int rowStride, int N, const u64 *__restrict__ hits,
-                                                               u64 minHits, unsigned *__restrict__ outBmu, float *__restrict__ outDist)
+// Exact full scan of the rows a slab's guard could not certify.  The row count lives in device memory (no host round trip
+// between the slabs of a batch): a fixed grid walks the list, and CTA 0 adds the count to the batch total.
+__global__ void __launch_bounds__(256) find_bmu_rowwise_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows,
+                                                               const unsigned *__restrict__ countPtr, const float *__restrict__ mean, int rowStride, int N,
+                                                               const u64 *__restrict__ hits, u64 minHits, unsigned *__restrict__ outBmu, float *__restrict__ outDist,
+                                                               unsigned long long *__restrict__ total)
 {
     extern __shared__ float xrow[];
     __shared__ u64 wkey[8];
-    const unsigned i = blockIdx.x;
-    if (i >= count)
-        return;
-    const size_t r = rows[i];
-    for (int k = threadIdx.x; k < D; k += blockDim.x)
-        xrow[k] = x[r * D + k];
-    __syncthreads();
-    u64 best = ~0ull;
-    for (int node = threadIdx.x; node < N; node += blockDim.x)
+    const unsigned count = *countPtr;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && count)
+        atomicAdd(total, static_cast<unsigned long long>(count));
+    for (unsigned i = blockIdx.x; i < count; i += gridDim.x)
     {
-        if (!(node == 0 || minHits == 0 || hits[node] >= minHits))
-            continue;
-        const float *m = mean + static_cast<size_t>(node) * rowStride;
-        float s = 0.0f;
-        int k = 0;
-        for (; k + 4 <= D; k += 4)
+        const size_t r = rows[i];
+        __syncthreads(); // xrow / wkey of the previous row are no longer read
+        for (int k = threadIdx.x; k < D; k += blockDim.x)
+            xrow[k] = x[r * D + k];
+        __syncthreads();
+        u64 best = ~0ull;
+        for (int node = threadIdx.x; node < N; node += blockDim.x)
         {
-            const float4 a = *reinterpret_cast<const float4 *>(m + k);
-            float q = __fsub_rn(a.x, xrow[k]);
-            s = __fadd_rn(s, __fmul_rn(q, q));
-            q = __fsub_rn(a.y, xrow[k + 1]);
-            s = __fadd_rn(s, __fmul_rn(q, q));
-            q = __fsub_rn(a.z, xrow[k + 2]);
-            s = __fadd_rn(s, __fmul_rn(q, q));
-            q = __fsub_rn(a.w, xrow[k + 3]);
-            s = __fadd_rn(s, __fmul_rn(q, q));
+            if (!(node == 0 || minHits == 0 || hits[node] >= minHits))
+                continue;
+            const float *m = mean + static_cast<size_t>(node) * rowStride;
+            float s = 0.0f;
+            int k = 0;
+            for (; k + 4 <= D; k += 4)
+            {
+                const float4 a = *reinterpret_cast<const float4 *>(m + k);
+                float q = __fsub_rn(a.x, xrow[k]);
+                s = __fadd_rn(s, __fmul_rn(q, q));
+                q = __fsub_rn(a.y, xrow[k + 1]);
+                s = __fadd_rn(s, __fmul_rn(q, q));
+                q = __fsub_rn(a.z, xrow[k + 2]);
+                s = __fadd_rn(s, __fmul_rn(q, q));
+                q = __fsub_rn(a.w, xrow[k + 3]);
+                s = __fadd_rn(s, __fmul_rn(q, q));
+            }
+            for (; k < D; ++k)
+            {
+                const float q = __fsub_rn(m[k], xrow[k]);
+                s = __fadd_rn(s, __fmul_rn(q, q));
+            }
+            best = u64_min(best, make_key(s, static_cast<unsigned>(node), (s != s) ? 1u : 0u));
         }
-        for (; k < D; ++k)
+        best = warp_min_u64(best);
+        if ((threadIdx.x & 31) == 0)
+            wkey[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0)
         {
-            const float q = __fsub_rn(m[k], xrow[k]);
-            s = __fadd_rn(s, __fmul_rn(q, q));
+            for (int w = 1; w < 8; ++w)
+                best = u64_min(best, wkey[w]);
+            if (outBmu)
+                outBmu[r] = key_node(best);
+            if (outDist)
+                outDist[r] = (best & 1ull) ? __uint_as_float(0x7fc00000u) : __uint_as_float(static_cast<unsigned>(best >> 32));
         }
-        best = u64_min(best, make_key(s, static_cast<unsigned>(node), (s != s) ? 1u : 0u));
     }
-    best = warp_min_u64(best);
-    if ((threadIdx.x & 31) == 0)
-        wkey[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        for (int w = 1; w < 8; ++w)
-            best = u64_min(best, wkey[w]);
-        if (outBmu)
-            outBmu[r] = key_node(best);
-        if (outDist)
-            outDist[r] = (best & 1ull) ? __uint_as_float(0x7fc00000u) : __uint_as_float(static_cast<unsigned>(best >> 32));
-    }
-}
-
-__global__ void gather_rows_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows, unsigned count, float *__restrict__ out)
-{
-    const unsigned i = blockIdx.x;
-    if (i >= count)
-        return;
-    const size_t r = rows[i];
-    for (int k = threadIdx.x; k < D; k += blockDim.x)
-        out[static_cast<size_t>(i) * D + k] = x[r * D + k];
-}
-__global__ void scatter_results_kernel(const unsigned *__restrict__ rows, unsigned count, const unsigned *__restrict__ bmuIn, const float *__restrict__ distIn,
-                                       unsigned *__restrict__ outBmu, float *__restrict__ outDist)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count)
-        return;
-    if (outBmu)
-        outBmu[rows[i]] = bmuIn[i];
-    if (outDist)
-        outDist[rows[i]] = distIn[i];
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -680,32 +706,53 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         attrSet = true;
     }
 
-    // ---- rows, in slabs that bound the bf16 staging buffer
-    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << 22); // 4M rows: 2 GB of bf16 at K=256
+    // ---- rows, in slabs of 4M (the bf16 staging buffer: 2 GB at K = 256).  Two streams: the context's stream converts a slab and runs the tensor-core search; an auxiliary
+    // stream re-scores the slab's candidates (and scans the few rows its guard could not certify) while the next slab is
+    // already being searched.  Candidate scratch is double-buffered by slab parity; nothing returns to the host in between.
+    const char *slabEnv = getenv("VSOM_TC_SLAB_LOG2"), *ovlEnv = getenv("VSOM_TC_OVERLAP"); // experiment knobs
+    const int slabLog2 = slabEnv ? atoi(slabEnv) : 22; // smaller slabs measured slower (per-slab ramp and tail of the persistent kernel)
+    const bool overlap = ovlEnv ? atoi(ovlEnv) != 0 : true;
+    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << slabLog2);
     rc = stage_reserve(ctx, 7, sizeof(__nv_bfloat16) * slabRows * Kpad);
     if (rc)
         return rc;
-    // per-row scratch: candidates, their count, |x|^2, fallback list + count, fallback results
-    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(float) * 2 + sizeof(unsigned) * 2 + sizeof(float);
-    rc = stage_reserve(ctx, 8, perRow * slabRows + 256);
+    // per-row scratch: candidates, their count, |x|^2, fallback list; per set: fallback count
+    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + sizeof(float) + sizeof(unsigned);
+    const size_t setBytes = (perRow * slabRows + 256 + 255) & ~static_cast<size_t>(255);
+    rc = stage_reserve(ctx, 8, 2 * setBytes + 256);
     if (rc)
         return rc;
+    if (!ctx->auxStream)
+    {
+        VSOM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->auxStream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i)
+        {
+            VSOM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evScore[i], cudaEventDisableTiming));
+            VSOM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evDone[i], cudaEventDisableTiming));
+        }
+    }
     __nv_bfloat16 *Xb = static_cast<__nv_bfloat16 *>(ctx->stage[7]);
-    unsigned *cand = static_cast<unsigned *>(ctx->stage[8]);
-    unsigned *candCount = cand + slabRows * TC_TOPK;
-    float *xnorm = reinterpret_cast<float *>(candCount + slabRows);
-    unsigned *fbRows = reinterpret_cast<unsigned *>(xnorm + slabRows);
-    unsigned *fbBmu = fbRows + slabRows;
-    float *fbDist = reinterpret_cast<float *>(fbBmu + slabRows);
-    unsigned *fbCount = reinterpret_cast<unsigned *>(fbDist + slabRows);
+    unsigned long long *totalDev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ctx->stage[8]) + 2 * setBytes);
+    VSOM_CUDA(ctx, cudaMemsetAsync(totalDev, 0, sizeof(unsigned long long), ctx->stream));
+    VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
 
-    unsigned long long totalFallback = 0;
     const char *stg = getenv("VSOM_TC_STAGGER");
     const int stagger = stg ? atoi(stg) : 1;
-    for (size_t r0 = 0; r0 < n; r0 += slabRows)
+    size_t slab = 0;
+    for (size_t r0 = 0; r0 < n; r0 += slabRows, ++slab)
     {
+        const int par = static_cast<int>(slab & 1);
+        unsigned char *set = static_cast<unsigned char *>(ctx->stage[8]) + par * setBytes;
+        unsigned *cand = reinterpret_cast<unsigned *>(set);
+        unsigned *candCount = cand + slabRows * TC_TOPK;
+        float *xnorm = reinterpret_cast<float *>(candCount + slabRows);
+        unsigned *fbRows = reinterpret_cast<unsigned *>(xnorm + slabRows);
+        unsigned *fbCount = fbRows + slabRows;
+
         const size_t rows = std::min(slabRows, n - r0);
         const float *xs = xDev + r0 * D;
+        if (slab >= 2)
+            VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[par], 0)); // slab - 2 is done with this scratch set
         to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), D, D, Xb, Kpad, xnorm);
         CUtensorMap mapX;
         rc = make_map(ctx, &mapX, Xb, rows, Kpad, TC_BM);
@@ -713,49 +760,33 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
             return rc;
         const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
         const int grid = std::min(rowTiles, ctx->numSMs);
-        VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
         VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
         score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, stagger, xnorm, maxNorm2, cand, candCount,
                                                                       ctx->errFlag);
-        rescore_kernel<<<static_cast<unsigned>((rows * TC_TOPK + 255) / 256), 256, 0, ctx->stream>>>(
+        cudaStream_t rs = overlap ? ctx->auxStream : ctx->stream;
+        VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
+        VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
+        rescore_kernel<<<static_cast<unsigned>((rows + RS_ROWS - 1) / RS_ROWS), RS_THREADS, 0, rs>>>(
             xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, candCount, outBmuDev ? outBmuDev + r0 : nullptr,
             outDistDev ? outDistDev + r0 : nullptr, fbRows, fbCount);
-        ctx->launches += 3;
+        // rows the guard could not certify: exact full scan, count read on the device
+        find_bmu_rowwise_kernel<<<2 * ctx->numSMs, 256, sizeof(float) * D, rs>>>(xs, D, fbRows, fbCount, ctx->mean, ctx->rowStride, N, ctx->hits, minHits,
+                                                                                             outBmuDev ? outBmuDev + r0 : nullptr,
+                                                                                             outDistDev ? outDistDev + r0 : nullptr, totalDev);
+        VSOM_CUDA(ctx, cudaEventRecord(ctx->evDone[par], rs));
+        ctx->launches += 4;
         VSOM_CUDA(ctx, cudaGetLastError());
-        // rows the guard could not certify: exact full scan
-        unsigned count = 0;
-        int flag = 0;
-        VSOM_CUDA(ctx, cudaMemcpyAsync(&count, fbCount, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-        VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (flag)
-            return set_error(ctx, VSOM_ERR_TIMEOUT, "score_tc: pipeline barrier timed out (kernel bug)");
-        if (count && count <= 8192)
-        {
-            // few rows: one CTA per row, results written in place
-            find_bmu_rowwise_kernel<<<count, 256, sizeof(float) * D, ctx->stream>>>(xs, D, fbRows, count, ctx->mean, ctx->rowStride, N, ctx->hits, minHits,
-                                                                                   outBmuDev ? outBmuDev + r0 : nullptr,
-                                                                                   outDistDev ? outDistDev + r0 : nullptr);
-            ctx->launches += 1;
-            totalFallback += count;
-        }
-        else if (count)
-        {
-            rc = stage_reserve(ctx, 9, sizeof(float) * static_cast<size_t>(count) * D);
-            if (rc)
-                return rc;
-            float *gx = static_cast<float *>(ctx->stage[9]);
-            gather_rows_kernel<<<count, 128, 0, ctx->stream>>>(xs, D, fbRows, count, gx);
-            ctx->launches += 1;
-            rc = launch_find_bmu(ctx, gx, count, minHits, fbBmu, fbDist);
-            if (rc)
-                return rc;
-            scatter_results_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(fbRows, count, fbBmu, fbDist, outBmuDev ? outBmuDev + r0 : nullptr,
-                                                                                 outDistDev ? outDistDev + r0 : nullptr);
-            ctx->launches += 1;
-            totalFallback += count;
-        }
     }
+    // the context's stream owns the results again
+    for (int i = 0; i < 2 && static_cast<size_t>(i) < slab; ++i)
+        VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[i], 0));
+    unsigned long long totalFallback = 0;
+    int flag = 0;
+    VSOM_CUDA(ctx, cudaMemcpyAsync(&totalFallback, totalDev, sizeof(totalFallback), cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag)
+        return set_error(ctx, VSOM_ERR_TIMEOUT, "score_tc: pipeline barrier timed out (kernel bug)");
     VSOM_CUDA(ctx, cudaGetLastError());
     if (fallbackRowsOut)
         *fallbackRowsOut = totalFallback;
