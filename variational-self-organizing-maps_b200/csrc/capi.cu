@@ -261,6 +261,7 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->lut);
     cudaFree(ctx->distBuf);
     cudaFree(ctx->winTab);
+    cudaFree(ctx->distTag);
     cudaFree(ctx->scanMapDev);
     cudaFree(ctx->rowPool);
     cudaFree(ctx->rowMeta);

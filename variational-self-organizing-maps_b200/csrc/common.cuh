@@ -69,6 +69,7 @@ struct StepParams
     unsigned *rowCtr;         // [0..1] rows claimed per die, [2] arrivals at the one-off grid barrier
     u64 *rowPool;
     int pollDelay;            // cycles between the pushes and the first poll
+    u64 *distTag;             // K1F, sigma <= 1: [2][N] (distance bits << 32 | step + 1) of every node, self-validating words
     int scanBufs, scanSeg, scanNSeg; // K1 on HBM-resident rows: streamed scan (ring of scanBufs buffers of 32 row segments of scanSeg floats)
     const void *scanMap;      // ... its TMA descriptor of the mean plane (device memory)
 };
@@ -121,6 +122,7 @@ struct vsom_ctx
     vsom::u64 *rowPool = nullptr; // K1F exchange rows: 1024 blocks of 2 KB
     int *rowMeta = nullptr;       // dieOfSm[256] | rowBlocks[640] | rowOf[160] | counters[4]
     int dieAware = 0;             // the row pool was classified by L2 die
+    vsom::u64 *distTag = nullptr; // K1F local-walk regime: tagged per-step distances
     int scanBufs = 0, scanSeg = 0, scanNSeg = 0; // K1: HBM-resident rows are streamed through a ring of segment buffers
     void *scanMapDev = nullptr;                   // TMA descriptor of the mean plane for that scan
     long long *profDev = nullptr; // diagnostics: per-phase cycle sums of the last online-step launch
@@ -272,6 +274,76 @@ __device__ __forceinline__ float dist_lanes(const float *m, const float *xs, int
         s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
     return s;
 }
+
+// Som::findLocalBmu (src/Som.cpp:335-454) on the per-step distances (read through `load(node)`): greedy walk from `start` over the
+// 8-neighbourhood, then three cells one step further in the X direction of travel, until the best node stops moving.
+// The reference's size_t arithmetic is kept: the "-1" offsets are 2^64-1, min(x + off, W-1) therefore wraps the left / up
+// neighbour of column / row 0 to the last column / row, and its Y-direction continuation loop never runs (it starts at
+// size_t(-1)).  Distances are compared as the reference does (strict '<', first candidate in its order wins).
+template <class Load>
+__device__ __forceinline__ unsigned local_bmu_walk(Load load, u64 W, u64 H, u64 start)
+{
+    const u64 M1 = ~0ull;
+    const u64 fx[8] = {M1, 0, 1, 1, 1, 0, M1, M1};
+    const u64 fy[8] = {1, 1, 1, 0, M1, M1, M1, 0};
+    u64 lastBMU = start, minIndex = start, lastMeasured = start;
+    float minDist = load(start);
+    for (;;)
+    {
+        const u64 lmX = lastMeasured % W, lmY = lastMeasured / W, lbX = lastBMU % W;
+        if (lastMeasured == lastBMU)
+        {
+            u64 idx[8];
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                const u64 cx = lmX + fx[i] < W - 1 ? lmX + fx[i] : W - 1; // min(x + off, W-1) in size_t
+                const u64 cy = lmY + fy[i] < H - 1 ? lmY + fy[i] : H - 1;
+                idx[i] = cy * W + cx;
+                v[i] = load(idx[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (v[i] < minDist)
+                {
+                    minDist = v[i];
+                    minIndex = idx[i];
+                }
+            if (minIndex == lastBMU)
+                return static_cast<unsigned>(minIndex);
+            lastMeasured = minIndex;
+        }
+        else
+        {
+            if (lmX - lbX) // moving in X
+            {
+                u64 idx[3];
+                float v[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                {
+                    const u64 ox = lmX + lmX - lbX, oy = lmY + static_cast<u64>(static_cast<long long>(i - 1));
+                    const u64 cx = ox < W - 1 ? ox : W - 1, cy = oy < H - 1 ? oy : H - 1;
+                    idx[i] = cy * W + cx;
+                    v[i] = load(idx[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (v[i] < minDist)
+                    {
+                        minDist = v[i];
+                        minIndex = idx[i];
+                    }
+            }
+            if (minIndex == lastMeasured)
+                return static_cast<unsigned>(minIndex);
+            lastBMU = lastMeasured;
+            lastMeasured = minIndex;
+        }
+    }
+}
+
 
 #endif // __CUDACC__
 

@@ -146,74 +146,6 @@ __device__ __forceinline__ void scan_tma_load(void *dst, const void *map, u64 *b
                  : "memory");
 }
 
-// Som::findLocalBmu (src/Som.cpp:335-454) on the per-step distance array: greedy walk from `start` over the
-// 8-neighbourhood, then three cells one step further in the X direction of travel, until the best node stops moving.
-// The reference's size_t arithmetic is kept: the "-1" offsets are 2^64-1, min(x + off, W-1) therefore wraps the left / up
-// neighbour of column / row 0 to the last column / row, and its Y-direction continuation loop never runs (it starts at
-// size_t(-1)).  Distances are compared as the reference does (strict '<', first candidate in its order wins).
-__device__ __forceinline__ unsigned local_bmu_walk(const float *dist, u64 W, u64 H, u64 start)
-{
-    const u64 M1 = ~0ull;
-    const u64 fx[8] = {M1, 0, 1, 1, 1, 0, M1, M1};
-    const u64 fy[8] = {1, 1, 1, 0, M1, M1, M1, 0};
-    u64 lastBMU = start, minIndex = start, lastMeasured = start;
-    float minDist = ld_relaxed_gpu_f32(dist + start);
-    for (;;)
-    {
-        const u64 lmX = lastMeasured % W, lmY = lastMeasured / W, lbX = lastBMU % W;
-        if (lastMeasured == lastBMU)
-        {
-            u64 idx[8];
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-            {
-                const u64 cx = lmX + fx[i] < W - 1 ? lmX + fx[i] : W - 1; // min(x + off, W-1) in size_t
-                const u64 cy = lmY + fy[i] < H - 1 ? lmY + fy[i] : H - 1;
-                idx[i] = cy * W + cx;
-                v[i] = ld_relaxed_gpu_f32(dist + idx[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (v[i] < minDist)
-                {
-                    minDist = v[i];
-                    minIndex = idx[i];
-                }
-            if (minIndex == lastBMU)
-                return static_cast<unsigned>(minIndex);
-            lastMeasured = minIndex;
-        }
-        else
-        {
-            if (lmX - lbX) // moving in X
-            {
-                u64 idx[3];
-                float v[3];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                {
-                    const u64 ox = lmX + lmX - lbX, oy = lmY + static_cast<u64>(static_cast<long long>(i - 1));
-                    const u64 cx = ox < W - 1 ? ox : W - 1, cy = oy < H - 1 ? oy : H - 1;
-                    idx[i] = cy * W + cx;
-                    v[i] = ld_relaxed_gpu_f32(dist + idx[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    if (v[i] < minDist)
-                    {
-                        minDist = v[i];
-                        minIndex = idx[i];
-                    }
-            }
-            if (minIndex == lastMeasured)
-                return static_cast<unsigned>(minIndex);
-            lastBMU = lastMeasured;
-            lastMeasured = minIndex;
-        }
-    }
-}
-
 template <int TR, int ORDER, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepParams p)
 {
@@ -610,7 +542,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 unsigned bmu = key_node(m);
                 if (p.localSearch && !abort)
                 {
-                    bmu = local_bmu_walk(p.distBuf + (t & 1) * static_cast<u64>(p.nodeCount), static_cast<u64>(p.W), static_cast<u64>(p.H),
+                    const float *dist = p.distBuf + (t & 1) * static_cast<u64>(p.nodeCount);
+                    bmu = local_bmu_walk([&](u64 i) { return ld_relaxed_gpu_f32(dist + i); }, static_cast<u64>(p.W), static_cast<u64>(p.H),
                                          p.lastIn ? p.lastIn[t] : 0ull);
                     if (b == 0 && p.outBmu)
                         p.outBmu[t] = bmu;
@@ -1188,6 +1121,7 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.xVec = (ctx->Din % 4 == 0 && (reinterpret_cast<uintptr_t>(xDev) & 15) == 0) ? 1 : 0;
 
     p.winTab = nullptr;
+    p.distTag = nullptr;
     p.pollDelay = 0;
     p.scanBufs = ctx->scanBufs;
     p.scanSeg = ctx->scanSeg;

@@ -41,6 +41,8 @@ constexpr int kFMaxSlotsPerLane = 5; // the exchange row of a CTA is read by one
 constexpr int kFMaxCtas = 32 * kFMaxSlotsPerLane;
 constexpr size_t kFStaticSmem = 4096;
 constexpr int kFPoolBlocks = 1024; // 2 KB blocks of the exchange row pool (2 MB per context)
+constexpr int kWalkReplicas = 1;   // copies of the per-step distance array of the local-walk regime (8 copies measured slower:
+                                   // the walk is bound by L2 round trips per step, not by readers queueing on a line)
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -508,7 +510,18 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         {
             u64 key = ~0ull;
             if (hasNode)
-                key = make_key_xy(chain_terms(myTerms, n16), myX, myY, tag);
+            {
+                const float d = chain_terms(myTerms, n16);
+                key = make_key_xy(d, myX, myY, tag);
+                if (p.localSearch) // sigma <= 1: the walk below reads distances of arbitrary nodes; the word validates itself.
+                {                  // (kWalkReplicas copies, CTA b reads copy b % kWalkReplicas)
+                    const u64 w = (static_cast<u64>(__float_as_uint(d)) << 32) | (t + 1u);
+                    u64 *dst = p.distTag + static_cast<size_t>(par) * kWalkReplicas * p.nodeCount + (myY * static_cast<unsigned>(p.W) + myX);
+#pragma unroll
+                    for (int r = 0; r < kWalkReplicas; ++r)
+                        st_relaxed_gpu(dst + static_cast<size_t>(r) * p.nodeCount, w);
+                }
+            }
             if (PROF && tid == 0)
                 c1 = clock64();
             key = warp_min_key(key);
@@ -576,6 +589,28 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                 }
                 m = warp_min_key(m);
                 bxy = static_cast<unsigned>(m >> 8) & 0xffffffu;
+                if (p.localSearch && !abort)
+                {
+                    // findLocalBmu regime (src/Som.cpp:889-892, :335-454): every CTA has seen every CTA's key of this step, so
+                    // every distance of this step has been stored; a word whose tag is not yet this step's is re-read.
+                    // Every CTA walks the same path (lane 0), like every CTA takes the same global minimum.
+                    if (lane == 0)
+                    {
+                        const u64 *dt = p.distTag + (static_cast<size_t>(par) * kWalkReplicas + (b % kWalkReplicas)) * p.nodeCount;
+                        const unsigned want = t + 1u;
+                        const unsigned bmu = local_bmu_walk(
+                            [&](u64 i) {
+                                u64 w;
+                                do
+                                    w = ld_relaxed_gpu(dt + i);
+                                while (static_cast<unsigned>(w) != want);
+                                return __uint_as_float(static_cast<unsigned>(w >> 32));
+                            },
+                            static_cast<u64>(p.W), static_cast<u64>(p.H), p.lastIn ? p.lastIn[t] : 0ull);
+                        bxy = ((bmu / static_cast<unsigned>(p.W)) << 12) | (bmu % static_cast<unsigned>(p.W));
+                    }
+                    bxy = __shfl_sync(0xffffffffu, bxy, 0);
+                }
                 if (lane == 0)
                 {
                     sBmu = bxy;
@@ -1286,8 +1321,16 @@ static int build_window_table(vsom_ctx *ctx, double sigma)
 // 0 when this launch is not eligible (sigma <= 1, ...), < 0 on error.
 int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma)
 {
-    if (!ctx->fastTrain || p.localSearch || p.world > 1 || p.n >= (1ull << 32))
+    if (!ctx->fastTrain || p.world > 1 || p.n >= (1ull << 32) - 1)
         return 0;
+    if (p.localSearch)
+    {
+        const size_t bytes = sizeof(u64) * 2 * kWalkReplicas * static_cast<size_t>(ctx->N);
+        if (!ctx->distTag)
+            VSOM_CUDA(ctx, cudaMalloc(&ctx->distTag, bytes));
+        VSOM_CUDA(ctx, cudaMemsetAsync(ctx->distTag, 0xff, bytes, ctx->stream)); // no word carries a tag of this launch yet
+    }
+    p.distTag = ctx->distTag;
     int rc = build_row_pool(ctx);
     if (rc)
         return rc;
