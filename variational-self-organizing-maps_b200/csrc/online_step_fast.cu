@@ -2,29 +2,36 @@
 // per sample chunk with the shortest per-sample dependency chain this library has.
 //
 // Same contract and the same bits as online_step.cu's generic kernel (Som::trainSingle src/Som.cpp:885-947 =
-// findBmu :291-309 over euclidianWeightedDist :124-141, window update :899-944, calculateNeighbourhoodWeight
-// :949-975, addBmu :1189-1192), for: Standard / Median transformation, reference summation order, planes resident
-// in shared memory, global BMU search (sigma > 1), one GPU, grid sides <= 4096.  Everything else runs the generic
-// kernel.
+// findBmu :291-309 / findLocalBmu :335-454 over euclidianWeightedDist :124-141, window update :899-944,
+// calculateNeighbourhoodWeight :949-975, addBmu :1189-1192), for: all three transformations, reference summation order,
+// planes that fit on chip, one GPU, grid sides <= 4096, at most 512 owned nodes per CTA.  Everything else (LANES order,
+// HBM-resident maps, node-sharded contexts) runs the generic kernel.
 //
 // Why a second kernel: the generic one measures (profiles/r01_bench_default_final_candidate.json, cycles per sample
 // at 64x64x128) wait 593 + scan 1535 + exchange 3323 + broadcast 248 + update 1643.  The strict per-sample dependency
-// makes these ADD, so each phase is rebuilt here for latency:
+// makes these ADD, so each phase is rebuilt here for latency (now: chain 896 + CTA min 135 + exchange 1560 +
+// coefficients 438 + barrier 114 + update 768 + barrier 61):
 //   * update and scan are fused where the work is parallel and split where it is sequential.  The warp that updates
 //     a node slice (lanes = 4 consecutive elements each, 128-bit accesses) also squares the residuals of the NEXT
 //     sample against the fresh means and leaves them in a `terms` row.  What remains of the scan is the part the
 //     reference order forces to be sequential: one lane per node adds its row's terms k = 0,1,2,... with a chain of
 //     FADDs (4 cycles each) fed by 128-bit shared-memory loads.  The f32 values added, and their order, are exactly
 //     the reference's `comparer.dot(comparer)` (src/Som.cpp:140).
-//   * the lanes of the scan warp keep their node's grid position and weightMap entry in registers for the whole
-//     chunk; after the exchange the same lanes turn the BMU into per-node update coefficients (window test against
-//     a host-built table of [start,end) per BMU column / row, neighbourhood table lookup) in ~40 instructions for
-//     32 nodes at once, instead of every update warp deriving them redundantly.
+//   * with at most four (node, slice) items per warp their mean and S values live in registers for the whole chunk;
+//     512 threads: the critical path is one warp's serial code, so registers count for more than warps.
+//   * packed f32x2 arithmetic where a contraction cannot change a bit (see the note at sub2 / add2 / mul2 below).
+//   * the lanes of the scan warps keep their node's grid position and weightMap entry in registers; after the exchange
+//     the same lanes turn the BMU into per-node update coefficients (window test against a host-built table of
+//     [start,end) per BMU column / row, neighbourhood table lookup), 32 nodes per instruction.
 //   * the (distance, y, x) key carries the BMU's grid position, so nobody divides by the map width.
 //   * trainSingle's return value (distance of the sample to its UPDATED BMU, :946) is produced the same way: the
 //     updating warp leaves the squared residuals in a `pend` row and an otherwise idle lane adds them up during the
 //     next sample's scan.  bmuHits are counted in shared memory and flushed once per chunk.
-//   * samples are prefetched two ahead with cp.async into a ring of four.
+//   * samples are prefetched two ahead with cp.async into a ring of four, by one warp.
+//   * the rows of the grid-wide exchange are placed by measured L2 die ("L2 die calibration" below,
+//     profiles/r01_exchange_micro.md): exchange 2975 -> 1545 cycles.
+//   * CLR: rows [A || B] in shared memory, pairs gathered once per sample; sigma <= 1: self-validating tagged distances
+//     in global memory and the reference's greedy walk after the exchange.
 #include "common.cuh"
 
 #include <algorithm>
