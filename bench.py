@@ -382,6 +382,9 @@ def main():
                               "unit": "GB/s per GPU", "window_nodes": kwin},
                  "planes_resident_in_smem": lctx.planes_resident, "reduction_order": args.order}
         if world == 1:
+            large["roofline"]["traffic"] = measured_traffic("online_step_kernel_large_map", LROWS)
+            large["roofline"]["traffic_source"] = "profiles/r01_traffic.json (ncu --set full of the streamed-scan kernel, scaled per sample)"
+        if world == 1:
             lctx.update_umatrix()
             lctx.synchronize()
             with torch.cuda.stream(lstream):
