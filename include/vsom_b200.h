@@ -66,8 +66,9 @@ typedef enum vsom_decay_kind
  *              reference compiles in this repository's oracle.  Distances, BMUs and the whole training
  *              trajectory are then bit-identical to the reference.
  *   LANES:     32 interleaved partial sums (k mod 32) each sequential, combined by a fixed xor-butterfly
- *              (16,8,4,2,1).  Deterministic, faster for long vectors; BMUs can differ from the reference
- *              only at near-ties (relative distance gap below 2*Dm*2^-24). */
+ *              (16,8,4,2,1).  Deterministic; BMUs can differ from the reference only at near-ties (relative
+ *              distance gap below 2*Dm*2^-24).  It runs on the generic online-step kernel; since
+ *              K1F (online_step_fast.cu) the REFERENCE order is the faster of the two for maps that fit on chip. */
 typedef enum vsom_reduction_order
 {
     VSOM_ORDER_REFERENCE = 0,
