@@ -1,0 +1,16 @@
+"""Small driver for ncu captures of the U-matrix kernel (not a test)."""
+import importlib, sys, time
+import numpy as np
+sys.path.insert(0, ".")
+v = importlib.import_module("variational-self-organizing-maps_b200")
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+D = 784
+rng = np.random.default_rng(0)
+ctx = v.VsomContext(W, W, D, v.STANDARD)
+m = (rng.integers(-1000, 1000, (W * W, D)) / 1000).astype(np.float32)
+ctx.upload_state(mean=m, sigma=np.abs(m) + 0.5)
+for _ in range(3):
+    t0 = time.perf_counter()
+    u = ctx.update_umatrix()
+    dt = time.perf_counter() - t0
+print(f"umatrix {W}x{W}x{D}: {dt * 1e3:.2f} ms incl. download, mean {float(u.mean()):.4f}")

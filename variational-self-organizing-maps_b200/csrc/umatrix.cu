@@ -8,29 +8,39 @@
 //
 // One thread owns one (node, neighbour) pair and sums its Dm terms sequentially in f32 — the order of the
 // reference's dot product — so every Raw value and every U value is bit-identical to the reference.  A CTA
-// covers 16 consecutive nodes of one grid row; the three grid rows it touches are staged through shared
-// memory in 32-wide slices of the model vector (coalesced 128-byte segments).
+// covers 16 consecutive nodes of one grid row.  The rows are read straight from global memory with 128-bit
+// read-only loads: a node's eight threads ask for the same words of its own mean and sigma rows (one
+// transaction), neighbouring nodes share neighbour rows, and L1 serves the reuse.  (A first version staged 32-wide
+// slices of three grid rows through shared memory; ncu showed 54 % of its instructions in the staging loop's
+// address arithmetic, issue slots 76 % busy: 2.78 ms at 512x512x784.)
 #include "common.cuh"
 
 namespace vsom
 {
 
-constexpr int UT = 16;  // nodes per CTA
-constexpr int UKC = 32; // slice of the model vector
+constexpr int UT = 16; // nodes per CTA
 
 // neighbour order of the reference's sums: W, E, S, N, then the diagonals NW, SW, NE, SE
 // (src/Som.cpp:1017-1025; the edge and corner cases drop the missing terms and keep this order).
 __constant__ int kDi[8] = {0, 0, +1, -1, -1, +1, -1, +1};
 __constant__ int kDj[8] = {-1, +1, 0, 0, -1, -1, +1, +1};
 
+// one term of Raw(p, u): a = (m_p - m_u) / sM with sM = max(sigma_p, 1e-5) (:150), accumulated as a * a (:156).
+// (m - v) * (valid * weights) / sM equals a bit for bit because valid * weights == 1.0f exactly (:1002-1003), so one
+// IEEE division serves both factors of the dot product.
+__device__ __forceinline__ void raw_term(float &s, float mc, float mu, float sg)
+{
+    const float sM = sg < 0.00001f ? 0.00001f : sg;
+    const float a = __fdiv_rn(__fsub_rn(mc, mu), sM);
+    s = __fadd_rn(s, __fmul_rn(a, a));
+}
+
 __global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *__restrict__ mean, const float *__restrict__ sigma, int W, int H, int Dm,
                                                          int rowStride, double *__restrict__ out)
 {
-    __shared__ float mt[3][UT + 2][UKC + 1];
-    __shared__ float st[UT][UKC + 1];
     __shared__ float res[UT][8];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int i = blockIdx.y;       // grid row
     const int j0 = blockIdx.x * UT; // first grid column of the tile
     const int t = tid >> 3, nb = tid & 7;
@@ -39,48 +49,24 @@ __global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *__restrict
     const bool active = j < W && ni >= 0 && ni < H && nj >= 0 && nj < W;
 
     float s = 0.0f;
-    for (int k0 = 0; k0 < Dm; k0 += UKC)
+    if (active)
     {
-        __syncthreads();
-        const int k = k0 + lane;
-        for (int item = warp; item < 3 * (UT + 2) + UT; item += UT * 8 / 32)
+        const float *mc = mean + (static_cast<size_t>(i) * W + j) * rowStride;
+        const float *sg = sigma + (static_cast<size_t>(i) * W + j) * rowStride;
+        const float *mu = mean + (static_cast<size_t>(ni) * W + nj) * rowStride;
+        const int quads = Dm >> 2; // rows start 16-byte aligned (rowStride is a multiple of 4 floats)
+        const float4 *mc4 = reinterpret_cast<const float4 *>(mc), *sg4 = reinterpret_cast<const float4 *>(sg), *mu4 = reinterpret_cast<const float4 *>(mu);
+#pragma unroll 2
+        for (int q = 0; q < quads; ++q)
         {
-            if (item < 3 * (UT + 2))
-            {
-                const int r = item / (UT + 2), c = item % (UT + 2);
-                const int gi = i + r - 1, gj = j0 + c - 1;
-                float v = 0.0f;
-                if (gi >= 0 && gi < H && gj >= 0 && gj < W && k < Dm)
-                    v = mean[(static_cast<size_t>(gi) * W + gj) * rowStride + k];
-                mt[r][c][lane] = v;
-            }
-            else
-            {
-                const int c = item - 3 * (UT + 2);
-                const int gj = j0 + c;
-                float v = 1.0f;
-                if (gj < W && k < Dm)
-                    v = sigma[(static_cast<size_t>(i) * W + gj) * rowStride + k];
-                st[c][lane] = v;
-            }
+            const float4 a = __ldg(mc4 + q), b = __ldg(mu4 + q), c = __ldg(sg4 + q);
+            raw_term(s, a.x, b.x, c.x);
+            raw_term(s, a.y, b.y, c.y);
+            raw_term(s, a.z, b.z, c.z);
+            raw_term(s, a.w, b.w, c.w);
         }
-        __syncthreads();
-        if (active)
-        {
-            const int kend = Dm - k0 < UKC ? Dm - k0 : UKC;
-            const float *mc = mt[1][t + 1];
-            const float *mu = mt[1 + kDi[nb]][t + 1 + kDj[nb]];
-            const float *sg = st[t];
-            for (int kk = 0; kk < kend; ++kk)
-            {
-                const float sM = sg[kk] < 0.00001f ? 0.00001f : sg[kk];  // :150
-                const float d = __fsub_rn(mc[kk], mu[kk]);
-                // a = (m - v) / sM and b = ((m - v) * valid*weights) / sM with valid*weights == 1.0f exactly (:1002-1003):
-                // d * 1.0f == d bit for bit, so b == a and one IEEE division serves both factors of the dot product
-                const float a = __fdiv_rn(d, sM);
-                s = __fadd_rn(s, __fmul_rn(a, a));                         // :156
-            }
-        }
+        for (int k = quads << 2; k < Dm; ++k)
+            raw_term(s, __ldg(mc + k), __ldg(mu + k), __ldg(sg + k));
     }
     res[t][nb] = s;
     __syncthreads();
