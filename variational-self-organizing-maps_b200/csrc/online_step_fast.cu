@@ -38,6 +38,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 namespace vsom
 {
@@ -1031,6 +1032,7 @@ struct DieMap
     int count[2] = {0, 0};
 };
 static DieMap g_dieMap[64];
+static std::mutex g_dieMapMutex; // contexts of several host threads may reach their first K1F launch together
 
 // Two-mode split of round-trip times: threshold halfway between the lower and the upper quartile (both maps are close
 // to half / half), accepted when the quartiles are clearly apart and few values sit near the threshold.
@@ -1055,6 +1057,7 @@ static bool split_bimodal(std::vector<float> v, float &thr)
 
 static int calibrate_die_map(vsom_ctx *ctx)
 {
+    std::lock_guard<std::mutex> lock(g_dieMapMutex);
     DieMap &dm = g_dieMap[ctx->device & 63];
     if (dm.tried)
         return VSOM_OK;
