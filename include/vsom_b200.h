@@ -68,11 +68,19 @@ typedef enum vsom_decay_kind
  *   LANES:     32 interleaved partial sums (k mod 32) each sequential, combined by a fixed xor-butterfly
  *              (16,8,4,2,1).  Deterministic; BMUs can differ from the reference only at near-ties (relative
  *              distance gap below 2*Dm*2^-24).  It runs on the generic online-step kernel; since
- *              K1F (online_step_fast.cu) the REFERENCE order is the faster of the two for maps that fit on chip. */
+ *              K1F (online_step_fast.cu) the REFERENCE order is the faster of the two for maps that fit on chip.
+ *   EIGEN_SSE: the order `dot()` / `squaredNorm()` have when the reference is built against real Eigen (3.3 / 3.4) with
+ *              its release flags (-msse2, README.md:64-69, build/Makefile:18): Eigen's vectorised redux over Packet4f —
+ *              two 4-wide accumulators over strides of 8 elements (eight interleaved sequential chains), res0 + res1,
+ *              one more packet when 4..7 elements remain, the horizontal sum (p0 + p2) + (p1 + p3), then the scalar tail.
+ *              Bit-identical to the reference compiled with -DVSOM_COMPAT_EIGEN_SSE_REDUX (oracle/Makefile), which makes
+ *              the stand-in Eigen header reduce in that published order.  Applies to every distance on the path
+ *              (training, scoring, evaluate, batch-map MSE) and to euclidianWeightedDistRaw's dot (U-matrix). */
 typedef enum vsom_reduction_order
 {
     VSOM_ORDER_REFERENCE = 0,
-    VSOM_ORDER_LANES = 1
+    VSOM_ORDER_LANES = 1,
+    VSOM_ORDER_EIGEN_SSE = 2
 } vsom_reduction_order;
 
 /* -------------------------------------------------------------------------------- context / state */
@@ -157,17 +165,25 @@ VSOM_API int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double si
 /* -------------------------------------------------------------------------------- scoring */
 
 /* Per row: Som::findBmu (min_hits == 0, src/Som.cpp:291-309) or Som::findRestrictedBmu (src/Som.cpp:313-332),
- * and out_dist = (float)euclidianWeightedDist(bmu, row) (src/Som.cpp:124-141).  Outputs may be NULL. */
+ * and out_dist = (float)euclidianWeightedDist(bmu, row) (src/Som.cpp:124-141).  Outputs may be NULL.
+ * This is the call behind Som::evaluate (:490-523), Som::measureSimilarity (:631-714) and Som::mapDataSet.
+ * Dispatch: batches of >= 1024 rows on shapes K2 covers (Standard / Median, Dm <= 256) run the tensor-core candidate
+ * search (tcgen05 + TMA, bf16 operands) + exact f32 rescore of the <= 16 listed candidates per row + a certificate that
+ * no unlisted node can win; rows that fail it are re-scored by the exact scan.  Everything else runs the exact scan.
+ * Results are bit-identical either way.  The host-pointer form streams the rows through two staging buffers (H2D of the
+ * next slab overlaps the search of the current one; pinned host memory gives full overlap). */
 VSOM_API int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist);
 VSOM_API int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev);
-/* Same contract and same results as vsom_find_bmu, for large batches: the candidate search runs on the tensor cores
- * (K2: tcgen05 + TMA, bf16 operands), the 8 best candidates per row are re-evaluated in the reference's f32 arithmetic,
- * and rows whose candidate set cannot be proven complete are re-scored by the exact scan.  Falls back to the exact
- * scan entirely for shapes K2 does not cover (CLR, Dm > 256) or small batches.  fallback_rows (may be NULL) receives the
- * number of rows that took the exact full scan. */
+/* Same contract, always the exact scan (K3) — what the tests compare the dispatching calls with. */
+VSOM_API int vsom_find_bmu_exact(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist);
+VSOM_API int vsom_find_bmu_exact_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev);
+/* vsom_find_bmu[_device] that also reports how many rows took the exact full scan (fallback_rows, may be NULL; = n when
+ * the whole batch ran on the exact scan). */
 VSOM_API int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, uint64_t *fallback_rows);
 VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev,
                                         uint64_t *fallback_rows);
+/* 1 when the last scoring call on ctx ran the tensor-core path. */
+VSOM_API int vsom_debug_last_score_tc(const vsom_ctx *ctx);
 
 /* Som::evaluate for all-continuous columns (src/Som.cpp:490-523): f64 running mean of the BMU distance in row
  * order.  (With binary columns the reference adds a cross-entropy term; that is host work on top of the

@@ -264,13 +264,25 @@ def test_tensor_core_scoring_equals_exact_scan(vsom, shape):
     ctx = vsom.VsomContext(W, H, D, vsom.STANDARD)
     hits = rng.integers(0, 4, W * H).astype(np.uint64)
     ctx.upload_state(mean=m, hits=hits)
-    eb, ed = ctx.find_bmu(x)
+    eb, ed = ctx.find_bmu_exact(x)
+    assert not ctx.last_score_tc
     tb, td, fb = ctx.find_bmu_batch(x)
+    assert ctx.last_score_tc
     print(f"K2 {W}x{H}x{D}, {n} rows, near={near}: {fb} rows ({100.0 * fb / n:.2f}%) took the exact-scan fallback")
     assert_bit_equal(tb, eb, "bmu")
     assert_bit_equal(td, ed, "dist")
     assert fb < n  # the tensor-core path did the selection for at least some rows
-    eb2, _ = ctx.find_bmu(x[:2000], min_hits=2)
+    # the reference-facing calls (vsom_find_bmu / vsom_evaluate: what Som::evaluate, measureSimilarity and mapDataSet use)
+    # dispatch to the same tensor-core path for batches like this one
+    db, dd = ctx.find_bmu(x)
+    assert ctx.last_score_tc
+    assert_bit_equal(db, eb, "dispatched bmu")
+    assert_bit_equal(dd, ed, "dispatched dist")
+    err = 0.0
+    for i, d in enumerate(ed):  # src/Som.cpp:519
+        err += 1.0 / (i + 1.0) * (float(d) - err)
+    assert ctx.evaluate(x) == err and ctx.last_score_tc
+    eb2, _ = ctx.find_bmu_exact(x[:2000], min_hits=2)
     tb2, _, _ = ctx.find_bmu_batch(x[:2000], min_hits=2)
     assert_bit_equal(tb2, eb2, "restricted bmu")
     ctx.close()
@@ -281,9 +293,9 @@ def test_tensor_core_scoring_unsupported_shapes_use_exact(vsom):
     rng = np.random.default_rng(1)
     ctx.upload_state(mean=rng.standard_normal((400, 784)).astype(np.float32))
     x = rng.standard_normal((1500, 784)).astype(np.float32)
-    eb, ed = ctx.find_bmu(x)
+    eb, ed = ctx.find_bmu_exact(x)
     tb, td, fb = ctx.find_bmu_batch(x)
-    assert fb == 1500
+    assert fb == 1500 and not ctx.last_score_tc
     assert_bit_equal(tb, eb, "bmu")
     assert_bit_equal(td, ed, "dist")
     ctx.close()
@@ -300,7 +312,7 @@ def test_tensor_core_scoring_ties_and_overflow_take_the_exact_scan(vsom):
     x = (base[rng.integers(0, 40, n)] + 0.01 * rng.standard_normal((n, D))).astype(np.float32)
     ctx = vsom.VsomContext(W, H, D, vsom.MEDIAN)
     ctx.upload_state(mean=m)
-    eb, ed = ctx.find_bmu(x)
+    eb, ed = ctx.find_bmu_exact(x)
     tb, td, fb = ctx.find_bmu_batch(x)
     assert eb.max() < 40  # lowest index among the copies
     assert_bit_equal(tb, eb, "bmu")
@@ -327,11 +339,74 @@ def _tc_scoring_pipelines_slabs(vsom):
     x[hot] = m[0] + 0.001 * rng.standard_normal((3000, D)).astype(np.float32)
     ctx = vsom.VsomContext(W, H, D, vsom.STANDARD)
     ctx.upload_state(mean=m)
-    eb, ed = ctx.find_bmu(x)
+    eb, ed = ctx.find_bmu_exact(x)
     tb, td, fb = ctx.find_bmu_batch(x)
     assert_bit_equal(tb, eb, "bmu")
     assert_bit_equal(td, ed, "dist")
     assert fb > 0
+    # host-buffer path: the rows cross PCIe in slabs behind the search of the previous slab (several slabs here)
+    hb, hd = ctx.find_bmu(x)
+    assert_bit_equal(hb, eb, "pipelined host bmu")
+    assert_bit_equal(hd, ed, "pipelined host dist")
+    ctx.close()
+
+
+def test_tensor_core_scoring_adversarial_bf16_rounding(vsom):
+    """Worst case for the bf16 operands: every component of every row and node sits next to a bf16 rounding midpoint
+    (1 + 2^-8 -+ 2^-20, scaled), so x^ . m^ is off by almost the full 2 (2u + u^2) |x| |m| bound, in both directions, on maps
+    with few dimensions where nothing averages out; many nodes are exact or near ties in the true distance.  Whatever the
+    tensor cores select, the certificate must send every row it cannot prove to the exact scan: results equal K3's."""
+    rng = np.random.default_rng(2024)
+    for D, W, H in ((2, 32, 32), (3, 40, 30), (8, 64, 32), (16, 48, 48)):
+        N, n = W * H, 4096
+        def midpoints(shape):
+            sign = rng.choice(np.float32([-1.0, 1.0]), shape)
+            eps = rng.choice(np.float32([-2.0 ** -20, 2.0 ** -20]), shape)
+            scale = np.float32(2.0) ** rng.integers(-1, 2, shape).astype(np.float32)
+            return (sign * scale * (np.float32(1.0) + np.float32(2.0 ** -8) + eps)).astype(np.float32)
+        m = midpoints((N, D))
+        m[N // 2:] = m[: N - N // 2] * np.float32(1.0)  # duplicated nodes: exact ties, the lowest index must win
+        m[N // 2:, 0] += rng.choice(np.float32([0.0, 2.0 ** -18]), N - N // 2)
+        x = midpoints((n, D))
+        ctx = vsom.VsomContext(W, H, D, vsom.STANDARD)
+        ctx.upload_state(mean=m)
+        eb, ed = ctx.find_bmu_exact(x)
+        tb, td, fb = ctx.find_bmu_batch(x)
+        assert ctx.last_score_tc
+        print(f"adversarial D={D}: {fb} of {n} rows took the exact scan")
+        assert_bit_equal(tb, eb, f"bmu D={D}")
+        assert_bit_equal(td, ed, f"dist D={D}")
+        ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 128, 1, 3000, 1536), (128, 128, 256, 0, 1500, 1100)])
+def test_scoring_on_a_trained_map_matches_the_oracle(vsom, po, shape):
+    """K2 and K3 against the ORACLE (not against each other) on a map the online step has clustered: neighbouring nodes
+    are close to each other there, so near-candidates crowd the lists.  Includes 128x128x256 (BASELINE configs[3])."""
+    W, H, D, tr, ntrain, n = shape
+    rng = np.random.default_rng(W + D)
+    centres = (rng.standard_normal((16, D)) * 2).astype(np.float32)
+    data = lambda k: (centres[rng.integers(0, 16, k)] + 0.3 * rng.standard_normal((k, D))).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, tr)
+    ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * H, D)) / 1000).astype(np.float32))
+    ctx.train_chunk(data(ntrain), 0.2, W / 6.0, vsom.EXPONENTIAL)
+    ctx.train_chunk(data(ntrain), 0.1, W / 16.0, vsom.EXPONENTIAL)
+    st = ctx.download_state()
+    o = po.Oracle(W, H, D, tr)
+    o.set_state(**st)
+    q = data(n)
+    ob, od = o.find_bmu(q)
+    tb, td, fb = ctx.find_bmu_batch(q)
+    assert ctx.last_score_tc
+    print(f"trained {W}x{H}x{D}: {fb} of {n} rows took the exact scan; {len(np.unique(ob))} distinct BMUs")
+    assert_bit_equal(tb, ob, "K2 bmu vs oracle")
+    assert_bit_equal(td, od, "K2 dist vs oracle")
+    eb, ed = ctx.find_bmu_exact(q[:512])
+    assert_bit_equal(eb, ob[:512], "K3 bmu vs oracle")
+    assert_bit_equal(ed, od[:512], "K3 dist vs oracle")
+    assert ctx.evaluate(q) == o.evaluate(q)
+    rb, _, _ = ctx.find_bmu_batch(q, min_hits=3)
+    assert_bit_equal(rb, o.find_restricted_bmu(q, 3), "restricted K2 bmu vs oracle")
     ctx.close()
 
 

@@ -11,7 +11,7 @@ from . import build as _build
 
 STANDARD, MEDIAN, CLR = 0, 1, 2
 EXPONENTIAL, INVERSE_PROPORTIONAL = 0, 1
-ORDER_REFERENCE, ORDER_LANES = 0, 1
+ORDER_REFERENCE, ORDER_LANES, ORDER_EIGEN_SSE = 0, 1, 2
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -47,6 +47,9 @@ _PROTOS = {
     "vsom_batch_epoch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_double, C.c_int, _u64p, _f32p]),
     "vsom_find_bmu": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
     "vsom_find_bmu_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
+    "vsom_find_bmu_exact": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
+    "vsom_find_bmu_exact_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
+    "vsom_debug_last_score_tc": (C.c_int, [_vp]),
     "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
     "vsom_find_bmu_batch_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, _u64p]),
     "vsom_evaluate": (C.c_int, [_vp, _f32p, C.c_size_t, _f64p]),
@@ -205,6 +208,29 @@ class VsomContext:
         self._check(lib().vsom_find_bmu_device(self._h, x_dev.data_ptr(), n, min_hits,
                                                out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
                                                out_dist_dev.data_ptr() if out_dist_dev is not None else None))
+
+    def find_bmu_exact(self, x, min_hits=0):
+        """Always the exact scan (K3), whatever the batch size."""
+        x = _f32(x).reshape(-1, self.Din)
+        n = x.shape[0]
+        bmu = np.empty(n, np.uint32)
+        dist = np.empty(n, np.float32)
+        self._check(lib().vsom_find_bmu_exact(self._h, _p(x, _f32p), n, min_hits, _p(bmu, _u32p), _p(dist, _f32p)))
+        return bmu, dist
+
+    def find_bmu_exact_device(self, x_dev, n, out_bmu_dev=None, out_dist_dev=None, min_hits=0):
+        self._check(lib().vsom_find_bmu_exact_device(self._h, x_dev.data_ptr(), n, min_hits,
+                                                     out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
+                                                     out_dist_dev.data_ptr() if out_dist_dev is not None else None))
+
+    def find_bmu_host_ptr(self, x_ptr: int, n: int, bmu_ptr: int, dist_ptr: int, min_hits=0):
+        """vsom_find_bmu on raw HOST addresses (e.g. pinned torch tensors): no numpy conversion in the way."""
+        self._check(lib().vsom_find_bmu(self._h, C.cast(x_ptr, _f32p), n, min_hits, C.cast(bmu_ptr, _u32p), C.cast(dist_ptr, _f32p)))
+
+    @property
+    def last_score_tc(self) -> bool:
+        """True when the last scoring call ran K2 (tcgen05 candidate search + exact rescore)."""
+        return bool(lib().vsom_debug_last_score_tc(self._h))
 
     def find_bmu_batch(self, x, min_hits=0):
         """Tensor-core candidate search + exact rescore; returns (bmu, dist, rows that took the exact full scan)."""

@@ -71,7 +71,7 @@ static int create_impl(vsom_ctx **out, int device, int width, int height, int d_
         return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: out is NULL");
     *out = nullptr;
     if (width < 1 || height < 1 || d_in < 1 || transform < VSOM_STANDARD || transform > VSOM_CLR || order < VSOM_ORDER_REFERENCE ||
-        order > VSOM_ORDER_LANES || (transform == VSOM_CLR && d_in < 2))
+        order > VSOM_ORDER_EIGEN_SSE || (transform == VSOM_CLR && d_in < 2))
         return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: bad width/height/d_in/transform/order");
     if (static_cast<long long>(width) * height >= (1ll << 24))
         return set_error(nullptr, VSOM_ERR_INVALID, "vsom_create: at most 2^24 - 1 nodes");
@@ -270,11 +270,18 @@ void vsom_destroy(vsom_ctx *ctx)
         cudaFree(p);
     if (ctx->auxStream)
     {
+        cudaStreamSynchronize(ctx->auxStream);
         cudaStreamDestroy(ctx->auxStream);
+        if (ctx->copyStream)
+        {
+            cudaStreamSynchronize(ctx->copyStream);
+            cudaStreamDestroy(ctx->copyStream);
+        }
         for (int i = 0; i < 2; ++i)
         {
             cudaEventDestroy(ctx->evScore[i]);
             cudaEventDestroy(ctx->evDone[i]);
+            cudaEventDestroy(ctx->evCopied[i]);
         }
     }
     if (ctx->stream)
@@ -547,25 +554,58 @@ int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double sigma, int 
     return VSOM_OK;
 }
 
-int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev)
+// Batches of at least kTcMinRows rows on a shape K2 covers take the tensor-core candidate search + exact rescore (same
+// results, bit for bit); everything else the exact scan.
+static const size_t kTcMinRows = 1024;
+static const char *kUnshardedOnly = "this entry point needs an unsharded context (scoring and index run on replicated maps)";
+
+static int find_bmu_device_impl(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev, bool allowTc,
+                                uint64_t *fallback_rows, const char *who)
 {
     if (ctx && ctx->world > 1)
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, kUnshardedOnly);
     if (!ctx || (!x_dev && n))
-        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_device: x is NULL") : VSOM_ERR_INVALID;
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, std::string(who) + ": x is NULL") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    return launch_find_bmu(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev);
+    if (fallback_rows)
+        *fallback_rows = 0;
+    if (!allowTc || !score_tc_supported(ctx) || n < kTcMinRows)
+    {
+        if (fallback_rows)
+            *fallback_rows = n;
+        ctx->lastScoreTc = 0;
+        return launch_find_bmu(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev);
+    }
+    unsigned long long fb = 0;
+    ctx->lastScoreTc = 1;
+    const int rc = launch_find_bmu_tc(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev, &fb);
+    if (fallback_rows)
+        *fallback_rows = fb;
+    return rc;
 }
 
-int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist)
+static int find_bmu_host_impl(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, bool allowTc, uint64_t *fallback_rows,
+                              const char *who)
 {
     if (ctx && ctx->world > 1)
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, kUnshardedOnly);
     if (!ctx || (!x && n))
-        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu: x is NULL") : VSOM_ERR_INVALID;
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, std::string(who) + ": x is NULL") : VSOM_ERR_INVALID;
+    if (fallback_rows)
+        *fallback_rows = 0;
     if (n == 0)
         return VSOM_OK;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (allowTc && score_tc_supported(ctx) && n >= kTcMinRows)
+    {
+        // pipelined: H2D of slab i + 1, search + re-scoring of slab i and D2H of slab i - 1 overlap (score_tc.cu)
+        unsigned long long fb = 0;
+        ctx->lastScoreTc = 1;
+        const int rc = launch_find_bmu_tc_host(ctx, x, n, min_hits, out_bmu, out_dist, &fb);
+        if (fallback_rows)
+            *fallback_rows = fb;
+        return rc;
+    }
     int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
     if (rc)
         return rc;
@@ -579,6 +619,9 @@ int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, ui
     unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
     float *distDev = static_cast<float *>(ctx->stage[2]);
     VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+    if (fallback_rows)
+        *fallback_rows = n;
+    ctx->lastScoreTc = 0;
     rc = launch_find_bmu(ctx, xDev, n, min_hits, bmuDev, distDev);
     if (rc)
         return rc;
@@ -590,63 +633,38 @@ int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, ui
     return VSOM_OK;
 }
 
+int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev)
+{
+    return find_bmu_device_impl(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev, true, nullptr, "vsom_find_bmu_device");
+}
+
+int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist)
+{
+    return find_bmu_host_impl(ctx, x, n, min_hits, out_bmu, out_dist, true, nullptr, "vsom_find_bmu");
+}
+
+int vsom_find_bmu_exact_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev)
+{
+    return find_bmu_device_impl(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev, false, nullptr, "vsom_find_bmu_exact_device");
+}
+
+int vsom_find_bmu_exact(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist)
+{
+    return find_bmu_host_impl(ctx, x, n, min_hits, out_bmu, out_dist, false, nullptr, "vsom_find_bmu_exact");
+}
+
 int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev,
                                uint64_t *fallback_rows)
 {
-    if (ctx && ctx->world > 1)
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
-    if (!ctx || (!x_dev && n))
-        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_batch_device: x is NULL") : VSOM_ERR_INVALID;
-    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (fallback_rows)
-        *fallback_rows = 0;
-    if (!score_tc_supported(ctx) || n < 1024)
-    {
-        if (fallback_rows)
-            *fallback_rows = n;
-        return launch_find_bmu(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev);
-    }
-    unsigned long long fb = 0;
-    const int rc = launch_find_bmu_tc(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev, &fb);
-    if (fallback_rows)
-        *fallback_rows = fb;
-    return rc;
+    return find_bmu_device_impl(ctx, x_dev, n, min_hits, out_bmu_dev, out_dist_dev, true, fallback_rows, "vsom_find_bmu_batch_device");
 }
 
 int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, uint64_t *fallback_rows)
 {
-    if (ctx && ctx->world > 1)
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
-    if (!ctx || (!x && n))
-        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_find_bmu_batch: x is NULL") : VSOM_ERR_INVALID;
-    if (fallback_rows)
-        *fallback_rows = 0;
-    if (n == 0)
-        return VSOM_OK;
-    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
-    if (rc)
-        return rc;
-    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
-    if (rc)
-        return rc;
-    rc = stage_reserve(ctx, 2, sizeof(float) * n);
-    if (rc)
-        return rc;
-    float *xDev = static_cast<float *>(ctx->stage[0]);
-    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
-    float *distDev = static_cast<float *>(ctx->stage[2]);
-    VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
-    rc = vsom_find_bmu_batch_device(ctx, xDev, n, min_hits, bmuDev, distDev, fallback_rows);
-    if (rc)
-        return rc;
-    if (out_bmu)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(out_bmu, bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_dist)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(out_dist, distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VSOM_OK;
+    return find_bmu_host_impl(ctx, x, n, min_hits, out_bmu, out_dist, true, fallback_rows, "vsom_find_bmu_batch");
 }
+
+int vsom_debug_last_score_tc(const vsom_ctx *ctx) { return ctx ? ctx->lastScoreTc : 0; }
 
 int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)
 {

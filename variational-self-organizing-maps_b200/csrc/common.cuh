@@ -92,7 +92,9 @@ struct vsom_ctx
     int numSMs = 0, smemOptin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t auxStream = nullptr;           // K2: re-scoring of slab i overlaps the search of slab i + 1
-    cudaEvent_t evScore[2] = {}, evDone[2] = {};
+    cudaStream_t copyStream = nullptr;          // host-buffer scoring: H2D of slab i + 1 overlaps the search of slab i
+    cudaEvent_t evScore[2] = {}, evDone[2] = {}, evCopied[2] = {};
+    int tcAttrSet = 0;                          // K2's dynamic shared-memory opt-in was set on this context's device
     float *mean = nullptr, *S = nullptr, *sigma = nullptr, *weight = nullptr;
     vsom::u64 *hits = nullptr;
     double *umatrix = nullptr;
@@ -108,6 +110,7 @@ struct vsom_ctx
     // grow-only device staging for the host entry points
     void *stage[10] = {};
     size_t stageCap[10] = {};
+    int lastScoreTc = 0;                     // the last scoring call ran K2 (tensor-core search + exact rescore)
     unsigned long long lastFallbackRows = 0; // rows of the last tensor-core scoring call that needed the exact full scan
     int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;
     size_t smemTrain = 0;
@@ -155,6 +158,7 @@ int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma);      //
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev);
 bool score_tc_supported(const vsom_ctx *ctx);
 int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut);
+int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut);
 int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma, int isFirst, const u64 *lastDev, unsigned *bmuDev, float *distDev);
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
 int launch_umatrix(vsom_ctx *ctx);
@@ -254,6 +258,100 @@ __device__ __forceinline__ float dist_sequential(const float *m, const float *xs
     {
         const float r = residual<TR>(m, xs, k, P, pi, pj);
         s = __fadd_rn(s, __fmul_rn(r, r));
+    }
+    return s;
+}
+
+// ---- summation orders of one squared distance (vsom_reduction_order, include/vsom_b200.h)
+// EIGEN_SSE restates what `a.dot(b)` / `squaredNorm()` compile to in the reference when it is built against real Eigen
+// (3.3 / 3.4, README.md:64-69) with its release flags (-msse2 only, build/Makefile:18): Eigen's redux_impl<...,
+// LinearVectorizedTraversal, NoUnrolling> over Packet4f — two packet accumulators over strides of 8 elements, the sum of
+// the two, one more packet if 4..7 elements remain, predux = (p0 + p2) + (p1 + p3), then the scalar tail in order.  The
+// reduced expression has no direct access, so the aligned start is element 0.
+struct EigenSseSum
+{
+    float a[8];
+    __device__ __forceinline__ EigenSseSum()
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            a[j] = 0.0f; // 0 + t == t exactly for the terms of this library (squares: never -0)
+    }
+    // terms t[8 b + j] of a full block of eight
+    __device__ __forceinline__ void block(const float (&t)[8])
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            a[j] = __fadd_rn(a[j], t[j]);
+    }
+    // after n / 8 blocks: `rest` = the n % 8 remaining terms in order
+    __device__ __forceinline__ float finish(const float *rest, int nrest) const
+    {
+        float r0 = __fadd_rn(a[0], a[4]), r1 = __fadd_rn(a[1], a[5]), r2 = __fadd_rn(a[2], a[6]), r3 = __fadd_rn(a[3], a[7]);
+        int k = 0;
+        if (nrest >= 4)
+        {
+            r0 = __fadd_rn(r0, rest[0]);
+            r1 = __fadd_rn(r1, rest[1]);
+            r2 = __fadd_rn(r2, rest[2]);
+            r3 = __fadd_rn(r3, rest[3]);
+            k = 4;
+        }
+        float s = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+        for (; k < nrest; ++k)
+            s = __fadd_rn(s, rest[k]);
+        return s;
+    }
+};
+
+// |m - x|^2 of two plain rows (Standard / Median Comparer, src/Transformation.cpp:7-8, :45-46) by ONE thread, in the given
+// order.  m is a row of a plane (16-byte aligned); x may be unaligned.
+__device__ __forceinline__ float dist_rows_f32(const float *__restrict__ m, const float *__restrict__ x, int D, int order)
+{
+    if (order == VSOM_ORDER_EIGEN_SSE)
+    {
+        EigenSseSum acc;
+        int k = 0;
+        for (; k + 8 <= D; k += 8)
+        {
+            const float4 m0 = *reinterpret_cast<const float4 *>(m + k), m1 = *reinterpret_cast<const float4 *>(m + k + 4);
+            float t[8];
+            const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const float d = __fsub_rn(mm[j], x[k + j]);
+                t[j] = __fmul_rn(d, d);
+            }
+            acc.block(t);
+        }
+        float rest[8];
+        const int nrest = D - k;
+        for (int j = 0; j < nrest; ++j)
+        {
+            const float d = __fsub_rn(m[k + j], x[k + j]);
+            rest[j] = __fmul_rn(d, d);
+        }
+        return acc.finish(rest, nrest);
+    }
+    float s = 0.0f;
+    int k = 0;
+    for (; k + 4 <= D; k += 4)
+    {
+        const float4 a = *reinterpret_cast<const float4 *>(m + k);
+        float q = __fsub_rn(a.x, x[k]);
+        s = __fadd_rn(s, __fmul_rn(q, q));
+        q = __fsub_rn(a.y, x[k + 1]);
+        s = __fadd_rn(s, __fmul_rn(q, q));
+        q = __fsub_rn(a.z, x[k + 2]);
+        s = __fadd_rn(s, __fmul_rn(q, q));
+        q = __fsub_rn(a.w, x[k + 3]);
+        s = __fadd_rn(s, __fmul_rn(q, q));
+    }
+    for (; k < D; ++k)
+    {
+        const float q = __fsub_rn(m[k], x[k]);
+        s = __fadd_rn(s, __fmul_rn(q, q));
     }
     return s;
 }

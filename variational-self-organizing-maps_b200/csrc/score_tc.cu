@@ -7,14 +7,17 @@
 // staged by TMA (128-byte swizzle).  The tensor cores only SELECT candidates; the exact pass re-evaluates them in
 // the reference's own f32 arithmetic and order (bit-identical distances) and applies findBmu's lowest-index rule.
 //
-// Candidate rule (margin list).  With approximate score a_p = c_p - 2 acc_p, E = 2^-7 |x| max_p|m_p| bounds
-// |a_p + |x|^2 - d_p| (bf16 rounding of both operands, Cauchy-Schwarz; f32 effects are covered by a relative slack).
-// While streaming over the node tiles each row keeps its running best score and appends every node with
-// a_p < best + Delta, Delta = 2.2 E + slack, to a small per-row list.  Any node NOT appended had a_p >= best_final +
-// Delta, hence d_p >= best_final + |x|^2 + Delta - E > d(best node): it cannot be the BMU, nor tie with it.  So the
-// BMU is always in the list — by construction, no statistical recall argument.  At the end of the row tile the list
-// is filtered against the final threshold; up to 8 survivors go to the exact rescore, rows with more (or whose list
-// overflowed) are re-scored by the exact full scan (score_exact.cu).
+// Candidate rule (margin list + certificate).  With approximate score a_p = c_p - 2 acc_p (c_p = |m_p|^2), the bf16
+// rounding of both operands gives |a_p + |x|^2 - d_p| <= E = 2 (2u + u^2) |x| max_p|m_p|, u = 2^-8 (Cauchy-Schwarz), i.e.
+// E = 2^-6 |x| max|m| plus a relative slack for every f32 effect (tensor-core accumulation, the norms, the reference's own
+// f32 chain).  While streaming over the node tiles each row keeps its running best score and appends every node with
+// a_p < best + Delta to a small per-row list (tc_margins: Delta = 1.25 E + slack).  Delta alone proves nothing; the proof
+// is the CERTIFICATE checked after the exact rescore: every node NOT in the list had a_q >= best_final + Delta, hence its
+// reference distance is >= best_final + |x|^2 + Delta - E.  If that bound is strictly above the best EXACT distance among
+// the listed nodes, no unlisted node can be the BMU or tie with it, and the row is done; otherwise the row is re-scored
+// by the exact full scan.  So the result never depends on a statistical recall argument: Delta only trades list length
+// against the share of rows that need the full scan.  Up to 16 survivors per row go to the exact rescore; rows with more
+// (or whose list overflowed) take the exact full scan as well.
 //
 // Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
 //   warp 0   TMA producer : A tile (128 rows x K, resident for the row tile) + B tiles (256 nodes x 64) through a
@@ -123,6 +126,14 @@ __device__ __forceinline__ u64 umma_desc_sw128(unsigned smemAddr)
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10), both K-major, N>>3 at 17, M>>4 at 24
 constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<unsigned>(TC_BN >> 3) << 17) | (static_cast<unsigned>(TC_BM >> 4) << 24);
 
+// Error bound E and list margin Delta of one row (see "Candidate rule" above).  xn = |x|^2, mx = max_p |m_p|^2.
+__device__ __forceinline__ void tc_margins(float xn, float mx, int Kpad, float &E, float &delta)
+{
+    const float slack = static_cast<float>(Kpad + 64) * 2.384185791015625e-7f * (xn + mx); // (K + 64) 2^-22 (|x|^2 + max|m|^2)
+    E = 0.0157f * sqrtf(xn * mx) + slack; // 2 (2u + u^2) = 2^-6 + 2^-15 < 0.0157
+    delta = 1.25f * E + 2.0f * slack;
+}
+
 struct TcShared
 {
     // offsets inside the dynamic shared buffer (1024-byte aligned base)
@@ -138,7 +149,7 @@ struct TcShared
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, const float *__restrict__ cnorm, int rowsTotal,
                 int numRowTiles, int numNodeTiles, int kBlocks, int stagger, const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, unsigned *__restrict__ candOut,
-                unsigned *__restrict__ countOut, int *err)
+                unsigned *__restrict__ countOut, float *__restrict__ bestOut, int *err)
 {
     // 128-byte-swizzled TMA / UMMA tiles need a 1024-byte aligned base; declaring the alignment (instead of rounding
     // a pointer up by hand) also lets the compiler keep every derived pointer in the shared address space (LDS/STS)
@@ -301,8 +312,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         {
             const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
             const float xn = row < rowsTotal ? xnorm2[row] : 0.0f;
-            const float E = 0.0079f * sqrtf(xn * mx) + 1e-5f * (xn + mx);
-            const float delta = 2.2f * E + 2e-4f * (xn + mx);
+            float E, delta;
+            tc_margins(xn, mx, kBlocks * TC_BK, E, delta);
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
@@ -396,7 +407,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             cnt = static_cast<int>((wp - mineAddr) >> 11);
             sBest[et] = best;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float thrF = fminf(best, sBest[et ^ 128]) + delta;
+            const float bestF = fminf(best, sBest[et ^ 128]);
+            const float thrF = bestF + delta;
             compact(cnt, thrF);
             sCnt[et] = ovf ? 1000 : cnt;
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -411,7 +423,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         candOut[row * TC_TOPK + off + e] = mine[e * 256].y;
                 }
                 if (half == 0)
+                {
                     countOut[row] = bad ? TC_OVERFLOW : static_cast<unsigned>(total);
+                    bestOut[row] = bestF; // the certificate's lower bound starts from the best APPROXIMATE score
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory"); // sBest / sCnt are reused by the next row tile
         }
@@ -462,18 +477,21 @@ __global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__
         atomicMax(reinterpret_cast<int *>(maxNorm2), __float_as_int(norm2[p])); // non-negative floats order like ints
 }
 
-// ------------------------------------------------------------------------------------------------ exact rescore + guard
+// ------------------------------------------------------------------------------------------------ exact rescore + certificate
 
 // Re-evaluation of the candidates with the reference's sequential f32 chain.  Rows keep 1-3 candidates on average, so a
 // thread per (row, slot) would leave nine lanes in ten idle: a CTA takes 128 rows, compacts their (row, candidate) items into
 // a list (block scan of the counts) and its 256 threads walk the list, all lanes busy; the per-row winner is an atomic min of
-// the (distance, node) key in shared memory — lowest index on ties, like the reference.  Rows whose list overflowed, or whose
-// winner is NaN, go to the fallback list (exact full scan).
+// the (distance, node) key in shared memory — lowest index on ties, like the reference.  Then the certificate (see the
+// head of this file): the row is final only if no unlisted node can reach the winner's exact distance.  Rows that fail it,
+// rows whose list overflowed and rows whose winner is NaN go to the fallback list (exact full scan).
 constexpr int RS_ROWS = 128;
 constexpr int RS_THREADS = 256;
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
-                                                             const unsigned *__restrict__ cand, const unsigned *__restrict__ count, unsigned *__restrict__ outBmu,
-                                                             float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
+                                                             const unsigned *__restrict__ cand, const unsigned *__restrict__ count, const float *__restrict__ bestA,
+                                                             const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, int Kpad, int order,
+                                                             unsigned *__restrict__ outBmu, float *__restrict__ outDist, unsigned *__restrict__ fallbackRows,
+                                                             unsigned *__restrict__ fallbackCount)
 {
     __shared__ unsigned sOff[RS_ROWS + 1];
     __shared__ unsigned sWarpTot[RS_ROWS / 32];
@@ -520,32 +538,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
         const int r = static_cast<int>(it >> 4), j = static_cast<int>(it & 15u);
         const long long row = row0 + r;
         const unsigned node = cand[row * TC_TOPK + j];
-        const float *m = mean + static_cast<size_t>(node) * rowStride, *xr = x + row * D;
-        float s = 0.0f;
-        int k = 0;
-        if ((D & 3) == 0) // rows of x are 16-byte aligned: 128-bit loads, same sequential order of the adds
-        {
-            const float4 *m4 = reinterpret_cast<const float4 *>(m), *x4 = reinterpret_cast<const float4 *>(xr);
-#pragma unroll 4
-            for (int q = 0; q < (D >> 2); ++q)
-            {
-                const float4 a = m4[q], b = x4[q];
-                float d = __fsub_rn(a.x, b.x);
-                s = __fadd_rn(s, __fmul_rn(d, d));
-                d = __fsub_rn(a.y, b.y);
-                s = __fadd_rn(s, __fmul_rn(d, d));
-                d = __fsub_rn(a.z, b.z);
-                s = __fadd_rn(s, __fmul_rn(d, d));
-                d = __fsub_rn(a.w, b.w);
-                s = __fadd_rn(s, __fmul_rn(d, d));
-            }
-            k = D;
-        }
-        for (; k < D; ++k)
-        {
-            const float d = __fsub_rn(m[k], xr[k]);
-            s = __fadd_rn(s, __fmul_rn(d, d));
-        }
+        const float s = dist_rows_f32(mean + static_cast<size_t>(node) * rowStride, x + row * D, D, order);
         atomicMin(&sKey[r], make_key(s, node, (s != s) ? 1u : 0u));
     }
     __syncthreads();
@@ -554,7 +547,17 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
         const long long row = row0 + tid;
         const u64 key = sKey[tid];
         const bool nan = (key & 1ull) != 0;
-        if (cnt == TC_OVERFLOW || nan || key == ~0ull)
+        bool certified = false;
+        if (cnt != TC_OVERFLOW && !nan && key != ~0ull)
+        {
+            // unlisted nodes: reference distance >= best approximate score + |x|^2 + Delta - E = ... + 0.25 E + slack (tc_margins)
+            const float xn = xnorm2[row];
+            float E, delta;
+            tc_margins(xn, maxNorm2[0], Kpad, E, delta);
+            const float lower = __fadd_rn(__fadd_rn(bestA[row], xn), __fmul_rn(0.25f, E));
+            certified = lower > __uint_as_float(static_cast<unsigned>(key >> 32));
+        }
+        if (!certified)
             fallbackRows[atomicAdd(fallbackCount, 1u)] = static_cast<unsigned>(row);
         else
         {
@@ -572,8 +575,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
 // between the slabs of a batch): a fixed grid walks the list, and CTA 0 adds the count to the batch total.
 __global__ void __launch_bounds__(256) find_bmu_rowwise_kernel(const float *__restrict__ x, int D, const unsigned *__restrict__ rows,
                                                                const unsigned *__restrict__ countPtr, const float *__restrict__ mean, int rowStride, int N,
-                                                               const u64 *__restrict__ hits, u64 minHits, unsigned *__restrict__ outBmu, float *__restrict__ outDist,
-                                                               unsigned long long *__restrict__ total)
+                                                               const u64 *__restrict__ hits, u64 minHits, int order, unsigned *__restrict__ outBmu,
+                                                               float *__restrict__ outDist, unsigned long long *__restrict__ total)
 {
     extern __shared__ float xrow[];
     __shared__ u64 wkey[8];
@@ -592,26 +595,7 @@ __global__ void __launch_bounds__(256) find_bmu_rowwise_kernel(const float *__re
         {
             if (!(node == 0 || minHits == 0 || hits[node] >= minHits))
                 continue;
-            const float *m = mean + static_cast<size_t>(node) * rowStride;
-            float s = 0.0f;
-            int k = 0;
-            for (; k + 4 <= D; k += 4)
-            {
-                const float4 a = *reinterpret_cast<const float4 *>(m + k);
-                float q = __fsub_rn(a.x, xrow[k]);
-                s = __fadd_rn(s, __fmul_rn(q, q));
-                q = __fsub_rn(a.y, xrow[k + 1]);
-                s = __fadd_rn(s, __fmul_rn(q, q));
-                q = __fsub_rn(a.z, xrow[k + 2]);
-                s = __fadd_rn(s, __fmul_rn(q, q));
-                q = __fsub_rn(a.w, xrow[k + 3]);
-                s = __fadd_rn(s, __fmul_rn(q, q));
-            }
-            for (; k < D; ++k)
-            {
-                const float q = __fsub_rn(m[k], xrow[k]);
-                s = __fadd_rn(s, __fmul_rn(q, q));
-            }
+            const float s = dist_rows_f32(mean + static_cast<size_t>(node) * rowStride, xrow, D, order);
             best = u64_min(best, make_key(s, static_cast<unsigned>(node), (s != s) ? 1u : 0u));
         }
         best = warp_min_u64(best);
@@ -666,123 +650,144 @@ static int make_map(vsom_ctx *ctx, CUtensorMap *map, void *base, unsigned long l
 
 bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR && ctx->Dm <= TC_MAXK; }
 
-// stage slots used here: 6 = bf16 map + node constants, 7 = bf16 rows of the current slab, 8 = per-row scratch
-int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut)
+// One batched scoring call: tc_begin (map side, once) -> tc_enqueue per slab of rows (no host synchronisation) -> tc_finish.
+// stage slots used: 6 = bf16 map + node constants, 7 = bf16 rows of the current slab, 8 = per-row scratch (two sets).
+struct TcCall
 {
-    if (!score_tc_supported(ctx))
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 256");
-    if (fallbackRowsOut)
-        *fallbackRowsOut = 0;
-    if (n == 0)
-        return VSOM_OK;
+    int D = 0, N = 0, Kpad = 0, kBlocks = 0, Npad = 0, nodeTiles = 0, stagger = 1;
+    bool overlap = true;
+    uint64_t minHits = 0;
+    size_t slabRows = 0, setBytes = 0, slab = 0;
+    __nv_bfloat16 *Xb = nullptr;
+    float *cnorm = nullptr, *maxNorm2 = nullptr;
+    unsigned long long *totalDev = nullptr;
+    CUtensorMap mapM;
+};
+
+static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHits)
+{
     const int D = ctx->Dm, N = ctx->N;
-    const int Kpad = (D + TC_BK - 1) / TC_BK * TC_BK, kBlocks = Kpad / TC_BK;
-    const int Npad = (N + TC_BN - 1) / TC_BN * TC_BN, nodeTiles = Npad / TC_BN;
+    c.D = D;
+    c.N = N;
+    c.Kpad = (D + TC_BK - 1) / TC_BK * TC_BK;
+    c.kBlocks = c.Kpad / TC_BK;
+    c.Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
+    c.nodeTiles = c.Npad / TC_BN;
+    c.minHits = minHits;
 
     // ---- map side: bf16 copy, |m|^2, node constants, max |m|^2
-    const size_t mbBytes = sizeof(__nv_bfloat16) * static_cast<size_t>(Npad) * Kpad;
-    int rc = stage_reserve(ctx, 6, mbBytes + sizeof(float) * (2 * static_cast<size_t>(Npad) + 64));
+    const size_t mbBytes = sizeof(__nv_bfloat16) * static_cast<size_t>(c.Npad) * c.Kpad;
+    int rc = stage_reserve(ctx, 6, mbBytes + sizeof(float) * (2 * static_cast<size_t>(c.Npad) + 64));
     if (rc)
         return rc;
     __nv_bfloat16 *Mb = static_cast<__nv_bfloat16 *>(ctx->stage[6]);
     float *mnorm = reinterpret_cast<float *>(static_cast<unsigned char *>(ctx->stage[6]) + mbBytes);
-    float *cnorm = mnorm + Npad;
-    float *maxNorm2 = cnorm + Npad;
+    c.cnorm = mnorm + c.Npad;
+    c.maxNorm2 = c.cnorm + c.Npad;
     VSOM_CUDA(ctx, cudaMemsetAsync(Mb, 0, mbBytes, ctx->stream));
-    VSOM_CUDA(ctx, cudaMemsetAsync(maxNorm2, 0, sizeof(float), ctx->stream));
-    to_bf16_rows_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, Mb, Kpad, mnorm);
-    node_const_kernel<<<(Npad + 255) / 256, 256, 0, ctx->stream>>>(mnorm, ctx->hits, minHits, N, Npad, cnorm, maxNorm2);
+    VSOM_CUDA(ctx, cudaMemsetAsync(c.maxNorm2, 0, sizeof(float), ctx->stream));
+    to_bf16_rows_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, Mb, c.Kpad, mnorm);
+    node_const_kernel<<<(c.Npad + 255) / 256, 256, 0, ctx->stream>>>(mnorm, ctx->hits, minHits, N, c.Npad, c.cnorm, c.maxNorm2);
     ctx->launches += 2;
-    CUtensorMap mapM;
-    rc = make_map(ctx, &mapM, Mb, static_cast<unsigned long long>(Npad), Kpad, TC_BN);
+    rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, TC_BN);
     if (rc)
         return rc;
-
-    static bool attrSet = false;
-    const int smemBytes = TcShared::TOTAL;
-    if (!attrSet)
+    // function attributes are per device: set it for every context (not once per process)
+    if (!ctx->tcAttrSet)
     {
-        VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
-        attrSet = true;
+        VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShared::TOTAL));
+        ctx->tcAttrSet = 1;
     }
 
-    // ---- rows, in slabs of 4M (the bf16 staging buffer: 2 GB at K = 256).  Two streams: the context's stream converts a slab and runs the tensor-core search; an auxiliary
-    // stream re-scores the slab's candidates (and scans the few rows its guard could not certify) while the next slab is
-    // already being searched.  Candidate scratch is double-buffered by slab parity; nothing returns to the host in between.
-    const char *slabEnv = getenv("VSOM_TC_SLAB_LOG2"), *ovlEnv = getenv("VSOM_TC_OVERLAP"); // experiment knobs
-    const int slabLog2 = slabEnv ? atoi(slabEnv) : 22; // smaller slabs measured slower (per-slab ramp and tail of the persistent kernel)
-    const bool overlap = ovlEnv ? atoi(ovlEnv) != 0 : true;
-    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << slabLog2);
-    rc = stage_reserve(ctx, 7, sizeof(__nv_bfloat16) * slabRows * Kpad);
+    // ---- rows go through in slabs (the bf16 staging buffer: 2 GB at K = 256 for 4M rows).  Two streams: the context's
+    // stream converts a slab and runs the tensor-core search; an auxiliary stream re-scores the slab's candidates (and scans
+    // the few rows the certificate rejected) while the next slab is already being searched.  Candidate scratch is
+    // double-buffered by slab parity; nothing returns to the host in between.
+    const char *ovlEnv = getenv("VSOM_TC_OVERLAP"), *stg = getenv("VSOM_TC_STAGGER"); // experiment knobs
+    c.overlap = ovlEnv ? atoi(ovlEnv) != 0 : true;
+    c.stagger = stg ? atoi(stg) : 1;
+    c.slabRows = maxSlabRows;
+    rc = stage_reserve(ctx, 7, sizeof(__nv_bfloat16) * c.slabRows * c.Kpad);
     if (rc)
         return rc;
-    // per-row scratch: candidates, their count, |x|^2, fallback list; per set: fallback count
-    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + sizeof(float) + sizeof(unsigned);
-    const size_t setBytes = (perRow * slabRows + 256 + 255) & ~static_cast<size_t>(255);
-    rc = stage_reserve(ctx, 8, 2 * setBytes + 256);
+    // per-row scratch: candidates, their count, |x|^2, best approximate score, fallback list; per set: fallback count
+    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + 2 * sizeof(float) + sizeof(unsigned);
+    c.setBytes = (perRow * c.slabRows + 256 + 255) & ~static_cast<size_t>(255);
+    rc = stage_reserve(ctx, 8, 2 * c.setBytes + 256);
     if (rc)
         return rc;
     if (!ctx->auxStream)
     {
         VSOM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->auxStream, cudaStreamNonBlocking));
+        VSOM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i)
         {
             VSOM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evScore[i], cudaEventDisableTiming));
             VSOM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evDone[i], cudaEventDisableTiming));
+            VSOM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
         }
     }
-    __nv_bfloat16 *Xb = static_cast<__nv_bfloat16 *>(ctx->stage[7]);
-    unsigned long long *totalDev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ctx->stage[8]) + 2 * setBytes);
-    VSOM_CUDA(ctx, cudaMemsetAsync(totalDev, 0, sizeof(unsigned long long), ctx->stream));
+    c.Xb = static_cast<__nv_bfloat16 *>(ctx->stage[7]);
+    c.totalDev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ctx->stage[8]) + 2 * c.setBytes);
+    VSOM_CUDA(ctx, cudaMemsetAsync(c.totalDev, 0, sizeof(unsigned long long), ctx->stream));
     VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
+    c.slab = 0;
+    return VSOM_OK;
+}
 
-    const char *stg = getenv("VSOM_TC_STAGGER");
-    const int stagger = stg ? atoi(stg) : 1;
-    size_t slab = 0;
-    for (size_t r0 = 0; r0 < n; r0 += slabRows, ++slab)
-    {
-        const int par = static_cast<int>(slab & 1);
-        unsigned char *set = static_cast<unsigned char *>(ctx->stage[8]) + par * setBytes;
-        unsigned *cand = reinterpret_cast<unsigned *>(set);
-        unsigned *candCount = cand + slabRows * TC_TOPK;
-        float *xnorm = reinterpret_cast<float *>(candCount + slabRows);
-        unsigned *fbRows = reinterpret_cast<unsigned *>(xnorm + slabRows);
-        unsigned *fbCount = fbRows + slabRows;
+// One slab: xs = rows x D f32 in device memory (must stay valid until the slab's evDone event).  Results go to outBmuDev /
+// outDistDev (device, may be null) and, when given, from there to host memory on the re-scoring stream.
+static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, unsigned *outBmuDev, float *outDistDev, unsigned *outBmuHost, float *outDistHost)
+{
+    const int par = static_cast<int>(c.slab & 1);
+    unsigned char *set = static_cast<unsigned char *>(ctx->stage[8]) + par * c.setBytes;
+    unsigned *cand = reinterpret_cast<unsigned *>(set);
+    unsigned *candCount = cand + c.slabRows * TC_TOPK;
+    float *xnorm = reinterpret_cast<float *>(candCount + c.slabRows);
+    float *bestA = xnorm + c.slabRows;
+    unsigned *fbRows = reinterpret_cast<unsigned *>(bestA + c.slabRows);
+    unsigned *fbCount = fbRows + c.slabRows;
+    const int order = ctx->order == VSOM_ORDER_EIGEN_SSE ? VSOM_ORDER_EIGEN_SSE : VSOM_ORDER_REFERENCE;
 
-        const size_t rows = std::min(slabRows, n - r0);
-        const float *xs = xDev + r0 * D;
-        if (slab >= 2)
-            VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[par], 0)); // slab - 2 is done with this scratch set
-        to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), D, D, Xb, Kpad, xnorm);
-        CUtensorMap mapX;
-        rc = make_map(ctx, &mapX, Xb, rows, Kpad, TC_BM);
-        if (rc)
-            return rc;
-        const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
-        const int grid = std::min(rowTiles, ctx->numSMs);
-        VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-        score_tc_kernel<<<grid, TC_THREADS, smemBytes, ctx->stream>>>(mapX, mapM, cnorm, static_cast<int>(rows), rowTiles, nodeTiles, kBlocks, stagger, xnorm, maxNorm2, cand, candCount,
-                                                                      ctx->errFlag);
-        cudaStream_t rs = overlap ? ctx->auxStream : ctx->stream;
-        VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
-        VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
-        rescore_kernel<<<static_cast<unsigned>((rows + RS_ROWS - 1) / RS_ROWS), RS_THREADS, 0, rs>>>(
-            xs, static_cast<long long>(rows), D, ctx->mean, ctx->rowStride, cand, candCount, outBmuDev ? outBmuDev + r0 : nullptr,
-            outDistDev ? outDistDev + r0 : nullptr, fbRows, fbCount);
-        // rows the guard could not certify: exact full scan, count read on the device
-        find_bmu_rowwise_kernel<<<2 * ctx->numSMs, 256, sizeof(float) * D, rs>>>(xs, D, fbRows, fbCount, ctx->mean, ctx->rowStride, N, ctx->hits, minHits,
-                                                                                             outBmuDev ? outBmuDev + r0 : nullptr,
-                                                                                             outDistDev ? outDistDev + r0 : nullptr, totalDev);
-        VSOM_CUDA(ctx, cudaEventRecord(ctx->evDone[par], rs));
-        ctx->launches += 4;
-        VSOM_CUDA(ctx, cudaGetLastError());
-    }
+    if (c.slab >= 2)
+        VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[par], 0)); // slab - 2 is done with this scratch set
+    to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), c.D, c.D, c.Xb, c.Kpad, xnorm);
+    CUtensorMap mapX;
+    int rc = make_map(ctx, &mapX, c.Xb, rows, c.Kpad, TC_BM);
+    if (rc)
+        return rc;
+    const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
+    const int grid = std::min(rowTiles, ctx->numSMs);
+    VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
+    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.cnorm, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.stagger, xnorm, c.maxNorm2,
+                                                                        cand, candCount, bestA, ctx->errFlag);
+    cudaStream_t rs = c.overlap ? ctx->auxStream : ctx->stream;
+    VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
+    rescore_kernel<<<static_cast<unsigned>((rows + RS_ROWS - 1) / RS_ROWS), RS_THREADS, 0, rs>>>(xs, static_cast<long long>(rows), c.D, ctx->mean, ctx->rowStride, cand, candCount, bestA,
+                                                                                                 xnorm, c.maxNorm2, c.Kpad, order, outBmuDev, outDistDev, fbRows, fbCount);
+    // rows the certificate rejected: exact full scan, count read on the device
+    find_bmu_rowwise_kernel<<<2 * ctx->numSMs, 256, sizeof(float) * c.D, rs>>>(xs, c.D, fbRows, fbCount, ctx->mean, ctx->rowStride, c.N, ctx->hits, c.minHits, order, outBmuDev,
+                                                                              outDistDev, c.totalDev);
+    if (outBmuHost && outBmuDev)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(outBmuHost, outBmuDev, sizeof(unsigned) * rows, cudaMemcpyDeviceToHost, rs));
+    if (outDistHost && outDistDev)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(outDistHost, outDistDev, sizeof(float) * rows, cudaMemcpyDeviceToHost, rs));
+    VSOM_CUDA(ctx, cudaEventRecord(ctx->evDone[par], rs));
+    ctx->launches += 4;
+    VSOM_CUDA(ctx, cudaGetLastError());
+    ++c.slab;
+    return VSOM_OK;
+}
+
+static int tc_finish(vsom_ctx *ctx, TcCall &c, unsigned long long *fallbackRowsOut)
+{
     // the context's stream owns the results again
-    for (int i = 0; i < 2 && static_cast<size_t>(i) < slab; ++i)
+    for (int i = 0; i < 2 && static_cast<size_t>(i) < c.slab; ++i)
         VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[i], 0));
     unsigned long long totalFallback = 0;
     int flag = 0;
-    VSOM_CUDA(ctx, cudaMemcpyAsync(&totalFallback, totalDev, sizeof(totalFallback), cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(&totalFallback, c.totalDev, sizeof(totalFallback), cudaMemcpyDeviceToHost, ctx->stream));
     VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flag)
@@ -792,6 +797,95 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         *fallbackRowsOut = totalFallback;
     ctx->lastFallbackRows = totalFallback;
     return VSOM_OK;
+}
+
+int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut)
+{
+    if (!score_tc_supported(ctx))
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 256");
+    if (fallbackRowsOut)
+        *fallbackRowsOut = 0;
+    if (n == 0)
+        return VSOM_OK;
+    const char *slabEnv = getenv("VSOM_TC_SLAB_LOG2"); // experiment knob; smaller slabs measured slower (per-slab ramp and tail of the persistent kernel)
+    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 22));
+    TcCall c;
+    int rc = tc_begin(ctx, c, slabRows, minHits);
+    if (rc)
+        return rc;
+    for (size_t r0 = 0; r0 < n; r0 += slabRows)
+    {
+        rc = tc_enqueue(ctx, c, xDev + r0 * c.D, std::min(slabRows, n - r0), outBmuDev ? outBmuDev + r0 : nullptr, outDistDev ? outDistDev + r0 : nullptr, nullptr, nullptr);
+        if (rc)
+            return rc;
+    }
+    return tc_finish(ctx, c, fallbackRowsOut);
+}
+
+// Rows in HOST memory (the call Som::evaluate / measureSimilarity / mapDataSet make): the chunk crosses PCIe in slabs on a
+// copy stream into one of two staging buffers while the previous slab is searched and re-scored, and each slab's results
+// return to the host behind its re-scoring.  With pinned host memory the three engines (H2D, SMs, D2H) overlap fully; the
+// call is then bound by the slower of PCIe (4 D bytes per row) and the kernel.  stage slots: 0 = two row slabs,
+// 1 / 2 = BMU / distance of the whole call.
+int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut)
+{
+    if (!score_tc_supported(ctx))
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 256");
+    if (fallbackRowsOut)
+        *fallbackRowsOut = 0;
+    if (n == 0)
+        return VSOM_OK;
+    const char *slabEnv = getenv("VSOM_TC_HOST_SLAB_LOG2");
+    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 19));
+    const size_t D = static_cast<size_t>(ctx->Dm);
+    int rc = stage_reserve(ctx, 0, sizeof(float) * 2 * slabRows * D);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 2, sizeof(float) * n);
+    if (rc)
+        return rc;
+    float *xbuf[2] = {static_cast<float *>(ctx->stage[0]), static_cast<float *>(ctx->stage[0]) + slabRows * D};
+    unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
+    float *distDev = static_cast<float *>(ctx->stage[2]);
+    TcCall c;
+    rc = tc_begin(ctx, c, slabRows, minHits);
+    if (rc)
+        return rc;
+    // the staging buffers may still be in use by earlier work of the context's stream
+    VSOM_CUDA(ctx, cudaEventRecord(ctx->evCopied[0], ctx->stream));
+    VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evCopied[0], 0));
+    auto copy_in = [&](size_t slab) -> int {
+        const size_t r0 = slab * slabRows, rows = std::min(slabRows, n - r0);
+        const int par = static_cast<int>(slab & 1);
+        if (slab >= 2)
+            VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evDone[par], 0)); // slab - 2 (same buffer) is fully re-scored
+        VSOM_CUDA(ctx, cudaMemcpyAsync(xbuf[par], xHost + r0 * D, sizeof(float) * rows * D, cudaMemcpyHostToDevice, ctx->copyStream));
+        VSOM_CUDA(ctx, cudaEventRecord(ctx->evCopied[par], ctx->copyStream));
+        return VSOM_OK;
+    };
+    const size_t slabs = (n + slabRows - 1) / slabRows;
+    rc = copy_in(0);
+    if (rc)
+        return rc;
+    for (size_t s = 0; s < slabs; ++s)
+    {
+        const size_t r0 = s * slabRows, rows = std::min(slabRows, n - r0);
+        const int par = static_cast<int>(s & 1);
+        VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopied[par], 0));
+        rc = tc_enqueue(ctx, c, xbuf[par], rows, bmuDev + r0, distDev + r0, outBmuHost ? outBmuHost + r0 : nullptr, outDistHost ? outDistHost + r0 : nullptr);
+        if (rc)
+            return rc;
+        if (s + 1 < slabs) // enqueued AFTER the search of slab s: a pageable source blocks the host here, not the device
+        {
+            rc = copy_in(s + 1);
+            if (rc)
+                return rc;
+        }
+    }
+    return tc_finish(ctx, c, fallbackRowsOut);
 }
 
 } // namespace vsom
