@@ -19,9 +19,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libvsom_ref.so")
+REF_SSE_SO = os.path.join(HERE, "_ref", "libvsom_ref_sse.so")  # same TUs, stand-in Eigen reducing in Eigen's SSE2 packet order
 
 STANDARD, MEDIAN, CLR = 0, 1, 2
 EXPONENTIAL, INVERSE = 0, 1
+ORDER_SEQUENTIAL, ORDER_EIGEN_SSE = 0, 2  # summation order of dot() / squaredNorm(); values match vsom_reduction_order
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -176,6 +178,7 @@ class Oracle(_Base):
             _sig(L.oracle_create, vp, [C.c_int] * 4)
             _sig(L.oracle_destroy, None, [vp])
             _sig(L.oracle_depth, C.c_int, [vp])
+            _sig(L.oracle_set_order, None, [vp, C.c_int])
             _sig(L.oracle_random_initialize, None, [vp, C.c_int, C.c_float])
             _sig(L.oracle_get_state, None, [vp, _f32p, _f32p, _f32p, _f32p, _u64p])
             _sig(L.oracle_set_state, None, [vp, _f32p, _f32p, _f32p, _f32p, _u64p])
@@ -199,10 +202,12 @@ class Oracle(_Base):
             cls._lib = L
         return cls._lib
 
-    def __init__(self, W, H, d_in, transform=STANDARD):
+    def __init__(self, W, H, d_in, transform=STANDARD, order=ORDER_SEQUENTIAL):
         L = self.lib()
         self.W, self.H, self.N, self.Din, self.transform = W, H, W * H, d_in, transform
         self._h = L.oracle_create(W, H, d_in, transform)
+        L.oracle_set_order(self._h, int(order))
+        self.order = order
         self.Dm = L.oracle_depth(self._h)
         self._get_state, self._set_state = L.oracle_get_state, L.oracle_set_state
         self._random_initialize = L.oracle_random_initialize
@@ -249,15 +254,16 @@ class Reference(_Base):
     """oracle/_ref/libvsom_ref.so — the reference's own code behind oracle/ref_shim.cpp."""
 
     _lib = None
+    SO = REF_SO
 
-    @staticmethod
-    def available() -> bool:
-        return os.path.exists(REF_SO)
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.SO)
 
     @classmethod
     def lib(cls):
         if cls._lib is None:
-            L = C.CDLL(REF_SO)
+            L = C.CDLL(cls.SO)
             vp = C.c_void_p
             _sig(L.ref_create, vp, [C.c_int] * 4)
             _sig(L.ref_destroy, None, [vp])
@@ -311,8 +317,18 @@ class Reference(_Base):
         return cls.lib().ref_eigen_kind().decode()
 
 
-def best_cpu_checker():
-    """Reference when the compiled library is present, else the C port.  Returns (class, kind)."""
-    if Reference.available():
-        return Reference, "reference"
-    return Oracle, "port"
+class ReferenceSse(Reference):
+    """oracle/_ref/libvsom_ref_sse.so — the same translation units compiled with -DVSOM_COMPAT_EIGEN_SSE_REDUX: dot() /
+    squaredNorm() reduce in the order real Eigen has in an -msse2 build (what users who installed libeigen3-dev run)."""
+
+    _lib = None
+    SO = REF_SSE_SO
+
+
+def best_cpu_checker(order=ORDER_SEQUENTIAL):
+    """Reference (in the requested summation order) when the compiled library is present, else the C port.
+    Returns (factory(W, H, d_in, transform), kind)."""
+    ref = ReferenceSse if order == ORDER_EIGEN_SSE else Reference
+    if ref.available():
+        return ref, "reference"
+    return (lambda W, H, d, t=STANDARD: Oracle(W, H, d, t, order)), "port"

@@ -335,7 +335,9 @@ extern "C"
     }
     const char *ref_eigen_kind()
     {
-#ifdef VSOM_COMPAT_EIGEN_DENSE
+#if defined(VSOM_COMPAT_EIGEN_DENSE) && defined(VSOM_COMPAT_EIGEN_SSE_REDUX)
+        return "compat-standin(Eigen SSE2 packet redux order)";
+#elif defined(VSOM_COMPAT_EIGEN_DENSE)
         return "compat-standin(sequential dot)";
 #else
         return "real-eigen";

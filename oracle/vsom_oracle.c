@@ -168,6 +168,68 @@ static void stepper(const vsom_oracle *o, const float *v, const float *m, float 
     }
 }
 
+/* ---------------------------------------------------------------- summation order of dot / squaredNorm */
+
+void oracle_set_order(vsom_oracle *o, int order) { o->order = order; }
+int oracle_get_order(const vsom_oracle *o) { return o->order; }
+
+/* The one order-dependent operation of the path: the f32 sum of the terms of `a.dot(b)` / `squaredNorm()`
+ * (src/Som.cpp:140, :156, :781, :804, :1167).
+ *   ORACLE_ORDER_SEQUENTIAL: t[0] + t[1] + ... left to right — what the reference does when compiled against this
+ *     repository's stand-in Eigen header (no Eigen on disk here).
+ *   ORACLE_ORDER_EIGEN_SSE: what real Eigen 3.3 / 3.4 does under the reference's release flags (-msse2 only,
+ *     build/Makefile:18; README.md:64-69 installs libeigen3-dev).  Restated from Eigen's published sources, which are
+ *     NOT in /root/reference (system package, unpinned): Eigen/src/Core/Redux.h, redux_impl<Func, Evaluator,
+ *     LinearVectorizedTraversal, NoUnrolling>::run with PacketType = Packet4f, and predux<Packet4f> of
+ *     Eigen/src/Core/arch/SSE/PacketMath.h (the non-SSE3 branch).  The reduced object is an expression
+ *     (cwiseProduct / cwiseAbs2), so the aligned start is 0.  In words: eight interleaved chains — lanes 0..3 of the even
+ *     packets and lanes 0..3 of the odd packets — over the first size/8*8 elements; the two 4-wide accumulators are added
+ *     lane by lane; if 4..7 elements remain, one more packet is added; the four lanes are combined as
+ *     (l0 + l2) + (l1 + l3); the last size%4 elements are added one by one. */
+static float sum_terms(int order, const float *t, int n)
+{
+    if (order == ORACLE_ORDER_EIGEN_SSE && n >= 4)
+    {
+        const int aligned2 = n / 8 * 8, aligned = n / 4 * 4;
+        float p0[4], p1[4];
+        for (int j = 0; j < 4; ++j)
+            p0[j] = t[j];
+        if (aligned > 4)
+        {
+            for (int j = 0; j < 4; ++j)
+                p1[j] = t[4 + j];
+            for (int i = 8; i < aligned2; i += 8)
+                for (int j = 0; j < 4; ++j)
+                {
+                    p0[j] = p0[j] + t[i + j];
+                    p1[j] = p1[j] + t[i + 4 + j];
+                }
+            for (int j = 0; j < 4; ++j)
+                p0[j] = p0[j] + p1[j];
+            if (aligned > aligned2)
+                for (int j = 0; j < 4; ++j)
+                    p0[j] = p0[j] + t[aligned2 + j];
+        }
+        float lo = p0[0] + p0[2], hi = p0[1] + p0[3];
+        float res = lo + hi;
+        for (int i = aligned; i < n; ++i)
+            res = res + t[i];
+        return res;
+    }
+    float s = 0.0f;
+    for (int k = 0; k < n; ++k)
+        s = s + t[k];
+    return s;
+}
+
+/* r[k] <- r[k] * r[k] (one rounding each), then the ordered sum */
+static float sum_squares(int order, float *r, int n)
+{
+    for (int k = 0; k < n; ++k)
+        r[k] = r[k] * r[k];
+    return sum_terms(order, r, n);
+}
+
 /* ---------------------------------------------------------------- distances */
 
 double oracle_dist(const vsom_oracle *o, size_t pos, const float *v)
@@ -176,12 +238,7 @@ double oracle_dist(const vsom_oracle *o, size_t pos, const float *v)
      * Comparer (which ignores them) and returns comparer.dot(comparer): f32 accumulate, returned as double. */
     float *r = (float *)malloc(sizeof(float) * (size_t)(o->Dm > 0 ? o->Dm : 1));
     int n = comparer(o, v, o->mean + pos * (size_t)o->Dm, r);
-    float s = 0.0f;
-    for (int k = 0; k < n; ++k)
-    {
-        float sq = r[k] * r[k];
-        s = s + sq;
-    }
+    float s = sum_squares(o->order, r, n);
     free(r);
     return (double)s;
 }
@@ -212,7 +269,7 @@ double oracle_dist_raw(const vsom_oracle *o, size_t pos, const float *u)
      *   return ((m - u)/sM) . (((m - u)*vw)/sM)   (f32 dot) */
     const float *m = o->mean + pos * (size_t)o->Dm;
     const float *sg = o->sigma + pos * (size_t)o->Dm;
-    float s = 0.0f;
+    float *t = (float *)malloc(sizeof(float) * (size_t)(o->Dm > 0 ? o->Dm : 1));
     for (int k = 0; k < o->Dm; ++k)
     {
         float sM = sg[k] < 0.00001f ? 0.00001f : sg[k];
@@ -220,9 +277,10 @@ double oracle_dist_raw(const vsom_oracle *o, size_t pos, const float *u)
         float d = m[k] - u[k];
         float a = d / sM;
         float b = (d * vw) / sM;
-        float ab = a * b;
-        s = s + ab;
+        t[k] = a * b;
     }
+    float s = sum_terms(o->order, t, o->Dm);
+    free(t);
     return (double)s;
 }
 
@@ -472,12 +530,7 @@ static void train_single(vsom_oracle *o, const float *v, double eta, double sigm
     if (outBmu)
         *outBmu = bmu;
     int n = comparer(o, v, o->mean + (size_t)bmu * (size_t)Dm, delta);
-    float s = 0.0f;
-    for (int k = 0; k < n; ++k)
-    {
-        float sq = delta[k] * delta[k];
-        s = s + sq;
-    }
+    float s = sum_squares(o->order, delta, n);
     if (outResid2)
         *outResid2 = s; /* residual.squaredNorm() — src/Som.cpp:1167 */
     if (outDist)
@@ -567,12 +620,7 @@ float oracle_batch_epoch(vsom_oracle *o, const float *x, size_t n, double sigma,
         lastBMU[j] = idx;
         o->hits[idx] += 1;
         int len = comparer(o, v, o->mean + (size_t)idx * (size_t)Dm, r);
-        float s = 0.0f;
-        for (int k = 0; k < len; ++k)
-        {
-            float sq = r[k] * r[k];
-            s = s + sq;
-        }
+        float s = sum_squares(o->order, r, len);
         mse = mse + s / (float)n;
     }
     /* phase B (:809-877): every neuron re-estimates its model as the incrementally weighted mean of ALL rows

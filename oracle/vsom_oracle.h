@@ -10,6 +10,14 @@
  * tests/golden/*.npz produced by oracle/gen_golden.py).  The reference's own test-suite holds no
  * numeric assertion for this path, so those two are the pins.
  *
+ * ORACLE_ORDER_EIGEN_SSE (the summation order of dot() under real Eigen + SSE2) restates a THIRD-PARTY algorithm: Eigen is
+ * a system package of the reference (README.md:64-69, version unpinned; 3.3.x and 3.4.0 share the code in question), absent
+ * from /root/reference and from this image.  Its pin is therefore indirect: the same order is restated a second time,
+ * independently, inside include/compat/Eigen/Dense (-DVSOM_COMPAT_EIGEN_SSE_REDUX), the reference's own translation units
+ * are compiled against that (oracle/_ref/libvsom_ref_sse.so), and the two are checked against each other bit for bit
+ * (tests/test_oracle_pin.py).  "Parity unpinned against a genuine Eigen build" for that mode — no Eigen exists here to
+ * run.
+ *
  * All citations are file:line in /root/reference.
  */
 #ifndef VSOM_ORACLE_H
@@ -23,6 +31,8 @@ extern "C" {
 
 enum { ORACLE_STANDARD = 0, ORACLE_MEDIAN = 1, ORACLE_CLR = 2 };
 enum { ORACLE_EXPONENTIAL = 0, ORACLE_INVERSE = 1 };
+/* summation order of dot() / squaredNorm(): see sum_terms() in vsom_oracle.c.  Values match vsom_reduction_order. */
+enum { ORACLE_ORDER_SEQUENTIAL = 0, ORACLE_ORDER_EIGEN_SSE = 2 };
 
 typedef struct vsom_oracle
 {
@@ -35,11 +45,14 @@ typedef struct vsom_oracle
     float *weight;           /* N: weightMap */
     uint64_t *hits;          /* N: bmuHits */
     double *umatrix;         /* N */
+    int order;               /* ORACLE_ORDER_* (default sequential) */
 } vsom_oracle;
 
 vsom_oracle *oracle_create(int W, int H, int Din, int transform);
 void oracle_destroy(vsom_oracle *o);
 int oracle_depth(const vsom_oracle *o);
+void oracle_set_order(vsom_oracle *o, int order);
+int oracle_get_order(const vsom_oracle *o);
 void oracle_random_initialize(vsom_oracle *o, int seed, float sigma);
 void oracle_get_state(const vsom_oracle *o, float *mean, float *S, float *sigma, float *weight, uint64_t *hits);
 void oracle_set_state(vsom_oracle *o, const float *mean, const float *S, const float *sigma, const float *weight, const uint64_t *hits);
