@@ -111,15 +111,20 @@ def synth(rng, n, Din, tr):
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("decay", [0, 1])
-def test_online_step_matches_oracle_bit_exact(vsom, po, shape, decay, online_kernel):
+@pytest.mark.parametrize("decay,order", [(0, 0), (1, 0), (0, 2), (1, 2)], ids=["exp-seq", "inv-seq", "exp-eigen_sse", "inv-eigen_sse"])
+def test_online_step_matches_oracle_bit_exact(vsom, po, shape, decay, order, online_kernel):
+    """order 0 = VSOM_ORDER_REFERENCE (sequential dot, the reference built against the stand-in Eigen header), order 2 =
+    VSOM_ORDER_EIGEN_SSE (the reference built against real Eigen under -msse2: Packet4f redux order); the oracle runs the
+    same order and the whole trajectory must be bit-identical either way."""
     W, H, Din, tr, n, eta, sigma = shape
     if online_kernel == "generic" and (W, H, Din) in ((100, 100, 784), (64, 64, 784), (150, 150, 784)):
         pytest.skip("the generic kernel is what runs these shapes in the fast variant too (K1F does not fit)")
+    if order == 2 and decay == 1 and (W * H > 5000 or Din > 200):
+        pytest.skip("the decay mode does not interact with the summation order: the large shapes run Exponential only in the Eigen order")
     rng = np.random.default_rng(hash((W, H, Din, tr, decay)) % (2 ** 32))
-    o = po.Oracle(W, H, Din, tr)
+    o = po.Oracle(W, H, Din, tr, order)
     o.random_initialize(42, 1.0)
-    ctx = vsom.VsomContext(W, H, Din, tr, vsom.ORDER_REFERENCE)
+    ctx = vsom.VsomContext(W, H, Din, tr, order)
     upload_like(ctx, o.get_state())
     x = synth(rng, 2 * n, Din, tr)
     # second chunk: smaller window, carried state; third and fourth: the findLocalBmu regime (sigma <= 1), once from node
@@ -141,6 +146,7 @@ def test_online_step_matches_oracle_bit_exact(vsom, po, shape, decay, online_ker
     assert_bit_equal(gb, ob, "score bmu")
     assert_bit_equal(gd, od, "score dist")
     assert_bit_equal(ctx.find_bmu(q, min_hits=1)[0], o.find_restricted_bmu(q, 1), "restricted")
+    assert_bit_equal(ctx.all_dists(q[3]), o.all_dists(q[3]), "all dists")
     if W >= 2 and H >= 2:  # the reference's updateUMatrix indexes out of bounds on one-row / one-column maps
         assert_bit_equal(ctx.update_umatrix(), o.update_umatrix(), "umatrix")
     if tr != 2:
@@ -379,20 +385,21 @@ def test_tensor_core_scoring_adversarial_bf16_rounding(vsom):
         ctx.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 128, 1, 3000, 1536), (128, 128, 256, 0, 1500, 1100)])
-def test_scoring_on_a_trained_map_matches_the_oracle(vsom, po, shape):
+@pytest.mark.parametrize("order", [0, 2], ids=["seq", "eigen_sse"])
+@pytest.mark.parametrize("shape", [(64, 64, 128, 1, 3000, 1536), (128, 128, 256, 0, 1500, 1100), (40, 30, 77, 0, 800, 1300)])
+def test_scoring_on_a_trained_map_matches_the_oracle(vsom, po, shape, order):
     """K2 and K3 against the ORACLE (not against each other) on a map the online step has clustered: neighbouring nodes
     are close to each other there, so near-candidates crowd the lists.  Includes 128x128x256 (BASELINE configs[3])."""
     W, H, D, tr, ntrain, n = shape
     rng = np.random.default_rng(W + D)
     centres = (rng.standard_normal((16, D)) * 2).astype(np.float32)
     data = lambda k: (centres[rng.integers(0, 16, k)] + 0.3 * rng.standard_normal((k, D))).astype(np.float32)
-    ctx = vsom.VsomContext(W, H, D, tr)
+    ctx = vsom.VsomContext(W, H, D, tr, order)
     ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * H, D)) / 1000).astype(np.float32))
     ctx.train_chunk(data(ntrain), 0.2, W / 6.0, vsom.EXPONENTIAL)
     ctx.train_chunk(data(ntrain), 0.1, W / 16.0, vsom.EXPONENTIAL)
     st = ctx.download_state()
-    o = po.Oracle(W, H, D, tr)
+    o = po.Oracle(W, H, D, tr, order)
     o.set_state(**st)
     q = data(n)
     ob, od = o.find_bmu(q)
@@ -413,14 +420,15 @@ def test_scoring_on_a_trained_map_matches_the_oracle(vsom, po, shape):
 # ------------------------------------------------------------------------------------------------ K6 (batch-map trainer)
 @pytest.mark.parametrize("shape", [(6, 6, 11, 0, 90), (7, 4, 11, 1, 90), (4, 9, 5, 2, 70), (20, 20, 784, 0, 60), (33, 17, 100, 1, 300),
                                    (12, 12, 32, 2, 150), (64, 64, 128, 0, 1500)])
-def test_batch_map_epochs_match_oracle_bit_exact(vsom, po, shape):
+@pytest.mark.parametrize("order", [0, 2], ids=["seq", "eigen_sse"])
+def test_batch_map_epochs_match_oracle_bit_exact(vsom, po, shape, order):
     """Som::trainBatchSom's loop over chunk-epochs (global BMU on the first epoch, local walks from node 0 afterwards,
     every neuron re-estimated from all rows) — bit-exact planes, hits, MSE and lastBMU against the oracle."""
     W, H, Din, tr, n = shape
     rng = np.random.default_rng(W * H + Din)
-    o = po.Oracle(W, H, Din, tr)
+    o = po.Oracle(W, H, Din, tr, order)
     o.random_initialize(3, 1.0)
-    ctx = vsom.VsomContext(W, H, Din, tr)
+    ctx = vsom.VsomContext(W, H, Din, tr, order)
     upload_like(ctx, o.get_state())
     x = synth(rng, n, Din, tr)
     chunk = n // 2 + 3
@@ -443,4 +451,64 @@ def test_batch_map_epochs_match_oracle_bit_exact(vsom, po, shape):
                 w[np.isnan(w)] = 0
                 assert_bit_equal(g, w, f"epoch {epoch} sigma {sigma}: {k}")
             assert_bit_equal(got["hits"], want["hits"], "hits")
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ K3 / K4 corner cases
+@pytest.mark.parametrize("order", [0, 2], ids=["seq", "eigen_sse"])
+@pytest.mark.parametrize("tr,Din", [(0, 1), (0, 3), (0, 4), (0, 7), (0, 8), (0, 13), (0, 37), (0, 64), (2, 2), (2, 4), (2, 5), (2, 9)])
+def test_exact_scan_every_residue_of_the_vector_length(vsom, po, tr, Din, order):
+    """K3 (both orders) on vector lengths that hit every branch of the reductions: fewer than 4 terms, 4..7, multiples of
+    8, an extra packet, a scalar tail; CLR pair counts likewise.  Ragged row / node counts (partial tiles)."""
+    rng = np.random.default_rng(Din * 7 + tr)
+    W, H, n = 11, 7, 131
+    o = po.Oracle(W, H, Din, tr, order)
+    o.random_initialize(5, 1.0)
+    st = o.get_state()
+    st["hits"] = rng.integers(0, 3, W * H).astype(np.uint64)
+    o.set_state(**st)
+    ctx = vsom.VsomContext(W, H, Din, tr, order)
+    upload_like(ctx, st)
+    x = synth(rng, n, Din, tr)
+    ob, od = o.find_bmu(x)
+    gb, gd = ctx.find_bmu_exact(x)
+    assert_bit_equal(gb, ob, "bmu")
+    assert_bit_equal(gd, od, "dist")
+    assert_bit_equal(ctx.find_bmu_exact(x, min_hits=2)[0], o.find_restricted_bmu(x, 2), "restricted")
+    assert_bit_equal(ctx.all_dists(x[0]), o.all_dists(x[0]), "all dists")
+    ctx.close()
+
+
+@pytest.mark.parametrize("order", [0, 2], ids=["seq", "eigen_sse"])
+@pytest.mark.parametrize("Dm", [5, 8, 12, 31, 64, 100])
+def test_umatrix_division_corner_cases(vsom, po, Dm, order):
+    """K4 replaces the reference's IEEE division by a shared reciprocal + one correction step; every term must still be
+    the reference's bits.  Sigmas: zero (clamped to 1e-5), tiny, ordinary, huge, 2^100 and beyond, infinite; differences:
+    exact zeros, denormals, tiny, ordinary, huge (the quotient or its square overflows), infinite."""
+    rng = np.random.default_rng(Dm)
+    W, H = 19, 6
+    N = W * H
+    mags = np.float32([0.0, 1e-42, 1e-38, 3e-33, 1e-30, 1e-20, 1e-6, 1.0, 3.7, 1e6, 1e20, 1.3e30, 1e35, np.inf])
+    mean = (rng.choice(mags, (N, Dm)) * rng.choice(np.float32([-1, 1]), (N, Dm)) + rng.standard_normal((N, Dm)).astype(np.float32) *
+            rng.choice(np.float32([0, 0, 1e-3, 1]), (N, Dm))).astype(np.float32)
+    mean[::5] = mean[1::5][: len(mean[::5])]  # exact zeros in many differences
+    sig_mags = np.float32([0.0, 1e-7, 1e-5, 1.0000001e-5, 1e-3, 0.5, 1.0, 3.0, 1e10, 1.2e30, 1.3e30, 1e38, np.inf])
+    sigma = rng.choice(sig_mags, (N, Dm)).astype(np.float32)
+    o = po.Oracle(W, H, Dm, 0, order)
+    o.set_state(mean=mean, sigma=sigma)
+    ctx = vsom.VsomContext(W, H, Dm, 0, order)
+    ctx.upload_state(mean=mean, sigma=sigma)
+    with np.errstate(all="ignore"):
+        want = o.update_umatrix()
+    got = ctx.update_umatrix()
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern"
+    ok = ~np.isnan(want)
+    assert_bit_equal(got[ok], want[ok], "umatrix")
+    assert ok.sum() > 0
+    # and an ordinary map next to it (no special values at all)
+    mean2 = rng.standard_normal((N, Dm)).astype(np.float32)
+    sigma2 = np.abs(rng.standard_normal((N, Dm))).astype(np.float32)
+    o.set_state(mean=mean2, sigma=sigma2)
+    ctx.upload_state(mean=mean2, sigma=sigma2)
+    assert_bit_equal(ctx.update_umatrix(), o.update_umatrix(), "umatrix (ordinary values)")
     ctx.close()

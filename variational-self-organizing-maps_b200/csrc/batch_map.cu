@@ -56,7 +56,7 @@ __global__ void hits_add_kernel(const unsigned *__restrict__ bmu, u64 n, u64 *__
 template <int TR>
 __global__ void __launch_bounds__(256) local_bmu_rows_kernel(const float *__restrict__ x, u64 n, const float *__restrict__ mean, int W, int H, int Din,
                                                              int Dr, int P, int rowStride, const unsigned short *__restrict__ pairI,
-                                                             const unsigned short *__restrict__ pairJ, const u64 *__restrict__ start,
+                                                             const unsigned short *__restrict__ pairJ, int order, const u64 *__restrict__ start,
                                                              unsigned *__restrict__ outBmu, float *__restrict__ outDist)
 {
     const u64 row = static_cast<u64>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) local_bmu_rows_kernel(const float *__rest
     if (row >= n)
         return;
     const float *xr = x + row * Din;
-    auto dist = [&](u64 node) { return dist_sequential<TR>(mean + node * rowStride, xr, Dr, P, pairI, pairJ); };
+    auto dist = [&](u64 node) { return dist_ordered<TR>(mean + node * rowStride, xr, Dr, P, pairI, pairJ, order); };
     const u64 uW = static_cast<u64>(W), uH = static_cast<u64>(H), M1 = ~0ull;
     const u64 fx[8] = {M1, 0, 1, 1, 1, 0, M1, M1}, fy[8] = {1, 1, 1, 0, M1, M1, M1, 0};
     u64 lastBMU = start ? start[row] : 0ull, minIndex = lastBMU, lastMeasured = lastBMU;
@@ -301,10 +301,10 @@ int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma,
         const unsigned grid = static_cast<unsigned>((n + 7) / 8);
         if (ctx->transform == VSOM_CLR)
             local_bmu_rows_kernel<VSOM_CLR><<<grid, 256, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->W, ctx->H, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride,
-                                                                           ctx->pairI, ctx->pairJ, lastDev, bmuDev, distDev);
+                                                                           ctx->pairI, ctx->pairJ, ctx->order, lastDev, bmuDev, distDev);
         else
             local_bmu_rows_kernel<VSOM_STANDARD><<<grid, 256, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->W, ctx->H, ctx->Din, ctx->Dr, ctx->P,
-                                                                                ctx->rowStride, ctx->pairI, ctx->pairJ, lastDev, bmuDev, distDev);
+                                                                                ctx->rowStride, ctx->pairI, ctx->pairJ, ctx->order, lastDev, bmuDev, distDev);
         ctx->launches += 1;
     }
     hits_add_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(bmuDev, n, ctx->hits);

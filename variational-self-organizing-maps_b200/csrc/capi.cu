@@ -266,6 +266,7 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->rowPool);
     cudaFree(ctx->rowMeta);
     cudaFree(ctx->profDev);
+    cudaFree(ctx->umTab);
     for (void *p : ctx->stage)
         cudaFree(p);
     if (ctx->auxStream)
@@ -705,6 +706,28 @@ int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out)
     return VSOM_OK;
 }
 
+// per-grid-row pointer tables of K4 (umatrix.cu): [H] mean rows, [H] sigma rows, [localRows] grid rows to compute
+static int umatrix_tables(vsom_ctx *ctx)
+{
+    if (ctx->umTab)
+        return VSOM_OK;
+    const int H = ctx->H;
+    std::vector<const float *> rows(2 * static_cast<size_t>(H), nullptr);
+    std::vector<int> ys;
+    for (int y = 0; y < H; ++y)
+    {
+        rows[y] = ctx->mean + static_cast<size_t>(y) * ctx->W * ctx->rowStride;
+        rows[H + y] = ctx->sigma + static_cast<size_t>(y) * ctx->W * ctx->rowStride;
+        ys.push_back(y);
+    }
+    const size_t ptrBytes = sizeof(float *) * rows.size();
+    VSOM_CUDA(ctx, cudaMalloc(&ctx->umTab, ptrBytes + sizeof(int) * ys.size()));
+    VSOM_CUDA(ctx, cudaMemcpy(ctx->umTab, rows.data(), ptrBytes, cudaMemcpyHostToDevice));
+    VSOM_CUDA(ctx, cudaMemcpy(static_cast<unsigned char *>(ctx->umTab) + ptrBytes, ys.data(), sizeof(int) * ys.size(), cudaMemcpyHostToDevice));
+    ctx->umRows = static_cast<int>(ys.size());
+    return VSOM_OK;
+}
+
 int vsom_update_umatrix(vsom_ctx *ctx, double *out)
 {
     if (ctx && ctx->world > 1)
@@ -712,7 +735,11 @@ int vsom_update_umatrix(vsom_ctx *ctx, double *out)
     if (!ctx)
         return VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = launch_umatrix(ctx);
+    int rc = umatrix_tables(ctx);
+    if (rc)
+        return rc;
+    const float *const *meanRows = static_cast<const float *const *>(ctx->umTab);
+    rc = launch_umatrix_rows(ctx, meanRows, meanRows + ctx->H, reinterpret_cast<const int *>(meanRows + 2 * ctx->H), ctx->umRows);
     if (rc)
         return rc;
     if (out)

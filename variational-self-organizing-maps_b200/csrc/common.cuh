@@ -53,6 +53,7 @@ struct StepParams
     long long timeoutCycles;
     int lutSmem, lutCount;    // copy the table into shared memory (it fits behind the resident rows)
     int xVec;                 // sample rows are 16-byte aligned: 16-byte cp.async
+    int order;                // vsom_reduction_order of the distances
     int world, rank;          // node-sharded training across GPUs (world == 1: single GPU)
     u64 *rankSlots;           // [2][world] keys pushed into THIS GPU's memory by every rank (peer stores over NVLink)
     u64 *peerSlots[8];        // rankSlots of every rank (index = rank), peer-mapped; peerSlots[rank] == rankSlots
@@ -128,6 +129,8 @@ struct vsom_ctx
     vsom::u64 *distTag = nullptr; // K1F local-walk regime: tagged per-step distances
     int scanBufs = 0, scanSeg = 0, scanNSeg = 0; // K1: HBM-resident rows are streamed through a ring of segment buffers
     void *scanMapDev = nullptr;                   // TMA descriptor of the mean plane for that scan
+    void *umTab = nullptr;        // K4: per-grid-row pointer tables (mean rows, sigma rows) + the grid rows this context computes
+    int umRows = 0;
     long long *profDev = nullptr; // diagnostics: per-phase cycle sums of the last online-step launch
     size_t profSamples = 0;
     std::string err;
@@ -161,7 +164,7 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
 int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut);
 int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma, int isFirst, const u64 *lastDev, unsigned *bmuDev, float *distDev);
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
-int launch_umatrix(vsom_ctx *ctx);
+int launch_umatrix_rows(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int *rowsDev, int nRows);
 int launch_build_index(vsom_ctx *ctx, const unsigned *bmuDev, size_t n, u64 *countsDev, u64 *offsetsDev, unsigned *rowIdsDev);
 
 // ------------------------------------------------------------------------------------------ device helpers
@@ -298,8 +301,10 @@ struct EigenSseSum
             k = 4;
         }
         float s = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-        for (; k < nrest; ++k)
-            s = __fadd_rn(s, rest[k]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) // static indices: `rest` stays in registers
+            if (j >= k && j < nrest)
+                s = __fadd_rn(s, rest[j]);
         return s;
     }
 };
@@ -354,6 +359,35 @@ __device__ __forceinline__ float dist_rows_f32(const float *__restrict__ m, cons
         s = __fadd_rn(s, __fmul_rn(q, q));
     }
     return s;
+}
+
+// Squared distance of one node by ONE thread in the given order (any transformation).
+template <int TR>
+__device__ __forceinline__ float dist_ordered(const float *m, const float *xs, int Dr, int P, const unsigned short *pi, const unsigned short *pj, int order)
+{
+    if (order != VSOM_ORDER_EIGEN_SSE)
+        return dist_sequential<TR>(m, xs, Dr, P, pi, pj);
+    EigenSseSum acc;
+    int k = 0;
+    for (; k + 8 <= Dr; k += 8)
+    {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const float r = residual<TR>(m, xs, k + j, P, pi, pj);
+            t[j] = __fmul_rn(r, r);
+        }
+        acc.block(t);
+    }
+    float rest[8];
+    const int nrest = Dr - k;
+    for (int j = 0; j < nrest; ++j)
+    {
+        const float r = residual<TR>(m, xs, k + j, P, pi, pj);
+        rest[j] = __fmul_rn(r, r);
+    }
+    return acc.finish(rest, nrest);
 }
 
 // Squared distance with 32 interleaved partial sums and a fixed xor butterfly (all 32 lanes call; all get the value).

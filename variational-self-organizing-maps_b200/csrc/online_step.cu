@@ -110,10 +110,58 @@ __device__ __forceinline__ float dist_sequential_v4(const float *m, const float 
     return s;
 }
 
-template <int TR>
+// Eigen SSE2 order over zero-padded rows (Standard / Median): full blocks of eight with two 128-bit loads each, then the
+// Dm % 8 remaining elements (common.cuh, EigenSseSum)
+__device__ __forceinline__ float dist_eigen_v4(const float *m, const float *xs, int Dm)
+{
+    const float4 *m4 = reinterpret_cast<const float4 *>(m);
+    const float4 *x4 = reinterpret_cast<const float4 *>(xs);
+    EigenSseSum acc;
+    const int n8 = Dm >> 3;
+#pragma unroll 2
+    for (int b = 0; b < n8; ++b)
+    {
+        const float4 a0 = m4[2 * b], b0 = x4[2 * b], a1 = m4[2 * b + 1], b1 = x4[2 * b + 1];
+        float t[8];
+        float r = __fsub_rn(a0.x, b0.x);
+        t[0] = __fmul_rn(r, r);
+        r = __fsub_rn(a0.y, b0.y);
+        t[1] = __fmul_rn(r, r);
+        r = __fsub_rn(a0.z, b0.z);
+        t[2] = __fmul_rn(r, r);
+        r = __fsub_rn(a0.w, b0.w);
+        t[3] = __fmul_rn(r, r);
+        r = __fsub_rn(a1.x, b1.x);
+        t[4] = __fmul_rn(r, r);
+        r = __fsub_rn(a1.y, b1.y);
+        t[5] = __fmul_rn(r, r);
+        r = __fsub_rn(a1.z, b1.z);
+        t[6] = __fmul_rn(r, r);
+        r = __fsub_rn(a1.w, b1.w);
+        t[7] = __fmul_rn(r, r);
+        acc.block(t);
+    }
+    float rest[8];
+    const int k0 = n8 << 3, nrest = Dm - k0;
+    for (int j = 0; j < nrest; ++j)
+    {
+        const float r = __fsub_rn(m[k0 + j], xs[k0 + j]);
+        rest[j] = __fmul_rn(r, r);
+    }
+    return acc.finish(rest, nrest);
+}
+
+// distance of one node by one thread, in the reference's sequential order or in Eigen's SSE2 order
+template <int TR, int ORDER>
 __device__ __forceinline__ float node_dist_reference(const float *m, const float *xs, const StepParams &p, int n4, const unsigned short *pi,
                                                      const unsigned short *pj)
 {
+    if (ORDER == VSOM_ORDER_EIGEN_SSE)
+    {
+        if (TR != VSOM_CLR)
+            return dist_eigen_v4(m, xs, p.Dm);
+        return dist_ordered<TR>(m, xs, p.Dr, p.P, pi, pj, VSOM_ORDER_EIGEN_SSE);
+    }
     if (TR != VSOM_CLR)
         return dist_sequential_v4(m, xs, n4); // the zero padding adds +0 terms: s + 0 == s exactly
     return dist_sequential<TR>(m, xs, p.Dr, p.P, pi, pj);
@@ -296,11 +344,11 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 
         // ---- scan: distance of sample t to every owned node, min key per thread
         u64 best = ~0ull;
-        if (ORDER == VSOM_ORDER_REFERENCE)
+        if (ORDER != VSOM_ORDER_LANES)
         {
             if (tid == kThreads - 1 && pendL >= 0)
             {
-                const float d = node_dist_reference<TR>(mBase + pendL * stride, xprev, p, n4, pi, pj);
+                const float d = node_dist_reference<TR, ORDER>(mBase + pendL * stride, xprev, p, n4, pi, pj);
                 const size_t q = static_cast<size_t>(pendL) * G + b;
                 if (p.outBmu)
                     p.outBmu[pendT] = static_cast<unsigned>(p.node0 + q);
@@ -345,6 +393,9 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     for (; issued < NB && issued < steps; ++issued)
                         issue();
                     float sacc = 0.0f;
+                    EigenSseSum eacc;   // ORDER == EIGEN_SSE: the eight chains of this lane's row, carried across its segments
+                    float erest[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const int nFull4 = (p.Dm >> 3) << 1; // 128-bit words of a row that belong to full blocks of eight
                     int sg = 0, g = warp;
                     for (int i = 0; i < steps; ++i)
                     {
@@ -358,9 +409,73 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                             }
                         const int n4s = min(Kseg, DmPad - sg * Kseg) >> 2;
                         if (sg == 0)
+                        {
                             sacc = 0.0f;
+                            if (ORDER == VSOM_ORDER_EIGEN_SSE)
+                                eacc = EigenSseSum();
+                        }
                         const int l = 32 * g + lane;
-                        if (l < L)
+                        if (l < L && ORDER == VSOM_ORDER_EIGEN_SSE)
+                        {
+                            // word Q of the row goes to lanes 0..3 (Q even) or 4..7 (Q odd) of the packet accumulators; the words
+                            // behind the full blocks (at most two, zero padded) are kept for the extra packet / scalar tail
+                            const float4 *m4 = reinterpret_cast<const float4 *>(ring + (static_cast<size_t>(scanBuf) * 32 + lane) * segStride);
+                            const float4 *x4 = reinterpret_cast<const float4 *>(xt + sg * Kseg);
+                            const int q0 = sg * (Kseg >> 2);
+#pragma unroll 2
+                            for (int q = 0; q < n4s; ++q)
+                            {
+                                const float4 a = m4[q], bq = x4[q];
+                                float r = __fsub_rn(a.x, bq.x);
+                                const float t0 = __fmul_rn(r, r);
+                                r = __fsub_rn(a.y, bq.y);
+                                const float t1 = __fmul_rn(r, r);
+                                r = __fsub_rn(a.z, bq.z);
+                                const float t2 = __fmul_rn(r, r);
+                                r = __fsub_rn(a.w, bq.w);
+                                const float t3 = __fmul_rn(r, r);
+                                const int Q = q0 + q;
+                                if (Q < nFull4)
+                                {
+                                    if (Q & 1)
+                                    {
+                                        eacc.a[4] = __fadd_rn(eacc.a[4], t0);
+                                        eacc.a[5] = __fadd_rn(eacc.a[5], t1);
+                                        eacc.a[6] = __fadd_rn(eacc.a[6], t2);
+                                        eacc.a[7] = __fadd_rn(eacc.a[7], t3);
+                                    }
+                                    else
+                                    {
+                                        eacc.a[0] = __fadd_rn(eacc.a[0], t0);
+                                        eacc.a[1] = __fadd_rn(eacc.a[1], t1);
+                                        eacc.a[2] = __fadd_rn(eacc.a[2], t2);
+                                        eacc.a[3] = __fadd_rn(eacc.a[3], t3);
+                                    }
+                                }
+                                else if (Q == nFull4)
+                                {
+                                    erest[0] = t0;
+                                    erest[1] = t1;
+                                    erest[2] = t2;
+                                    erest[3] = t3;
+                                }
+                                else
+                                {
+                                    erest[4] = t0;
+                                    erest[5] = t1;
+                                    erest[6] = t2;
+                                    erest[7] = t3;
+                                }
+                            }
+                            if (sg == nSeg - 1)
+                            {
+                                sacc = eacc.finish(erest, p.Dm & 7);
+                                if (p.localSearch)
+                                    p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = sacc;
+                                best = u64_min(best, make_key(sacc, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                            }
+                        }
+                        else if (l < L)
                         {
                             // s += (m_k - x_k)^2 in order, loads a pair of 128-bit words ahead of the adds
                             const float4 *m4 = reinterpret_cast<const float4 *>(ring + (static_cast<size_t>(scanBuf) * 32 + lane) * segStride);
@@ -413,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             else
                 for (int l = tid; l < L; l += kThreads)
                 {
-                    const float d = node_dist_reference<TR>(mBase + l * stride, xt, p, n4, pi, pj);
+                    const float d = node_dist_reference<TR, ORDER>(mBase + l * stride, xt, p, n4, pi, pj);
                     if (p.localSearch)
                         p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
                     best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
@@ -445,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         if (p.localSearch)
             __threadfence(); // the distances written above must be visible before this CTA's key is
         // REFERENCE order with at most 32 owned nodes: every key already sits in warp 0 — no CTA barrier
-        const bool crossWarp = ORDER != VSOM_ORDER_REFERENCE || L > 32;
+        const bool crossWarp = ORDER == VSOM_ORDER_LANES || L > 32;
         if (crossWarp)
         {
             best = warp_min_key(best);
@@ -820,11 +935,11 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         const float *xprev = xs + static_cast<int>(pendT % 3) * DinPad;
         float d = 0.0f;
         bool writer = false;
-        if (ORDER == VSOM_ORDER_REFERENCE)
+        if (ORDER != VSOM_ORDER_LANES)
         {
             if (tid == 0)
             {
-                d = node_dist_reference<TR>(mBase + pendL * stride, xprev, p, n4, pi, pj);
+                d = node_dist_reference<TR, ORDER>(mBase + pendL * stride, xprev, p, n4, pi, pj);
                 writer = true;
             }
         }
@@ -899,9 +1014,9 @@ typedef void (*StepKernel)(const StepParams);
 static StepKernel pick_kernel(int transform, int order, int resident)
 {
 #define VSOM_K(TR, ORD) {online_step_kernel<TR, ORD, false>, online_step_kernel<TR, ORD, true>}
-    static const StepKernel table[3][2][2] = {{VSOM_K(VSOM_STANDARD, VSOM_ORDER_REFERENCE), VSOM_K(VSOM_STANDARD, VSOM_ORDER_LANES)},
-                                              {VSOM_K(VSOM_MEDIAN, VSOM_ORDER_REFERENCE), VSOM_K(VSOM_MEDIAN, VSOM_ORDER_LANES)},
-                                              {VSOM_K(VSOM_CLR, VSOM_ORDER_REFERENCE), VSOM_K(VSOM_CLR, VSOM_ORDER_LANES)}};
+#define VSOM_KO(TR) {VSOM_K(TR, VSOM_ORDER_REFERENCE), VSOM_K(TR, VSOM_ORDER_LANES), VSOM_K(TR, VSOM_ORDER_EIGEN_SSE)}
+    static const StepKernel table[3][3][2] = {VSOM_KO(VSOM_STANDARD), VSOM_KO(VSOM_MEDIAN), VSOM_KO(VSOM_CLR)};
+#undef VSOM_KO
 #undef VSOM_K
     return table[transform][order][resident ? 1 : 0];
 }
@@ -956,7 +1071,7 @@ int configure_online_step(vsom_ctx *ctx)
         if (bytes + statics > static_cast<size_t>(ctx->smemOptin))
             return set_error(ctx, VSOM_ERR_UNSUPPORTED, "online step: per-CTA bookkeeping does not fit in shared memory for this map");
         // streamed scan of the HBM-resident rows (Standard / Median, reference order): as many segment buffers as fit
-        if (ctx->transform != VSOM_CLR && ctx->order == VSOM_ORDER_REFERENCE)
+        if (ctx->transform != VSOM_CLR && ctx->order != VSOM_ORDER_LANES)
         {
             const int DmPad = (ctx->Dm + 3) & ~3;
             int seg = DmPad < kScanSegMax ? DmPad : kScanSegMax;
@@ -1073,6 +1188,7 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.H = ctx->H;
     p.node0 = ctx->node0;
     p.nodeCount = ctx->localN;
+    p.order = ctx->order;
     p.world = ctx->world;
     p.rank = ctx->rank;
     p.rankSlots = ctx->rankSlots;

@@ -169,6 +169,39 @@ __device__ __forceinline__ float chain_terms(const float *row, int n16)
     return s;
 }
 
+// The same row of terms in Eigen's SSE2 packet order (VSOM_ORDER_EIGEN_SSE, common.cuh): eight interleaved chains over the
+// first Dr / 8 * 8 terms, res0 + res1, the extra packet, (p0 + p2) + (p1 + p3), the scalar tail.  Eight independent chains:
+// the adds issue back to back (one per cycle) instead of waiting 4 cycles each.
+__device__ __forceinline__ float chain_terms_eigen(const float *row, int Dr)
+{
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+    EigenSseSum acc;
+    const int n8 = Dr >> 3;
+#pragma unroll 4
+    for (int b = 0; b < n8; ++b)
+    {
+        const float4 u = r4[2 * b], v = r4[2 * b + 1];
+        const float t[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+        acc.block(t);
+    }
+    const int nrest = Dr & 7;
+    float rest[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (nrest) // the row is at least 4 floats longer than its padded length: these reads stay inside it
+    {
+        const float4 u = r4[2 * n8], v = r4[2 * n8 + 1];
+        rest[0] = u.x;
+        rest[1] = u.y;
+        rest[2] = u.z;
+        rest[3] = u.w;
+        rest[4] = v.x;
+        rest[5] = v.y;
+        rest[6] = v.z;
+        rest[7] = v.w;
+    }
+    return acc.finish(rest, nrest);
+}
+__device__ __forceinline__ float chain_any(const float *row, int n16, int Dr, int eigen) { return eigen ? chain_terms_eigen(row, Dr) : chain_terms(row, n16); }
+
 // ---- CLR (src/Transformation.cpp:79-167), scalar round-to-nearest operations only: a * x + b must never contract
 // residual of a pair: (A x' + B) - y'  (:104)
 __device__ __forceinline__ float clr_res(float a, float b, float xi, float xj) { return __fsub_rn(__fadd_rn(__fmul_rn(a, xi), b), xj); }
@@ -486,8 +519,8 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     int curOff = 0, nextOff = XS; // ring offsets of samples t and t+1
     int gSlot = 0;                // CLR: gather slot of sample t (t mod 3)
     // the scan warp's serial code is the critical path: keep what it reads from the parameter block in registers
-    int lutW = p.lutW, lutInSmem = p.lutSmem, expDecay = p.decay == VSOM_EXPONENTIAL ? 1 : 0;
-    asm volatile("" : "+r"(lutW), "+r"(lutInSmem), "+r"(expDecay));
+    int lutW = p.lutW, lutInSmem = p.lutSmem, expDecay = p.decay == VSOM_EXPONENTIAL ? 1 : 0, eigenOrder = p.order == VSOM_ORDER_EIGEN_SSE ? 1 : 0;
+    asm volatile("" : "+r"(lutW), "+r"(lutInSmem), "+r"(expDecay), "+r"(eigenOrder));
     for (unsigned t = 0; t < n; ++t)
     {
         if (PROF && tid == 0)
@@ -504,7 +537,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             const int pl = sPend[par ^ 1];
             if (pl >= 0)
             {
-                const float d = chain_terms(pendRow, n16);
+                const float d = chain_any(pendRow, n16, p.Dr, eigenOrder);
                 if (p.outBmu)
                     p.outBmu[t - 1] = static_cast<unsigned>(p.node0 + pl * G + b);
                 if (p.outDist)
@@ -519,7 +552,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
             u64 key = ~0ull;
             if (hasNode)
             {
-                const float d = chain_terms(myTerms, n16);
+                const float d = chain_any(myTerms, n16, p.Dr, eigenOrder);
                 key = make_key_xy(d, myX, myY, tag);
                 if (p.localSearch) // sigma <= 1: the walk below reads distances of arbitrary nodes; the word validates itself.
                 {                  // (kWalkReplicas copies, CTA b reads copy b % kWalkReplicas)
@@ -821,7 +854,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         const int pl = sPend[(n - 1) & 1];
         if (pl >= 0)
         {
-            const float d = chain_terms(pendRow, n16);
+            const float d = chain_any(pendRow, n16, p.Dr, eigenOrder);
             if (p.outBmu)
                 p.outBmu[n - 1] = static_cast<unsigned>(p.node0 + pl * G + b);
             if (p.outDist)
@@ -1266,7 +1299,7 @@ static int build_row_pool(vsom_ctx *ctx)
 int configure_online_step_fast(vsom_ctx *ctx)
 {
     ctx->fastTrain = 0;
-    if (ctx->order != VSOM_ORDER_REFERENCE || ctx->world > 1 || ctx->W > 4096 || ctx->H > 4096)
+    if (ctx->order == VSOM_ORDER_LANES || ctx->world > 1 || ctx->W > 4096 || ctx->H > 4096)
         return 0;
     if (ctx->transform == VSOM_CLR && ((ctx->Din + 3) & ~3) + 4 > 65535)
         return 0; // pair tables are 16-bit

@@ -10,6 +10,11 @@
 // operands staged through shared memory in 32-wide slices of the model vector).  This is the exact path:
 // it is what the tensor-core candidate search (score_tc.cu) rescoring falls back to, and it is the scorer
 // for small / medium batches.
+//
+// VSOM_ORDER_EIGEN_SSE (the order of dot() under real Eigen, common.cuh): a pair is EIGHT interleaved chains, owned by
+// eight consecutive lanes (find_bmu_exact_eigen_kernel): lane c sums the terms k = c mod 8, the lanes combine with the
+// fixed butterfly xor 4 (res0 + res1), [+ the extra packet], xor 2, xor 1 ((p0 + p2) + (p1 + p3); float addition
+// commutes, so every lane ends with the same bits), then the scalar tail.
 #include "common.cuh"
 
 namespace vsom
@@ -155,20 +160,206 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
     }
 }
 
+// ---------------------------------------------------------------------------------------- Eigen SSE2 order
+constexpr int ER = 32, EN = 32, EMS = 40; // rows / nodes per CTA tile; row stride of the node slice (bank = 8 gx + c: conflict-free)
+
+template <int TR>
+__global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(const float *__restrict__ x, u64 n, const float *__restrict__ mean,
+                                                                             const u64 *__restrict__ hits, u64 minHits, int N, int Din, int Dr, int P,
+                                                                             int rowStride, const unsigned short *__restrict__ pairI,
+                                                                             const unsigned short *__restrict__ pairJ, unsigned *__restrict__ outBmu,
+                                                                             float *__restrict__ outDist)
+{
+    constexpr bool kClr = TR == VSOM_CLR;
+    __shared__ float xa[ER][KC + 1], ma[EN][EMS];
+    __shared__ float xb[kClr ? ER : 1][KC + 1], mb[kClr ? EN : 1][EMS];
+    __shared__ float xr[ER][8], mr[EN][8];                       // the Dr % 8 elements behind the full blocks of eight
+    __shared__ float xrb[kClr ? ER : 1][8], mrb[kClr ? EN : 1][8];
+    __shared__ u64 sBest[ER][8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = tid & 7, g = tid >> 3, gx = g & 7, gy = g >> 3; // chain; nodes gx + 8 j (j < 4), rows gy + 4 i (i < 8)
+    const u64 row0 = static_cast<u64>(blockIdx.x) * ER;
+    const int n8 = Dr & ~7, nrest = Dr - n8;
+
+    u64 best[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        best[i] = ~0ull;
+
+    auto term = [&](float xv, float yv, float mv, float bv) {
+        const float r = kClr ? __fsub_rn(__fadd_rn(__fmul_rn(mv, xv), bv), yv) : __fsub_rn(mv, xv);
+        return __fmul_rn(r, r);
+    };
+    // one element of a row / node (0 outside): what the slices and the rest arrays hold
+    auto load_x = [&](u64 row, int k, float &a, float &bq) {
+        a = 0.0f;
+        bq = 0.0f;
+        if (row < n && k < Dr)
+        {
+            if (!kClr)
+                a = x[row * Din + k];
+            else
+            {
+                a = x[row * Din + pairI[k]];
+                bq = x[row * Din + pairJ[k]];
+            }
+        }
+    };
+    auto load_m = [&](int node, int k, float &a, float &bq) {
+        a = 0.0f;
+        bq = 0.0f;
+        if (node < N && k < Dr)
+        {
+            a = mean[static_cast<size_t>(node) * rowStride + k];
+            if (kClr)
+                bq = mean[static_cast<size_t>(node) * rowStride + P + k];
+        }
+    };
+    {
+        const int r = tid >> 3, e = tid & 7; // 32 rows x 8 rest elements
+        float a, bq;
+        load_x(row0 + r, e < nrest ? n8 + e : Dr, a, bq);
+        xr[r][e] = a;
+        if (kClr)
+            xrb[r][e] = bq;
+    }
+
+    for (int node0 = 0; node0 < N; node0 += EN)
+    {
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                acc[i][j] = 0.0f;
+        __syncthreads(); // the previous node tile's rest elements are no longer read
+        {
+            const int r = tid >> 3, e = tid & 7;
+            float a, bq;
+            load_m(node0 + r, e < nrest ? n8 + e : Dr, a, bq);
+            mr[r][e] = a;
+            if (kClr)
+                mrb[r][e] = bq;
+        }
+        for (int k0 = 0; k0 < n8; k0 += KC)
+        {
+            __syncthreads(); // previous slice fully consumed
+            const int k = k0 + lane, kk = k < n8 ? k : Dr; // beyond the full blocks: zeros on both sides (term +0)
+            for (int r = warp; r < ER; r += kScoreThreads / 32)
+            {
+                float a, bq;
+                load_x(row0 + r, kk, a, bq);
+                xa[r][lane] = a;
+                if (kClr)
+                    xb[r][lane] = bq;
+                load_m(node0 + r, kk, a, bq);
+                ma[r][lane] = a;
+                if (kClr)
+                    mb[r][lane] = bq;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < KC / 8; ++s)
+            {
+                const int q = c + 8 * s;
+                float xv[8], yv[8], mv[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                {
+                    xv[i] = xa[gy + 4 * i][q];
+                    yv[i] = kClr ? xb[gy + 4 * i][q] : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    mv[j] = ma[gx + 8 * j][q];
+                    bv[j] = kClr ? mb[gx + 8 * j][q] : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        acc[i][j] = __fadd_rn(acc[i][j], term(xv[i], yv[i], mv[j], bv[j]));
+            }
+        }
+        __syncthreads(); // mr / xr visible (also when there was no full block)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const int node = node0 + gx + 8 * j;
+            const bool eligible = node < N && (node == 0 || minHits == 0 || hits[node] >= minHits);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+            {
+                const int r = gy + 4 * i, nl = gx + 8 * j;
+                float v = __fadd_rn(acc[i][j], __shfl_xor_sync(0xffffffffu, acc[i][j], 4)); // packet_res0 + packet_res1, lane by lane
+                int e = 0;
+                if (nrest >= 4)
+                {
+                    const int q = c & 3; // the extra packet
+                    v = __fadd_rn(v, term(xr[r][q], kClr ? xrb[r][q] : 0.0f, mr[nl][q], kClr ? mrb[nl][q] : 0.0f));
+                    e = 4;
+                }
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2)); // p0 + p2 | p1 + p3
+                v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1)); // (p0 + p2) + (p1 + p3)
+                for (; e < nrest; ++e)                                // scalar tail
+                    v = __fadd_rn(v, term(xr[r][e], kClr ? xrb[r][e] : 0.0f, mr[nl][e], kClr ? mrb[nl][e] : 0.0f));
+                if (eligible)
+                    best[i] = u64_min(best[i], make_key(v, static_cast<unsigned>(node), (v != v) ? 1u : 0u));
+            }
+        }
+    }
+    if (c == 0)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            sBest[gy + 4 * i][gx] = best[i];
+    __syncthreads();
+    if (tid < ER && row0 + tid < n)
+    {
+        u64 k = sBest[tid][0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q)
+            k = u64_min(k, sBest[tid][q]);
+        if (outBmu)
+            outBmu[row0 + tid] = key_node(k);
+        if (outDist)
+        {
+            float d = __uint_as_float(static_cast<unsigned>(k >> 32));
+            if (k & 1ull)
+                d = __uint_as_float(0x7fc00000u);
+            outDist[row0 + tid] = d;
+        }
+    }
+}
+
 template <int TR>
 __global__ void all_dists_kernel(const float *__restrict__ v, const float *__restrict__ mean, int N, int Dr, int P, int rowStride,
-                                 const unsigned short *__restrict__ pairI, const unsigned short *__restrict__ pairJ, double *__restrict__ out)
+                                 const unsigned short *__restrict__ pairI, const unsigned short *__restrict__ pairJ, int order, double *__restrict__ out)
 {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= N)
         return;
-    out[node] = static_cast<double>(dist_sequential<TR>(mean + static_cast<size_t>(node) * rowStride, v, Dr, P, pairI, pairJ));
+    out[node] = static_cast<double>(dist_ordered<TR>(mean + static_cast<size_t>(node) * rowStride, v, Dr, P, pairI, pairJ, order));
 }
 
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev)
 {
     if (n == 0)
         return VSOM_OK;
+    if (ctx->order == VSOM_ORDER_EIGEN_SSE)
+    {
+        const unsigned egrid = static_cast<unsigned>((n + ER - 1) / ER);
+        if (ctx->transform == VSOM_CLR)
+            find_bmu_exact_eigen_kernel<VSOM_CLR><<<egrid, kScoreThreads, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride,
+                                                                                            ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+        else
+            find_bmu_exact_eigen_kernel<VSOM_STANDARD><<<egrid, kScoreThreads, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P,
+                                                                                                 ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+        VSOM_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        return VSOM_OK;
+    }
     const unsigned grid = static_cast<unsigned>((n + RT - 1) / RT);
 #define VSOM_LAUNCH_SCORE(TR)                                                                                                              \
     find_bmu_exact_kernel<TR><<<grid, kScoreThreads, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr,   \
@@ -193,9 +384,9 @@ int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev)
 {
     const int threads = 128, grid = (ctx->N + threads - 1) / threads;
     if (ctx->transform == VSOM_CLR)
-        all_dists_kernel<VSOM_CLR><<<grid, threads, 0, ctx->stream>>>(vDev, ctx->mean, ctx->N, ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outDev);
+        all_dists_kernel<VSOM_CLR><<<grid, threads, 0, ctx->stream>>>(vDev, ctx->mean, ctx->N, ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, ctx->order, outDev);
     else
-        all_dists_kernel<VSOM_STANDARD><<<grid, threads, 0, ctx->stream>>>(vDev, ctx->mean, ctx->N, ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outDev);
+        all_dists_kernel<VSOM_STANDARD><<<grid, threads, 0, ctx->stream>>>(vDev, ctx->mean, ctx->N, ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, ctx->order, outDev);
     VSOM_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VSOM_OK;

@@ -6,13 +6,30 @@
 // the source and divided by 8 / 5 / 3 (interior / edge / corner).  Raw(p, u) always divides by p's OWN
 // clamped sigma, so the stencil is not symmetric.
 //
-// One thread owns one (node, neighbour) pair and sums its Dm terms sequentially in f32 — the order of the
-// reference's dot product — so every Raw value and every U value is bit-identical to the reference.  A CTA
-// covers 16 consecutive nodes of one grid row.  The rows are read straight from global memory with 128-bit
-// read-only loads: a node's eight threads ask for the same words of its own mean and sigma rows (one
-// transaction), neighbouring nodes share neighbour rows, and L1 serves the reuse.  (A first version staged 32-wide
-// slices of three grid rows through shared memory; ncu showed 54 % of its instructions in the staging loop's
-// address arithmetic, issue slots 76 % busy: 2.78 ms at 512x512x784.)
+// One thread owns one (node, neighbour) pair and sums its Dm terms in f32 in the context's summation order (sequential
+// like the stand-in dot product, or Eigen's SSE2 packet order: eight interleaved chains, common.cuh) — every Raw value
+// and every U value is bit-identical to the reference.  A CTA covers 16 consecutive nodes of one grid row; the eight
+// threads of a node are eight consecutive lanes.  Rows are read straight from global memory with 128-bit read-only
+// loads (a node's eight threads ask for the same words of its own rows: one transaction; neighbouring nodes share
+// neighbour rows, L1 serves the reuse).
+//
+// The arithmetic is what bounds this kernel: the reference formula has one IEEE division per element AND neighbour
+// (div.rn.f32 is ~9 issue slots).  Here the eight neighbour threads of a node share ONE correctly rounded reciprocal per
+// element (each lane computes y = RN(1 / sM) for the elements k = lane mod 8 and hands it round by shuffle) and every
+// division becomes Markstein's correction step:  q = RN(d y),  r = d - sM q (exact, one FMA),  d / sM = RN(q + r y),
+// which IS the correctly rounded quotient when y is the correctly rounded reciprocal and nothing overflows or underflows
+// on the way (Markstein 1990; Cornea, Harrison & Tang, "Scientific computing on Itanium-based systems").  Range argument,
+// with sM in [1e-5, 2^100] (checked once per block of eight; the clamp gives the lower end):
+//   * |d| >= 2^100, infinities and NaN take div.rn itself (one predicate per element);
+//   * the residual r is a multiple of 2^(e_d - 46); whenever the TERM a^2 can be non-zero at all (|a| >= 2^-75, i.e.
+//     |d| >= 2^-75 sM >= 2^-92) that is >= 2^-138, representable, so r is exact and a is correctly rounded;
+//   * for smaller |d| both the fast and the exact quotient are below 2^-83 in magnitude and their squares round to +0:
+//     the term is +0 either way (and d == 0 gives a == 0 on both paths).
+// So every TERM is bit-identical to the reference's although the division is 3 issue slots instead of ~9.  The U-matrix
+// parity tests (tests/test_gpu_parity.py) cover maps with zero / tiny / huge sigma and differences.
+//
+// Rows are addressed through per-grid-row pointer tables, so the same kernel serves node-sharded contexts: the rows of
+// other ranks that border this rank's row blocks are fetched into a halo buffer over NVLink first (capi.cu).
 #include "common.cuh"
 
 namespace vsom
@@ -25,52 +42,113 @@ constexpr int UT = 16; // nodes per CTA
 __constant__ int kDi[8] = {0, 0, +1, -1, -1, +1, -1, +1};
 __constant__ int kDj[8] = {-1, +1, 0, 0, -1, -1, +1, +1};
 
-// one term of Raw(p, u): a = (m_p - m_u) / sM with sM = max(sigma_p, 1e-5) (:150), accumulated as a * a (:156).
-// (m - v) * (valid * weights) / sM equals a bit for bit because valid * weights == 1.0f exactly (:1002-1003), so one
-// IEEE division serves both factors of the dot product.
-__device__ __forceinline__ void raw_term(float &s, float mc, float mu, float sg)
+// sM = max(sigma, 1e-5) as the reference's select (:150; a NaN sigma stays NaN)
+__device__ __forceinline__ float clamp_sigma(float sg) { return sg < 0.00001f ? 0.00001f : sg; }
+
+// sM inside the range the correction step is proven for (a NaN sigma fails)
+__device__ __forceinline__ bool rcp_ok(float sM) { return sM <= 1.2676506e30f; }
+
+// one term of Raw(p, u): a = (m_p - m_u) / sM (:156), returned as a * a.  (m - v) * (valid * weights) / sM equals a bit for
+// bit because valid * weights == 1.0f exactly (:1002-1003), so one division serves both factors of the dot product.
+// `bad` collects the elements whose fast quotient is not proven (see the head of this file).
+__device__ __forceinline__ float raw_term_fast(float mc, float mu, float sM, float y, bool &bad)
 {
-    const float sM = sg < 0.00001f ? 0.00001f : sg;
-    const float a = __fdiv_rn(__fsub_rn(mc, mu), sM);
-    s = __fadd_rn(s, __fmul_rn(a, a));
+    const float d = __fsub_rn(mc, mu);
+    const float q = __fmul_rn(d, y);
+    const float r = __fmaf_rn(-sM, q, d);
+    const float a = __fmaf_rn(r, y, q);
+    bad = bad || !(fabsf(d) < 1.2676506e30f); // 2^100; NaN fails the comparison
+    return __fmul_rn(a, a);
+}
+// the reference's own arithmetic, for the blocks the fast path cannot prove (rare; one branch per block of eight)
+__device__ __forceinline__ void raw_terms_exact(const float (&mcv)[8], const float (&muv)[8], const float (&sMv)[8], float (&tv)[8])
+{
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+    {
+        const float a = __fdiv_rn(__fsub_rn(mcv[e], muv[e]), sMv[e]);
+        tv[e] = __fmul_rn(a, a);
+    }
 }
 
-__global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *__restrict__ mean, const float *__restrict__ sigma, int W, int H, int Dm,
-                                                         int rowStride, double *__restrict__ out)
+template <int ORDER>
+__global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *const *__restrict__ meanRow, const float *const *__restrict__ sigmaRow,
+                                                         const int *__restrict__ rowsY, int W, int H, int Dm, int rowStride, double *__restrict__ out)
 {
     __shared__ float res[UT][8];
 
-    const int tid = threadIdx.x;
-    const int i = blockIdx.y;       // grid row
-    const int j0 = blockIdx.x * UT; // first grid column of the tile
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int i = rowsY[blockIdx.y]; // grid row
+    const int j0 = blockIdx.x * UT;  // first grid column of the tile
     const int t = tid >> 3, nb = tid & 7;
     const int j = j0 + t;
     const int ni = i + kDi[nb], nj = j + kDj[nb];
-    const bool active = j < W && ni >= 0 && ni < H && nj >= 0 && nj < W;
+    const bool node = j < W;
+    const bool active = node && ni >= 0 && ni < H && nj >= 0 && nj < W;
+    const int grp = lane & ~7; // first lane of this node's eight threads
 
+    // every lane takes part in the shuffles; lanes without a neighbour read their own row as the neighbour (distance 0)
+    const int jc = node ? j : 0;
+    const float *mc = meanRow[i] + static_cast<size_t>(jc) * rowStride;
+    const float *sg = sigmaRow[i] + static_cast<size_t>(jc) * rowStride;
+    const float *mu = active ? meanRow[ni] + static_cast<size_t>(nj) * rowStride : mc;
+
+    EigenSseSum acc;
     float s = 0.0f;
-    if (active)
+    const int blocks8 = Dm >> 3;
+    const float4 *mc4 = reinterpret_cast<const float4 *>(mc), *mu4 = reinterpret_cast<const float4 *>(mu);
+#pragma unroll 1
+    for (int b8 = 0; b8 < blocks8; ++b8)
     {
-        const float *mc = mean + (static_cast<size_t>(i) * W + j) * rowStride;
-        const float *sg = sigma + (static_cast<size_t>(i) * W + j) * rowStride;
-        const float *mu = mean + (static_cast<size_t>(ni) * W + nj) * rowStride;
-        const int quads = Dm >> 2; // rows start 16-byte aligned (rowStride is a multiple of 4 floats)
-        const float4 *mc4 = reinterpret_cast<const float4 *>(mc), *sg4 = reinterpret_cast<const float4 *>(sg), *mu4 = reinterpret_cast<const float4 *>(mu);
-#pragma unroll 2
-        for (int q = 0; q < quads; ++q)
+        const float4 a0 = __ldg(mc4 + 2 * b8), a1 = __ldg(mc4 + 2 * b8 + 1), b0 = __ldg(mu4 + 2 * b8), b1 = __ldg(mu4 + 2 * b8 + 1);
+        const float sMown = clamp_sigma(__ldg(sg + 8 * b8 + nb)); // this lane's element of the block
+        const float yown = __frcp_rn(sMown);
+        const float mcv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, muv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float tv[8], sMv[8];
+        bool bad = ((__ballot_sync(0xffffffffu, !rcp_ok(sMown)) >> grp) & 0xffu) != 0; // some sM of this node's block is out of range
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
         {
-            const float4 a = __ldg(mc4 + q), b = __ldg(mu4 + q), c = __ldg(sg4 + q);
-            raw_term(s, a.x, b.x, c.x);
-            raw_term(s, a.y, b.y, c.y);
-            raw_term(s, a.z, b.z, c.z);
-            raw_term(s, a.w, b.w, c.w);
+            sMv[e] = __shfl_sync(0xffffffffu, sMown, grp + e);
+            tv[e] = raw_term_fast(mcv[e], muv[e], sMv[e], __shfl_sync(0xffffffffu, yown, grp + e), bad);
         }
-        for (int k = quads << 2; k < Dm; ++k)
-            raw_term(s, __ldg(mc + k), __ldg(mu + k), __ldg(sg + k));
+        if (bad)
+            raw_terms_exact(mcv, muv, sMv, tv);
+        if (ORDER == VSOM_ORDER_EIGEN_SSE)
+            acc.block(tv);
+        else
+        {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                s = __fadd_rn(s, tv[e]);
+        }
+    }
+    // the last Dm % 8 elements
+    {
+        const int k0 = blocks8 << 3, nrest = Dm - k0;
+        const float sMown = nb < nrest ? clamp_sigma(__ldg(sg + k0 + nb)) : 1.0f;
+        const float yown = __frcp_rn(sMown);
+        float tv[8], sMv[8], mcv[8], muv[8];
+        bool bad = ((__ballot_sync(0xffffffffu, !rcp_ok(sMown)) >> grp) & 0xffu) != 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+        {
+            sMv[e] = __shfl_sync(0xffffffffu, sMown, grp + e);
+            mcv[e] = e < nrest ? __ldg(mc + k0 + e) : 0.0f;
+            muv[e] = e < nrest ? __ldg(mu + k0 + e) : 0.0f;
+            tv[e] = raw_term_fast(mcv[e], muv[e], sMv[e], __shfl_sync(0xffffffffu, yown, grp + e), bad);
+        }
+        if (bad)
+            raw_terms_exact(mcv, muv, sMv, tv);
+        if (ORDER == VSOM_ORDER_EIGEN_SSE)
+            s = acc.finish(tv, nrest);
+        else
+            for (int e = 0; e < nrest; ++e)
+                s = __fadd_rn(s, tv[e]);
     }
     res[t][nb] = s;
     __syncthreads();
-    if (nb == 0 && j < W)
+    if (nb == 0 && node)
     {
         double u = 0.0;
         int cnt = 0;
@@ -89,12 +167,20 @@ __global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *__restrict
     }
 }
 
-int launch_umatrix(vsom_ctx *ctx)
+// meanRowDev / sigmaRowDev: [H] device pointers to the first node of every grid row this context can read (own rows, and
+// for node-sharded contexts the halo rows; sigma only for the own rows); rowsDev: the nRows grid rows to compute.
+// The result lands in ctx->umatrix at the node's GLOBAL index.
+int launch_umatrix_rows(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int *rowsDev, int nRows)
 {
     if (ctx->W < 2 || ctx->H < 2)
         return set_error(ctx, VSOM_ERR_INVALID, "updateUMatrix needs width >= 2 and height >= 2 (the reference indexes out of bounds otherwise)");
-    dim3 grid((ctx->W + UT - 1) / UT, ctx->H);
-    umatrix_kernel<<<grid, UT * 8, 0, ctx->stream>>>(ctx->mean, ctx->sigma, ctx->W, ctx->H, ctx->Dm, ctx->rowStride, ctx->umatrix);
+    if (nRows <= 0)
+        return VSOM_OK;
+    dim3 grid((ctx->W + UT - 1) / UT, nRows);
+    if (ctx->order == VSOM_ORDER_EIGEN_SSE)
+        umatrix_kernel<VSOM_ORDER_EIGEN_SSE><<<grid, UT * 8, 0, ctx->stream>>>(meanRowDev, sigmaRowDev, rowsDev, ctx->W, ctx->H, ctx->Dm, ctx->rowStride, ctx->umatrix);
+    else
+        umatrix_kernel<VSOM_ORDER_REFERENCE><<<grid, UT * 8, 0, ctx->stream>>>(meanRowDev, sigmaRowDev, rowsDev, ctx->W, ctx->H, ctx->Dm, ctx->rowStride, ctx->umatrix);
     VSOM_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VSOM_OK;
