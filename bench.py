@@ -263,6 +263,7 @@ def main():
     import torch.distributed as dist
 
     vsom = importlib.import_module("variational-self-organizing-maps_b200")
+    sharding = importlib.import_module("variational-self-organizing-maps_b200.sharding")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -475,7 +476,7 @@ def main():
         kwin = min(int(np.ceil(2.5 * LSIG)) + int(np.floor(2.5 * LSIG)), LW) ** 2
         lbytes = algorithmic_bytes_per_sample(LW * LH, LD, LD, kwin)
         large = {"workload": "512x512 grid x 784-dim online training (BASELINE configs[4] shape), sigma=16, Standard, Exponential",
-                 "layout": "single GPU" if world == 1 else f"grid rows node-sharded over {world} GPUs, per-sample 8-byte min-loc exchange inside the persistent kernel over NVLink peer memory",
+                 "layout": "single GPU" if world == 1 else f"grid rows dealt to {world} GPUs round-robin in blocks of {lctx.shard_rows()[0]} rows, per-sample 8-byte min-loc exchange inside the persistent kernel over NVLink peer memory",
                  "samples": LROWS, "bmu_crc32": bmu_crc, "dist_crc32": dist_crc,
                  "crc_note": "CRC-32 of the timed chunk's per-sample BMU ids / distance bits: equal for every --gpus N (same map, same samples, bit-exact kernels)",
                  "ms": lms, "value": LROWS / (lms / 1e3), "unit": "samples/s", "us_per_sample": 1e3 * lms / LROWS,
@@ -485,17 +486,28 @@ def main():
         if world == 1:
             large["roofline"]["traffic"] = measured_traffic("online_step_kernel_large_map", LROWS)
             large["roofline"]["traffic_source"] = "profiles/r01_traffic.json (ncu --set full of the streamed-scan kernel, scaled per sample)"
-        if world == 1:
-            lctx.update_umatrix()
-            lctx.synchronize()
-            with torch.cuda.stream(lstream):
-                e0.record(lstream)
-                lib_rc = vsom.lib().vsom_update_umatrix(lctx._h, None)
-                e1.record(lstream)
-            lctx.synchronize()
-            ums = e0.elapsed_time(e1)
-            ubytes = 8 * LW * LH * LD + 8 * LW * LH
-            large["umatrix"] = {"ms": ums, "algorithmic_bytes": ubytes, "achieved_gbs": ubytes / (ums / 1e3) / 1e9}
+        # full U-matrix of the large map (config 5: "plus full UMatrix"): every rank computes its own grid rows; on sharded
+        # contexts the border rows of means are read from the neighbours' planes over NVLink first (inside the timed call)
+        barrier()
+        um_host = lctx.update_umatrix()  # warm-up + the values
+        barrier()
+        with torch.cuda.stream(lstream):
+            e0.record(lstream)
+            lib_rc = vsom.lib().vsom_update_umatrix(lctx._h, None)
+            e1.record(lstream)
+        lctx.synchronize()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        umt = torch.from_numpy(um_host.view(np.int64).copy()).to(dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(umt)  # the rows of other ranks are zero
+        ums = float(tt.item())
+        ubytes = 8 * LW * LH * LD + 8 * LW * LH
+        halo = len(sharding.halo_rows(LH, rank, world)) if world > 1 else 0
+        large["umatrix"] = {"ms": ums, "algorithmic_bytes": ubytes, "achieved_gbs_per_gpu": ubytes / world / (ums / 1e3) / 1e9, "frac_of_hbm_peak": ubytes / world / (ums / 1e3) / 1e9 / peaks()[0],
+                            "halo_rows_per_gpu": halo, "halo_bytes_per_gpu": halo * LW * LD * 4, "crc32": zlib.crc32(umt.cpu().numpy().tobytes()),
+                            "layout": "single GPU" if world == 1 else f"grid rows in blocks of {lctx.shard_rows()[0]} dealt round-robin to {world} GPUs, halo rows over NVLink peer memory"}
         lctx.close()
         del lx
 

@@ -89,18 +89,30 @@ typedef enum vsom_reduction_order
  * all planes zero.  `device` is a CUDA ordinal. */
 VSOM_API int vsom_create(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order);
 VSOM_API void vsom_destroy(vsom_ctx *ctx);
-/* Node-sharded training of a large map across the GPUs of one NVLink box (BASELINE config 5): rank r of `world` holds the
- * contiguous band of grid rows [H*r/world, H*(r+1)/world).  Every rank calls vsom_train_chunk[_device] with the SAME
- * samples; inside the persistent kernel each GPU scans its band, CTA 0 pushes the GPU-local (distance,node) key into every
- * rank's memory over NVLink (peer-mapped pointers, system-scope stores) and every CTA takes the min of the `world` keys —
- * one 8-byte exchange per sample, no host round trip, no NCCL call on the data path.  Setup: each rank exports the handle of
- * its slot buffer (vsom_peer_export), the handles are all-gathered by the caller (e.g. torch.distributed) and imported
- * (vsom_peer_import) before the first chunk.  upload / download take FULL-map arrays and touch only the rank's band.
- * Scoring, U-matrix and index entry points need an unsharded context. */
+/* Node-sharded training of a large map across the GPUs of one NVLink box (BASELINE config 5).  Grid rows are dealt to the
+ * ranks round-robin in blocks of a few rows (vsom_shard_rows; block b of 4 rows -> rank b % world), so that every update
+ * window — and the U-matrix — spreads over all GPUs.  Every rank calls vsom_train_chunk[_device] with the SAME samples;
+ * inside the persistent kernel each GPU scans its rows, CTA 0 pushes the GPU-local (distance, node) key into every rank's
+ * memory over NVLink (peer-mapped pointers, system-scope stores) and every CTA takes the min of the `world` keys — one
+ * 8-byte exchange per sample, no host round trip, no NCCL call on the data path.
+ * Setup, one process per GPU: each rank exports two handles — its exchange slots (vsom_peer_export) and its mean plane
+ * (vsom_peer_export_planes, read by the neighbours for the U-matrix halo); the caller all-gathers them (e.g.
+ * torch.distributed) and imports them (vsom_peer_import, vsom_peer_import_planes) before the first chunk.  Several ranks
+ * inside ONE process (a thread per GPU) attach each other directly with vsom_peer_attach.
+ * upload / download / vsom_update_umatrix take FULL-map arrays and touch only the rank's own grid rows.
+ * vsom_update_umatrix on a sharded context is a collective in the caller's hands: every rank's training stream must be
+ * idle before any rank calls it (the call reads one border row of means per neighbouring block out of the owners' planes),
+ * and no rank may train again before every rank has returned.  Scoring and index entry points need an unsharded context;
+ * the findLocalBmu regime (sigma <= 1) is not available on sharded contexts. */
 VSOM_API int vsom_create_sharded(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order, int rank, int world);
 VSOM_API int vsom_peer_export(vsom_ctx *ctx, unsigned char handle[64]);
 VSOM_API int vsom_peer_import(vsom_ctx *ctx, int rank, const unsigned char handle[64]);
-VSOM_API int vsom_shard_range(const vsom_ctx *ctx, int *first_node, int *node_count);
+VSOM_API int vsom_peer_export_planes(vsom_ctx *ctx, unsigned char handle[64]);
+VSOM_API int vsom_peer_import_planes(vsom_ctx *ctx, int rank, const unsigned char handle[64]);
+VSOM_API int vsom_peer_attach(vsom_ctx *ctx, int rank, vsom_ctx *peer);
+/* Layout of this rank's share: rows per block, number of local rows, and (global_rows, may be NULL, local_rows entries)
+ * the grid row of every local row in local order.  Unsharded: one block of all `height` rows. */
+VSOM_API int vsom_shard_rows(const vsom_ctx *ctx, int *block_rows, int *local_rows, int *global_rows);
 /* Text of the last error on ctx (or of the last failed vsom_create when ctx is NULL). */
 VSOM_API const char *vsom_last_error(const vsom_ctx *ctx);
 /* Transformation::Length (src/Transformation.cpp:31-35, :69-73, :162-165). */
@@ -195,7 +207,8 @@ VSOM_API int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out);
 /* -------------------------------------------------------------------------------- U-matrix / index */
 
 /* Som::updateUMatrix + Som::getUMatrix (src/Som.cpp:999-1111, :159-162; euclidianWeightedDistRaw :143-157).
- * out: N doubles, may be NULL (the matrix is kept on the device either way).  Needs width, height >= 2. */
+ * out: N doubles, may be NULL (the matrix is kept on the device either way).  Needs width, height >= 2.
+ * Node-sharded contexts compute their own grid rows (halo rows come from the neighbouring ranks, see vsom_create_sharded). */
 VSOM_API int vsom_update_umatrix(vsom_ctx *ctx, double *out);
 /* "SomIndex build": histogram of BMU ids (what Som::addBmu accumulates, src/Som.cpp:1189-1192) and the rows
  * grouped by BMU in ascending row order (the per-neuron row set of src/Som.cpp:845-868).

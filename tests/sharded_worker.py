@@ -38,7 +38,8 @@ def main():
         dist.all_gather_object(handles, ctx.peer_export())
         for r, h in enumerate(handles):
             ctx.peer_import(r, h)
-        assert ctx.shard_range() == sh.node_band(W, H, rank, world)
+        blk, rows = ctx.shard_rows()
+        assert blk == sh.shard_block_rows(H, world) and np.array_equal(rows, sh.node_rows(H, rank, world))
         ctx.upload_state(init["mean"], init["S"], init["sigma"], init["weight"], init["hits"])
         dist.barrier()
         for seg, sg in ((x[:n], sigma), (x[n:], sigma * 0.7)):  # two chunks: the global step counter carries over
@@ -65,8 +66,17 @@ def main():
         if not np.array_equal(t.numpy().astype(np.uint64), want["hits"]):
             ok = False
             print(f"[rank {rank}] case {ci}: hits differ", flush=True)
+        # sharded U-matrix: every rank computes its own grid rows, border rows of means come from the neighbours over NVLink
+        dist.barrier()  # every rank's training stream is idle (train_chunk is synchronous)
+        um = ctx.update_umatrix()
+        dist.barrier()
+        t = torch.from_numpy(um.view(np.int64).copy())
+        dist.all_reduce(t)  # rows of other ranks are zero
+        if H >= 2 and W >= 2 and not np.array_equal(t.numpy().view(np.uint64), o.update_umatrix().view(np.uint64)):
+            ok = False
+            print(f"[rank {rank}] case {ci}: sharded U-matrix differs", flush=True)
         if rank == 0:
-            print(f"case {ci} {W}x{H}x{D} transform {tr}: {'ok' if ok else 'FAILED'} (resident={ctx.planes_resident})", flush=True)
+            print(f"case {ci} {W}x{H}x{D} transform {tr}: {'ok' if ok else 'FAILED'} (resident={ctx.planes_resident}, block rows={blk})", flush=True)
         ctx.close()
         dist.barrier()
     flag = torch.tensor([0 if ok else 1])

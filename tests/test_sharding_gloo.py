@@ -26,12 +26,12 @@ def _worker(rank, world, port, q):
     o.random_initialize(3, 1.0)
     x = rng.standard_normal((n, D)).astype(np.float32)
     x[7] = o.get_state()["mean"][0]  # exact hit on node 0
-    n0, cnt = sh.node_band(W, H, rank, world)
-    # ---- node sharding: each rank scans only its band, then one min over packed keys
+    ids = sh.node_ids(W, H, rank, world, block=2)
+    # ---- node sharding: each rank scans only its blocks of grid rows, then one min over packed keys
     keys = np.empty(n, np.uint64)
     for r in range(n):
-        d = o.all_dists(x[r]).astype(np.float32)[n0:n0 + cnt]
-        k = sh.pack_key(d, np.arange(n0, n0 + cnt))
+        d = o.all_dists(x[r]).astype(np.float32)[ids]
+        k = sh.pack_key(d, ids)
         keys[r] = k.min()
     t = torch.from_numpy(keys.view(np.int64).copy())  # keys < 2^63: signed min == unsigned min
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -45,8 +45,30 @@ def _worker(rank, world, port, q):
     parts = [torch.empty(b - a, dtype=torch.int64) for a, b in sizes]
     dist.all_gather(parts, mine)
     ok_rows = np.array_equal(torch.cat(parts).numpy().astype(np.uint32), ob)
+    # ---- row-shard combines: hits = sum over ranks, evaluate = f64 running mean folded in rank order
+    hits = torch.from_numpy(np.bincount(mine.numpy(), minlength=W * H).astype(np.int64))
+    dist.all_reduce(hits)
+    ok_rows = ok_rows and np.array_equal(hits.numpy(), np.bincount(ob, minlength=W * H))
+    dl = [None] * world
+    dist.all_gather_object(dl, o.find_bmu(x[lo:hi])[1])
+    ok_rows = ok_rows and sh.evaluate_from_shards(dl) == o.evaluate(x)
+    # ---- sharded U-matrix: own rows + halo rows of means are all a rank needs
+    st = o.get_state()
+    st["sigma"] = np.abs(rng.standard_normal(st["sigma"].shape)).astype(np.float32)
+    o.set_state(**st)
+    want = o.update_umatrix()
+    rows = sh.node_rows(H, rank, world, block=2)
+    have = np.concatenate([rows, sh.halo_rows(H, rank, world, block=2)])
+    part = po.Oracle(W, H, D, po.STANDARD)
+    mean = np.full_like(st["mean"], np.nan).reshape(H, W, D)
+    mean[have] = st["mean"].reshape(H, W, D)[have]        # everything else is NaN: touching it would poison the result
+    sig = np.full_like(st["sigma"], np.nan).reshape(H, W, D)
+    sig[rows] = st["sigma"].reshape(H, W, D)[rows]
+    part.set_state(mean=mean.reshape(-1, D), sigma=sig.reshape(-1, D))
+    got = part.update_umatrix().reshape(H, W)[rows]
+    ok_um = np.array_equal(got.view(np.uint64), want.reshape(H, W)[rows].view(np.uint64))
     if rank == 0:
-        q.put((ok_nodes, ok_rows, [sh.node_band(W, H, r, world) for r in range(world)]))
+        q.put((ok_nodes, ok_rows and ok_um, [sh.node_rows(H, r, world, block=2).tolist() for r in range(world)]))
     dist.destroy_process_group()
 
 
@@ -63,7 +85,7 @@ def test_node_band_and_row_shard_world2_gloo():
         assert p.exitcode == 0
     assert ok_nodes, "min over packed band keys differs from the oracle's findBmu"
     assert ok_rows, "row-sharded scoring differs from the oracle"
-    assert bands[0][0] == 0 and bands[0][0] + bands[0][1] == bands[1][0] and bands[1][0] + bands[1][1] == 63
+    assert bands == [[0, 1, 4, 5], [2, 3, 6]]
 
 
 def test_partition_helpers():
@@ -71,9 +93,15 @@ def test_partition_helpers():
     for n, w in [(10, 3), (7, 8), (100, 8), (0, 2)]:
         spans = [sh.row_shard(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
-    for W, H, w in [(512, 512, 8), (9, 7, 2), (5, 3, 3)]:
-        bands = [sh.node_band(W, H, r, w) for r in range(w)]
-        assert bands[0][0] == 0 and sum(c for _, c in bands) == W * H and all(c % W == 0 and c > 0 for _, c in bands)
+    for W, H, w in [(512, 512, 8), (9, 7, 2), (5, 3, 3), (4, 9, 2)]:
+        rows = [sh.node_rows(H, r, w) for r in range(w)]
+        assert sorted(np.concatenate(rows).tolist()) == list(range(H)) and all(len(r) > 0 for r in rows)
+        ids = [sh.node_ids(W, H, r, w) for r in range(w)]
+        assert sorted(np.concatenate(ids).tolist()) == list(range(W * H)) and all(np.all(np.diff(i) > 0) for i in ids)
+        for r in range(w):
+            assert not set(sh.halo_rows(H, r, w).tolist()) & set(rows[r].tolist())
+    assert sh.node_rows(512, 3, 8).tolist()[:6] == [12, 13, 14, 15, 44, 45]
+    assert sh.sum_hits([np.array([1, 2], np.uint64), np.array([3, 0], np.uint64)]).tolist() == [4, 2]
     d = np.array([1.5, 1.5, np.nan, 0.0], np.float32)
     k = sh.pack_key(d, np.array([5, 2, 1, 9]))
     assert k.argmin() == 3 and sorted(k.tolist())[1] == k[1]

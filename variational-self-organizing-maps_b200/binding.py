@@ -25,7 +25,10 @@ _PROTOS = {
     "vsom_create_sharded": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vsom_peer_export": (C.c_int, [_vp, C.c_char_p]),
     "vsom_peer_import": (C.c_int, [_vp, C.c_int, C.c_char_p]),
-    "vsom_shard_range": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vsom_peer_export_planes": (C.c_int, [_vp, C.c_char_p]),
+    "vsom_peer_import_planes": (C.c_int, [_vp, C.c_int, C.c_char_p]),
+    "vsom_peer_attach": (C.c_int, [_vp, C.c_int, _vp]),
+    "vsom_shard_rows": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vsom_last_error": (C.c_char_p, [_vp]),
     "vsom_model_length": (C.c_int, [C.c_int, C.c_int]),
     "vsom_depth": (C.c_int, [_vp]),
@@ -263,7 +266,7 @@ class VsomContext:
 
     # ---- U-matrix / index
     def update_umatrix(self):
-        out = np.empty(self.N, np.float64)
+        out = np.zeros(self.N, np.float64)  # a sharded context fills in its own grid rows only
         self._check(lib().vsom_update_umatrix(self._h, _p(out, _f64p)))
         return out
 
@@ -278,17 +281,27 @@ class VsomContext:
 
     # ---- node sharding across GPUs
     def peer_export(self) -> bytes:
-        buf = C.create_string_buffer(64)
-        self._check(lib().vsom_peer_export(self._h, buf))
-        return buf.raw
+        """Both IPC handles of this rank (exchange slots + mean plane), 128 bytes, for an all-gather by the caller."""
+        a, b = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._check(lib().vsom_peer_export(self._h, a))
+        self._check(lib().vsom_peer_export_planes(self._h, b))
+        return a.raw + b.raw
 
     def peer_import(self, rank: int, handle: bytes):
-        self._check(lib().vsom_peer_import(self._h, rank, handle))
+        self._check(lib().vsom_peer_import(self._h, rank, handle[:64]))
+        self._check(lib().vsom_peer_import_planes(self._h, rank, handle[64:128]))
 
-    def shard_range(self):
-        a, b = C.c_int(0), C.c_int(0)
-        self._check(lib().vsom_shard_range(self._h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+    def peer_attach(self, rank: int, peer: "VsomContext"):
+        """Ranks living in the same process attach each other directly (no IPC handles)."""
+        self._check(lib().vsom_peer_attach(self._h, rank, peer._h))
+
+    def shard_rows(self):
+        """(rows per block, global grid row of every local row)."""
+        blk, cnt = C.c_int(0), C.c_int(0)
+        self._check(lib().vsom_shard_rows(self._h, C.byref(blk), C.byref(cnt), None))
+        rows = (C.c_int * max(cnt.value, 1))()
+        self._check(lib().vsom_shard_rows(self._h, C.byref(blk), C.byref(cnt), rows))
+        return blk.value, np.array(rows[: cnt.value], dtype=np.int64)
 
     # ---- diagnostics
     def debug_profile(self, enable=True):

@@ -103,11 +103,20 @@ static int create_impl(vsom_ctx **out, int device, int width, int height, int d_
     ctx->rank = rank;
     ctx->world = world;
     {
-        // contiguous bands of grid rows per rank
-        const int y0 = static_cast<int>(static_cast<long long>(height) * rank / world);
-        const int y1 = static_cast<int>(static_cast<long long>(height) * (rank + 1) / world);
-        ctx->node0 = y0 * width;
-        ctx->localN = (y1 - y0) * width;
+        // Node sharding: grid rows are dealt to the ranks round-robin in blocks of shardBlock rows (block b -> rank b % world).
+        // Contiguous bands (SURVEY.md §8e's first proposal) put a whole update window (80 x 80 nodes at sigma = 16 on a
+        // 512 x 512 map) on one or two GPUs; small blocks spread it over all of them, at the price of more U-matrix halo rows.
+        const char *e = getenv("VSOM_SHARD_BLOCK_ROWS");
+        int block = world == 1 ? height : (e && atoi(e) > 0 ? atoi(e) : 4);
+        if (world > 1 && block * world > height)
+            block = height / world; // every rank holds at least one row (world <= height was checked above)
+        ctx->shardBlock = block;
+        for (int y = 0; y < height; ++y)
+            if ((y / block) % world == rank)
+                ctx->localRowY.push_back(y);
+        ctx->localRows = static_cast<int>(ctx->localRowY.size());
+        ctx->node0 = 0;
+        ctx->localN = ctx->localRows * width;
     }
 
     auto fail = [&](int rc) {
@@ -152,6 +161,7 @@ static int create_impl(vsom_ctx **out, int device, int width, int height, int d_
     CREATE_CUDA(cudaMalloc(&ctx->rankSlots, sizeof(u64) * 2 * 8));
     CREATE_CUDA(cudaMemsetAsync(ctx->rankSlots, 0xff, sizeof(u64) * 2 * 8, ctx->stream));
     ctx->peerSlots[rank] = ctx->rankSlots;
+    ctx->peerMean[rank] = ctx->mean;
     CREATE_CUDA(cudaMalloc(&ctx->umatrix, sizeof(double) * ctx->N));
     CREATE_CUDA(cudaMalloc(&ctx->slots, sizeof(u64) * 2 * static_cast<size_t>(ctx->numSMs) * ((ctx->numSMs + 15) & ~15)));
     CREATE_CUDA(cudaMalloc(&ctx->errFlag, sizeof(int)));
@@ -226,14 +236,68 @@ int vsom_peer_import(vsom_ctx *ctx, int rank, const unsigned char handle[64])
     return VSOM_OK;
 }
 
-int vsom_shard_range(const vsom_ctx *ctx, int *first_node, int *node_count)
+int vsom_peer_export_planes(vsom_ctx *ctx, unsigned char handle[64])
+{
+    if (!ctx || !handle)
+        return VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    VSOM_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->mean));
+    std::memcpy(handle, &h, 64);
+    return VSOM_OK;
+}
+
+int vsom_peer_import_planes(vsom_ctx *ctx, int rank, const unsigned char handle[64])
+{
+    if (!ctx || !handle || rank < 0 || rank >= ctx->world)
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_peer_import_planes: bad rank") : VSOM_ERR_INVALID;
+    if (rank == ctx->rank)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void *ptr = nullptr;
+    VSOM_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peerMean[rank] = static_cast<float *>(ptr);
+    ctx->peerMeanOpened[rank] = true;
+    return VSOM_OK;
+}
+
+int vsom_peer_attach(vsom_ctx *ctx, int rank, vsom_ctx *peer)
+{
+    if (!ctx || !peer || rank < 0 || rank >= ctx->world || peer->rank != rank || peer->world != ctx->world || peer->W != ctx->W || peer->H != ctx->H ||
+        peer->Dm != ctx->Dm)
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_peer_attach: peer is not rank `rank` of the same sharded map") : VSOM_ERR_INVALID;
+    if (rank == ctx->rank)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (peer->device != ctx->device)
+    {
+        int can = 0;
+        VSOM_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+        if (!can)
+            return set_error(ctx, VSOM_ERR_UNSUPPORTED, "vsom_peer_attach: no peer access between the two devices");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return cuda_fail(ctx, e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        cudaGetLastError();
+    }
+    ctx->peerSlots[rank] = peer->rankSlots;
+    ctx->peerMean[rank] = peer->mean;
+    return VSOM_OK;
+}
+
+int vsom_shard_rows(const vsom_ctx *ctx, int *block_rows, int *local_rows, int *global_rows)
 {
     if (!ctx)
         return VSOM_ERR_INVALID;
-    if (first_node)
-        *first_node = ctx->node0;
-    if (node_count)
-        *node_count = ctx->localN;
+    if (block_rows)
+        *block_rows = ctx->shardBlock;
+    if (local_rows)
+        *local_rows = ctx->localRows;
+    if (global_rows)
+        for (int i = 0; i < ctx->localRows; ++i)
+            global_rows[i] = ctx->localRowY[i];
     return VSOM_OK;
 }
 
@@ -254,8 +318,13 @@ void vsom_destroy(vsom_ctx *ctx)
     cudaFree(ctx->pairJ);
     cudaFree(ctx->slots);
     for (int r = 0; r < 8; ++r)
+    {
         if (ctx->peerOpened[r])
             cudaIpcCloseMemHandle(ctx->peerSlots[r]);
+        if (ctx->peerMeanOpened[r])
+            cudaIpcCloseMemHandle(ctx->peerMean[r]);
+    }
+    cudaFree(ctx->haloBuf);
     cudaFree(ctx->rankSlots);
     cudaFree(ctx->errFlag);
     cudaFree(ctx->lut);
@@ -380,44 +449,52 @@ int vsom_synchronize(vsom_ctx *ctx)
     return VSOM_OK;
 }
 
+// Planes cross the boundary as FULL-map arrays; a node-sharded context touches only its own blocks of grid rows.
+// `toDevice`: host -> device, else device -> host.
+static int copy_state(vsom_ctx *ctx, bool toDevice, float *mean, float *S, float *sigma, float *weight, uint64_t *hits)
+{
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
+    const cudaMemcpyKind kind = toDevice ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    for (int lr = 0; lr < ctx->localRows;)
+    {
+        int rows = 1; // run of local rows that are also consecutive grid rows (one block; the whole map when unsharded)
+        while (lr + rows < ctx->localRows && ctx->localRowY[lr + rows] == ctx->localRowY[lr] + rows)
+            ++rows;
+        const size_t nodes = static_cast<size_t>(rows) * ctx->W, lnode = static_cast<size_t>(lr) * ctx->W, gnode = static_cast<size_t>(ctx->localRowY[lr]) * ctx->W;
+        float *planesHost[3] = {mean, S, sigma}, *planesDev[3] = {ctx->mean, ctx->S, ctx->sigma};
+        for (int k = 0; k < 3; ++k)
+            if (planesHost[k])
+            {
+                float *h = planesHost[k] + gnode * ctx->Dm, *d = planesDev[k] + lnode * ctx->rowStride;
+                if (toDevice)
+                    VSOM_CUDA(ctx, cudaMemcpy2DAsync(d, pitch, h, w, w, nodes, kind, ctx->stream));
+                else
+                    VSOM_CUDA(ctx, cudaMemcpy2DAsync(h, w, d, pitch, w, nodes, kind, ctx->stream));
+            }
+        if (weight)
+            VSOM_CUDA(ctx, cudaMemcpyAsync(toDevice ? ctx->weight + lnode : weight + gnode, toDevice ? weight + gnode : ctx->weight + lnode, sizeof(float) * nodes, kind, ctx->stream));
+        if (hits)
+            VSOM_CUDA(ctx, cudaMemcpyAsync(toDevice ? static_cast<void *>(ctx->hits + lnode) : static_cast<void *>(hits + gnode),
+                                           toDevice ? static_cast<const void *>(hits + gnode) : static_cast<const void *>(ctx->hits + lnode), sizeof(u64) * nodes, kind, ctx->stream));
+        lr += rows;
+    }
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VSOM_OK;
+}
+
 int vsom_upload_state(vsom_ctx *ctx, const float *mean, const float *S, const float *sigma, const float *weight, const uint64_t *hits)
 {
     if (!ctx)
         return VSOM_ERR_INVALID;
-    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
-    if (mean)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->mean, pitch, mean + static_cast<size_t>(ctx->node0) * ctx->Dm, w, w, ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
-    if (S)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->S, pitch, S + static_cast<size_t>(ctx->node0) * ctx->Dm, w, w, ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
-    if (sigma)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(ctx->sigma, pitch, sigma + static_cast<size_t>(ctx->node0) * ctx->Dm, w, w, ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
-    if (weight)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->weight, weight + ctx->node0, sizeof(float) * ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
-    if (hits)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->hits, hits + ctx->node0, sizeof(u64) * ctx->localN, cudaMemcpyHostToDevice, ctx->stream));
-    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VSOM_OK;
+    return copy_state(ctx, true, const_cast<float *>(mean), const_cast<float *>(S), const_cast<float *>(sigma), const_cast<float *>(weight), const_cast<uint64_t *>(hits));
 }
 
 int vsom_download_state(vsom_ctx *ctx, float *mean, float *S, float *sigma, float *weight, uint64_t *hits)
 {
     if (!ctx)
         return VSOM_ERR_INVALID;
-    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t w = sizeof(float) * ctx->Dm, pitch = sizeof(float) * ctx->rowStride;
-    if (mean)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(mean + static_cast<size_t>(ctx->node0) * ctx->Dm, w, ctx->mean, pitch, w, ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
-    if (S)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(S + static_cast<size_t>(ctx->node0) * ctx->Dm, w, ctx->S, pitch, w, ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
-    if (sigma)
-        VSOM_CUDA(ctx, cudaMemcpy2DAsync(sigma + static_cast<size_t>(ctx->node0) * ctx->Dm, w, ctx->sigma, pitch, w, ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
-    if (weight)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(weight + ctx->node0, ctx->weight, sizeof(float) * ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
-    if (hits)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(hits + ctx->node0, ctx->hits, sizeof(u64) * ctx->localN, cudaMemcpyDeviceToHost, ctx->stream));
-    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VSOM_OK;
+    return copy_state(ctx, false, mean, S, sigma, weight, hits);
 }
 
 int vsom_get_node(vsom_ctx *ctx, size_t node, float *mean, float *sigma)
@@ -706,44 +783,95 @@ int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out)
     return VSOM_OK;
 }
 
-// per-grid-row pointer tables of K4 (umatrix.cu): [H] mean rows, [H] sigma rows, [localRows] grid rows to compute
+// per-grid-row pointer tables of K4 (umatrix.cu): [H] mean rows, [H] sigma rows, [localRows] grid rows to compute.  A
+// node-sharded context reads its neighbours' border rows from the halo buffer (filled by fetch_halo below).
 static int umatrix_tables(vsom_ctx *ctx)
 {
     if (ctx->umTab)
         return VSOM_OK;
     const int H = ctx->H;
+    const size_t rowFloats = static_cast<size_t>(ctx->W) * ctx->rowStride;
     std::vector<const float *> rows(2 * static_cast<size_t>(H), nullptr);
-    std::vector<int> ys;
-    for (int y = 0; y < H; ++y)
+    std::vector<int> halo; // grid rows of other ranks that border this rank's rows
+    for (int lr = 0; lr < ctx->localRows; ++lr)
     {
-        rows[y] = ctx->mean + static_cast<size_t>(y) * ctx->W * ctx->rowStride;
-        rows[H + y] = ctx->sigma + static_cast<size_t>(y) * ctx->W * ctx->rowStride;
-        ys.push_back(y);
+        const int y = ctx->localRowY[lr];
+        rows[y] = ctx->mean + lr * rowFloats;
+        rows[H + y] = ctx->sigma + lr * rowFloats;
     }
+    for (int lr = 0; lr < ctx->localRows; ++lr)
+        for (int dy = -1; dy <= 1; dy += 2)
+        {
+            const int y = ctx->localRowY[lr] + dy;
+            if (y >= 0 && y < H && !rows[y] && std::find(halo.begin(), halo.end(), y) == halo.end())
+                halo.push_back(y);
+        }
+    if (!halo.empty())
+    {
+        const size_t need = sizeof(float) * rowFloats * halo.size();
+        if (need > ctx->haloCap)
+        {
+            cudaFree(ctx->haloBuf);
+            ctx->haloBuf = nullptr;
+            VSOM_CUDA(ctx, cudaMalloc(&ctx->haloBuf, need));
+            ctx->haloCap = need;
+        }
+        for (size_t i = 0; i < halo.size(); ++i)
+            rows[halo[i]] = ctx->haloBuf + i * rowFloats;
+    }
+    ctx->haloRows = halo;
     const size_t ptrBytes = sizeof(float *) * rows.size();
-    VSOM_CUDA(ctx, cudaMalloc(&ctx->umTab, ptrBytes + sizeof(int) * ys.size()));
+    VSOM_CUDA(ctx, cudaMalloc(&ctx->umTab, ptrBytes + sizeof(int) * ctx->localRowY.size()));
     VSOM_CUDA(ctx, cudaMemcpy(ctx->umTab, rows.data(), ptrBytes, cudaMemcpyHostToDevice));
-    VSOM_CUDA(ctx, cudaMemcpy(static_cast<unsigned char *>(ctx->umTab) + ptrBytes, ys.data(), sizeof(int) * ys.size(), cudaMemcpyHostToDevice));
-    ctx->umRows = static_cast<int>(ys.size());
+    VSOM_CUDA(ctx, cudaMemcpy(static_cast<unsigned char *>(ctx->umTab) + ptrBytes, ctx->localRowY.data(), sizeof(int) * ctx->localRowY.size(), cudaMemcpyHostToDevice));
+    ctx->umRows = ctx->localRows;
+    return VSOM_OK;
+}
+
+// Halo exchange of the sharded U-matrix: one grid row of MEANS per border (sigma is the centre's own), read
+// straight out of the owner's plane over NVLink (peer-mapped pointer, device-to-device copy).
+static int fetch_halo(vsom_ctx *ctx)
+{
+    const size_t rowFloats = static_cast<size_t>(ctx->W) * ctx->rowStride;
+    for (size_t i = 0; i < ctx->haloRows.size(); ++i)
+    {
+        const int y = ctx->haloRows[i], owner = (y / ctx->shardBlock) % ctx->world;
+        const int lr = shard_local_row(y, ctx->shardBlock, owner, ctx->world);
+        if (!ctx->peerMean[owner])
+            return set_error(ctx, VSOM_ERR_INVALID, "vsom_update_umatrix: sharded context without vsom_peer_import_planes / vsom_peer_attach for every rank");
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->haloBuf + i * rowFloats, ctx->peerMean[owner] + lr * rowFloats, sizeof(float) * rowFloats, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return VSOM_OK;
 }
 
 int vsom_update_umatrix(vsom_ctx *ctx, double *out)
 {
-    if (ctx && ctx->world > 1)
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "this entry point needs an unsharded context (scoring, U-matrix and index run on replicated maps)");
     if (!ctx)
         return VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = umatrix_tables(ctx);
     if (rc)
         return rc;
+    if (ctx->world > 1)
+    {
+        rc = fetch_halo(ctx);
+        if (rc)
+            return rc;
+    }
     const float *const *meanRows = static_cast<const float *const *>(ctx->umTab);
     rc = launch_umatrix_rows(ctx, meanRows, meanRows + ctx->H, reinterpret_cast<const int *>(meanRows + 2 * ctx->H), ctx->umRows);
     if (rc)
         return rc;
-    if (out)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(out, ctx->umatrix, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out) // full-map array; a sharded context fills in its own grid rows only
+        for (int lr = 0; lr < ctx->localRows;)
+        {
+            int rows = 1;
+            while (lr + rows < ctx->localRows && ctx->localRowY[lr + rows] == ctx->localRowY[lr] + rows)
+                ++rows;
+            const size_t g = static_cast<size_t>(ctx->localRowY[lr]) * ctx->W;
+            VSOM_CUDA(ctx, cudaMemcpyAsync(out + g, ctx->umatrix + g, sizeof(double) * rows * ctx->W, cudaMemcpyDeviceToHost, ctx->stream));
+            lr += rows;
+        }
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VSOM_OK;
 }

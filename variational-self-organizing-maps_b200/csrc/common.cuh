@@ -32,7 +32,8 @@ struct LutEntry
 struct StepParams
 {
     int W, H;                 // full grid
-    int node0, nodeCount;     // shard of the grid held by this device: global nodes [node0, node0+nodeCount)
+    int node0, nodeCount;     // nodes held by this device (node0 is 0; sharded contexts map local <-> global with shard_*_node below)
+    int shardBlock;           // node-sharded contexts: grid rows are dealt to the ranks round-robin in blocks of this many rows
     int Din, Dm, Dr, P;       // sample length, model length, residual length (Dm or P), CLR pair count
     int rowStride;            // floats between rows of the global planes
     float *mean, *S, *sigma, *weight;
@@ -81,8 +82,15 @@ struct vsom_ctx
 {
     int device = 0;
     int W = 0, H = 0, N = 0, Din = 0, Dm = 0, Dr = 0, P = 0;
-    int rank = 0, world = 1;      // node sharding: this context holds grid rows [y0, y1) = nodes [node0, node0 + localN)
-    int node0 = 0, localN = 0;
+    int rank = 0, world = 1;      // node sharding: grid rows are dealt to the ranks round-robin in blocks of shardBlock rows
+    int node0 = 0, localN = 0;    // node0 stays 0; localN = localRows * W
+    int shardBlock = 0, localRows = 0;
+    std::vector<int> localRowY;   // global grid row of every local row
+    float *peerMean[8] = {};      // mean planes of the ranks (U-matrix halo rows), peer-mapped; peerMean[rank] == mean
+    bool peerMeanOpened[8] = {};
+    float *haloBuf = nullptr;     // neighbour rows fetched from other ranks for the U-matrix
+    size_t haloCap = 0;
+    std::vector<int> haloRows;    // the grid rows held in haloBuf, in order
     vsom::u64 *rankSlots = nullptr;
     vsom::u64 *peerSlots[8] = {};
     bool peerOpened[8] = {};
@@ -239,6 +247,37 @@ __device__ __forceinline__ u64 make_key(float d, unsigned node, unsigned tag)
     return (static_cast<u64>(bits) << 32) | (static_cast<u64>(node) << 8) | tag;
 }
 __device__ __forceinline__ unsigned key_node(u64 k) { return static_cast<unsigned>((k >> 8) & 0xffffffu); }
+
+// ---- node-sharded contexts (BASELINE config 5): block b of `shardBlock` grid rows lives on rank b % world as that rank's
+// local block b / world.  Local node order is global node order restricted to the rank (monotone), so keys compare the same
+// way inside a rank whichever index they carry.
+__host__ __device__ __forceinline__ int shard_local_row(int y, int block, int rank, int world)
+{
+    const int b = y / block;
+    if (b % world != rank)
+        return -1;
+    return (b / world) * block + (y - b * block);
+}
+__host__ __device__ __forceinline__ int shard_global_row(int ly, int block, int rank, int world)
+{
+    const int lb = ly / block;
+    return (lb * world + rank) * block + (ly - lb * block);
+}
+__device__ __forceinline__ unsigned shard_global_node(const StepParams &p, unsigned q)
+{
+    if (p.world == 1)
+        return q;
+    const unsigned ly = q / static_cast<unsigned>(p.W);
+    return static_cast<unsigned>(shard_global_row(static_cast<int>(ly), p.shardBlock, p.rank, p.world)) * static_cast<unsigned>(p.W) + (q - ly * static_cast<unsigned>(p.W));
+}
+// local linear index of grid cell (x, y), -1 when another rank holds that row
+__device__ __forceinline__ int shard_local_node(const StepParams &p, int x, int y)
+{
+    if (p.world == 1)
+        return y * p.W + x;
+    const int ly = shard_local_row(y, p.shardBlock, p.rank, p.world);
+    return ly < 0 ? -1 : ly * p.W + x;
+}
 
 // One residual of the Comparer, and its square accumulated in f32 (src/Som.cpp:136-140).
 //   Standard / Median: r = m - v           (src/Transformation.cpp:7-8, :45-46)

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ u64 sWarpKey[kWarps];
-    __shared__ int sWin[8]; // bmu, bx, by, startX, endX, startY, endY of the current sample
+    __shared__ int sWin[8]; // local index of the BMU (-1: another rank's), bx, by, startX, endX, startY, endY of the current sample
     __shared__ int sAbort;
     __shared__ int sPendL; // local node whose post-update distance is still owed (-1: none)
     __shared__ u64 sPendT; // ... for this sample
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             lutS[i] = p.lut[i];
     for (int l = tid; l < L; l += kThreads)
     {
-        const unsigned node = static_cast<unsigned>(p.node0 + l * G + b);
+        const unsigned node = shard_global_node(p, static_cast<unsigned>(l * G + b));
         wbuf[l] = p.weight[static_cast<size_t>(l) * G + b];
         if (!useList)
             nodeXY[l] = make_int2(static_cast<int>(node % static_cast<unsigned>(p.W)), static_cast<int>(node / static_cast<unsigned>(p.W)));
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 const float d = node_dist_reference<TR, ORDER>(mBase + pendL * stride, xprev, p, n4, pi, pj);
                 const size_t q = static_cast<size_t>(pendL) * G + b;
                 if (p.outBmu)
-                    p.outBmu[pendT] = static_cast<unsigned>(p.node0 + q);
+                    p.outBmu[pendT] = shard_global_node(p, static_cast<unsigned>(q));
                 if (p.outDist)
                     p.outDist[pendT] = d;
                 p.hits[q] += 1;
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                                 sacc = eacc.finish(erest, p.Dm & 7);
                                 if (p.localSearch)
                                     p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = sacc;
-                                best = u64_min(best, make_key(sacc, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                                best = u64_min(best, make_key(sacc, static_cast<unsigned>(l * G + b), tag));
                             }
                         }
                         else if (l < L)
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                             {
                                 if (p.localSearch)
                                     p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = sacc;
-                                best = u64_min(best, make_key(sacc, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                                best = u64_min(best, make_key(sacc, static_cast<unsigned>(l * G + b), tag));
                             }
                         }
                         __syncwarp(); // every lane is done with this buffer before it is refilled
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     const float d = node_dist_reference<TR, ORDER>(mBase + l * stride, xt, p, n4, pi, pj);
                     if (p.localSearch)
                         p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
-                    best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                    best = u64_min(best, make_key(d, static_cast<unsigned>(l * G + b), tag));
                 }
         }
         else
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 {
                     const size_t q = static_cast<size_t>(pendL) * G + b;
                     if (p.outBmu)
-                        p.outBmu[pendT] = static_cast<unsigned>(p.node0 + q);
+                        p.outBmu[pendT] = shard_global_node(p, static_cast<unsigned>(q));
                     if (p.outDist)
                         p.outDist[pendT] = d;
                     p.hits[q] += 1;
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 const float d = dist_lanes<TR>(mBase + l * stride, xt, p.Dr, p.P, pi, pj, lane);
                 if (p.localSearch && lane == 0)
                     p.distBuf[(t & 1) * static_cast<u64>(p.nodeCount) + static_cast<u64>(l) * G + b] = d;
-                best = u64_min(best, make_key(d, static_cast<unsigned>(p.node0 + l * G + b), tag));
+                best = u64_min(best, make_key(d, static_cast<unsigned>(l * G + b), tag));
             }
         }
         if (p.localSearch)
@@ -622,7 +622,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 const u64 gs = p.stepBase + t;
                 const unsigned gtag = static_cast<unsigned>((gs >> 1) & 0xff);
                 const int gbuf = static_cast<int>(gs & 1);
-                const u64 mine = (m & ~0xffull) | gtag;
+                // keys carry LOCAL node indices inside a GPU (they order like the global ones there); across GPUs the global index
+                const u64 mine = (m & 0xffffffff00000000ull) | (static_cast<u64>(shard_global_node(p, key_node(m))) << 8) | gtag;
                 if (b == 0 && lane < p.world)
                     st_relaxed_sys(p.peerSlots[lane] + gbuf * p.world + p.rank, mine);
                 const u64 *grow = p.rankSlots + gbuf * p.world;
@@ -663,9 +664,9 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     if (b == 0 && p.outBmu)
                         p.outBmu[t] = bmu;
                 }
-                wbmu = static_cast<int>(bmu);
                 wbx = static_cast<int>(bmu % static_cast<unsigned>(p.W));
                 wby = static_cast<int>(bmu / static_cast<unsigned>(p.W));
+                wbmu = shard_local_node(p, wbx, wby); // local index of the BMU, -1 when another rank holds it
                 double lo = __dsub_rn(static_cast<double>(wbx), p.radius);
                 wsx = static_cast<int>(static_cast<u64>(lo > 0. ? lo : 0.));
                 lo = __dsub_rn(static_cast<double>(wby), p.radius);
@@ -734,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     wbuf[l] = w;
                     touched[l] = 1;
                     cf = make_float2(c, nwf);
-                    if (static_cast<unsigned>(p.node0 + l * G + b) == static_cast<unsigned>(wbmu))
+                    if (l * G + b == wbmu)
                     {
                         sPendL = l;
                         sPendT = t;
@@ -762,8 +763,8 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
             {
                 const int cy = cidx / ww, cx = cidx - cy * ww;
                 const int x = wsx + cx, y = wsy + cy;
-                const int rel = y * p.W + x - p.node0;
-                if (rel < 0 || rel >= p.nodeCount)
+                const int rel = shard_local_node(p, x, y);
+                if (rel < 0)
                     continue;
                 const int l = rel / G;
                 if (rel - l * G != b)
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                 wbuf[l] = w;
                 touched[l] = 1;
                 coef[l] = make_float2(c, nwf);
-                if (rel + p.node0 == wbmu)
+                if (rel == wbmu)
                 {
                     sPendL = l;
                     sPendT = t;
@@ -860,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     {
                         wbuf[l] = w;
                         touched[l] = 1;
-                        if (static_cast<unsigned>(p.node0 + l * G + b) == static_cast<unsigned>(sWin[0]))
+                        if (l * G + b == sWin[0])
                         {
                             sPendL = l;
                             sPendT = t;
@@ -952,7 +953,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
         {
             const size_t q = static_cast<size_t>(pendL) * G + b;
             if (p.outBmu)
-                p.outBmu[pendT] = static_cast<unsigned>(p.node0 + q);
+                p.outBmu[pendT] = shard_global_node(p, static_cast<unsigned>(q));
             if (p.outDist)
                 p.outDist[pendT] = d;
             p.hits[q] += 1;
@@ -1186,7 +1187,8 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     StepParams p;
     p.W = ctx->W;
     p.H = ctx->H;
-    p.node0 = ctx->node0;
+    p.node0 = 0;
+    p.shardBlock = ctx->shardBlock;
     p.nodeCount = ctx->localN;
     p.order = ctx->order;
     p.world = ctx->world;

@@ -1,8 +1,11 @@
 """Host-side helpers for the two multi-GPU layouts.  No compute: partitioning and result merging only.
 
 * rows   : batch scoring / evaluate / index shard by data rows, map replicated, no communication.
-* nodes  : large-map training shards contiguous bands of grid rows across ranks; per sample the ranks exchange one packed
-           64-bit (distance, node) key and take the minimum (inside the persistent kernel, over NVLink peer memory).
+* nodes  : large-map training deals blocks of a few grid rows to the ranks round-robin (block b -> rank b % world); per
+           sample the ranks exchange one packed 64-bit (distance, node) key and take the minimum (inside the persistent
+           kernel, over NVLink peer memory).  The U-matrix needs one halo row of means per block border.
+* row-shard combines: bmuHits are summed over the ranks; Som::evaluate's running mean is order dependent in f64, so the
+           per-row distances are gathered in rank order and folded on one rank exactly like the reference does.
 """
 from __future__ import annotations
 
@@ -16,11 +19,50 @@ def row_shard(n_rows: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def node_band(width: int, height: int, rank: int, world: int):
-    """(first_node, node_count) of the band of grid rows held by `rank` — same rule as vsom_create_sharded."""
-    y0 = height * rank // world
-    y1 = height * (rank + 1) // world
-    return y0 * width, (y1 - y0) * width
+DEFAULT_BLOCK_ROWS = 4
+
+
+def shard_block_rows(height: int, world: int, block: int = DEFAULT_BLOCK_ROWS) -> int:
+    """Rows per block — same rule as vsom_create_sharded: every rank holds at least one row."""
+    if world == 1:
+        return height
+    return block if block * world <= height else height // world
+
+
+def node_rows(height: int, rank: int, world: int, block: int = DEFAULT_BLOCK_ROWS) -> np.ndarray:
+    """Global grid rows held by `rank`, in local order: block b of `block` rows belongs to rank b % world."""
+    b = shard_block_rows(height, world, block)
+    y = np.arange(height)
+    return y[(y // b) % world == rank]
+
+
+def node_ids(width: int, height: int, rank: int, world: int, block: int = DEFAULT_BLOCK_ROWS) -> np.ndarray:
+    """Global node ids held by `rank`, in local order."""
+    return (node_rows(height, rank, world, block)[:, None] * width + np.arange(width)[None, :]).reshape(-1)
+
+
+def halo_rows(height: int, rank: int, world: int, block: int = DEFAULT_BLOCK_ROWS) -> np.ndarray:
+    """Grid rows of OTHER ranks that border this rank's rows (what the sharded U-matrix fetches)."""
+    mine = set(node_rows(height, rank, world, block).tolist())
+    out = sorted({y + d for y in mine for d in (-1, 1) if 0 <= y + d < height} - mine)
+    return np.array(out, dtype=np.int64)
+
+
+def sum_hits(per_rank_hits):
+    """bmuHits of row-sharded scoring / training replicas: plain sum over the ranks (what an NCCL sum-allreduce gives)."""
+    return np.sum(np.stack([np.asarray(h, np.uint64) for h in per_rank_hits]), axis=0, dtype=np.uint64)
+
+
+def evaluate_from_shards(per_rank_dists) -> float:
+    """Som::evaluate (src/Som.cpp:490-523) over row shards: the f64 running mean  e += (d_i - e) / (i + 1)  depends on the
+    row order, so the shards' per-row BMU distances are concatenated in rank order and folded exactly like the reference."""
+    err = 0.0
+    i = 0
+    for d in per_rank_dists:
+        for v in np.asarray(d, np.float32):
+            err += 1.0 / (i + 1.0) * (float(v) + 0.0 - err)
+            i += 1
+    return err
 
 
 def pack_key(dist: np.ndarray, node: np.ndarray) -> np.ndarray:
