@@ -1,16 +1,24 @@
 // SOM.hpp — class Som with the public surface of the reference (include/SOM.hpp:39-189), re-implemented for
 // B200: the model state lives on the GPU behind the C-ABI of vsom_b200.h and the hot methods
-//   train / trainBasicSom / trainSingle      -> vsom_train_chunk        (K1, persistent online-step kernel)
-//   findBmu / findRestrictedBmu / evaluate    -> vsom_find_bmu / vsom_evaluate (K3 exact scan)
-//   euclidianWeightedDist                     -> vsom_all_dists
-//   updateUMatrix / getUMatrix                -> vsom_update_umatrix     (K4)
+//   train / trainBasicSom / trainSingle              -> vsom_train_chunk   (K1F / K1, persistent online-step kernels)
+//   train(BatchMap) / trainBatchSom[Epoch]           -> vsom_batch_epoch   (K6)
+//   evaluate / measureSimilarity / mapDataSet         -> vsom_find_bmu / vsom_evaluate: batches of >= 1024 rows run the
+//                                                        tensor-core candidate search + exact rescore (K2), smaller ones
+//                                                        the exact scan (K3); same bits either way
+//   findBmu / findRestrictedBmu (one row)             -> vsom_find_bmu      (K3)
+//   euclidianWeightedDist / findLocalBmu / findRestrictedBmd -> vsom_all_dists
+//   variationalAutoEncoder / autoEncoder              -> vsom_soft_assign + host sampling
+//   updateUMatrix / getUMatrix                        -> vsom_update_umatrix (K4)
 // forward to it.  Getters read a host mirror that is refreshed from the device on demand.  There is no CPU
 // implementation of the hot path behind this class: if the CUDA library cannot run, the methods throw.
 //
 // save / load / getSizeFromFile / Som(const char*) keep the reference's Octave-text checkpoint format byte for byte
-// (host code over the mirror).  Not carried over (batch-map trainer, (variational)
-// auto-encoder sampling, CLI): those members are declared for source compatibility and throw
-// std::logic_error("not on the B200 hot path") when called.
+// (host code over the mirror).
+//
+// Summation order of dot() / squaredNorm() (the one order-dependent operation of the path): by default the order of the
+// Eigen this library is compiled against — real Eigen: its SSE2 packet redux (VSOM_ORDER_EIGEN_SSE); the stand-in header
+// of include/compat: sequential, or the packet order with -DVSOM_COMPAT_EIGEN_SSE_REDUX.  The environment variable
+// VSOM_REDUCTION_ORDER=reference|eigen_sse|lanes, or setReductionOrder(), overrides it.
 #pragma once
 
 #include "DataSet.hpp"
@@ -64,7 +72,7 @@ class Som
     mutable std::shared_ptr<Device> device;
     mutable bool hostIsStale{false};   // the device holds newer planes than the mirror
     mutable bool deviceIsStale{true};  // the mirror holds planes the device has not seen
-    mutable bool reductionOrderLanes{false};
+    mutable int reductionOrder{-1};    // vsom_reduction_order; -1: the build's default (see the note at the top)
     vsom_ctx *context() const;         // creates the context on first use, pushes the mirror if needed
     void pull() const;                 // refresh the mirror from the device
     size_t inputLength() const;        // sample length the model vector was built for
@@ -148,6 +156,9 @@ class Som
     void mapDataSet(const DataSet &dataset, std::vector<size_t> &bmuOut, std::vector<float> &distOut, size_t minBmuHits = 0) const;
     // Rows grouped by BMU: counts[N], offsets[N+1], rowIds[n] (the "SomIndex build").
     void buildIndex(const std::vector<size_t> &bmu, std::vector<size_t> &counts, std::vector<size_t> &offsets, std::vector<unsigned> &rowIds) const;
-    // Reduction order of the online step's distances: false (default) = the reference's sequential order.
-    void setFastReductionOrder(bool lanes);
+    // Summation order of the distances (vsom_reduction_order of vsom_b200.h): 0 sequential, 1 lanes (online step only, near-tie
+    // rule), 2 Eigen's SSE2 packet order.  Re-creates the device context on the next call.
+    void setReductionOrder(int order);
+    int getReductionOrder() const;
+    void setFastReductionOrder(bool lanes); // kept from round 1: lanes ? order 1 : order 0
 };

@@ -142,6 +142,12 @@ VSOM_API int vsom_debug_phase_cycles_raw(vsom_ctx *ctx, double out[8]);
 /* 1 when K1F's exchange rows were placed by L2 die (the SM -> die and block -> die maps were measured and are clean). */
 VSOM_API int vsom_debug_die_aware(const vsom_ctx *ctx);
 
+/* Measured on-chip bandwidth of this device (not a product path; bench.py's roofline denominators for maps that stay on
+ * chip): out[0] = aggregate shared-memory read bandwidth (GB/s, conflict-free LDS.128 on every SM), out[1] = the same per SM,
+ * out[2] = L2 read bandwidth (GB/s, every SM reading one L2-resident buffer with L2-only 128-bit loads), out[3] = size of
+ * that buffer in MiB. */
+VSOM_API int vsom_debug_measure_peaks(vsom_ctx *ctx, double out[4]);
+
 /* Replace / read the model state: Som::map, SMap, sigmaMap, weightMap, bmuHits (include/SOM.hpp:56-61).
  * Any pointer may be NULL (skipped).  Initial planes come from the host (Som::randomInitialize,
  * src/Som.cpp:977-997, runs on the host so that glibc's rand() sequence is the reference's). */
@@ -204,6 +210,13 @@ VSOM_API int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean
 /* Distance of one row to every node: N x euclidianWeightedDist (src/Som.cpp:124-141), as the double it returns. */
 VSOM_API int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out);
 
+/* Soft assignment of a batch of rows: Som::findRestrictedBmd (src/Som.cpp:457-487) per row — out_prob[r*N + i] =
+ * exp(-d_i^2 / 2) / C for nodes with hits >= min_hits (d_i = the already squared distance, as the reference has it), 0 for
+ * the others; C sums the terms in node order.  What Som::variationalAutoEncoder / autoEncoder (:525-623) sample from
+ * (the sampling itself stays on the host: std::discrete_distribution over these probabilities).  Distances are the
+ * reference's bits; exp() is the device's f64 exp, so probabilities agree with the reference to a few ulp (1e-14 relative). */
+VSOM_API int vsom_soft_assign(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, double *out_prob);
+
 /* -------------------------------------------------------------------------------- U-matrix / index */
 
 /* Som::updateUMatrix + Som::getUMatrix (src/Som.cpp:999-1111, :159-162; euclidianWeightedDistRaw :143-157).
@@ -214,6 +227,8 @@ VSOM_API int vsom_update_umatrix(vsom_ctx *ctx, double *out);
  * grouped by BMU in ascending row order (the per-neuron row set of src/Som.cpp:845-868).
  * counts[N], offsets[N+1], row_ids[n]; each may be NULL. */
 VSOM_API int vsom_build_index(vsom_ctx *ctx, const uint32_t *bmu, size_t n, uint64_t *counts, uint64_t *offsets, uint32_t *row_ids);
+/* Same on device arrays (enqueue only; an out-of-range BMU id raises the context's error flag, reported by the host form). */
+VSOM_API int vsom_build_index_device(vsom_ctx *ctx, const uint32_t *bmu_dev, size_t n, uint64_t *counts_dev, uint64_t *offsets_dev, uint32_t *row_ids_dev);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,12 @@
 // and tests/test_gpu_host_api.py requires the two output files to be identical byte for byte.
 //
 // usage: api_driver <case.bin> <out.bin>
-// case.bin: int32 W,H,Din,transform,decay,epochs,chunk,seed,n ; float64 eta0,etaDecay,sigma0,sigmaDecay ; float32 x[n*Din]
+// case.bin: int32 W,H,Din,transform,decay,epochs,chunk,seed,n,trainRows ; float64 eta0,etaDecay,sigma0,sigmaDecay ;
+//           float32 x[n*Din]
+// trainRows > 0 selects the LIGHT layout for large maps: training sees only the first trainRows rows, and the output holds
+// the per-epoch MSE, hit counts, U-matrix, evaluate(), measureSimilarity() and the restricted BMU of every one of the n rows
+// (no plane dumps, no checkpoint) — the scoring calls then run over thousands of rows, i.e. on the tensor-core path of the
+// B200 build.
 #include "DataSet.hpp"
 #include "IDataLoader.hpp"
 #include "SOM.hpp"
@@ -74,11 +79,12 @@ int main(int argc, char **argv)
     FILE *in = std::fopen(argv[1], "rb");
     if (!in)
         return 3;
-    int32_t h[9];
+    int32_t h[10];
     double sched[4];
-    if (std::fread(h, sizeof(int32_t), 9, in) != 9 || std::fread(sched, sizeof(double), 4, in) != 4)
+    if (std::fread(h, sizeof(int32_t), 10, in) != 10 || std::fread(sched, sizeof(double), 4, in) != 4)
         return 4;
-    const int W = h[0], H = h[1], Din = h[2], transform = h[3], decay = h[4], epochs = h[5], chunk = h[6], seed = h[7], n = h[8];
+    const int W = h[0], H = h[1], Din = h[2], transform = h[3], decay = h[4], epochs = h[5], chunk = h[6], seed = h[7], n = h[8], trainRows = h[9];
+    const bool light = trainRows > 0;
     std::vector<float> x(static_cast<size_t>(n) * Din);
     if (std::fread(x.data(), sizeof(float), x.size(), in) != x.size())
         return 5;
@@ -93,7 +99,7 @@ int main(int argc, char **argv)
                                         : Transformation::Standard(names);
     Som som(static_cast<size_t>(W), static_cast<size_t>(H), t.Length(static_cast<size_t>(Din)), t);
     som.randomInitialize(seed, 1.0f);
-    RowsLoader loader(x.data(), static_cast<size_t>(n), static_cast<size_t>(Din), static_cast<size_t>(chunk));
+    RowsLoader loader(x.data(), static_cast<size_t>(light ? trainRows : n), static_cast<size_t>(Din), static_cast<size_t>(chunk));
     DataSet ds(loader);
     som.train(ds, static_cast<size_t>(epochs), sched[0], sched[1], sched[2], sched[3], static_cast<Som::WeigthDecayFunction>(decay), true);
 
@@ -103,7 +109,7 @@ int main(int argc, char **argv)
     const auto metrics = som.getMetrics();
     put(out, metrics.MeanSquaredError.data(), metrics.MeanSquaredError.size());
     const size_t N = som.getWidth() * som.getHeight();
-    for (size_t p = 0; p < N; ++p)
+    for (size_t p = 0; p < N && !light; ++p)
     {
         const Eigen::VectorXf m = som.getNeuron(p), s = som.getSigmaNeuron(p);
         put(out, m.data(), static_cast<size_t>(m.size()));
@@ -135,6 +141,99 @@ int main(int argc, char **argv)
         put(out, &sim, 1);
     }
     const Eigen::VectorXf ones = Eigen::VectorXf::Ones(Din);
+    // ---- restricted BMU of EVERY row (the per-row loop a user of the reference writes; Som::mapDataSet in one device pass)
+    //      and the rows grouped by BMU (SomIndex build)
+    {
+        std::vector<size_t> bmuAll(static_cast<size_t>(n));
+        std::vector<float> distAll(static_cast<size_t>(n));
+#ifdef VSOM_B200_API
+        som.mapDataSet(ds2, bmuAll, distAll, 2);
+#else
+        for (int r = 0; r < n; ++r)
+        {
+            Eigen::VectorXf v(Din);
+            std::memcpy(v.data(), x.data() + static_cast<size_t>(r) * Din, sizeof(float) * Din);
+            const SomIndex b = som.findRestrictedBmu(v, ones, 2, ones);
+            bmuAll[static_cast<size_t>(r)] = som.getIndex(b);
+            distAll[static_cast<size_t>(r)] = light ? 0.0f : static_cast<float>(som.euclidianWeightedDist(b, v, ones, ones));
+        }
+#endif
+        for (int r = 0; r < n; ++r)
+        {
+            const uint64_t b = bmuAll[static_cast<size_t>(r)];
+            put(out, &b, 1);
+            if (!light)
+                put(out, &distAll[static_cast<size_t>(r)], 1);
+        }
+        std::vector<size_t> counts(N, 0), offsets(N + 1, 0);
+        std::vector<unsigned> rowIds(static_cast<size_t>(n));
+#ifdef VSOM_B200_API
+        som.buildIndex(bmuAll, counts, offsets, rowIds);
+#else
+        for (size_t b : bmuAll)
+            counts[b] += 1;
+        for (size_t p = 0; p < N; ++p)
+            offsets[p + 1] = offsets[p] + counts[p];
+        std::vector<size_t> fill(offsets.begin(), offsets.end() - 1);
+        for (int r = 0; r < n; ++r)
+            rowIds[fill[bmuAll[static_cast<size_t>(r)]]++] = static_cast<unsigned>(r);
+#endif
+        for (size_t p = 0; p < N; ++p)
+        {
+            const uint64_t c = counts[p], o = offsets[p + 1];
+            put(out, &c, 1);
+            put(out, &o, 1);
+        }
+        put(out, rowIds.data(), rowIds.size());
+    }
+    if (light)
+    {
+        std::fclose(out);
+        std::cout.rdbuf(old);
+        return 0;
+    }
+    // ---- Som::trainSingle + Som::addBmu by hand (the caller-side loop of src/Som.cpp:1161-1171) on a copy of the map:
+    //      the hit must be counted once per sample; global-BMU and local-BMU (sigma == 1) regimes
+    {
+        Som copy(som);
+        size_t last = 0;
+        for (int r = 0; r < std::min(n, 12); ++r)
+        {
+            Eigen::VectorXf v(Din);
+            std::memcpy(v.data(), x.data() + static_cast<size_t>(r) * Din, sizeof(float) * Din);
+            const auto ret = copy.trainSingle(v, ones, ones, transform == 2 ? 0.005 : 0.2, r < 8 ? 2.0 : 1.0, last, static_cast<Som::WeigthDecayFunction>(decay == 2 ? 0 : decay));
+            copy.addBmu(ret.bmu);
+            const uint64_t bi = copy.getIndex(ret.bmu), lb = last;
+            put(out, &bi, 1);
+            put(out, &lb, 1);
+            put(out, &ret.distanceError, 1);
+            put(out, ret.residual.data(), static_cast<size_t>(ret.residual.size()));
+        }
+        for (size_t v : copy.getBmuHits())
+        {
+            const uint64_t u = v;
+            put(out, &u, 1);
+        }
+        const Eigen::VectorXf m0 = copy.getNeuron(size_t{0}), w2 = copy.getWeigthMap();
+        put(out, m0.data(), static_cast<size_t>(m0.size()));
+        put(out, w2.data(), static_cast<size_t>(w2.size()));
+    }
+    // ---- findLocalBmu from several start nodes (column 0 / row 0 wrap quirks included), findRestrictedBmd
+    {
+        const size_t starts[6] = {0, static_cast<size_t>(W - 1), N - 1, static_cast<size_t>(H - 1) * W, N / 2, static_cast<size_t>(W)};
+        for (int r = 0; r < std::min(n, 6); ++r)
+        {
+            Eigen::VectorXf v(Din);
+            std::memcpy(v.data(), x.data() + static_cast<size_t>(r) * Din, sizeof(float) * Din);
+            for (size_t st : starts)
+            {
+                const uint64_t li = som.getIndex(som.findLocalBmu(v, ones, st, ones));
+                put(out, &li, 1);
+            }
+            const std::vector<double> bmd = som.findRestrictedBmd(v, ones, r % 3, ones);
+            put(out, bmd.data(), bmd.size());
+        }
+    }
     for (int r = 0; r < std::min(n, 16); ++r)
     {
         Eigen::VectorXf v(Din);

@@ -16,7 +16,21 @@ import pytest
 from conftest import REPO
 
 REF_DRIVER = os.path.join(REPO, "oracle", "_ref", "api_driver_ref")
+REF_DRIVER_SSE = os.path.join(REPO, "oracle", "_ref", "api_driver_ref_sse")  # reference TUs + stand-in Eigen in Eigen's SSE2 redux order
 B200_DRIVER = os.path.join(REPO, "tests", "cpp", "api_driver_b200")
+BIG_GOLDEN = os.path.join(REPO, "tests", "golden", "api_driver_big.json")
+
+# The LIGHT layout on BASELINE configs[3]'s map: 128x128, D=256, 4096 rows scored (evaluate, measureSimilarity, restricted BMU
+# of every row, index) after a short training on the first 192 rows.  The CPU reference needs minutes for this, so its output
+# is pinned by SHA-256 (tests/golden/make_api_driver_big.py ran both reference drivers; the hashes are committed).
+BIG_CASE = (128, 128, 256, 0, 0, 1, 64, 42, 4096, 0.2, 0.0, 3.0, 0.0)
+BIG_TRAIN_ROWS = 192
+
+
+def make_big_x():
+    rng = np.random.default_rng(2026)
+    centres = (rng.standard_normal((24, 256)) * 0.6).astype(np.float32)
+    return (centres[rng.integers(0, 24, 4096)] + 0.25 * rng.standard_normal((4096, 256))).astype(np.float32)
 
 # W, H, Din, transform, decay, epochs, chunk, seed, n, eta0, etaDecay, sigma0, sigmaDecay
 # (the last three schedules decay into the sigma == 1 findLocalBmu regime)
@@ -35,10 +49,10 @@ CASES = [
 ]
 
 
-def write_case(path, case, x):
+def write_case(path, case, x, train_rows=0):
     W, H, Din, tr, dec, epochs, chunk, seed, n, eta0, eta_d, s0, s_d = case
     with open(path, "wb") as f:
-        f.write(struct.pack("<9i", W, H, Din, tr, dec, epochs, chunk, seed, n))
+        f.write(struct.pack("<10i", W, H, Din, tr, dec, epochs, chunk, seed, n, train_rows))
         f.write(struct.pack("<4d", eta0, eta_d, s0, s_d))
         f.write(np.ascontiguousarray(x, np.float32).tobytes())
 
@@ -75,17 +89,26 @@ def test_reference_driver_runs_on_cpu(tmp_path, case):
     assert os.path.getsize(tmp_path / "ref.bin") > expected_size(case)
 
 
+def run_b200(case_path, out_path, order):
+    """order: "reference" (sequential dot, = api_driver_ref) or "eigen_sse" (= api_driver_ref_sse); the host classes pick it
+    up from VSOM_REDUCTION_ORDER (include/SOM.hpp)."""
+    env = dict(os.environ, VSOM_REDUCTION_ORDER=order)
+    subprocess.run([B200_DRIVER, str(case_path), str(out_path)], check=True, timeout=600, env=env)
+
+
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("order", ["reference", "eigen_sse"])
 @pytest.mark.parametrize("case", CASES)
-def test_host_api_is_a_drop_in(tmp_path, vsom, case):
-    if not os.path.exists(REF_DRIVER):
-        pytest.skip("oracle/_ref/api_driver_ref not built (needs /root/reference)")
+def test_host_api_is_a_drop_in(tmp_path, vsom, case, order):
+    ref_driver = REF_DRIVER if order == "reference" else REF_DRIVER_SSE
+    if not os.path.exists(ref_driver):
+        pytest.skip(f"{ref_driver} not built (needs /root/reference)")
     vsom.lib()  # builds libvsom_b200.so, libvsom_host.so and the B200 driver when sources are newer
     assert os.path.exists(B200_DRIVER)
     write_case(tmp_path / "case.bin", case, make_x(case))
-    subprocess.run([REF_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "ref.bin")], check=True, timeout=300)
-    subprocess.run([B200_DRIVER, str(tmp_path / "case.bin"), str(tmp_path / "b200.bin")], check=True, timeout=300)
+    subprocess.run([ref_driver, str(tmp_path / "case.bin"), str(tmp_path / "ref.bin")], check=True, timeout=300)
+    run_b200(tmp_path / "case.bin", tmp_path / "b200.bin", order)
     ref = open(tmp_path / "ref.bin", "rb").read()
     got = open(tmp_path / "b200.bin", "rb").read()
     assert len(ref) > expected_size(case) and len(got) == len(ref)
@@ -93,3 +116,23 @@ def test_host_api_is_a_drop_in(tmp_path, vsom, case):
         a, b = np.frombuffer(ref, np.uint8), np.frombuffer(got, np.uint8)
         first = int(np.nonzero(a != b)[0][0])
         raise AssertionError(f"outputs differ in {int((a != b).sum())} bytes, first at byte {first} of {len(ref)}")
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("order", ["reference", "eigen_sse"])
+def test_host_api_large_map_scoring_takes_the_tensor_core_path(tmp_path, vsom, order):
+    """Som::evaluate / measureSimilarity / mapDataSet over 4096 rows at 128x128x256 reach vsom_find_bmu with a batch the
+    library scores on the tensor cores (K2); the driver's output must still be the reference's, byte for byte (pinned by the
+    committed SHA-256 of the reference drivers' outputs)."""
+    import hashlib
+    import json
+
+    golden = json.load(open(BIG_GOLDEN))
+    vsom.lib()
+    write_case(tmp_path / "case.bin", BIG_CASE, make_big_x(), BIG_TRAIN_ROWS)
+    assert hashlib.sha256(open(tmp_path / "case.bin", "rb").read()).hexdigest() == golden["case_sha256"], "the case file is not the one the golden was made from"
+    run_b200(tmp_path / "case.bin", tmp_path / "b200.bin", order)
+    got = open(tmp_path / "b200.bin", "rb").read()
+    assert len(got) == golden["bytes"]
+    assert hashlib.sha256(got).hexdigest() == golden[order], f"B200 output differs from the {order} reference driver's"

@@ -41,6 +41,7 @@ _PROTOS = {
     "vsom_debug_last_train_fast": (C.c_int, [_vp]),
     "vsom_debug_phase_cycles_raw": (C.c_int, [_vp, _f64p]),
     "vsom_debug_die_aware": (C.c_int, [_vp]),
+    "vsom_debug_measure_peaks": (C.c_int, [_vp, _f64p]),
     "vsom_debug_phase_cycles": (C.c_int, [_vp, _f64p]),
     "vsom_upload_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
     "vsom_download_state": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p, _u64p]),
@@ -56,8 +57,10 @@ _PROTOS = {
     "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
     "vsom_find_bmu_batch_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, _u64p]),
     "vsom_evaluate": (C.c_int, [_vp, _f32p, C.c_size_t, _f64p]),
+    "vsom_soft_assign": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _f64p]),
     "vsom_all_dists": (C.c_int, [_vp, _f32p, _f64p]),
     "vsom_update_umatrix": (C.c_int, [_vp, _f64p]),
+    "vsom_build_index_device": (C.c_int, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "vsom_build_index": (C.c_int, [_vp, _u32p, C.c_size_t, _u64p, _u64p, _u32p]),
 }
 
@@ -258,6 +261,13 @@ class VsomContext:
         self._check(lib().vsom_evaluate(self._h, _p(x, _f32p), x.shape[0], C.byref(out)))
         return out.value
 
+    def soft_assign(self, x, min_hits=0):
+        """Som::findRestrictedBmd per row: (n, N) probabilities."""
+        x = _f32(x).reshape(-1, self.Din)
+        out = np.empty((x.shape[0], self.N), np.float64)
+        self._check(lib().vsom_soft_assign(self._h, _p(x, _f32p), x.shape[0], min_hits, _p(out, _f64p)))
+        return out
+
     def all_dists(self, v):
         v = _f32(v).reshape(self.Din)
         out = np.empty(self.N, np.float64)
@@ -278,6 +288,10 @@ class VsomContext:
         rows = np.empty(n, np.uint32)
         self._check(lib().vsom_build_index(self._h, _p(bmu, _u32p), n, _p(counts, _u64p), _p(offsets, _u64p), _p(rows, _u32p)))
         return counts, offsets, rows
+
+    def build_index_device(self, bmu_dev, n, counts_dev, offsets_dev, row_ids_dev):
+        self._check(lib().vsom_build_index_device(self._h, bmu_dev.data_ptr(), n, counts_dev.data_ptr(), offsets_dev.data_ptr(),
+                                                  row_ids_dev.data_ptr() if row_ids_dev is not None else None))
 
     # ---- node sharding across GPUs
     def peer_export(self) -> bytes:
@@ -320,6 +334,12 @@ class VsomContext:
         else:
             names = ("wait_sample", "scan_min", "exchange", "broadcast", "update")
         return dict(zip(names, out.tolist()))
+
+    def measure_peaks(self):
+        """Measured on-chip read bandwidths of this device (GB/s): shared memory (all SMs / per SM) and L2."""
+        out = np.zeros(4, np.float64)
+        self._check(lib().vsom_debug_measure_peaks(self._h, _p(out, _f64p)))
+        return {"smem_gbs": out[0], "smem_gbs_per_sm": out[1], "l2_gbs": out[2], "l2_set_mib": out[3]}
 
     @property
     def die_aware(self) -> bool:

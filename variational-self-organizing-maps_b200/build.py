@@ -12,6 +12,9 @@ REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libvsom_b200.so")
+HOST_LIB = os.path.join(LIB_DIR, "libvsom_host.so")
+API_DRIVER = os.path.join(REPO, "tests", "cpp", "api_driver_b200")
+MNIST_TEST = os.path.join(REPO, "tests", "cpp", "mnist_loader_test")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -35,10 +38,10 @@ def sources():
 
 
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
+    if not (os.path.exists(LIB) and os.path.exists(HOST_LIB) and os.path.exists(API_DRIVER) and os.path.exists(MNIST_TEST)):
         return False
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(PKG, "host", "*.cpp")) + glob.glob(os.path.join(REPO, "include", "*.hpp")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(REPO, "include", "*.h")) + [os.path.abspath(__file__)]
+    t = min(os.path.getmtime(LIB), os.path.getmtime(HOST_LIB), os.path.getmtime(API_DRIVER), os.path.getmtime(MNIST_TEST))
+    deps = sources() + glob.glob(os.path.join(REPO, "tests", "cpp", "*.cpp")) + glob.glob(os.path.join(REPO, "include", "compat", "Eigen", "*")) + glob.glob(os.path.join(PKG, "host", "*.cpp")) + glob.glob(os.path.join(REPO, "include", "*.hpp")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(REPO, "include", "*.h")) + [os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
@@ -75,8 +78,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-HOST_LIB = os.path.join(LIB_DIR, "libvsom_host.so")
-API_DRIVER = os.path.join(REPO, "tests", "cpp", "api_driver_b200")
 
 
 def build_host() -> str:
@@ -90,12 +91,13 @@ def build_host() -> str:
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if out.returncode != 0:
         raise RuntimeError(f"host library failed to build:\n{out.stdout}")
-    drv = os.path.join(REPO, "tests", "cpp", "api_driver.cpp")
-    if os.path.exists(drv):
-        cmd = [cxx, *flags, drv, "-o", API_DRIVER, "-L", LIB_DIR, "-lvsom_host", "-lvsom_b200", f"-Wl,-rpath,{LIB_DIR}", *stdcxx]
-        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if out.returncode != 0:
-            raise RuntimeError(f"api driver failed to build:\n{out.stdout}")
+    for src, exe, defs in ((os.path.join(REPO, "tests", "cpp", "api_driver.cpp"), API_DRIVER, ["-DVSOM_B200_API"]),
+                           (os.path.join(REPO, "tests", "cpp", "mnist_loader_test.cpp"), MNIST_TEST, [])):
+        if os.path.exists(src):
+            cmd = [cxx, *flags, *defs, src, "-o", exe, "-L", LIB_DIR, "-lvsom_host", "-lvsom_b200", f"-Wl,-rpath,{LIB_DIR}", *stdcxx]
+            out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if out.returncode != 0:
+                raise RuntimeError(f"{os.path.basename(src)} failed to build:\n{out.stdout}")
     return HOST_LIB
 
 

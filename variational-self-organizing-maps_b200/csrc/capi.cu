@@ -783,6 +783,37 @@ int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out)
     return VSOM_OK;
 }
 
+int vsom_soft_assign(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, double *out_prob)
+{
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, kUnshardedOnly);
+    if (!ctx || (!x && n) || (!out_prob && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_soft_assign: NULL argument") : VSOM_ERR_INVALID;
+    if (n == 0)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = ctx->N, batch = std::max<size_t>(1, std::min<size_t>(n, (size_t{256} << 20) / (sizeof(double) * N))); // <= 256 MiB of probabilities at a time
+    int rc = stage_reserve(ctx, 0, sizeof(float) * batch * ctx->Din);
+    if (rc)
+        return rc;
+    rc = stage_reserve(ctx, 5, sizeof(double) * (batch * N + batch));
+    if (rc)
+        return rc;
+    float *xDev = static_cast<float *>(ctx->stage[0]);
+    double *probDev = static_cast<double *>(ctx->stage[5]), *sumsDev = probDev + batch * N;
+    for (size_t r0 = 0; r0 < n; r0 += batch)
+    {
+        const size_t rows = std::min(batch, n - r0);
+        VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x + r0 * ctx->Din, sizeof(float) * rows * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_soft_assign(ctx, xDev, rows, min_hits, probDev, sumsDev);
+        if (rc)
+            return rc;
+        VSOM_CUDA(ctx, cudaMemcpyAsync(out_prob + r0 * N, probDev, sizeof(double) * rows * N, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return VSOM_OK;
+}
+
 // per-grid-row pointer tables of K4 (umatrix.cu): [H] mean rows, [H] sigma rows, [localRows] grid rows to compute.  A
 // node-sharded context reads its neighbours' border rows from the halo buffer (filled by fetch_halo below).
 static int umatrix_tables(vsom_ctx *ctx)
@@ -874,6 +905,16 @@ int vsom_update_umatrix(vsom_ctx *ctx, double *out)
         }
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VSOM_OK;
+}
+
+int vsom_build_index_device(vsom_ctx *ctx, const uint32_t *bmu_dev, size_t n, uint64_t *counts_dev, uint64_t *offsets_dev, uint32_t *row_ids_dev)
+{
+    if (ctx && ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, kUnshardedOnly);
+    if (!ctx || (!bmu_dev && n) || !counts_dev || !offsets_dev)
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_build_index_device: NULL argument") : VSOM_ERR_INVALID;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_build_index(ctx, bmu_dev, n, reinterpret_cast<u64 *>(counts_dev), reinterpret_cast<u64 *>(offsets_dev), row_ids_dev);
 }
 
 int vsom_build_index(vsom_ctx *ctx, const uint32_t *bmu, size_t n, uint64_t *counts, uint64_t *offsets, uint32_t *row_ids)

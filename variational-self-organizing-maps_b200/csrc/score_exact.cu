@@ -343,6 +343,67 @@ __global__ void all_dists_kernel(const float *__restrict__ v, const float *__res
     out[node] = static_cast<double>(dist_ordered<TR>(mean + static_cast<size_t>(node) * rowStride, v, Dr, P, pairI, pairJ, order));
 }
 
+// ---------------------------------------------------------------------------------------- soft assignment
+// Som::findRestrictedBmd (src/Som.cpp:457-487) for a batch of rows: p_i = exp(-d_i * d_i / 2) of the (already squared)
+// distance for nodes with hits >= minHits, 0 otherwise, normalised by their sum.  One thread per (row, node) for the
+// distances (exact f32 chain in the context's order) and exp in f64; then one thread per row adds the N terms in node
+// order like the reference's loop (the f64 sum is order dependent) and the row is scaled.
+template <int TR>
+__global__ void soft_assign_terms_kernel(const float *__restrict__ x, u64 n, const float *__restrict__ mean, const u64 *__restrict__ hits, u64 minHits, int N,
+                                         int Din, int Dr, int P, int rowStride, const unsigned short *__restrict__ pairI, const unsigned short *__restrict__ pairJ,
+                                         int order, double *__restrict__ out)
+{
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 row = blockIdx.y;
+    if (node >= N || row >= n)
+        return;
+    double pr = 0.0;
+    if (hits[node] >= minHits)
+    {
+        const double d = static_cast<double>(dist_ordered<TR>(mean + static_cast<size_t>(node) * rowStride, x + row * Din, Dr, P, pairI, pairJ, order));
+        pr = exp(__ddiv_rn(__dmul_rn(-d, d), 2.0));
+    }
+    out[row * N + node] = pr;
+}
+
+__global__ void soft_assign_norm_kernel(u64 n, int N, double *__restrict__ prob, double *__restrict__ sums)
+{
+    __shared__ double C;
+    const u64 row = blockIdx.x;
+    if (row >= n)
+        return;
+    double *pr = prob + row * N;
+    if (threadIdx.x == 0)
+    {
+        double c = 0.0;
+        for (int i = 0; i < N; ++i)
+            c = __dadd_rn(c, pr[i]);
+        C = c;
+        sums[row] = c;
+    }
+    __syncthreads();
+    const double c = C;
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        pr[i] = __ddiv_rn(pr[i], c);
+}
+
+int launch_soft_assign(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, double *probDev, double *sumsDev)
+{
+    if (n == 0)
+        return VSOM_OK;
+    dim3 grid((ctx->N + 127) / 128, static_cast<unsigned>(n));
+    if (ctx->transform == VSOM_CLR)
+        soft_assign_terms_kernel<VSOM_CLR><<<grid, 128, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI,
+                                                                          ctx->pairJ, ctx->order, probDev);
+    else
+        soft_assign_terms_kernel<VSOM_STANDARD><<<grid, 128, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride,
+                                                                               ctx->pairI, ctx->pairJ, ctx->order, probDev);
+    soft_assign_norm_kernel<<<static_cast<unsigned>(n), 256, 0, ctx->stream>>>(n, ctx->N, probDev, sumsDev);
+    VSOM_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return VSOM_OK;
+}
+
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev)
 {
     if (n == 0)

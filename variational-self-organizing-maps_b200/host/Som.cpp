@@ -12,8 +12,10 @@
 #include <cctype>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <fstream>
 #include <iostream>
+#include <random>
 #include <stdexcept>
 
 struct Som::Device
@@ -47,6 +49,61 @@ void unflatten(const std::vector<float> &flat, std::vector<Eigen::VectorXf> &row
 {
     for (size_t p = 0; p < rows.size(); ++p)
         std::memcpy(rows[p].data(), flat.data() + p * depth, depth * sizeof(float));
+}
+// the order dot() has in the Eigen this translation unit sees (see the note at the top of SOM.hpp)
+int defaultReductionOrder()
+{
+    if (const char *e = std::getenv("VSOM_REDUCTION_ORDER"))
+    {
+        const std::string v(e);
+        if (v == "eigen_sse")
+            return VSOM_ORDER_EIGEN_SSE;
+        if (v == "lanes")
+            return VSOM_ORDER_LANES;
+        if (v == "reference" || v == "sequential")
+            return VSOM_ORDER_REFERENCE;
+    }
+#if !defined(VSOM_COMPAT_EIGEN_DENSE) || defined(VSOM_COMPAT_EIGEN_SSE_REDUX)
+    return VSOM_ORDER_EIGEN_SSE;
+#else
+    return VSOM_ORDER_REFERENCE;
+#endif
+}
+// f32 sum of squares in a given order, for the few reductions that stay on the host (binary cross-entropy term of evaluate)
+float orderedSquaredNorm(const std::vector<float> &t, int order)
+{
+    const size_t n = t.size();
+    if (order != VSOM_ORDER_EIGEN_SSE || n < 4)
+    {
+        float s = 0.0f;
+        for (float v : t)
+            s = s + v * v;
+        return s;
+    }
+    const size_t a2 = n / 8 * 8, a = n / 4 * 4;
+    float p0[4], p1[4];
+    for (size_t j = 0; j < 4; ++j)
+        p0[j] = t[j] * t[j];
+    if (a > 4)
+    {
+        for (size_t j = 0; j < 4; ++j)
+            p1[j] = t[4 + j] * t[4 + j];
+        for (size_t i = 8; i < a2; i += 8)
+            for (size_t j = 0; j < 4; ++j)
+            {
+                p0[j] = p0[j] + t[i + j] * t[i + j];
+                p1[j] = p1[j] + t[i + 4 + j] * t[i + 4 + j];
+            }
+        for (size_t j = 0; j < 4; ++j)
+            p0[j] = p0[j] + p1[j];
+        if (a > a2)
+            for (size_t j = 0; j < 4; ++j)
+                p0[j] = p0[j] + t[a2 + j] * t[a2 + j];
+    }
+    float s = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+    for (size_t i = a; i < n; ++i)
+        s = s + t[i] * t[i];
+    return s;
 }
 } // namespace
 
@@ -88,7 +145,7 @@ Som::Som(const Som &som)
     weightMap = som.weightMap;
     bmuHits = som.bmuHits;
     uMatrix = som.uMatrix;
-    reductionOrderLanes = som.reductionOrderLanes;
+    reductionOrder = som.reductionOrder;
     _isTraining.store(som._isTraining.load());
     hostIsStale = false;
     deviceIsStale = true; // the copy gets its own context on first use
@@ -109,7 +166,7 @@ Som &Som::operator=(const Som &other)
     height = other.height;
     width = other.width;
     depth = other.depth;
-    reductionOrderLanes = other.reductionOrderLanes;
+    reductionOrder = other.reductionOrder;
     _isTraining.store(other._isTraining.load());
     device.reset();
     hostIsStale = false;
@@ -145,7 +202,7 @@ vsom_ctx *Som::context() const
             throw std::runtime_error("Som: this Transformation is not one of the shipped factories (Standard, StandardMedianEstimator, "
                                      "CombinatorialLinearRegression); std::function strategies cannot run on the device and there is no CPU fallback");
         const int rc = vsom_create(&device->ctx, 0, static_cast<int>(width), static_cast<int>(height), static_cast<int>(inputLength()),
-                                   static_cast<int>(kind), reductionOrderLanes ? VSOM_ORDER_LANES : VSOM_ORDER_REFERENCE);
+                                   static_cast<int>(kind), getReductionOrder());
         if (rc != VSOM_OK)
             throw std::runtime_error(std::string("Som: vsom_create failed: ") + vsom_last_error(nullptr));
         deviceIsStale = true;
@@ -179,15 +236,21 @@ void Som::pull() const
     hostIsStale = false;
 }
 
-void Som::setFastReductionOrder(bool lanes)
+int Som::getReductionOrder() const { return reductionOrder >= 0 ? reductionOrder : defaultReductionOrder(); }
+
+void Som::setReductionOrder(int order)
 {
-    if (lanes == reductionOrderLanes)
+    if (order < VSOM_ORDER_REFERENCE || order > VSOM_ORDER_EIGEN_SSE)
+        throw std::invalid_argument("Som::setReductionOrder: 0 (sequential), 1 (lanes) or 2 (Eigen SSE2)");
+    if (order == getReductionOrder() && reductionOrder >= 0)
         return;
     pull();
     device.reset();
     deviceIsStale = true;
-    reductionOrderLanes = lanes;
+    reductionOrder = order;
 }
+
+void Som::setFastReductionOrder(bool lanes) { setReductionOrder(lanes ? VSOM_ORDER_LANES : VSOM_ORDER_REFERENCE); }
 
 // Som::randomInitialize of the reference (src/Som.cpp:977-997): host-side, glibc rand() in node-major order,
 // so that the initial planes are the reference's for the same seed.
@@ -540,16 +603,16 @@ double Som::evaluate(const DataSet &dataset) const
         const Eigen::VectorXf x = dataset.getData(i);
         const Eigen::VectorXi ok = dataset.getValidity(i);
         const Eigen::ArrayXi cont = dataset.getContinuous();
-        float ce2 = 0.0f;
+        std::vector<float> ce(static_cast<size_t>(x.size()));
         for (Eigen::Index k = 0; k < x.size(); ++k)
         {
             const float m = map[bmu[i]][k];
             float e = std::log(m) * x[k] + std::log(1.0f - m) * (1.0f - x[k]);
             if (std::isnan(e) || std::isinf(e))
                 e = -99999;
-            e = e * static_cast<float>(binary[k]) * static_cast<float>(ok[k] * cont[k]);
-            ce2 = ce2 + e * e;
+            ce[static_cast<size_t>(k)] = e * static_cast<float>(binary[k]) * static_cast<float>(ok[k] * cont[k]);
         }
+        const float ce2 = orderedSquaredNorm(ce, getReductionOrder()); // binaryError.dot(binaryError), src/Som.cpp:519
         error += 1. / (static_cast<double>(i) + 1.0) * (static_cast<double>(dist[i]) + std::sqrt(ce2) - error);
     }
     return error;
@@ -575,6 +638,7 @@ int Som::measureSimilarity(const DataSet *dataset, int numberOfSigmas, size_t mi
     auto visit = [&](size_t i, bool judge) {
         const float *v = dataset->contiguousRows() + i * D;
         const Eigen::VectorXf &m = map[bmu[i]], &sg = sigmaMap[bmu[i]];
+        const Eigen::VectorXi ok = dataset->getValidity(i);
         for (size_t d = 0; d < D; ++d)
         {
             const float sM = sg[d] > 0.00001f ? 0.00001f : sg[d];
@@ -584,7 +648,8 @@ int Som::measureSimilarity(const DataSet *dataset, int numberOfSigmas, size_t mi
                 largest = static_cast<float>(std::fabs(static_cast<double>(delta)));
                 largestRow = i;
             }
-            if (judge && (v[d] < m[d] - sM * k || v[d] > m[d] + sM * k))
+            // only columns that are present in the row are judged (src/Som.cpp:697-703)
+            if (judge && ok[static_cast<Eigen::Index>(d)] && (v[d] < m[d] - sM * k || v[d] > m[d] + sM * k))
                 success = 0;
         }
     };
@@ -594,8 +659,59 @@ int Som::measureSimilarity(const DataSet *dataset, int numberOfSigmas, size_t mi
     return success;
 }
 
-int Som::autoEncoder(const DataSet *, size_t) const { offPath("autoEncoder"); }
-size_t Som::variationalAutoEncoder(const DataSet *, size_t) const { offPath("variationalAutoEncoder"); }
+// reference src/Som.cpp:525-566.  Every row's distribution is computed and sampled there, but only the LAST row's sample
+// is returned and the generator is freshly seeded from std::random_device on every call, so the earlier rows have no
+// observable effect: the device computes the last row's soft assignment (vsom_soft_assign) and one sample is drawn on
+// the host exactly like the reference draws it (std::mt19937 + std::discrete_distribution).
+size_t Som::variationalAutoEncoder(const DataSet *dataset, size_t minBmuHits) const
+{
+    const size_t rows = dataset->size();
+    if (rows == 0)
+        return 0;
+    vsom_ctx *ctx = context();
+    std::vector<double> probability(width * height);
+    const float *lastRow = dataset->contiguousRows() + (rows - 1) * dataset->vectorLength();
+    if (vsom_soft_assign(ctx, lastRow, 1, minBmuHits, probability.data()) != VSOM_OK)
+        fail(ctx, "Som::variationalAutoEncoder");
+    std::random_device rd;
+    std::mt19937 gen(rd());
+    std::discrete_distribution<size_t> d(probability.begin(), probability.end());
+    return d(gen);
+}
+
+// reference src/Som.cpp:568-623: per row, a model vector drawn from the (last row's, see above) soft assignment, then per
+// column the record value and a logistic approximation of a normal sample around that neuron, printed to std::cout.
+int Som::autoEncoder(const DataSet *dataset, size_t minBmuHits) const
+{
+    const size_t rows = dataset->size();
+    if (rows == 0)
+        return 1;
+    vsom_ctx *ctx = context();
+    std::vector<double> probability(width * height);
+    const float *lastRow = dataset->contiguousRows() + (rows - 1) * dataset->vectorLength();
+    if (vsom_soft_assign(ctx, lastRow, 1, minBmuHits, probability.data()) != VSOM_OK)
+        fail(ctx, "Som::autoEncoder");
+    pull();
+    std::srand(static_cast<unsigned>(std::time(nullptr) + std::clock()));
+    std::random_device rd;
+    std::mt19937 gen(rd());
+    std::discrete_distribution<size_t> draw(probability.begin(), probability.end());
+    for (size_t i = 0; i < rows; ++i)
+    {
+        const Eigen::VectorXf v = dataset->getData(i);
+        const size_t node = draw(gen);
+        for (Eigen::Index n = 0; n < v.size(); ++n)
+        {
+            std::cout << v(n) << "\n";
+            const double L = static_cast<double>(std::rand() % 1000) / 1000;
+            const double N = std::log(L / (1 - L)) / 1.6 * sigmaMap[node][n] + map[node][n];
+            std::cout << dataset->getName(static_cast<size_t>(n)) << "\t" << N << "\t"
+                      << "\n";
+        }
+        std::cout << "\n";
+    }
+    return 1;
+}
 
 // ------------------------------------------------------------------------------------------------ U-matrix
 
