@@ -52,7 +52,10 @@ static int check_error_flag(vsom_ctx *ctx, const char *what)
     VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flag)
+    {
+        ctx->poisoned = true; // only the online step raises the flag through this path (vsom_build_index re-maps it and clears this)
         return set_error(ctx, VSOM_ERR_TIMEOUT, std::string(what) + ": device reported an error flag");
+    }
     return VSOM_OK;
 }
 
@@ -446,6 +449,11 @@ int vsom_synchronize(vsom_ctx *ctx)
         return VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->trainEnqueued) // a chunk enqueued by vsom_train_chunk_device may have aborted: report it here
+    {
+        ctx->trainEnqueued = false;
+        return check_error_flag(ctx, "vsom_synchronize (after vsom_train_chunk_device)");
+    }
     return VSOM_OK;
 }
 
@@ -519,6 +527,7 @@ int vsom_train_chunk_device(vsom_ctx *ctx, const float *x_dev, size_t n, double 
     if (!ctx || (!x_dev && n))
         return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_train_chunk_device: x is NULL") : VSOM_ERR_INVALID;
     VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->trainEnqueued = true;
     return launch_online_step(ctx, x_dev, n, eta, sigma, decay, out_bmu_dev, out_dist_dev);
 }
 
@@ -951,7 +960,10 @@ int vsom_build_index(vsom_ctx *ctx, const uint32_t *bmu, size_t n, uint64_t *cou
         VSOM_CUDA(ctx, cudaMemcpyAsync(row_ids, rowDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
     rc = check_error_flag(ctx, "vsom_build_index");
     if (rc)
+    {
+        ctx->poisoned = false;
         return set_error(ctx, VSOM_ERR_INVALID, "vsom_build_index: a BMU id is >= width*height");
+    }
     return VSOM_OK;
 }
 

@@ -51,7 +51,7 @@ struct StepParams
     float *outDist;           // per sample, may be null
     int resident;             // planes of the owned nodes live in shared memory for the whole chunk
     int smStride;             // row stride (floats) of the resident copy
-    long long timeoutCycles;
+    long long timeoutCycles, peerTimeoutCycles; // waiting for a CTA of this launch / for another rank's launch
     int lutSmem, lutCount;    // copy the table into shared memory (it fits behind the resident rows)
     int xVec;                 // sample rows are 16-byte aligned: 16-byte cp.async
     int order;                // vsom_reduction_order of the distances
@@ -119,6 +119,8 @@ struct vsom_ctx
     // grow-only device staging for the host entry points
     void *stage[10] = {};
     size_t stageCap[10] = {};
+    bool trainEnqueued = false;              // vsom_train_chunk_device work not yet checked for an abort
+    bool poisoned = false;                   // an online-step chunk aborted: the context refuses further chunks
     int lastScoreTc = 0;                     // the last scoring call ran K2 (tensor-core search + exact rescore)
     unsigned long long lastFallbackRows = 0; // rows of the last tensor-core scoring call that needed the exact full scan
     int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;

@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <string>
 
 namespace vsom
@@ -634,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                     gv = lane < p.world ? ld_relaxed_sys(grow + lane) : ((~0ull << 8) | gtag);
                     if (__all_sync(0xffffffffu, static_cast<unsigned>(gv & 0xff) == gtag))
                         break;
-                    if (__any_sync(0xffffffffu, clock64() - g0 > p.timeoutCycles))
+                    if (__any_sync(0xffffffffu, clock64() - g0 > p.peerTimeoutCycles)) // ranks start their chunks at different times
                     {
                         abort = true;
                         break;
@@ -1225,7 +1226,17 @@ int launch_online_step(vsom_ctx *ctx, const float *xDev, size_t n, double eta, d
     p.outDist = outDistDev;
     p.resident = ctx->residentTrain;
     p.smStride = ctx->smStrideTrain;
-    p.timeoutCycles = 4000000000ll; // ~2 s at 1.9 GHz: a peer CTA that never publishes is a bug, not a wait
+    p.timeoutCycles = 4000000000ll; // ~2 s at 1.9 GHz: a peer CTA of the same launch that never publishes is a bug, not a wait
+    {
+        // other RANKS launch their chunk from their own process: a pageable H2D copy, a buffer re-allocation or a scheduler
+        // stall on one of them delays its first key by far more than a CTA ever lags.  Default 60 s, VSOM_PEER_TIMEOUT_S overrides.
+        const char *e = getenv("VSOM_PEER_TIMEOUT_S");
+        const double secs = e && atof(e) > 0 ? atof(e) : 60.0;
+        p.peerTimeoutCycles = static_cast<long long>(secs * 2.0e9);
+    }
+    if (ctx->poisoned)
+        return set_error(ctx, VSOM_ERR_TIMEOUT, "online step: an earlier chunk of this context aborted (a CTA or a rank never published its key); "
+                                                "the map and the cross-rank step counter are no longer consistent — re-create the context");
     p.localSearch = localSearch ? 1 : 0;
     p.distBuf = ctx->distBuf;
     p.lastIn = lastInDev;

@@ -329,8 +329,13 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         p.rowOf[b] = die * kFMaxCtas + static_cast<int>(idx);
         __threadfence();
         atomicAdd(p.rowCtr + 2, 1u);
+        const long long b0 = clock64();
         while (ld_relaxed_gpu_u32(p.rowCtr + 2) < static_cast<unsigned>(G))
-            ;
+            if (clock64() - b0 > p.timeoutCycles) // cooperative launch: all CTAs are resident, so this is a bug, not a wait
+            {
+                *p.err = 1;
+                break;
+            }
         __threadfence();
     }
     if (p.lutSmem)
@@ -641,10 +646,16 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
                         const unsigned want = t + 1u;
                         const unsigned bmu = local_bmu_walk(
                             [&](u64 i) {
-                                u64 w;
-                                do
-                                    w = ld_relaxed_gpu(dt + i);
-                                while (static_cast<unsigned>(w) != want);
+                                u64 w = ld_relaxed_gpu(dt + i);
+                                if (static_cast<unsigned>(w) != want) // written by a CTA whose key this CTA has already seen: a re-read or two
+                                {
+                                    const long long w0 = clock64();
+                                    do
+                                        w = ld_relaxed_gpu(dt + i);
+                                    while (static_cast<unsigned>(w) != want && clock64() - w0 < p.timeoutCycles);
+                                    if (static_cast<unsigned>(w) != want)
+                                        *p.err = 1;
+                                }
                                 return __uint_as_float(static_cast<unsigned>(w >> 32));
                             },
                             static_cast<u64>(p.W), static_cast<u64>(p.H), p.lastIn ? p.lastIn[t] : 0ull);

@@ -7,6 +7,10 @@
 // staged by TMA (128-byte swizzle).  The tensor cores only SELECT candidates; the exact pass re-evaluates them in
 // the reference's own f32 arithmetic and order (bit-identical distances) and applies findBmu's lowest-index rule.
 //
+// The node constant rides in the contraction: the map operand holds -2 m_p (exact in bf16) followed by three columns with a
+// hi / mid / lo bf16 split of c_p = |m_p|^2 (24 bits), the row operand x followed by three ones, so the f32 accumulator IS the
+// approximate score a_p = c_p - 2 x^ . m^_p and the epilogue only takes minima (K = D + 3, rounded up to 16 per MMA).
+//
 // Candidate rule (margin list + certificate).  With approximate score a_p = c_p - 2 acc_p (c_p = |m_p|^2), the bf16
 // rounding of both operands gives |a_p + |x|^2 - d_p| <= E = 2 (2u + u^2) |x| max_p|m_p|, u = 2^-8 (Cauchy-Schwarz), i.e.
 // E = 2^-6 |x| max|m| plus a relative slack for every f32 effect (tensor-core accumulation, the norms, the reference's own
@@ -42,10 +46,12 @@ namespace vsom
 {
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 16, TC_THREADS = 384;
-constexpr int TC_LIST = 24;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
-constexpr int TC_LIST_HI = 12; // lists are compacted against the current threshold when one passes this length
+constexpr int TC_LIST = 16;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
+constexpr int TC_LIST_HI = 10; // lists are compacted against the current threshold when one passes this length
 constexpr unsigned TC_OVERFLOW = 255;
-constexpr int TC_MAXK = 256;
+constexpr int TC_MAXK = 256;   // longest model vector; the operands carry 3 more columns for the node constant (below)
+constexpr int TC_MAXKB = (TC_MAXK + 16 + TC_BK - 1) / TC_BK; // k-blocks of the extended operands at most (5)
+constexpr float TC_BIG = 1.0e38f; // node constant of nodes that must never be selected (padding, below min_hits)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB per k-block
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB per stage
 
@@ -137,17 +143,16 @@ __device__ __forceinline__ void tc_margins(float xn, float mx, int Kpad, float &
 struct TcShared
 {
     // offsets inside the dynamic shared buffer (1024-byte aligned base)
-    static constexpr int A_OFF = 0;                                   // up to 4 k-blocks x 16 KB
-    static constexpr int B_OFF = A_OFF + (TC_MAXK / TC_BK) * TC_A_BYTES; // 4 stages x 32 KB
-    static constexpr int CN_OFF = B_OFF + TC_STAGES * TC_B_BYTES;      // 2 x 256 floats
-    static constexpr int BAR_OFF = CN_OFF + 2 * TC_BN * 4;             // mbarriers
+    static constexpr int A_OFF = 0;                                   // up to 5 k-blocks x 16 KB
+    static constexpr int B_OFF = A_OFF + TC_MAXKB * TC_A_BYTES;        // 3 stages x 32 KB
+    static constexpr int BAR_OFF = B_OFF + TC_STAGES * TC_B_BYTES;     // mbarriers
     static constexpr int LIST_OFF = BAR_OFF + 256;                     // TC_LIST x 256 x {score, node}: per-thread candidate lists
     static constexpr int MERGE_OFF = LIST_OFF + TC_LIST * 256 * 8;     // 256 floats + 256 ints: merge of the two half rows
     static constexpr int TOTAL = MERGE_OFF + 256 * 8;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, const float *__restrict__ cnorm, int rowsTotal,
+score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, int kSteps, int rowsTotal,
                 int numRowTiles, int numNodeTiles, int kBlocks, int stagger, const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, unsigned *__restrict__ candOut,
                 unsigned *__restrict__ countOut, float *__restrict__ bestOut, int *err)
 {
@@ -156,7 +161,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *sA = smem + TcShared::A_OFF;
     unsigned char *sB = smem + TcShared::B_OFF;
-    float *sCn = reinterpret_cast<float *>(smem + TcShared::CN_OFF);
     u64 *bars = reinterpret_cast<u64 *>(smem + TcShared::BAR_OFF);
     u64 *bFull = bars, *bEmpty = bars + TC_STAGES, *aFull = bars + 2 * TC_STAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
     unsigned *tmemBaseSlot = reinterpret_cast<unsigned *>(tEmpty + 2);
@@ -246,13 +250,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         ok = mbar_wait(&bFull[stage], phase, err);
                         tc_fence_after();
                         const unsigned aAddr = smem_u32(sA + kb * TC_A_BYTES), bAddr = smem_u32(sB + stage * TC_B_BYTES);
+                        const int steps = min(TC_BK / 16, kSteps - kb * (TC_BK / 16)); // the last k-block may be partly used
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)
-                        {
-                            // +32 bytes per K=16 step inside the 128-byte swizzle row
-                            const u64 da = umma_desc_sw128(aAddr + k * 32), db = umma_desc_sw128(bAddr + k * 32);
-                            umma_f16(tmemC, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
-                        }
+                            if (k < steps)
+                            {
+                                // +32 bytes per K=16 step inside the 128-byte swizzle row
+                                const u64 da = umma_desc_sw128(aAddr + k * 32), db = umma_desc_sw128(bAddr + k * 32);
+                                umma_f16(tmemC, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                            }
                         umma_commit(&bEmpty[stage]); // frees the B stage when the MMAs above have read it
                         if (++stage == TC_STAGES)
                         {
@@ -321,14 +327,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             for (int i = 0; i < numNodeTiles && ok; ++i)
             {
                 const int nt = (i + ntStart) % numNodeTiles;
-                // per-node constants of this tile
-                float *cn = sCn + acc * TC_BN;
-                cn[et] = cnorm[nt * TC_BN + et];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
                 ok = mbar_wait(&tFull[acc], accPhase, err);
                 tc_fence_after();
                 const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
-                const float *cnh = cn + half * (TC_BN / 2);
                 unsigned v[2][32];
                 if ((stagger & 2) == 0) // bit 1 of the debug word: skip the column work (pipeline-only timing)
                 {
@@ -347,29 +348,24 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         }
                         unsigned(&w)[32] = v[c & 1];
                         const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
-                        // All 32 scores of the chunk and the per-group minima first (independent instructions, no
-                        // branch).  gm = groups of four columns in which this row may have something to append.
-                        unsigned gm = 0;
-                        float cm = inf;
+                        // The accumulators ARE the scores.  Group minima (of four columns) and the chunk minimum first: a tree of
+                        // independent min instructions (FMNMX3 where it fits), nothing else on the common path.
+                        float m4[8];
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
-                        {
-                            const float4 k4 = *reinterpret_cast<const float4 *>(cnh + c * 32 + j4 * 4);
-                            const float s0 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 0]), k4.x);
-                            const float s1 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 1]), k4.y);
-                            const float s2 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 2]), k4.z);
-                            const float s3 = fmaf(-2.0f, __uint_as_float(w[j4 * 4 + 3]), k4.w);
-                            w[j4 * 4 + 0] = __float_as_uint(s0);
-                            w[j4 * 4 + 1] = __float_as_uint(s1);
-                            w[j4 * 4 + 2] = __float_as_uint(s2);
-                            w[j4 * 4 + 3] = __float_as_uint(s3);
-                            const float m4 = fminf(fminf(s0, s1), fminf(s2, s3));
-                            gm |= (m4 < thr) ? (1u << j4) : 0u; // against the (valid, possibly stale) old threshold
-                            cm = fminf(cm, m4);
-                        }
+                            m4[j4] = fminf(fminf(__uint_as_float(w[j4 * 4 + 0]), __uint_as_float(w[j4 * 4 + 1])),
+                                           fminf(__uint_as_float(w[j4 * 4 + 2]), __uint_as_float(w[j4 * 4 + 3])));
+                        const float cm = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+                        const float thrOld = thr; // valid, possibly stale: whatever must be appended lies below it
                         // the chunk's own minimum tightens the threshold BEFORE anything is appended
                         best = fminf(best, cm);
                         thr = best + delta;
+                        if (!__any_sync(0xffffffffu, cm < thrOld))
+                            continue; // no lane of the warp has a candidate in this chunk (the common case once the rows have settled)
+                        unsigned gm = 0; // groups of four columns in which this row may have something to append
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            gm |= (m4[j4] < thrOld) ? (1u << j4) : 0u;
                         // one REDUX tells the whole warp which groups need the (predicated) appends; the branches
                         // below are on a warp-uniform value
                         const unsigned any = __reduce_or_sync(0xffffffffu, gm);
@@ -440,8 +436,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
 // ------------------------------------------------------------------------------------------------ operand preparation
 
-// rows of f32 -> bf16 (zero padded to Kpad), optional |row|^2 (f32, any order: only used by the guard)
-__global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long rows, int D, int srcStride, __nv_bfloat16 *__restrict__ dst, int Kpad,
+// rows of f32 -> bf16 operand rows of Kpad columns: scale * row (scale = 1 for the data rows, -2 for the map: exact in
+// bf16), then `tail` in the three columns D .. D+2 (1 for the data rows — they multiply the node constant — 0 for the map,
+// whose constant columns node_const_kernel fills), zeros behind.  Optional |row|^2 (f32, any order: margins only).
+__global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long rows, int D, int srcStride, float scale, float tail, __nv_bfloat16 *__restrict__ dst, int Kpad,
                                     float *__restrict__ norm2)
 {
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -452,7 +450,7 @@ __global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long row
     for (int k = lane; k < Kpad; k += 32)
     {
         const float v = k < D ? src[row * srcStride + k] : 0.0f;
-        dst[row * Kpad + k] = __float2bfloat16_rn(v);
+        dst[row * Kpad + k] = __float2bfloat16_rn(k < D ? scale * v : (k < D + 3 ? tail : 0.0f));
         s += v * v;
     }
     for (int o = 16; o; o >>= 1)
@@ -461,20 +459,29 @@ __global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long row
         norm2[row] = s;
 }
 
-// per-node constant of the score: |m_p|^2 for nodes that may win, +inf for padding and for nodes below min_hits
-// (node 0 always competes: it seeds findRestrictedBmu regardless of its hit count, src/Som.cpp:316-322)
-__global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__restrict__ hits, u64 minHits, int N, int Npad, float *__restrict__ cnorm,
-                                  float *__restrict__ maxNorm2)
+// node constant of the score, written into the map operand's columns D .. D+2 as a hi / mid / lo bf16 split (8 + 8 + 8
+// bits: the three products with the data rows' ones add up to c_p in the f32 accumulator): |m_p|^2 for nodes that may win,
+// TC_BIG for padding rows and for nodes below min_hits (node 0 always competes: it seeds findRestrictedBmu regardless of
+// its hit count, src/Som.cpp:316-322)
+__global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__restrict__ hits, u64 minHits, int N, int Npad, int D, int Kpad,
+                                  __nv_bfloat16 *__restrict__ Mb, float *__restrict__ maxNorm2)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= Npad)
         return;
-    float c = __int_as_float(0x7f800000);
+    float c = TC_BIG;
     if (p < N && (p == 0 || minHits == 0 || hits[p] >= minHits))
-        c = norm2[p];
-    cnorm[p] = c;
+        c = fminf(norm2[p], TC_BIG); // a NaN norm (NaN in the map) becomes TC_BIG: that node cannot win in the reference either
+    const __nv_bfloat16 hi = __float2bfloat16_rn(c);
+    const float r1 = c - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    __nv_bfloat16 *row = Mb + static_cast<size_t>(p) * Kpad + D;
+    row[0] = hi;
+    row[1] = mid;
+    row[2] = lo;
     if (p < N)
-        atomicMax(reinterpret_cast<int *>(maxNorm2), __float_as_int(norm2[p])); // non-negative floats order like ints
+        atomicMax(reinterpret_cast<int *>(maxNorm2), __float_as_int(fminf(norm2[p], TC_BIG))); // non-negative floats order like ints
 }
 
 // ------------------------------------------------------------------------------------------------ exact rescore + certificate
@@ -654,12 +661,12 @@ bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR
 // stage slots used: 6 = bf16 map + node constants, 7 = bf16 rows of the current slab, 8 = per-row scratch (two sets).
 struct TcCall
 {
-    int D = 0, N = 0, Kpad = 0, kBlocks = 0, Npad = 0, nodeTiles = 0, stagger = 1;
+    int D = 0, N = 0, Kpad = 0, kBlocks = 0, kSteps = 0, Npad = 0, nodeTiles = 0, stagger = 1;
     bool overlap = true;
     uint64_t minHits = 0;
     size_t slabRows = 0, setBytes = 0, slab = 0;
     __nv_bfloat16 *Xb = nullptr;
-    float *cnorm = nullptr, *maxNorm2 = nullptr;
+    float *maxNorm2 = nullptr;
     unsigned long long *totalDev = nullptr;
     CUtensorMap mapM;
 };
@@ -669,7 +676,8 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     const int D = ctx->Dm, N = ctx->N;
     c.D = D;
     c.N = N;
-    c.Kpad = (D + TC_BK - 1) / TC_BK * TC_BK;
+    c.kSteps = (D + 3 + 15) / 16;                 // K = 16 per MMA: the model vector + the three node-constant columns
+    c.Kpad = (c.kSteps * 16 + TC_BK - 1) / TC_BK * TC_BK; // operand rows are whole 128-byte swizzle rows
     c.kBlocks = c.Kpad / TC_BK;
     c.Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
     c.nodeTiles = c.Npad / TC_BN;
@@ -677,17 +685,16 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
 
     // ---- map side: bf16 copy, |m|^2, node constants, max |m|^2
     const size_t mbBytes = sizeof(__nv_bfloat16) * static_cast<size_t>(c.Npad) * c.Kpad;
-    int rc = stage_reserve(ctx, 6, mbBytes + sizeof(float) * (2 * static_cast<size_t>(c.Npad) + 64));
+    int rc = stage_reserve(ctx, 6, mbBytes + sizeof(float) * (static_cast<size_t>(c.Npad) + 64));
     if (rc)
         return rc;
     __nv_bfloat16 *Mb = static_cast<__nv_bfloat16 *>(ctx->stage[6]);
     float *mnorm = reinterpret_cast<float *>(static_cast<unsigned char *>(ctx->stage[6]) + mbBytes);
-    c.cnorm = mnorm + c.Npad;
-    c.maxNorm2 = c.cnorm + c.Npad;
+    c.maxNorm2 = mnorm + c.Npad;
     VSOM_CUDA(ctx, cudaMemsetAsync(Mb, 0, mbBytes, ctx->stream));
     VSOM_CUDA(ctx, cudaMemsetAsync(c.maxNorm2, 0, sizeof(float), ctx->stream));
-    to_bf16_rows_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, Mb, c.Kpad, mnorm);
-    node_const_kernel<<<(c.Npad + 255) / 256, 256, 0, ctx->stream>>>(mnorm, ctx->hits, minHits, N, c.Npad, c.cnorm, c.maxNorm2);
+    to_bf16_rows_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, -2.0f, 0.0f, Mb, c.Kpad, mnorm);
+    node_const_kernel<<<(c.Npad + 255) / 256, 256, 0, ctx->stream>>>(mnorm, ctx->hits, minHits, N, c.Npad, D, c.Kpad, Mb, c.maxNorm2);
     ctx->launches += 2;
     rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, TC_BN);
     if (rc)
@@ -751,7 +758,7 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
 
     if (c.slab >= 2)
         VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[par], 0)); // slab - 2 is done with this scratch set
-    to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), c.D, c.D, c.Xb, c.Kpad, xnorm);
+    to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), c.D, c.D, 1.0f, 1.0f, c.Xb, c.Kpad, xnorm);
     CUtensorMap mapX;
     int rc = make_map(ctx, &mapX, c.Xb, rows, c.Kpad, TC_BM);
     if (rc)
@@ -759,7 +766,7 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
     const int grid = std::min(rowTiles, ctx->numSMs);
     VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.cnorm, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.stagger, xnorm, c.maxNorm2,
+    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.kSteps, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.stagger, xnorm, c.maxNorm2,
                                                                         cand, candCount, bestA, ctx->errFlag);
     cudaStream_t rs = c.overlap ? ctx->auxStream : ctx->stream;
     VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
