@@ -488,12 +488,16 @@ def test_umatrix_division_corner_cases(vsom, po, Dm, order):
     rng = np.random.default_rng(Dm)
     W, H = 19, 6
     N = W * H
-    mags = np.float32([0.0, 1e-42, 1e-38, 3e-33, 1e-30, 1e-20, 1e-6, 1.0, 3.7, 1e6, 1e20, 1.3e30, 1e35, np.inf])
+    mags = np.float32([0.0, 1e-42, 1e-38, 3e-33, 1e-30, 1e-20, 1e-6, 1.0, 3.7, 1e6, 1e20, 1.3e30])
     mean = (rng.choice(mags, (N, Dm)) * rng.choice(np.float32([-1, 1]), (N, Dm)) + rng.standard_normal((N, Dm)).astype(np.float32) *
             rng.choice(np.float32([0, 0, 1e-3, 1]), (N, Dm))).astype(np.float32)
     mean[::5] = mean[1::5][: len(mean[::5])]  # exact zeros in many differences
-    sig_mags = np.float32([0.0, 1e-7, 1e-5, 1.0000001e-5, 1e-3, 0.5, 1.0, 3.0, 1e10, 1.2e30, 1.3e30, 1e38, np.inf])
+    sig_mags = np.float32([0.0, 1e-7, 1e-5, 1.0000001e-5, 1e-3, 0.5, 1.0, 3.0, 1e10, 1.2e30, 1.3e30, 1e38])
     sigma = rng.choice(sig_mags, (N, Dm)).astype(np.float32)
+    # a few cells that turn whole nodes into NaN / inf (inf - inf, inf / inf): present, but not everywhere
+    for cell in rng.integers(0, N * Dm, 6):
+        mean.flat[cell] = rng.choice(np.float32([1e35, np.inf, -np.inf]))
+        sigma.flat[(cell * 7) % (N * Dm)] = np.inf
     o = po.Oracle(W, H, Dm, 0, order)
     o.set_state(mean=mean, sigma=sigma)
     ctx = vsom.VsomContext(W, H, Dm, 0, order)

@@ -3,25 +3,35 @@
 // Replaces the same row loops as score_exact.cu (Som::evaluate src/Som.cpp:503-520, findBmu :291-309,
 // findRestrictedBmu :313-332 over a loaded DataSet) when the batch is large:
 //     d(r,p) = |x_r|^2 - 2 x_r . m_p + |m_p|^2            (Standard / Median Comparer, src/Transformation.cpp:7-8)
-// The cross term X[R x K] . M^T[K x N] runs as tcgen05.mma (bf16 operands, fp32 accumulators in TMEM), operands
+// The cross term X[R x K] . M^T[K x N] runs as tcgen05.mma (fp16 operands, fp32 accumulators in TMEM), operands
 // staged by TMA (128-byte swizzle).  The tensor cores only SELECT candidates; the exact pass re-evaluates them in
 // the reference's own f32 arithmetic and order (bit-identical distances) and applies findBmu's lowest-index rule.
 //
-// The node constant rides in the contraction: the map operand holds -2 m_p (exact in bf16) followed by three columns with a
-// hi / mid / lo bf16 split of c_p = |m_p|^2 (24 bits), the row operand x followed by three ones, so the f32 accumulator IS the
-// approximate score a_p = c_p - 2 x^ . m^_p and the epilogue only takes minima (K = D + 3, rounded up to 16 per MMA).
+// Operands are IEEE half (fp16, u = 2^-11), not bf16: same tensor-core rate, 8x tighter products — on a TRAINED map the
+// neighbours of the BMU differ from it by less than a bf16 product's error, and the candidate lists would hold the whole
+// neighbourhood.  fp16's narrow range is handled by power-of-two scales (exact): one per ROW of the data, s_r, putting the
+// row's largest |x_k| in [2^9, 2^10), and one for the map, s_m, likewise (values far below the largest one may become fp16
+// subnormals: their absolute error 2^-25 is part of the bound below).
 //
-// Candidate rule (margin list + certificate).  With approximate score a_p = c_p - 2 acc_p (c_p = |m_p|^2), the bf16
-// rounding of both operands gives |a_p + |x|^2 - d_p| <= E = 2 (2u + u^2) |x| max_p|m_p|, u = 2^-8 (Cauchy-Schwarz), i.e.
-// E = 2^-6 |x| max|m| plus a relative slack for every f32 effect (tensor-core accumulation, the norms, the reference's own
-// f32 chain).  While streaming over the node tiles each row keeps its running best score and appends every node with
-// a_p < best + Delta to a small per-row list (tc_margins: Delta = 1.25 E + slack).  Delta alone proves nothing; the proof
-// is the CERTIFICATE checked after the exact rescore: every node NOT in the list had a_q >= best_final + Delta, hence its
-// reference distance is >= best_final + |x|^2 + Delta - E.  If that bound is strictly above the best EXACT distance among
-// the listed nodes, no unlisted node can be the BMU or tie with it, and the row is done; otherwise the row is re-scored
-// by the exact full scan.  So the result never depends on a statistical recall argument: Delta only trades list length
-// against the share of rows that need the full scan.  Up to 16 survivors per row go to the exact rescore; rows with more
-// (or whose list overflowed) take the exact full scan as well.
+// The node constant rides in the contraction: the map operand holds -2 s_m m_p followed by three columns with a hi / mid / lo
+// fp16 split of s_m c_p / tau (c_p = |m_p|^2, tau a power of two that keeps the pieces inside fp16), the row operand s_r x
+// followed by three columns s_r tau, so the f32 accumulator IS the scaled approximate score
+//     a'_p = S_r (c_p - 2 x^ . m^_p),  S_r = s_r s_m,
+// and the epilogue only takes minima (K = D + 3, rounded up to 16 per MMA).  Everything per row (best, threshold, margins)
+// lives in that row's scaled units; powers of two commute with every comparison.
+//
+// Candidate rule (margin list + certificate).  |a'_p + S_r |x|^2 - S_r d_p| <= E', with
+//     E' = 2 (2u + u^2) |s_r x| max_p |s_m m_p|  +  2^-25 sqrt(D) (2 max|s_m m_p| + |s_r x|)  +  slack
+// (rounding of both operands + Cauchy-Schwarz; the subnormal term; a relative slack for every f32 effect: tensor-core
+// accumulation, the norms, the reference's own f32 chain).  While streaming over the node tiles each row keeps its running
+// best score and appends every node with a'_p < best + Delta' to a small per-row list (tc_margins: Delta' = 1.25 E' + slack).
+// Delta' alone proves nothing; the proof is the CERTIFICATE checked after the exact rescore: every node NOT in the list had
+// a'_q >= best_final + Delta', hence S_r times its reference distance is >= best_final + S_r |x|^2 + Delta' - E'.  If that
+// bound is strictly above S_r times the best EXACT distance among the listed nodes, no unlisted node can be the BMU or tie
+// with it, and the row is done; otherwise the row is re-scored by the exact full scan.  So the result never depends on a
+// statistical recall argument: Delta' only trades list length against the share of rows that need the full scan.  Up to
+// 16 survivors per row go to the exact rescore (which also re-checks min_hits eligibility, so nothing depends on the large
+// constant given to excluded nodes); rows with more (or whose list overflowed) take the exact full scan as well.
 //
 // Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
 //   warp 0   TMA producer : A tile (128 rows x K, resident for the row tile) + B tiles (256 nodes x 64) through a
@@ -36,7 +46,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
@@ -129,14 +139,26 @@ __device__ __forceinline__ u64 umma_desc_sw128(unsigned smemAddr)
 {
     return static_cast<u64>((smemAddr & 0x3ffff) >> 4) | (1ull << 16) | (static_cast<u64>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10), both K-major, N>>3 at 17, M>>4 at 24
-constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<unsigned>(TC_BN >> 3) << 17) | (static_cast<unsigned>(TC_BM >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=f16 (format 0 at bits 7 and 10; bf16 would be 1), both K-major, N>>3 at 17, M>>4 at 24
+constexpr unsigned kIdesc = (1u << 4) | (static_cast<unsigned>(TC_BN >> 3) << 17) | (static_cast<unsigned>(TC_BM >> 4) << 24);
 
-// Error bound E and list margin Delta of one row (see "Candidate rule" above).  xn = |x|^2, mx = max_p |m_p|^2.
-__device__ __forceinline__ void tc_margins(float xn, float mx, int Kpad, float &E, float &delta)
+// scales of one scoring call, computed on the device (tc_scale_kernel)
+struct TcScale
 {
-    const float slack = static_cast<float>(Kpad + 64) * 2.384185791015625e-7f * (xn + mx); // (K + 64) 2^-22 (|x|^2 + max|m|^2)
-    E = 0.0157f * sqrtf(xn * mx) + slack; // 2 (2u + u^2) = 2^-6 + 2^-15 < 0.0157
+    float sm;       // power of two: map values are multiplied by it
+    float tau;      // power of two: the node-constant columns hold s_m c_p / tau, the rows' tail columns s_r tau
+    float mm;       // max_p |s_m m_p|^2
+    float maxAbs;   // max |m_pk| (bits, via atomicMax) — input of the scale
+    float maxNorm2; // max_p |m_p|^2                   — input of the scale
+};
+
+// Error bound E' and list margin Delta' of one row in its scaled units (see "Candidate rule" above).
+// xn = |s_r x|^2, mm = max_p |s_m m_p|^2, ratio = s_m / s_r (so that S_r |x|^2 = xn ratio and S_r max|m|^2 = mm / ratio).
+__device__ __forceinline__ void tc_margins(float xn, float mm, float ratio, int Kpad, int D, float &E, float &delta)
+{
+    const float slack = static_cast<float>(Kpad + 64) * 2.384185791015625e-7f * (xn * ratio + mm / ratio); // (K + 64) 2^-22 S (|x|^2 + max|m|^2)
+    const float sx = sqrtf(xn), smx = sqrtf(mm);
+    E = 0.00196f * sx * smx + 2.99e-8f * sqrtf(static_cast<float>(D)) * (2.0f * smx + sx) + slack; // 2 (2u + u^2) = 2^-9 (1 + 2^-12) < 0.00196; 2^-25 (1 + u) < 2.99e-8
     delta = 1.25f * E + 2.0f * slack;
 }
 
@@ -153,7 +175,8 @@ struct TcShared
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, int kSteps, int rowsTotal,
-                int numRowTiles, int numNodeTiles, int kBlocks, int stagger, const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, unsigned *__restrict__ candOut,
+                int numRowTiles, int numNodeTiles, int kBlocks, int stagger, int D, const float *__restrict__ xnorm2, const float *__restrict__ xratio, const TcScale *__restrict__ scale,
+                unsigned *__restrict__ candOut,
                 unsigned *__restrict__ countOut, float *__restrict__ bestOut, int *err)
 {
     // 128-byte-swizzled TMA / UMMA tiles need a 1024-byte aligned base; declaring the alignment (instead of rounding
@@ -293,7 +316,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         const unsigned mineEnd = mineAddr + TC_LIST * 2048u;
         unsigned acc = 0, accPhase = 0;
         bool ok = true;
-        const float mx = maxNorm2[0];
+        const float mm = scale->mm;
         const float inf = __int_as_float(0x7f800000);
 
         // drop list entries that are no longer below the (tightened) threshold; warp-uniform control flow
@@ -317,9 +340,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
         {
             const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
-            const float xn = row < rowsTotal ? xnorm2[row] : 0.0f;
+            const float xn = row < rowsTotal ? xnorm2[row] : 0.0f, ratio = row < rowsTotal ? xratio[row] : 1.0f;
             float E, delta;
-            tc_margins(xn, mx, kBlocks * TC_BK, E, delta);
+            tc_margins(xn, mm, ratio, kBlocks * TC_BK, D, E, delta);
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
@@ -436,52 +459,116 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
 // ------------------------------------------------------------------------------------------------ operand preparation
 
-// rows of f32 -> bf16 operand rows of Kpad columns: scale * row (scale = 1 for the data rows, -2 for the map: exact in
-// bf16), then `tail` in the three columns D .. D+2 (1 for the data rows — they multiply the node constant — 0 for the map,
-// whose constant columns node_const_kernel fills), zeros behind.  Optional |row|^2 (f32, any order: margins only).
-__global__ void to_bf16_rows_kernel(const float *__restrict__ src, long long rows, int D, int srcStride, float scale, float tail, __nv_bfloat16 *__restrict__ dst, int Kpad,
-                                    float *__restrict__ norm2)
+// power of two 2^(target - e) for v = f 2^e, f in [0.5, 1): v times it lies in [2^(target-1), 2^target); 1 for 0 / NaN / inf
+__device__ __forceinline__ float pow2_scale(float v, int target, int lo, int hi)
+{
+    if (!(v > 0.0f) || v > 3.0e38f)
+        return 1.0f;
+    int e;
+    frexpf(v, &e);
+    int k = target - e;
+    k = k < lo ? lo : (k > hi ? hi : k);
+    return ldexpf(1.0f, k);
+}
+
+// map statistics: |m_p|^2 per node (f32, any order: margins only), max |m_pk| and max |m_p|^2 (atomic max on the bits of
+// non-negative floats).  One warp per node.
+__global__ void map_stats_kernel(const float *__restrict__ mean, int N, int D, int rowStride, float *__restrict__ norm2, TcScale *__restrict__ scale)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= N)
+        return;
+    float s = 0.0f, mx = 0.0f;
+    for (int k = lane; k < D; k += 32)
+    {
+        const float v = mean[static_cast<size_t>(p) * rowStride + k];
+        s += v * v;
+        mx = fmaxf(mx, fabsf(v)); // NaN is ignored here; a NaN node gets the large constant below
+    }
+    for (int o = 16; o; o >>= 1)
+    {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0)
+    {
+        norm2[p] = s;
+        atomicMax(reinterpret_cast<int *>(&scale->maxAbs), __float_as_int(fminf(mx, 3.0e38f)));
+        if (s == s)
+            atomicMax(reinterpret_cast<int *>(&scale->maxNorm2), __float_as_int(fminf(s, 3.0e38f)));
+    }
+}
+
+__global__ void tc_scale_kernel(TcScale *scale)
+{
+    const float sm = pow2_scale(scale->maxAbs, 10, -100, 100); // max |s_m m| in [2^9, 2^10)
+    const float cmax = sm * scale->maxNorm2;                    // largest s_m c_p
+    scale->sm = sm;
+    scale->tau = 1.0f / pow2_scale(cmax, 13, -120, 120);        // s_m c_p / tau in [2^12, 2^13) for the largest node constant
+    scale->mm = sm * sm * scale->maxNorm2;
+}
+
+// map rows -> fp16 operand rows of Kpad columns: -2 s_m m_p, then the hi / mid / lo split of s_m c_p / tau in columns
+// D .. D+2, zeros behind.  c_p = |m_p|^2 for nodes that may win; padding rows and nodes below min_hits get a constant above
+// every real one (node 0 always competes: it seeds findRestrictedBmu regardless of its hit count, src/Som.cpp:316-322).
+__global__ void map_operand_kernel(const float *__restrict__ mean, const float *__restrict__ norm2, const u64 *__restrict__ hits, u64 minHits, int N, int Npad, int D,
+                                   int rowStride, const TcScale *__restrict__ scale, __half *__restrict__ Mb, int Kpad)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= Npad)
+        return;
+    const float sm = scale->sm, tau = scale->tau;
+    __half *row = Mb + static_cast<size_t>(p) * Kpad;
+    for (int k = lane; k < Kpad; k += 32)
+        row[k] = __float2half_rn(p < N && k < D ? -2.0f * sm * mean[static_cast<size_t>(p) * rowStride + k] : 0.0f);
+    __syncwarp();
+    if (lane == 0)
+    {
+        float c = 60000.0f; // pieces of real nodes stay below 2^13
+        if (p < N && (p == 0 || minHits == 0 || hits[p] >= minHits) && norm2[p] == norm2[p])
+            c = fminf(sm * norm2[p] / tau, 60000.0f);
+        const __half hi = __float2half_rn(c);
+        const float r1 = c - __half2float(hi);
+        const __half mid = __float2half_rn(r1);
+        row[D] = hi;
+        row[D + 1] = mid;
+        row[D + 2] = __float2half_rn(r1 - __half2float(mid));
+    }
+}
+
+// data rows -> fp16 operand rows: s_r x (s_r = the row's own power-of-two scale), then s_r tau in the three columns D .. D+2,
+// zeros behind; per row |s_r x|^2 and the ratio s_m / s_r (margins and certificate).  One warp per row.
+__global__ void row_operand_kernel(const float *__restrict__ src, long long rows, int D, const TcScale *__restrict__ scale, __half *__restrict__ dst, int Kpad,
+                                   float *__restrict__ norm2, float *__restrict__ ratio)
 {
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows)
         return;
+    const float *x = src + row * D;
+    float mx = 0.0f;
+    for (int k = lane; k < D; k += 32)
+        mx = fmaxf(mx, fabsf(x[k]));
+    for (int o = 16; o; o >>= 1)
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float tau = scale->tau;
+    int te;
+    frexpf(tau, &te); // tau = 2^(te - 1); the tail s_r tau must stay inside [2^-14, 2^15]
+    const float sr = pow2_scale(mx, 10, -14 - (te - 1), 15 - (te - 1));
     float s = 0.0f;
     for (int k = lane; k < Kpad; k += 32)
     {
-        const float v = k < D ? src[row * srcStride + k] : 0.0f;
-        dst[row * Kpad + k] = __float2bfloat16_rn(k < D ? scale * v : (k < D + 3 ? tail : 0.0f));
+        const float v = k < D ? sr * x[k] : 0.0f;
+        dst[row * Kpad + k] = __float2half_rn(k < D ? v : (k < D + 3 ? sr * tau : 0.0f)); // a NaN / inf element poisons the row's scores: it takes the exact scan
         s += v * v;
     }
     for (int o = 16; o; o >>= 1)
         s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0 && norm2)
+    if (lane == 0)
+    {
         norm2[row] = s;
-}
-
-// node constant of the score, written into the map operand's columns D .. D+2 as a hi / mid / lo bf16 split (8 + 8 + 8
-// bits: the three products with the data rows' ones add up to c_p in the f32 accumulator): |m_p|^2 for nodes that may win,
-// TC_BIG for padding rows and for nodes below min_hits (node 0 always competes: it seeds findRestrictedBmu regardless of
-// its hit count, src/Som.cpp:316-322)
-__global__ void node_const_kernel(const float *__restrict__ norm2, const u64 *__restrict__ hits, u64 minHits, int N, int Npad, int D, int Kpad,
-                                  __nv_bfloat16 *__restrict__ Mb, float *__restrict__ maxNorm2)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= Npad)
-        return;
-    float c = TC_BIG;
-    if (p < N && (p == 0 || minHits == 0 || hits[p] >= minHits))
-        c = fminf(norm2[p], TC_BIG); // a NaN norm (NaN in the map) becomes TC_BIG: that node cannot win in the reference either
-    const __nv_bfloat16 hi = __float2bfloat16_rn(c);
-    const float r1 = c - __bfloat162float(hi);
-    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
-    __nv_bfloat16 *row = Mb + static_cast<size_t>(p) * Kpad + D;
-    row[0] = hi;
-    row[1] = mid;
-    row[2] = lo;
-    if (p < N)
-        atomicMax(reinterpret_cast<int *>(maxNorm2), __float_as_int(fminf(norm2[p], TC_BIG))); // non-negative floats order like ints
+        ratio[row] = scale->sm / sr;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ exact rescore + certificate
@@ -496,9 +583,9 @@ constexpr int RS_ROWS = 128;
 constexpr int RS_THREADS = 256;
 __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__restrict__ x, long long rows, int D, const float *__restrict__ mean, int rowStride,
                                                              const unsigned *__restrict__ cand, const unsigned *__restrict__ count, const float *__restrict__ bestA,
-                                                             const float *__restrict__ xnorm2, const float *__restrict__ maxNorm2, int Kpad, int order,
-                                                             unsigned *__restrict__ outBmu, float *__restrict__ outDist, unsigned *__restrict__ fallbackRows,
-                                                             unsigned *__restrict__ fallbackCount)
+                                                             const float *__restrict__ xnorm2, const float *__restrict__ xratio, const TcScale *__restrict__ scale,
+                                                             int Kpad, int order, int N, const u64 *__restrict__ hits, u64 minHits, unsigned *__restrict__ outBmu,
+                                                             float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
 {
     __shared__ unsigned sOff[RS_ROWS + 1];
     __shared__ unsigned sWarpTot[RS_ROWS / 32];
@@ -545,6 +632,10 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
         const int r = static_cast<int>(it >> 4), j = static_cast<int>(it & 15u);
         const long long row = row0 + r;
         const unsigned node = cand[row * TC_TOPK + j];
+        // eligibility is re-checked here: padding nodes and nodes below min_hits may be listed when their large constant does
+        // not dominate (rows much larger than the map); they must not win
+        if (node >= static_cast<unsigned>(N) || !(node == 0 || minHits == 0 || hits[node] >= minHits))
+            continue;
         const float s = dist_rows_f32(mean + static_cast<size_t>(node) * rowStride, x + row * D, D, order);
         atomicMin(&sKey[r], make_key(s, node, (s != s) ? 1u : 0u));
     }
@@ -557,12 +648,14 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
         bool certified = false;
         if (cnt != TC_OVERFLOW && !nan && key != ~0ull)
         {
-            // unlisted nodes: reference distance >= best approximate score + |x|^2 + Delta - E = ... + 0.25 E + slack (tc_margins)
-            const float xn = xnorm2[row];
+            // unlisted nodes, in the row's scaled units (S_r = s_r s_m = s_m^2 / ratio): S_r d_q >= best approximate score +
+            // S_r |x|^2 + Delta' - E' = ... + 0.25 E' + slack (tc_margins)
+            const float xn = xnorm2[row], ratio = xratio[row], sm = scale->sm;
             float E, delta;
-            tc_margins(xn, maxNorm2[0], Kpad, E, delta);
-            const float lower = __fadd_rn(__fadd_rn(bestA[row], xn), __fmul_rn(0.25f, E));
-            certified = lower > __uint_as_float(static_cast<unsigned>(key >> 32));
+            tc_margins(xn, scale->mm, ratio, Kpad, D, E, delta);
+            const float lower = __fadd_rn(__fadd_rn(bestA[row], __fmul_rn(xn, ratio)), __fmul_rn(0.25f, E));
+            const float sd = __fmul_rn(__fdiv_rn(__fmul_rn(sm, sm), ratio), __uint_as_float(static_cast<unsigned>(key >> 32))); // S_r d*: a power of two times d*
+            certified = lower > sd;
         }
         if (!certified)
             fallbackRows[atomicAdd(fallbackCount, 1u)] = static_cast<unsigned>(row);
@@ -648,7 +741,7 @@ static int make_map(vsom_ctx *ctx, CUtensorMap *map, void *base, unsigned long l
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kpad) * 2};
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(TC_BK), static_cast<cuuint32_t>(boxRows)};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(ctx, VSOM_ERR_CUDA, "score_tc: cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ")");
@@ -658,15 +751,15 @@ static int make_map(vsom_ctx *ctx, CUtensorMap *map, void *base, unsigned long l
 bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR && ctx->Dm <= TC_MAXK; }
 
 // One batched scoring call: tc_begin (map side, once) -> tc_enqueue per slab of rows (no host synchronisation) -> tc_finish.
-// stage slots used: 6 = bf16 map + node constants, 7 = bf16 rows of the current slab, 8 = per-row scratch (two sets).
+// stage slots used: 6 = fp16 map operand + statistics, 7 = fp16 rows of the current slab, 8 = per-row scratch (two sets).
 struct TcCall
 {
     int D = 0, N = 0, Kpad = 0, kBlocks = 0, kSteps = 0, Npad = 0, nodeTiles = 0, stagger = 1;
     bool overlap = true;
     uint64_t minHits = 0;
     size_t slabRows = 0, setBytes = 0, slab = 0;
-    __nv_bfloat16 *Xb = nullptr;
-    float *maxNorm2 = nullptr;
+    __half *Xb = nullptr;
+    TcScale *scale = nullptr;
     unsigned long long *totalDev = nullptr;
     CUtensorMap mapM;
 };
@@ -683,19 +776,19 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     c.nodeTiles = c.Npad / TC_BN;
     c.minHits = minHits;
 
-    // ---- map side: bf16 copy, |m|^2, node constants, max |m|^2
-    const size_t mbBytes = sizeof(__nv_bfloat16) * static_cast<size_t>(c.Npad) * c.Kpad;
+    // ---- map side: statistics -> scales -> fp16 operand with the node constants folded in
+    const size_t mbBytes = sizeof(__half) * static_cast<size_t>(c.Npad) * c.Kpad;
     int rc = stage_reserve(ctx, 6, mbBytes + sizeof(float) * (static_cast<size_t>(c.Npad) + 64));
     if (rc)
         return rc;
-    __nv_bfloat16 *Mb = static_cast<__nv_bfloat16 *>(ctx->stage[6]);
+    __half *Mb = static_cast<__half *>(ctx->stage[6]);
     float *mnorm = reinterpret_cast<float *>(static_cast<unsigned char *>(ctx->stage[6]) + mbBytes);
-    c.maxNorm2 = mnorm + c.Npad;
-    VSOM_CUDA(ctx, cudaMemsetAsync(Mb, 0, mbBytes, ctx->stream));
-    VSOM_CUDA(ctx, cudaMemsetAsync(c.maxNorm2, 0, sizeof(float), ctx->stream));
-    to_bf16_rows_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, -2.0f, 0.0f, Mb, c.Kpad, mnorm);
-    node_const_kernel<<<(c.Npad + 255) / 256, 256, 0, ctx->stream>>>(mnorm, ctx->hits, minHits, N, c.Npad, D, c.Kpad, Mb, c.maxNorm2);
-    ctx->launches += 2;
+    c.scale = reinterpret_cast<TcScale *>(mnorm + c.Npad);
+    VSOM_CUDA(ctx, cudaMemsetAsync(c.scale, 0, sizeof(TcScale), ctx->stream));
+    map_stats_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, mnorm, c.scale);
+    tc_scale_kernel<<<1, 1, 0, ctx->stream>>>(c.scale);
+    map_operand_kernel<<<(c.Npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, mnorm, ctx->hits, minHits, N, c.Npad, D, ctx->rowStride, c.scale, Mb, c.Kpad);
+    ctx->launches += 3;
     rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, TC_BN);
     if (rc)
         return rc;
@@ -706,7 +799,7 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
         ctx->tcAttrSet = 1;
     }
 
-    // ---- rows go through in slabs (the bf16 staging buffer: 2 GB at K = 256 for 4M rows).  Two streams: the context's
+    // ---- rows go through in slabs (the fp16 staging buffer: 2.7 GB at K = 256 + 3 for 4M rows).  Two streams: the context's
     // stream converts a slab and runs the tensor-core search; an auxiliary stream re-scores the slab's candidates (and scans
     // the few rows the certificate rejected) while the next slab is already being searched.  Candidate scratch is
     // double-buffered by slab parity; nothing returns to the host in between.
@@ -714,11 +807,11 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     c.overlap = ovlEnv ? atoi(ovlEnv) != 0 : true;
     c.stagger = stg ? atoi(stg) : 1;
     c.slabRows = maxSlabRows;
-    rc = stage_reserve(ctx, 7, sizeof(__nv_bfloat16) * c.slabRows * c.Kpad);
+    rc = stage_reserve(ctx, 7, sizeof(__half) * c.slabRows * c.Kpad);
     if (rc)
         return rc;
-    // per-row scratch: candidates, their count, |x|^2, best approximate score, fallback list; per set: fallback count
-    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + 2 * sizeof(float) + sizeof(unsigned);
+    // per-row scratch: candidates, their count, |s_r x|^2, s_m / s_r, best approximate score, fallback list; per set: fallback count
+    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + 3 * sizeof(float) + sizeof(unsigned);
     c.setBytes = (perRow * c.slabRows + 256 + 255) & ~static_cast<size_t>(255);
     rc = stage_reserve(ctx, 8, 2 * c.setBytes + 256);
     if (rc)
@@ -734,7 +827,7 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
             VSOM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evCopied[i], cudaEventDisableTiming));
         }
     }
-    c.Xb = static_cast<__nv_bfloat16 *>(ctx->stage[7]);
+    c.Xb = static_cast<__half *>(ctx->stage[7]);
     c.totalDev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ctx->stage[8]) + 2 * c.setBytes);
     VSOM_CUDA(ctx, cudaMemsetAsync(c.totalDev, 0, sizeof(unsigned long long), ctx->stream));
     VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
@@ -751,14 +844,15 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     unsigned *cand = reinterpret_cast<unsigned *>(set);
     unsigned *candCount = cand + c.slabRows * TC_TOPK;
     float *xnorm = reinterpret_cast<float *>(candCount + c.slabRows);
-    float *bestA = xnorm + c.slabRows;
+    float *xratio = xnorm + c.slabRows;
+    float *bestA = xratio + c.slabRows;
     unsigned *fbRows = reinterpret_cast<unsigned *>(bestA + c.slabRows);
     unsigned *fbCount = fbRows + c.slabRows;
     const int order = ctx->order == VSOM_ORDER_EIGEN_SSE ? VSOM_ORDER_EIGEN_SSE : VSOM_ORDER_REFERENCE;
 
     if (c.slab >= 2)
         VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[par], 0)); // slab - 2 is done with this scratch set
-    to_bf16_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), c.D, c.D, 1.0f, 1.0f, c.Xb, c.Kpad, xnorm);
+    row_operand_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, ctx->stream>>>(xs, static_cast<long long>(rows), c.D, c.scale, c.Xb, c.Kpad, xnorm, xratio);
     CUtensorMap mapX;
     int rc = make_map(ctx, &mapX, c.Xb, rows, c.Kpad, TC_BM);
     if (rc)
@@ -766,13 +860,13 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
     const int grid = std::min(rowTiles, ctx->numSMs);
     VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.kSteps, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.stagger, xnorm, c.maxNorm2,
+    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.kSteps, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.stagger, c.D, xnorm, xratio, c.scale,
                                                                         cand, candCount, bestA, ctx->errFlag);
     cudaStream_t rs = c.overlap ? ctx->auxStream : ctx->stream;
     VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
     VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
     rescore_kernel<<<static_cast<unsigned>((rows + RS_ROWS - 1) / RS_ROWS), RS_THREADS, 0, rs>>>(xs, static_cast<long long>(rows), c.D, ctx->mean, ctx->rowStride, cand, candCount, bestA,
-                                                                                                 xnorm, c.maxNorm2, c.Kpad, order, outBmuDev, outDistDev, fbRows, fbCount);
+                                                                                                 xnorm, xratio, c.scale, c.Kpad, order, c.N, ctx->hits, c.minHits, outBmuDev, outDistDev, fbRows, fbCount);
     // rows the certificate rejected: exact full scan, count read on the device
     find_bmu_rowwise_kernel<<<2 * ctx->numSMs, 256, sizeof(float) * c.D, rs>>>(xs, c.D, fbRows, fbCount, ctx->mean, ctx->rowStride, c.N, ctx->hits, c.minHits, order, outBmuDev,
                                                                               outDistDev, c.totalDev);
