@@ -10,6 +10,7 @@ from .binding import (  # noqa: F401
     EXPONENTIAL,
     INVERSE_PROPORTIONAL,
     MEDIAN,
+    ORDER_EIGEN_SSE,
     ORDER_LANES,
     ORDER_REFERENCE,
     STANDARD,

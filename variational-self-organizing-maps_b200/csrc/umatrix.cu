@@ -97,13 +97,31 @@ __global__ void __launch_bounds__(UT * 8) umatrix_kernel(const float *const *__r
     float s = 0.0f;
     const int blocks8 = Dm >> 3;
     const float4 *mc4 = reinterpret_cast<const float4 *>(mc), *mu4 = reinterpret_cast<const float4 *>(mu);
+    // software pipeline: the next block's five loads are in flight while the current block is computed
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+    float sgn = 1.0f;
+    if (blocks8 > 0)
+    {
+        a0 = __ldg(mc4);
+        a1 = __ldg(mc4 + 1);
+        b0 = __ldg(mu4);
+        b1 = __ldg(mu4 + 1);
+        sgn = __ldg(sg + nb);
+    }
 #pragma unroll 1
     for (int b8 = 0; b8 < blocks8; ++b8)
     {
-        const float4 a0 = __ldg(mc4 + 2 * b8), a1 = __ldg(mc4 + 2 * b8 + 1), b0 = __ldg(mu4 + 2 * b8), b1 = __ldg(mu4 + 2 * b8 + 1);
-        const float sMown = clamp_sigma(__ldg(sg + 8 * b8 + nb)); // this lane's element of the block
-        const float yown = __frcp_rn(sMown);
         const float mcv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, muv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float sMown = clamp_sigma(sgn); // this lane's element of the block
+        if (b8 + 1 < blocks8)
+        {
+            a0 = __ldg(mc4 + 2 * b8 + 2);
+            a1 = __ldg(mc4 + 2 * b8 + 3);
+            b0 = __ldg(mu4 + 2 * b8 + 2);
+            b1 = __ldg(mu4 + 2 * b8 + 3);
+            sgn = __ldg(sg + 8 * b8 + 8 + nb);
+        }
+        const float yown = __frcp_rn(sMown);
         float tv[8], sMv[8];
         bool bad = ((__ballot_sync(0xffffffffu, !rcp_ok(sMown)) >> grp) & 0xffu) != 0; // some sM of this node's block is out of range
 #pragma unroll
