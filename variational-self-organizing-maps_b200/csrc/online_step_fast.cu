@@ -177,8 +177,30 @@ __device__ __forceinline__ float chain_terms_eigen(const float *row, int Dr)
     const float4 *r4 = reinterpret_cast<const float4 *>(row);
     EigenSseSum acc;
     const int n8 = Dr >> 3;
-#pragma unroll 4
-    for (int b = 0; b < n8; ++b)
+    // two blocks of eight per turn, the next turn's four 128-bit loads issued before this turn's adds (the loads' latency
+    // must stay off the chains, exactly like in chain_terms)
+    int b = 0;
+    if (n8 >= 2)
+    {
+        float4 u0 = r4[0], v0 = r4[1], u1 = r4[2], v1 = r4[3];
+        for (b = 2; b + 2 <= n8; b += 2)
+        {
+            const float4 nu0 = r4[2 * b], nv0 = r4[2 * b + 1], nu1 = r4[2 * b + 2], nv1 = r4[2 * b + 3];
+            const float t0[8] = {u0.x, u0.y, u0.z, u0.w, v0.x, v0.y, v0.z, v0.w}, t1[8] = {u1.x, u1.y, u1.z, u1.w, v1.x, v1.y, v1.z, v1.w};
+            acc.block(t0);
+            acc.block(t1);
+            u0 = nu0;
+            v0 = nv0;
+            u1 = nu1;
+            v1 = nv1;
+        }
+        const float t0[8] = {u0.x, u0.y, u0.z, u0.w, v0.x, v0.y, v0.z, v0.w}, t1[8] = {u1.x, u1.y, u1.z, u1.w, v1.x, v1.y, v1.z, v1.w};
+        acc.block(t0);
+        acc.block(t1);
+    }
+    else
+        b = 0;
+    for (; b < n8; ++b) // an odd block count (or a single block)
     {
         const float4 u = r4[2 * b], v = r4[2 * b + 1];
         const float t[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
