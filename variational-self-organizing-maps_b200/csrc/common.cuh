@@ -55,6 +55,7 @@ struct StepParams
     int lutSmem, lutCount;    // copy the table into shared memory (it fits behind the resident rows)
     int xVec;                 // sample rows are 16-byte aligned: 16-byte cp.async
     int order;                // vsom_reduction_order of the distances
+    int lanesPerNode;         // K1F: lanes that share one node's distance chain (1, or 8 in the Eigen order)
     int world, rank;          // node-sharded training across GPUs (world == 1: single GPU)
     u64 *rankSlots;           // [2][world] keys pushed into THIS GPU's memory by every rank (peer stores over NVLink)
     u64 *peerSlots[8];        // rankSlots of every rank (index = rank), peer-mapped; peerSlots[rank] == rankSlots
@@ -132,6 +133,7 @@ struct vsom_ctx
     unsigned *winTab = nullptr;
     double winSigma = -1;
     int lastTrainFast = 0;        // the last online-step launch ran K1F
+    int fastLanes = 1;            // K1F: lanes per node in the scan
     int fastReg = 0;              // K1F: items per warp whose rows live in registers (0: rows in shared memory)
     vsom::u64 *rowPool = nullptr; // K1F exchange rows: 1024 blocks of 2 KB
     int *rowMeta = nullptr;       // dieOfSm[256] | rowBlocks[640] | rowOf[160] | counters[4]

@@ -222,6 +222,33 @@ __device__ __forceinline__ float chain_terms_eigen(const float *row, int Dr)
     }
     return acc.finish(rest, nrest);
 }
+// The eight chains of the Eigen SSE2 order on EIGHT consecutive lanes (lane c sums the terms k = c mod 8), combined with the
+// fixed butterfly xor 4 (res0 + res1), [+ the extra packet], xor 2, xor 1 ((p0 + p2) + (p1 + p3): float addition commutes, so
+// every lane ends with the same bits), then the scalar tail — Dr / 8 dependent adds instead of Dr (or Dr / 8 turns of eight).
+// All 32 lanes of the warp call it (shuffles).
+__device__ __forceinline__ float chain_lanes8(const float *row, int Dr, int c)
+{
+    const int n8 = Dr >> 3;
+    float a = 0.0f;
+    const float *q = row + c;
+#pragma unroll 8
+    for (int b = 0; b < n8; ++b)
+        a = __fadd_rn(a, q[8 * b]);
+    float r = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 4));
+    const int nrest = Dr & 7;
+    const float *rest = row + (n8 << 3);
+    int k = 0;
+    if (nrest >= 4)
+    {
+        r = __fadd_rn(r, rest[c & 3]);
+        k = 4;
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    for (; k < nrest; ++k)
+        r = __fadd_rn(r, rest[k]);
+    return r;
+}
 __device__ __forceinline__ float chain_any(const float *row, int n16, int Dr, int eigen) { return eigen ? chain_terms_eigen(row, Dr) : chain_terms(row, n16); }
 
 // ---- CLR (src/Transformation.cpp:79-167), scalar round-to-nearest operations only: a * x + b must never contract
@@ -307,7 +334,9 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
     const int stride = p.smStride;     // terms rows: 16 q + 4 floats, 16 q >= DmPad
     const int rstride = kClr ? 2 * Ppad : stride; // mean / S rows (shared-memory-row mode)
     const int n16 = (stride - 4) >> 4; // blocks of 16 terms the chain walks
-    const int nSW = (L + 31) >> 5;     // warps whose lanes own a node each
+    // lanes per owned node in the scan: 1, or 8 in the Eigen order when the host chose so (long rows, or all nodes still fit one warp)
+    const int LPN = p.lanesPerNode;
+    const int nSW = (L * LPN + 31) >> 5; // warps whose lanes own a node (or an eighth of one) each
     const int nCh = (DmPad + 127) >> 7;
     const int items = L * nCh;
     const unsigned n = static_cast<unsigned>(p.n); // the host keeps chunks below 2^32 samples on this path
@@ -437,8 +466,9 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         }
     }
     // per-lane state of the scan warps: thread <-> owned node
-    const int myL = tid;
-    const bool hasNode = myL < L;
+    const int myL = LPN == 8 ? tid >> 3 : tid, mySub = LPN == 8 ? tid & 7 : 0;
+    const bool inScan = myL < L;               // this lane takes part in its node's chain
+    const bool hasNode = inScan && mySub == 0; // ... and keeps the node's state (position, weightMap entry, coefficients)
     unsigned myX = 0, myY = 0;
     float myW = 0.0f;
     unsigned myTouched = 0;
@@ -449,7 +479,7 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         myY = node / static_cast<unsigned>(p.W);
         myW = p.weight[static_cast<size_t>(myL) * G + b];
     }
-    const float *myTerms = tBase + myL * stride;
+    const float *myTerms = tBase + (inScan ? myL : 0) * stride;
     __syncthreads();
     for (int i = tid; i < 2 * G; i += kFThreads)
     {
@@ -577,9 +607,14 @@ __global__ void __launch_bounds__(kFThreads, 1) online_step_fast_kernel(const St
         if (warp < nSW)
         {
             u64 key = ~0ull;
+            float dScan = 0.0f;
+            if (LPN == 8)
+                dScan = chain_lanes8(myTerms, p.Dr, mySub); // every lane of the scan warps (shuffles); lanes without a node read row 0
+            else if (hasNode)
+                dScan = chain_any(myTerms, n16, p.Dr, eigenOrder);
             if (hasNode)
             {
-                const float d = chain_any(myTerms, n16, p.Dr, eigenOrder);
+                const float d = dScan;
                 key = make_key_xy(d, myX, myY, tag);
                 if (p.localSearch) // sigma <= 1: the walk below reads distances of arbitrary nodes; the word validates itself.
                 {                  // (kWalkReplicas copies, CTA b reads copy b % kWalkReplicas)
@@ -1346,6 +1381,18 @@ int configure_online_step_fast(vsom_ctx *ctx)
     const int Lmax = (ctx->localN + G - 1) / G;
     if (Lmax > kFThreads)
         return 0; // one scan lane per owned node
+    // Eigen order: eight lanes per node cut the chain from Dr to Dr / 8 dependent adds; worth it when the rows are long or when
+    // all the CTA's nodes still fit one warp (no extra CTA-level reduction).  VSOM_K1F_LANES=1|8 overrides (experiments).
+    {
+        const int Dr = ctx->Dr;
+        int lpn = 1;
+        if (ctx->order == VSOM_ORDER_EIGEN_SSE && Lmax * 8 <= kFThreads && (Lmax * 8 <= 32 || Dr >= 256))
+            lpn = 8;
+        if (const char *e = getenv("VSOM_K1F_LANES"))
+            if (ctx->order == VSOM_ORDER_EIGEN_SSE && Lmax * 8 <= kFThreads && (atoi(e) == 1 || atoi(e) == 8))
+                lpn = atoi(e);
+        ctx->fastLanes = lpn;
+    }
     const int ipw = fast_ipw(ctx, G);
     for (int prof = 0; prof < 2; ++prof)
     {
@@ -1429,6 +1476,7 @@ int launch_online_step_fast(vsom_ctx *ctx, StepParams &p, double sigma)
     p.rowCtr = ctr;
     p.rowPool = ctx->rowPool;
     p.resident = 1;
+    p.lanesPerNode = ctx->fastLanes;
     p.smStride = ctx->fastStride;
     const size_t lutBytes = sizeof(LutEntry) * static_cast<size_t>(p.lutCount);
     p.lutSmem = (ctx->fastSmem + lutBytes + kFStaticSmem <= static_cast<size_t>(ctx->smemOptin)) ? 1 : 0;
