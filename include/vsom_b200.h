@@ -200,7 +200,9 @@ VSOM_API int vsom_find_bmu_exact_device(vsom_ctx *ctx, const float *x_dev, size_
 VSOM_API int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist, uint64_t *fallback_rows);
 VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev,
                                         uint64_t *fallback_rows);
-/* 1 when the last scoring call on ctx ran the tensor-core path. */
+/* 0 when the last scoring call on ctx ran the exact scan, else the precision tier of its tensor-core search: 1 = one fp16
+ * value per operand element, 2 = hi / lo pairs (three products per element; chosen when a probe of the first rows shows that
+ * tier 1 cannot separate the BMU from its neighbours on this map). */
 VSOM_API int vsom_debug_last_score_tc(const vsom_ctx *ctx);
 
 /* Som::evaluate for all-continuous columns (src/Som.cpp:490-523): f64 running mean of the BMU distance in row

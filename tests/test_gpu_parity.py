@@ -295,15 +295,48 @@ def test_tensor_core_scoring_equals_exact_scan(vsom, shape):
 
 
 def test_tensor_core_scoring_unsupported_shapes_use_exact(vsom):
-    ctx = vsom.VsomContext(20, 20, 784, vsom.STANDARD)  # Dm > 256: exact scan
+    ctx = vsom.VsomContext(12, 12, 9, vsom.CLR)  # CLR residuals are not a plain |m - x|^2: exact scan
     rng = np.random.default_rng(1)
-    ctx.upload_state(mean=rng.standard_normal((400, 784)).astype(np.float32))
-    x = rng.standard_normal((1500, 784)).astype(np.float32)
+    ctx.upload_state(mean=rng.standard_normal((144, 72)).astype(np.float32))
+    x = rng.standard_normal((1500, 9)).astype(np.float32)
     eb, ed = ctx.find_bmu_exact(x)
     tb, td, fb = ctx.find_bmu_batch(x)
     assert fb == 1500 and not ctx.last_score_tc
     assert_bit_equal(tb, eb, "bmu")
     assert_bit_equal(td, ed, "dist")
+    ctx.close()
+
+
+@pytest.mark.parametrize("tier", ["1", "2", "auto"])
+@pytest.mark.parametrize("shape", [(20, 20, 784, 1500), (64, 64, 128, 3000), (128, 128, 256, 2500), (40, 25, 300, 1300), (9, 9, 5, 1100)])
+def test_tensor_core_tiers_and_long_rows(vsom, po, monkeypatch, shape, tier):
+    """Both precision tiers of K2 (one fp16 value per operand element / hi-lo pairs) and rows longer than the resident A area
+    (A k-blocks streamed with B: BASELINE configs 1 and 5 have 784-dim rows) against the ORACLE, on a clustered map."""
+    if tier != "auto":
+        monkeypatch.setenv("VSOM_TC_TIER", tier)
+    else:
+        monkeypatch.delenv("VSOM_TC_TIER", raising=False)
+    W, H, D, n = shape
+    rng = np.random.default_rng(W * D)
+    centres = (rng.standard_normal((12, D)) * 2).astype(np.float32)
+    data = lambda k: (centres[rng.integers(0, 12, k)] + 0.4 * rng.standard_normal((k, D))).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, vsom.STANDARD, vsom.ORDER_EIGEN_SSE)
+    ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * H, D)) / 1000).astype(np.float32))
+    for sg, eta in ((W / 3.0, 0.4), (W / 8.0, 0.2), (2.0, 0.1)):
+        ctx.train_chunk(data(1500), eta, sg, vsom.EXPONENTIAL)
+    o = po.Oracle(W, H, D, po.STANDARD, po.ORDER_EIGEN_SSE)
+    o.set_state(**ctx.download_state())
+    q = data(n)
+    ob, od = o.find_bmu(q[:1024] if W * H * D > 2_000_000 else q)
+    tb, td, fb = ctx.find_bmu_batch(q)
+    print(f"{W}x{H}x{D} tier {tier}: ran tier {ctx.last_score_tc}, {fb} of {n} rows took the exact scan")
+    assert ctx.last_score_tc == (int(tier) if tier != "auto" else ctx.last_score_tc) and ctx.last_score_tc in (1, 2)
+    assert_bit_equal(tb[:len(ob)], ob, "bmu vs oracle")
+    assert_bit_equal(td[:len(od)], od, "dist vs oracle")
+    if len(ob) < n:
+        eb, ed = ctx.find_bmu_exact(q)
+        assert_bit_equal(tb, eb, "bmu vs exact scan")
+        assert_bit_equal(td, ed, "dist vs exact scan")
     ctx.close()
 
 

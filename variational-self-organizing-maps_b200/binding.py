@@ -234,9 +234,10 @@ class VsomContext:
         self._check(lib().vsom_find_bmu(self._h, C.cast(x_ptr, _f32p), n, min_hits, C.cast(bmu_ptr, _u32p), C.cast(dist_ptr, _f32p)))
 
     @property
-    def last_score_tc(self) -> bool:
-        """True when the last scoring call ran K2 (tcgen05 candidate search + exact rescore)."""
-        return bool(lib().vsom_debug_last_score_tc(self._h))
+    def last_score_tc(self) -> int:
+        """0 when the last scoring call ran the exact scan, else the precision tier (1 or 2) of K2 (tcgen05 candidate search +
+        exact rescore)."""
+        return int(lib().vsom_debug_last_score_tc(self._h))
 
     def find_bmu_batch(self, x, min_hits=0):
         """Tensor-core candidate search + exact rescore; returns (bmu, dist, rows that took the exact full scan)."""

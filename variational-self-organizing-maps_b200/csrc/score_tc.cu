@@ -150,16 +150,22 @@ struct TcScale
     float mm;       // max_p |s_m m_p|^2
     float maxAbs;   // max |m_pk| (bits, via atomicMax) — input of the scale
     float maxNorm2; // max_p |m_p|^2                   — input of the scale
+    int split;      // 1: operands are hi / lo pairs of halves (three products per element), 0: one half each
 };
 
 // Error bound E' and list margin Delta' of one row in its scaled units (see "Candidate rule" above).
 // xn = |s_r x|^2, mm = max_p |s_m m_p|^2, ratio = s_m / s_r (so that S_r |x|^2 = xn ratio and S_r max|m|^2 = mm / ratio).
-__device__ __forceinline__ void tc_margins(float xn, float mm, float ratio, int Kpad, int D, float &E, float &delta)
+// split: the precise tier — X = xh + xl + ex, M = mh + ml + em with |ex_k| <= u^2 |X_k| + 2^-25, the contraction computes
+// xh.mh + xl.mh + xh.ml, so X.M - (...) = xl.ml + ex.M + (X - ex).em  <=  3 u^2 (1 + ...) |X||M| + 2^-25 sqrt(D) (|M| + |X|).
+// slack: f32 accumulation of K products inside the tensor core (assumed no better than truncation, 2^-23 each), the
+// reference's own f32 chain and the f32 norms (D 2^-24 each).
+__device__ __forceinline__ void tc_margins(float xn, float mm, float ratio, int Kpad, int D, int split, float &E, float &delta)
 {
-    const float slack = static_cast<float>(Kpad + 64) * 2.384185791015625e-7f * (xn * ratio + mm / ratio); // (K + 64) 2^-22 S (|x|^2 + max|m|^2)
+    const float slack = static_cast<float>(Kpad + D + 64) * 1.1920928955078125e-7f * (xn * ratio + mm / ratio); // (K + D + 64) 2^-23 S (|x|^2 + max|m|^2)
     const float sx = sqrtf(xn), smx = sqrtf(mm);
-    E = 0.00196f * sx * smx + 2.99e-8f * sqrtf(static_cast<float>(D)) * (2.0f * smx + sx) + slack; // 2 (2u + u^2) = 2^-9 (1 + 2^-12) < 0.00196; 2^-25 (1 + u) < 2.99e-8
-    delta = 1.25f * E + 2.0f * slack;
+    // one half each: 2 (2u + u^2) = 2^-9 (1 + 2^-12) < 0.00196; hi / lo pairs: 6 u^2 (1 + ...) < 1.45e-6; 2^-25 (1 + u) < 2.99e-8
+    E = (split ? 1.45e-6f : 0.00196f) * sx * smx + 2.99e-8f * sqrtf(static_cast<float>(D)) * (2.0f * smx + sx) + slack;
+    delta = 1.25f * E + 0.25f * slack;
 }
 
 struct TcShared
@@ -192,6 +198,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     int *sCnt = reinterpret_cast<int *>(sBest + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool streamed = kBlocks > TC_MAXKB; // the row tile's K does not fit the resident A area: A k-blocks ride in the stage ring
     // CTAs walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
     // of L2 (all starting at tile 0 makes 148 SMs ask the same lines at once)
     const int ntStart = (stagger & 1) ? static_cast<int>((static_cast<unsigned>(blockIdx.x) * 7u) % static_cast<unsigned>(numNodeTiles)) : 0;
@@ -231,18 +238,32 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             bool ok = true;
             for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
             {
-                ok = mbar_wait(aEmpty, aPhase ^ 1, err); // previous row tile's MMAs are done with A
-                aPhase ^= 1;
-                mbar_expect_tx(aFull, static_cast<unsigned>(kBlocks) * TC_A_BYTES);
-                for (int kb = 0; kb < kBlocks; ++kb)
-                    tma_load_2d(sA + kb * TC_A_BYTES, &mapX, aFull, kb * TC_BK, rt * TC_BM);
+                if (!streamed)
+                {
+                    ok = mbar_wait(aEmpty, aPhase ^ 1, err); // previous row tile's MMAs are done with A
+                    aPhase ^= 1;
+                    mbar_expect_tx(aFull, static_cast<unsigned>(kBlocks) * TC_A_BYTES);
+                    for (int kb = 0; kb < kBlocks; ++kb)
+                        tma_load_2d(sA + kb * TC_A_BYTES, &mapX, aFull, kb * TC_BK, rt * TC_BM);
+                }
                 for (int i = 0; i < numNodeTiles && ok; ++i)
                     for (int kb = 0; kb < kBlocks && ok; ++kb)
                     {
                         const int nt = (i + ntStart) % numNodeTiles;
                         ok = mbar_wait(&bEmpty[stage], phase ^ 1, err);
-                        mbar_expect_tx(&bFull[stage], TC_B_BYTES);
-                        tma_load_2d(sB + stage * TC_B_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
+                        if (!streamed)
+                        {
+                            mbar_expect_tx(&bFull[stage], TC_B_BYTES);
+                            tma_load_2d(sB + stage * TC_B_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
+                        }
+                        else
+                        {
+                            // long rows: the A k-block travels with the B k-block (re-read from L2 for every node tile)
+                            unsigned char *st = smem + stage * (TC_A_BYTES + TC_B_BYTES);
+                            mbar_expect_tx(&bFull[stage], TC_A_BYTES + TC_B_BYTES);
+                            tma_load_2d(st, &mapX, &bFull[stage], kb * TC_BK, rt * TC_BM);
+                            tma_load_2d(st + TC_A_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
+                        }
                         if (++stage == TC_STAGES)
                         {
                             stage = 0;
@@ -261,8 +282,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             bool ok = true;
             for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
             {
-                ok = mbar_wait(aFull, aPhase, err);
-                aPhase ^= 1;
+                if (!streamed)
+                {
+                    ok = mbar_wait(aFull, aPhase, err);
+                    aPhase ^= 1;
+                }
                 for (int nt = 0; nt < numNodeTiles && ok; ++nt)
                 {
                     ok = mbar_wait(&tEmpty[acc], accPhase ^ 1, err); // epilogue drained this accumulator
@@ -272,7 +296,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     {
                         ok = mbar_wait(&bFull[stage], phase, err);
                         tc_fence_after();
-                        const unsigned aAddr = smem_u32(sA + kb * TC_A_BYTES), bAddr = smem_u32(sB + stage * TC_B_BYTES);
+                        const unsigned aAddr = streamed ? smem_u32(smem + stage * (TC_A_BYTES + TC_B_BYTES)) : smem_u32(sA + kb * TC_A_BYTES);
+                        const unsigned bAddr = streamed ? aAddr + TC_A_BYTES : smem_u32(sB + stage * TC_B_BYTES);
                         const int steps = min(TC_BK / 16, kSteps - kb * (TC_BK / 16)); // the last k-block may be partly used
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)
@@ -296,7 +321,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         accPhase ^= 1;
                     }
                 }
-                umma_commit(aEmpty); // all MMAs of this row tile are done reading A
+                if (!streamed)
+                    umma_commit(aEmpty); // all MMAs of this row tile are done reading A
             }
         }
     }
@@ -342,7 +368,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
             const float xn = row < rowsTotal ? xnorm2[row] : 0.0f, ratio = row < rowsTotal ? xratio[row] : 1.0f;
             float E, delta;
-            tc_margins(xn, mm, ratio, kBlocks * TC_BK, D, E, delta);
+            tc_margins(xn, mm, ratio, kBlocks * TC_BK, D, scale->split, E, delta);
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
@@ -499,8 +525,9 @@ __global__ void map_stats_kernel(const float *__restrict__ mean, int N, int D, i
     }
 }
 
-__global__ void tc_scale_kernel(TcScale *scale)
+__global__ void tc_scale_kernel(TcScale *scale, int split)
 {
+    scale->split = split;
     const float sm = pow2_scale(scale->maxAbs, 10, -100, 100); // max |s_m m| in [2^9, 2^10)
     const float cmax = sm * scale->maxNorm2;                    // largest s_m c_p
     scale->sm = sm;
@@ -518,10 +545,23 @@ __global__ void map_operand_kernel(const float *__restrict__ mean, const float *
     if (p >= Npad)
         return;
     const float sm = scale->sm, tau = scale->tau;
+    const int split = scale->split, cbase = split ? 3 * D : D;
     __half *row = Mb + static_cast<size_t>(p) * Kpad;
     for (int k = lane; k < Kpad; k += 32)
-        row[k] = __float2half_rn(p < N && k < D ? -2.0f * sm * mean[static_cast<size_t>(p) * rowStride + k] : 0.0f);
-    __syncwarp();
+        if (k >= cbase + 3 || (k < cbase && p >= N)) // padding columns, and the data columns of padding rows
+            row[k] = __float2half_rn(0.0f);
+    if (p < N)
+        for (int k = lane; k < D; k += 32)
+        {
+            const float v = -2.0f * sm * mean[static_cast<size_t>(p) * rowStride + k];
+            const __half h = __float2half_rn(v);
+            row[k] = h;
+            if (split) // columns [0, D) and [D, 2D) meet the rows' hi and lo halves, [2D, 3D) carries the map's lo half
+            {
+                row[D + k] = h;
+                row[2 * D + k] = __float2half_rn(v - __half2float(h));
+            }
+        }
     if (lane == 0)
     {
         float c = 60000.0f; // pieces of real nodes stay below 2^13
@@ -530,9 +570,9 @@ __global__ void map_operand_kernel(const float *__restrict__ mean, const float *
         const __half hi = __float2half_rn(c);
         const float r1 = c - __half2float(hi);
         const __half mid = __float2half_rn(r1);
-        row[D] = hi;
-        row[D + 1] = mid;
-        row[D + 2] = __float2half_rn(r1 - __half2float(mid));
+        row[cbase] = hi;
+        row[cbase + 1] = mid;
+        row[cbase + 2] = __float2half_rn(r1 - __half2float(mid));
     }
 }
 
@@ -556,10 +596,21 @@ __global__ void row_operand_kernel(const float *__restrict__ src, long long rows
     frexpf(tau, &te); // tau = 2^(te - 1); the tail s_r tau must stay inside [2^-14, 2^15]
     const float sr = pow2_scale(mx, 10, -14 - (te - 1), 15 - (te - 1));
     float s = 0.0f;
+    const int split = scale->split, cbase = split ? 3 * D : D;
+    __half *out = dst + row * Kpad;
     for (int k = lane; k < Kpad; k += 32)
+        if (k >= cbase)
+            out[k] = __float2half_rn(k < cbase + 3 ? sr * tau : 0.0f);
+    for (int k = lane; k < D; k += 32)
     {
-        const float v = k < D ? sr * x[k] : 0.0f;
-        dst[row * Kpad + k] = __float2half_rn(k < D ? v : (k < D + 3 ? sr * tau : 0.0f)); // a NaN / inf element poisons the row's scores: it takes the exact scan
+        const float v = sr * x[k]; // a NaN / inf element poisons the row's scores: it takes the exact scan
+        const __half h = __float2half_rn(v);
+        out[k] = h;
+        if (split) // hi | lo | hi against the map's hi | hi | lo
+        {
+            out[D + k] = __float2half_rn(v - __half2float(h));
+            out[2 * D + k] = h;
+        }
         s += v * v;
     }
     for (int o = 16; o; o >>= 1)
@@ -652,7 +703,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
             // S_r |x|^2 + Delta' - E' = ... + 0.25 E' + slack (tc_margins)
             const float xn = xnorm2[row], ratio = xratio[row], sm = scale->sm;
             float E, delta;
-            tc_margins(xn, scale->mm, ratio, Kpad, D, E, delta);
+            tc_margins(xn, scale->mm, ratio, Kpad, D, scale->split, E, delta);
             const float lower = __fadd_rn(__fadd_rn(bestA[row], __fmul_rn(xn, ratio)), __fmul_rn(0.25f, E));
             const float sd = __fmul_rn(__fdiv_rn(__fmul_rn(sm, sm), ratio), __uint_as_float(static_cast<unsigned>(key >> 32))); // S_r d*: a power of two times d*
             certified = lower > sd;
@@ -748,13 +799,14 @@ static int make_map(vsom_ctx *ctx, CUtensorMap *map, void *base, unsigned long l
     return VSOM_OK;
 }
 
-bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR && ctx->Dm <= TC_MAXK; }
+// Standard / Median Comparer (the contraction form of |m - x|^2); rows longer than TC_MAXK stream their A k-blocks
+bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR && ctx->Dm <= 2048; }
 
 // One batched scoring call: tc_begin (map side, once) -> tc_enqueue per slab of rows (no host synchronisation) -> tc_finish.
 // stage slots used: 6 = fp16 map operand + statistics, 7 = fp16 rows of the current slab, 8 = per-row scratch (two sets).
 struct TcCall
 {
-    int D = 0, N = 0, Kpad = 0, kBlocks = 0, kSteps = 0, Npad = 0, nodeTiles = 0, stagger = 1;
+    int D = 0, N = 0, Kpad = 0, kBlocks = 0, kSteps = 0, Npad = 0, nodeTiles = 0, stagger = 1, split = 0;
     bool overlap = true;
     uint64_t minHits = 0;
     size_t slabRows = 0, setBytes = 0, slab = 0;
@@ -764,12 +816,13 @@ struct TcCall
     CUtensorMap mapM;
 };
 
-static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHits)
+static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHits, int split)
 {
     const int D = ctx->Dm, N = ctx->N;
     c.D = D;
     c.N = N;
-    c.kSteps = (D + 3 + 15) / 16;                 // K = 16 per MMA: the model vector + the three node-constant columns
+    c.split = split;
+    c.kSteps = ((split ? 3 * D : D) + 3 + 15) / 16; // K = 16 per MMA: the model vector (three segments in the precise tier) + the three node-constant columns
     c.Kpad = (c.kSteps * 16 + TC_BK - 1) / TC_BK * TC_BK; // operand rows are whole 128-byte swizzle rows
     c.kBlocks = c.Kpad / TC_BK;
     c.Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
@@ -786,7 +839,7 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     c.scale = reinterpret_cast<TcScale *>(mnorm + c.Npad);
     VSOM_CUDA(ctx, cudaMemsetAsync(c.scale, 0, sizeof(TcScale), ctx->stream));
     map_stats_kernel<<<(N + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, N, D, ctx->rowStride, mnorm, c.scale);
-    tc_scale_kernel<<<1, 1, 0, ctx->stream>>>(c.scale);
+    tc_scale_kernel<<<1, 1, 0, ctx->stream>>>(c.scale, split);
     map_operand_kernel<<<(c.Npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, mnorm, ctx->hits, minHits, N, c.Npad, D, ctx->rowStride, c.scale, Mb, c.Kpad);
     ctx->launches += 3;
     rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, TC_BN);
@@ -900,18 +953,33 @@ static int tc_finish(vsom_ctx *ctx, TcCall &c, unsigned long long *fallbackRowsO
     return VSOM_OK;
 }
 
-int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut)
+// Which tier scores this call.  Tier 1 (one half per operand) costs 2 N D tensor flops per row; on a trained map the BMU's
+// neighbours differ from it by less than its product error and most rows would end in the exact scan, so tier 2 (hi / lo
+// pairs, 6 N D flops, ~2^-20 relative error) takes over when a probe of the first rows sends more than 4 % of them there
+// (tier 1 at f fallback costs ~ t1 + f t_exact per row, tier 2 ~ 3 t1: break-even near 4 %).  VSOM_TC_TIER=1|2 forces one.
+static const size_t kTcProbeRows = 8192;
+static const double kTcTierSwitch = 0.04;
+
+// rows per slab such that the fp16 operand staging of a slab stays below 2.5 GiB
+static size_t tc_slab_cap(const vsom_ctx *ctx, int split)
 {
-    if (!score_tc_supported(ctx))
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 256");
-    if (fallbackRowsOut)
-        *fallbackRowsOut = 0;
-    if (n == 0)
-        return VSOM_OK;
-    const char *slabEnv = getenv("VSOM_TC_SLAB_LOG2"); // experiment knob; smaller slabs measured slower (per-slab ramp and tail of the persistent kernel)
-    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 22));
+    const size_t kext = static_cast<size_t>(split ? 3 * ctx->Dm : ctx->Dm) + 3, kpad = (kext + TC_BK - 1) / TC_BK * TC_BK;
+    return std::max<size_t>(TC_BM, ((size_t{5} << 29) / (kpad * 2)) & ~static_cast<size_t>(TC_BM - 1));
+}
+
+static int tc_forced_tier()
+{
+    const char *e = getenv("VSOM_TC_TIER");
+    return e ? atoi(e) : 0;
+}
+
+// rows [0, n) of xDev through one tier; slabs of the given size
+static int tc_run_device(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, int split, size_t slabRows, unsigned *outBmuDev, float *outDistDev,
+                         unsigned long long *fallbackRowsOut)
+{
+    slabRows = std::min(n, std::min(slabRows, tc_slab_cap(ctx, split)));
     TcCall c;
-    int rc = tc_begin(ctx, c, slabRows, minHits);
+    int rc = tc_begin(ctx, c, slabRows, minHits, split);
     if (rc)
         return rc;
     for (size_t r0 = 0; r0 < n; r0 += slabRows)
@@ -923,21 +991,49 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
     return tc_finish(ctx, c, fallbackRowsOut);
 }
 
-// Rows in HOST memory (the call Som::evaluate / measureSimilarity / mapDataSet make): the chunk crosses PCIe in slabs on a
-// copy stream into one of two staging buffers while the previous slab is searched and re-scored, and each slab's results
-// return to the host behind its re-scoring.  With pinned host memory the three engines (H2D, SMs, D2H) overlap fully; the
-// call is then bound by the slower of PCIe (4 D bytes per row) and the kernel.  stage slots: 0 = two row slabs,
-// 1 / 2 = BMU / distance of the whole call.
-int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut)
+int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut)
 {
     if (!score_tc_supported(ctx))
-        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 256");
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 2048");
     if (fallbackRowsOut)
         *fallbackRowsOut = 0;
     if (n == 0)
         return VSOM_OK;
-    const char *slabEnv = getenv("VSOM_TC_HOST_SLAB_LOG2");
-    const size_t slabRows = std::min<size_t>(n, static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 19));
+    const char *slabEnv = getenv("VSOM_TC_SLAB_LOG2"); // experiment knob; smaller slabs measured slower (per-slab ramp and tail of the persistent kernel)
+    const size_t slab1 = static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 22), slab2 = std::min<size_t>(slab1, static_cast<size_t>(1) << 20);
+    int tier = tc_forced_tier();
+    size_t done = 0;
+    unsigned long long fb = 0, total = 0;
+    if (tier != 1 && tier != 2)
+    {
+        // probe: the first rows through tier 1 (their results stand), then decide
+        done = std::min(n, kTcProbeRows);
+        const int rc = tc_run_device(ctx, xDev, done, minHits, 0, slab1, outBmuDev, outDistDev, &fb);
+        if (rc)
+            return rc;
+        total += fb;
+        tier = static_cast<double>(fb) > kTcTierSwitch * static_cast<double>(done) ? 2 : 1;
+    }
+    ctx->lastScoreTier = tier;
+    if (done < n)
+    {
+        const int rc = tc_run_device(ctx, xDev + done * ctx->Dm, n - done, minHits, tier == 2 ? 1 : 0, tier == 2 ? slab2 : slab1, outBmuDev ? outBmuDev + done : nullptr,
+                                     outDistDev ? outDistDev + done : nullptr, &fb);
+        if (rc)
+            return rc;
+        total += fb;
+    }
+    if (fallbackRowsOut)
+        *fallbackRowsOut = total;
+    ctx->lastFallbackRows = total;
+    return VSOM_OK;
+}
+
+// rows [0, n) of xHost through one tier, pipelined over the copy / search / re-scoring streams
+static int tc_run_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, int split, size_t slabRows, unsigned *outBmuHost, float *outDistHost,
+                       unsigned long long *fallbackRowsOut)
+{
+    slabRows = std::min(n, std::min(slabRows, tc_slab_cap(ctx, split)));
     const size_t D = static_cast<size_t>(ctx->Dm);
     int rc = stage_reserve(ctx, 0, sizeof(float) * 2 * slabRows * D);
     if (rc)
@@ -952,7 +1048,7 @@ int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_
     unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
     float *distDev = static_cast<float *>(ctx->stage[2]);
     TcCall c;
-    rc = tc_begin(ctx, c, slabRows, minHits);
+    rc = tc_begin(ctx, c, slabRows, minHits, split);
     if (rc)
         return rc;
     // the staging buffers may still be in use by earlier work of the context's stream
@@ -971,22 +1067,64 @@ int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_
     rc = copy_in(0);
     if (rc)
         return rc;
-    for (size_t s = 0; s < slabs; ++s)
+    for (size_t sl = 0; sl < slabs; ++sl)
     {
-        const size_t r0 = s * slabRows, rows = std::min(slabRows, n - r0);
-        const int par = static_cast<int>(s & 1);
+        const size_t r0 = sl * slabRows, rows = std::min(slabRows, n - r0);
+        const int par = static_cast<int>(sl & 1);
         VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopied[par], 0));
         rc = tc_enqueue(ctx, c, xbuf[par], rows, bmuDev + r0, distDev + r0, outBmuHost ? outBmuHost + r0 : nullptr, outDistHost ? outDistHost + r0 : nullptr);
         if (rc)
             return rc;
-        if (s + 1 < slabs) // enqueued AFTER the search of slab s: a pageable source blocks the host here, not the device
+        if (sl + 1 < slabs) // enqueued AFTER the search of slab sl: a pageable source blocks the host here, not the device
         {
-            rc = copy_in(s + 1);
+            rc = copy_in(sl + 1);
             if (rc)
                 return rc;
         }
     }
     return tc_finish(ctx, c, fallbackRowsOut);
+}
+
+// Rows in HOST memory (the call Som::evaluate / measureSimilarity / mapDataSet make): the chunk crosses PCIe in slabs on a
+// copy stream into one of two staging buffers while the previous slab is searched and re-scored, and each slab's results
+// return to the host behind its re-scoring.  With pinned host memory the three engines (H2D, SMs, D2H) overlap fully; the
+// call is then bound by the slower of PCIe (4 D bytes per row) and the kernel.  stage slots: 0 = two row slabs,
+// 1 / 2 = BMU / distance of the whole call.  Same probe and tier choice as the device form.
+int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut)
+{
+    if (!score_tc_supported(ctx))
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 2048");
+    if (fallbackRowsOut)
+        *fallbackRowsOut = 0;
+    if (n == 0)
+        return VSOM_OK;
+    const char *slabEnv = getenv("VSOM_TC_HOST_SLAB_LOG2");
+    const size_t slabRows = static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 19);
+    int tier = tc_forced_tier();
+    size_t done = 0;
+    unsigned long long fb = 0, total = 0;
+    if (tier != 1 && tier != 2)
+    {
+        done = std::min(n, kTcProbeRows);
+        const int rc = tc_run_host(ctx, xHost, done, minHits, 0, slabRows, outBmuHost, outDistHost, &fb);
+        if (rc)
+            return rc;
+        total += fb;
+        tier = static_cast<double>(fb) > kTcTierSwitch * static_cast<double>(done) ? 2 : 1;
+    }
+    ctx->lastScoreTier = tier;
+    if (done < n)
+    {
+        const int rc = tc_run_host(ctx, xHost + done * ctx->Dm, n - done, minHits, tier == 2 ? 1 : 0, slabRows, outBmuHost ? outBmuHost + done : nullptr,
+                                   outDistHost ? outDistHost + done : nullptr, &fb);
+        if (rc)
+            return rc;
+        total += fb;
+    }
+    if (fallbackRowsOut)
+        *fallbackRowsOut = total;
+    ctx->lastFallbackRows = total;
+    return VSOM_OK;
 }
 
 } // namespace vsom
