@@ -185,9 +185,11 @@ VSOM_API int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double si
 /* Per row: Som::findBmu (min_hits == 0, src/Som.cpp:291-309) or Som::findRestrictedBmu (src/Som.cpp:313-332),
  * and out_dist = (float)euclidianWeightedDist(bmu, row) (src/Som.cpp:124-141).  Outputs may be NULL.
  * This is the call behind Som::evaluate (:490-523), Som::measureSimilarity (:631-714) and Som::mapDataSet.
- * Dispatch: batches of >= 1024 rows on shapes K2 covers (Standard / Median, Dm <= 256) run the tensor-core candidate
- * search (tcgen05 + TMA, bf16 operands) + exact f32 rescore of the <= 16 listed candidates per row + a certificate that
- * no unlisted node can win; rows that fail it are re-scored by the exact scan.  Everything else runs the exact scan.
+ * Dispatch: batches of >= 1024 rows on shapes K2 covers (Standard / Median, Dm <= 2048) run the tensor-core candidate
+ * search (tcgen05 + TMA, fp16 operands with exact power-of-two scaling; one value per element, or hi / lo pairs when a probe
+ * of the first rows shows the map needs the precision) + exact f32 rescore of the <= 32 listed candidates per row + a
+ * certificate that no unlisted node can win; rows that fail it are re-scored by the exact scan.  Everything else runs the
+ * exact scan.
  * Results are bit-identical either way.  The host-pointer form streams the rows through two staging buffers (H2D of the
  * next slab overlaps the search of the current one; pinned host memory gives full overlap). */
 VSOM_API int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist);

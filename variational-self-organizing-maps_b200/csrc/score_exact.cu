@@ -23,7 +23,8 @@ namespace vsom
 constexpr int RT = 64, NT = 64, KC = 32, kScoreThreads = 256;
 
 template <int TR>
-__global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const float *__restrict__ x, u64 n, const float *__restrict__ mean,
+__global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const float *__restrict__ x, u64 nIn, const unsigned *__restrict__ rowList,
+ const unsigned *__restrict__ rowCount, const float *__restrict__ mean,
                                                                        const u64 *__restrict__ hits, u64 minHits, int N, int Din, int Dr, int P,
                                                                        int rowStride, const unsigned short *__restrict__ pairI,
                                                                        const unsigned short *__restrict__ pairJ, unsigned *__restrict__ outBmu,
@@ -37,6 +38,11 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4; // nodes tx + 16 j, rows ty + 16 i
     const u64 row0 = static_cast<u64>(blockIdx.x) * RT;
+    // with a row list (the rows a tensor-core slab could not certify): item i is row rowList[i], the count lives on the device
+    const u64 n = rowList ? static_cast<u64>(*rowCount) : nIn;
+    if (row0 >= n)
+        return;
+    auto src_row = [&](u64 item) -> u64 { return rowList ? static_cast<u64>(rowList[item]) : item; };
 
     u64 best[4];
 #pragma unroll
@@ -59,10 +65,11 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
             // stage the slice: one warp per row / node, lanes along k (128-byte coalesced segments)
             for (int r = warp; r < RT; r += kScoreThreads / 32)
             {
-                const u64 row = row0 + r;
+                const u64 item = row0 + r;
                 float a = 0.0f, bq = 0.0f;
-                if (row < n && k < Dr)
+                if (item < n && k < Dr)
                 {
+                    const u64 row = src_row(item);
                     if (TR != VSOM_CLR)
                         a = x[row * Din + k];
                     else
@@ -144,9 +151,10 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
 #pragma unroll
         for (int o = 8; o; o >>= 1)
             k = u64_min(k, __shfl_xor_sync(0xffffffffu, k, o));
-        const u64 row = row0 + ty + 16 * i;
-        if (tx == 0 && row < n)
+        const u64 item = row0 + ty + 16 * i;
+        if (tx == 0 && item < n)
         {
+            const u64 row = src_row(item);
             if (outBmu)
                 outBmu[row] = key_node(k);
             if (outDist)
@@ -164,7 +172,8 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
 constexpr int ER = 32, EN = 32, EMS = 40; // rows / nodes per CTA tile; row stride of the node slice (bank = 8 gx + c: conflict-free)
 
 template <int TR>
-__global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(const float *__restrict__ x, u64 n, const float *__restrict__ mean,
+__global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(const float *__restrict__ x, u64 nIn, const unsigned *__restrict__ rowList,
+ const unsigned *__restrict__ rowCount, const float *__restrict__ mean,
                                                                              const u64 *__restrict__ hits, u64 minHits, int N, int Din, int Dr, int P,
                                                                              int rowStride, const unsigned short *__restrict__ pairI,
                                                                              const unsigned short *__restrict__ pairJ, unsigned *__restrict__ outBmu,
@@ -181,6 +190,9 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
     const int c = tid & 7, g = tid >> 3, gx = g & 7, gy = g >> 3; // chain; nodes gx + 8 j (j < 4), rows gy + 4 i (i < 8)
     const u64 row0 = static_cast<u64>(blockIdx.x) * ER;
     const int n8 = Dr & ~7, nrest = Dr - n8;
+    const u64 n = rowList ? static_cast<u64>(*rowCount) : nIn; // see find_bmu_exact_kernel
+    if (row0 >= n)
+        return;
 
     u64 best[8];
 #pragma unroll
@@ -192,11 +204,12 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
         return __fmul_rn(r, r);
     };
     // one element of a row / node (0 outside): what the slices and the rest arrays hold
-    auto load_x = [&](u64 row, int k, float &a, float &bq) {
+    auto load_x = [&](u64 item, int k, float &a, float &bq) {
         a = 0.0f;
         bq = 0.0f;
-        if (row < n && k < Dr)
+        if (item < n && k < Dr)
         {
+            const u64 row = rowList ? static_cast<u64>(rowList[item]) : item;
             if (!kClr)
                 a = x[row * Din + k];
             else
@@ -321,14 +334,15 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
 #pragma unroll
         for (int q = 1; q < 8; ++q)
             k = u64_min(k, sBest[tid][q]);
+        const u64 row = rowList ? static_cast<u64>(rowList[row0 + tid]) : row0 + tid;
         if (outBmu)
-            outBmu[row0 + tid] = key_node(k);
+            outBmu[row] = key_node(k);
         if (outDist)
         {
             float d = __uint_as_float(static_cast<unsigned>(k >> 32));
             if (k & 1ull)
                 d = __uint_as_float(0x7fc00000u);
-            outDist[row0 + tid] = d;
+            outDist[row] = d;
         }
     }
 }
@@ -404,7 +418,11 @@ int launch_soft_assign(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
     return VSOM_OK;
 }
 
-int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev)
+// rowListDev == null: rows 0 .. n-1 of xDev.  Otherwise the rows rowListDev[0 .. *rowCountDev) (at most n of them: the grid
+// covers n, tiles past the count return at once) — the exact scan of the rows a tensor-core slab could not certify, with
+// the count staying on the device.
+int launch_find_bmu_list(vsom_ctx *ctx, const float *xDev, size_t n, const unsigned *rowListDev, const unsigned *rowCountDev, uint64_t minHits, unsigned *outBmuDev,
+                         float *outDistDev, cudaStream_t stream)
 {
     if (n == 0)
         return VSOM_OK;
@@ -412,33 +430,30 @@ int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits
     {
         const unsigned egrid = static_cast<unsigned>((n + ER - 1) / ER);
         if (ctx->transform == VSOM_CLR)
-            find_bmu_exact_eigen_kernel<VSOM_CLR><<<egrid, kScoreThreads, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride,
-                                                                                            ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+            find_bmu_exact_eigen_kernel<VSOM_CLR><<<egrid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr,
+                                                                                   ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
         else
-            find_bmu_exact_eigen_kernel<VSOM_STANDARD><<<egrid, kScoreThreads, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P,
-                                                                                                 ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+            find_bmu_exact_eigen_kernel<VSOM_STANDARD><<<egrid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din,
+                                                                                        ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
         VSOM_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
         return VSOM_OK;
     }
     const unsigned grid = static_cast<unsigned>((n + RT - 1) / RT);
-#define VSOM_LAUNCH_SCORE(TR)                                                                                                              \
-    find_bmu_exact_kernel<TR><<<grid, kScoreThreads, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr,   \
-                                                                       ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev)
-    switch (ctx->transform)
-    {
-    case VSOM_STANDARD:
-    case VSOM_MEDIAN: // same Comparer (src/Transformation.cpp:7-8, :45-46)
-        VSOM_LAUNCH_SCORE(VSOM_STANDARD);
-        break;
-    default:
-        VSOM_LAUNCH_SCORE(VSOM_CLR);
-        break;
-    }
-#undef VSOM_LAUNCH_SCORE
+    if (ctx->transform == VSOM_CLR)
+        find_bmu_exact_kernel<VSOM_CLR><<<grid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P,
+                                                                          ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+    else // Standard and Median share the Comparer (src/Transformation.cpp:7-8, :45-46)
+        find_bmu_exact_kernel<VSOM_STANDARD><<<grid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr,
+                                                                               ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
     VSOM_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VSOM_OK;
+}
+
+int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev)
+{
+    return launch_find_bmu_list(ctx, xDev, n, nullptr, nullptr, minHits, outBmuDev, outDistDev, ctx->stream);
 }
 
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev)

@@ -30,7 +30,7 @@
 // bound is strictly above S_r times the best EXACT distance among the listed nodes, no unlisted node can be the BMU or tie
 // with it, and the row is done; otherwise the row is re-scored by the exact full scan.  So the result never depends on a
 // statistical recall argument: Delta' only trades list length against the share of rows that need the full scan.  Up to
-// 16 survivors per row go to the exact rescore (which also re-checks min_hits eligibility, so nothing depends on the large
+// 32 survivors per row go to the exact rescore (which also re-checks min_hits eligibility, so nothing depends on the large
 // constant given to excluded nodes); rows with more (or whose list overflowed) take the exact full scan as well.
 //
 // Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
@@ -55,7 +55,7 @@
 namespace vsom
 {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 16, TC_THREADS = 384;
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 32, TC_THREADS = 384;
 constexpr int TC_LIST = 16;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
 constexpr int TC_LIST_HI = 10; // lists are compacted against the current threshold when one passes this length
 constexpr unsigned TC_OVERFLOW = 255;
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
             base += sWarpTot[w];
         const unsigned off = sOff[tid] + base;
         for (unsigned j = 0; j < c; ++j)
-            sItem[off + j] = static_cast<unsigned short>((tid << 4) | j);
+            sItem[off + j] = static_cast<unsigned short>((tid << 5) | j);
         if (tid == RS_ROWS - 1)
             sOff[RS_ROWS] = off + c;
     }
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
     for (unsigned i = tid; i < total; i += RS_THREADS)
     {
         const unsigned it = sItem[i];
-        const int r = static_cast<int>(it >> 4), j = static_cast<int>(it & 15u);
+        const int r = static_cast<int>(it >> 5), j = static_cast<int>(it & 31u);
         const long long row = row0 + r;
         const unsigned node = cand[row * TC_TOPK + j];
         // eligibility is re-checked here: padding nodes and nodes below min_hits may be listed when their large constant does
@@ -719,6 +719,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
         }
     }
 }
+
+__global__ void add_count_kernel(const unsigned *count, unsigned long long *total) { *total += *count; }
 
 // Exact full scan for a FEW rows (the rows the candidate lists could not certify): one CTA per row, threads over
 // nodes, every (row, node) distance summed sequentially in f32 like the reference.  Same key rule as K3.
@@ -920,9 +922,11 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
     rescore_kernel<<<static_cast<unsigned>((rows + RS_ROWS - 1) / RS_ROWS), RS_THREADS, 0, rs>>>(xs, static_cast<long long>(rows), c.D, ctx->mean, ctx->rowStride, cand, candCount, bestA,
                                                                                                  xnorm, xratio, c.scale, c.Kpad, order, c.N, ctx->hits, c.minHits, outBmuDev, outDistDev, fbRows, fbCount);
-    // rows the certificate rejected: exact full scan, count read on the device
-    find_bmu_rowwise_kernel<<<2 * ctx->numSMs, 256, sizeof(float) * c.D, rs>>>(xs, c.D, fbRows, fbCount, ctx->mean, ctx->rowStride, c.N, ctx->hits, c.minHits, order, outBmuDev,
-                                                                              outDistDev, c.totalDev);
+    // rows the certificate rejected: exact scan (K3 tiles over the row list; the count stays on the device)
+    add_count_kernel<<<1, 1, 0, rs>>>(fbCount, c.totalDev);
+    rc = launch_find_bmu_list(ctx, xs, rows, fbRows, fbCount, c.minHits, outBmuDev, outDistDev, rs);
+    if (rc)
+        return rc;
     if (outBmuHost && outBmuDev)
         VSOM_CUDA(ctx, cudaMemcpyAsync(outBmuHost, outBmuDev, sizeof(unsigned) * rows, cudaMemcpyDeviceToHost, rs));
     if (outDistHost && outDistDev)
