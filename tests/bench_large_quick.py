@@ -9,7 +9,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 sigma = float(sys.argv[3]) if len(sys.argv) > 3 else 16.0
 D = 784
 rng = np.random.default_rng(0)
-ctx = v.VsomContext(W, W, D, v.STANDARD)
+order = {'seq': v.ORDER_REFERENCE, 'eigen': v.ORDER_EIGEN_SSE}[sys.argv[4] if len(sys.argv) > 4 else 'eigen']
+ctx = v.VsomContext(W, W, D, v.STANDARD, order)
 ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * W, D)) / 1000).astype(np.float32))
 x = rng.standard_normal((n, D)).astype(np.float32)
 xd = torch.from_numpy(x).cuda(); ob = torch.empty(n, dtype=torch.int32, device="cuda"); od = torch.empty(n, dtype=torch.float32, device="cuda")

@@ -860,11 +860,23 @@ static int umatrix_tables(vsom_ctx *ctx)
             rows[halo[i]] = ctx->haloBuf + i * rowFloats;
     }
     ctx->haloRows = halo;
-    const size_t ptrBytes = sizeof(float *) * rows.size();
-    VSOM_CUDA(ctx, cudaMalloc(&ctx->umTab, ptrBytes + sizeof(int) * ctx->localRowY.size()));
+    // tiles of the tiled kernel: runs of at most umatrix_tile_rows() consecutive grid rows this context owns
+    std::vector<int2> tiles;
+    for (int lr = 0; lr < ctx->localRows;)
+    {
+        int rows_ = 1;
+        while (rows_ < umatrix_tile_rows() && lr + rows_ < ctx->localRows && ctx->localRowY[lr + rows_] == ctx->localRowY[lr] + rows_)
+            ++rows_;
+        tiles.push_back(make_int2(ctx->localRowY[lr], rows_));
+        lr += rows_;
+    }
+    const size_t ptrBytes = sizeof(float *) * rows.size(), rowBytes = sizeof(int) * ctx->localRowY.size();
+    VSOM_CUDA(ctx, cudaMalloc(&ctx->umTab, ptrBytes + rowBytes + sizeof(int2) * tiles.size() + 16));
     VSOM_CUDA(ctx, cudaMemcpy(ctx->umTab, rows.data(), ptrBytes, cudaMemcpyHostToDevice));
-    VSOM_CUDA(ctx, cudaMemcpy(static_cast<unsigned char *>(ctx->umTab) + ptrBytes, ctx->localRowY.data(), sizeof(int) * ctx->localRowY.size(), cudaMemcpyHostToDevice));
+    VSOM_CUDA(ctx, cudaMemcpy(static_cast<unsigned char *>(ctx->umTab) + ptrBytes, ctx->localRowY.data(), rowBytes, cudaMemcpyHostToDevice));
+    VSOM_CUDA(ctx, cudaMemcpy(static_cast<unsigned char *>(ctx->umTab) + ptrBytes + ((rowBytes + 7) & ~size_t{7}), tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
     ctx->umRows = ctx->localRows;
+    ctx->umTiles = static_cast<int>(tiles.size());
     return VSOM_OK;
 }
 
@@ -899,7 +911,13 @@ int vsom_update_umatrix(vsom_ctx *ctx, double *out)
             return rc;
     }
     const float *const *meanRows = static_cast<const float *const *>(ctx->umTab);
-    rc = launch_umatrix_rows(ctx, meanRows, meanRows + ctx->H, reinterpret_cast<const int *>(meanRows + 2 * ctx->H), ctx->umRows);
+    const int *rowsDev = reinterpret_cast<const int *>(meanRows + 2 * ctx->H);
+    const char *kenv = getenv("VSOM_UMATRIX_KERNEL"); // "rows": the one-thread-per-pair kernel without shared-memory tiles (A/B measurements)
+    if (kenv && std::string(kenv) == "rows")
+        rc = launch_umatrix_rows(ctx, meanRows, meanRows + ctx->H, rowsDev, ctx->umRows);
+    else
+        rc = launch_umatrix_tiles(ctx, meanRows, meanRows + ctx->H,
+                                  reinterpret_cast<const int2 *>(reinterpret_cast<const unsigned char *>(rowsDev) + ((sizeof(int) * ctx->localRowY.size() + 7) & ~size_t{7})), ctx->umTiles);
     if (rc)
         return rc;
     if (out) // full-map array; a sharded context fills in its own grid rows only

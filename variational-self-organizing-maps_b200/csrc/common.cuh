@@ -143,7 +143,7 @@ struct vsom_ctx
     int scanBufs = 0, scanSeg = 0, scanNSeg = 0; // K1: HBM-resident rows are streamed through a ring of segment buffers
     void *scanMapDev = nullptr;                   // TMA descriptor of the mean plane for that scan
     void *umTab = nullptr;        // K4: per-grid-row pointer tables (mean rows, sigma rows) + the grid rows this context computes
-    int umRows = 0;
+    int umRows = 0, umTiles = 0;
     long long *profDev = nullptr; // diagnostics: per-phase cycle sums of the last online-step launch
     size_t profSamples = 0;
     std::string err;
@@ -180,6 +180,8 @@ int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_
 int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma, int isFirst, const u64 *lastDev, unsigned *bmuDev, float *distDev);
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
 int launch_soft_assign(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, double *probDev, double *sumsDev);
+int launch_umatrix_tiles(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int2 *tilesDev, int nTiles);
+int umatrix_tile_rows();
 int launch_umatrix_rows(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int *rowsDev, int nRows);
 int launch_build_index(vsom_ctx *ctx, const unsigned *bmuDev, size_t n, u64 *countsDev, u64 *offsetsDev, unsigned *rowIdsDev);
 

@@ -423,37 +423,66 @@ __global__ void __launch_bounds__(kThreads, 1) online_step_kernel(const StepPara
                             const float4 *m4 = reinterpret_cast<const float4 *>(ring + (static_cast<size_t>(scanBuf) * 32 + lane) * segStride);
                             const float4 *x4 = reinterpret_cast<const float4 *>(xt + sg * Kseg);
                             const int q0 = sg * (Kseg >> 2);
-#pragma unroll 2
-                            for (int q = 0; q < n4s; ++q)
-                            {
-                                const float4 a = m4[q], bq = x4[q];
+                            const int qFull = max(0, min(n4s, nFull4 - q0)); // words of this segment inside full blocks of eight
+                            auto sq4 = [](const float4 a, const float4 bq, float &t0, float &t1, float &t2, float &t3) {
                                 float r = __fsub_rn(a.x, bq.x);
-                                const float t0 = __fmul_rn(r, r);
+                                t0 = __fmul_rn(r, r);
                                 r = __fsub_rn(a.y, bq.y);
-                                const float t1 = __fmul_rn(r, r);
+                                t1 = __fmul_rn(r, r);
                                 r = __fsub_rn(a.z, bq.z);
-                                const float t2 = __fmul_rn(r, r);
+                                t2 = __fmul_rn(r, r);
                                 r = __fsub_rn(a.w, bq.w);
-                                const float t3 = __fmul_rn(r, r);
-                                const int Q = q0 + q;
-                                if (Q < nFull4)
+                                t3 = __fmul_rn(r, r);
+                            };
+                            auto add_lo = [&](const float4 a, const float4 bq) {
+                                float t0, t1, t2, t3;
+                                sq4(a, bq, t0, t1, t2, t3);
+                                eacc.a[0] = __fadd_rn(eacc.a[0], t0);
+                                eacc.a[1] = __fadd_rn(eacc.a[1], t1);
+                                eacc.a[2] = __fadd_rn(eacc.a[2], t2);
+                                eacc.a[3] = __fadd_rn(eacc.a[3], t3);
+                            };
+                            auto add_hi = [&](const float4 a, const float4 bq) {
+                                float t0, t1, t2, t3;
+                                sq4(a, bq, t0, t1, t2, t3);
+                                eacc.a[4] = __fadd_rn(eacc.a[4], t0);
+                                eacc.a[5] = __fadd_rn(eacc.a[5], t1);
+                                eacc.a[6] = __fadd_rn(eacc.a[6], t2);
+                                eacc.a[7] = __fadd_rn(eacc.a[7], t3);
+                            };
+                            int q = 0;
+                            if ((q0 & 1) && q < qFull) // the segment starts in the middle of a block of eight
+                            {
+                                add_hi(m4[0], x4[0]);
+                                q = 1;
+                            }
+                            // (even, odd) word pairs: no branches, the next pair's loads in flight during the adds
+                            if (q + 2 <= qFull)
+                            {
+                                float4 a0 = m4[q], b0 = x4[q], a1 = m4[q + 1], b1 = x4[q + 1];
+                                for (q += 2; q + 2 <= qFull; q += 2)
                                 {
-                                    if (Q & 1)
-                                    {
-                                        eacc.a[4] = __fadd_rn(eacc.a[4], t0);
-                                        eacc.a[5] = __fadd_rn(eacc.a[5], t1);
-                                        eacc.a[6] = __fadd_rn(eacc.a[6], t2);
-                                        eacc.a[7] = __fadd_rn(eacc.a[7], t3);
-                                    }
-                                    else
-                                    {
-                                        eacc.a[0] = __fadd_rn(eacc.a[0], t0);
-                                        eacc.a[1] = __fadd_rn(eacc.a[1], t1);
-                                        eacc.a[2] = __fadd_rn(eacc.a[2], t2);
-                                        eacc.a[3] = __fadd_rn(eacc.a[3], t3);
-                                    }
+                                    const float4 c0 = m4[q], d0 = x4[q], c1 = m4[q + 1], d1 = x4[q + 1];
+                                    add_lo(a0, b0);
+                                    add_hi(a1, b1);
+                                    a0 = c0;
+                                    b0 = d0;
+                                    a1 = c1;
+                                    b1 = d1;
                                 }
-                                else if (Q == nFull4)
+                                add_lo(a0, b0);
+                                add_hi(a1, b1);
+                            }
+                            if (q < qFull)
+                            {
+                                add_lo(m4[q], x4[q]);
+                                ++q;
+                            }
+                            for (; q < n4s; ++q) // behind the full blocks: the extra packet and / or the scalar tail (zero padded)
+                            {
+                                float t0, t1, t2, t3;
+                                sq4(m4[q], x4[q], t0, t1, t2, t3);
+                                if (q0 + q == nFull4)
                                 {
                                     erest[0] = t0;
                                     erest[1] = t1;
