@@ -101,7 +101,8 @@ VSOM_API void vsom_destroy(vsom_ctx *ctx);
  * inside ONE process (a thread per GPU) attach each other directly with vsom_peer_attach.
  * upload / download / vsom_update_umatrix take FULL-map arrays and touch only the rank's own grid rows.
  * vsom_update_umatrix on a sharded context is a collective in the caller's hands: every rank's training stream must be
- * idle before any rank calls it (the call reads one border row of means per neighbouring block out of the owners' planes),
+ * idle before any rank calls it (the kernel reads one border row of means per neighbouring block straight out of the owners'
+ * planes over NVLink peer memory — no staging copy),
  * and no rank may train again before every rank has returned.  Scoring and index entry points need an unsharded context;
  * the findLocalBmu regime (sigma <= 1) is not available on sharded contexts. */
 VSOM_API int vsom_create_sharded(vsom_ctx **out, int device, int width, int height, int d_in, int transform, int order, int rank, int world);

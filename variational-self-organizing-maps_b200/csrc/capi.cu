@@ -327,7 +327,6 @@ void vsom_destroy(vsom_ctx *ctx)
         if (ctx->peerMeanOpened[r])
             cudaIpcCloseMemHandle(ctx->peerMean[r]);
     }
-    cudaFree(ctx->haloBuf);
     cudaFree(ctx->rankSlots);
     cudaFree(ctx->errFlag);
     cudaFree(ctx->lut);
@@ -824,7 +823,7 @@ int vsom_soft_assign(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits,
 }
 
 // per-grid-row pointer tables of K4 (umatrix.cu): [H] mean rows, [H] sigma rows, [localRows] grid rows to compute.  A
-// node-sharded context reads its neighbours' border rows from the halo buffer (filled by fetch_halo below).
+// node-sharded context reads its neighbours' border rows straight out of the owners' planes (peer-mapped pointers).
 static int umatrix_tables(vsom_ctx *ctx)
 {
     if (ctx->umTab)
@@ -846,18 +845,15 @@ static int umatrix_tables(vsom_ctx *ctx)
             if (y >= 0 && y < H && !rows[y] && std::find(halo.begin(), halo.end(), y) == halo.end())
                 halo.push_back(y);
         }
-    if (!halo.empty())
+    // Halo rows are not copied: their table entries point INTO the owner's mean plane (peer-mapped over NVLink), and the
+    // tiled kernel's cp.async copies read them from there while it computes — one border row of means per neighbouring
+    // block (sigma is the centre's own).
+    for (int y : halo)
     {
-        const size_t need = sizeof(float) * rowFloats * halo.size();
-        if (need > ctx->haloCap)
-        {
-            cudaFree(ctx->haloBuf);
-            ctx->haloBuf = nullptr;
-            VSOM_CUDA(ctx, cudaMalloc(&ctx->haloBuf, need));
-            ctx->haloCap = need;
-        }
-        for (size_t i = 0; i < halo.size(); ++i)
-            rows[halo[i]] = ctx->haloBuf + i * rowFloats;
+        const int owner = (y / ctx->shardBlock) % ctx->world, lr = shard_local_row(y, ctx->shardBlock, owner, ctx->world);
+        if (!ctx->peerMean[owner])
+            return set_error(ctx, VSOM_ERR_INVALID, "vsom_update_umatrix: sharded context without vsom_peer_import_planes / vsom_peer_attach for every rank");
+        rows[y] = ctx->peerMean[owner] + lr * rowFloats;
     }
     ctx->haloRows = halo;
     // tiles of the tiled kernel: runs of at most umatrix_tile_rows() consecutive grid rows this context owns
@@ -880,22 +876,6 @@ static int umatrix_tables(vsom_ctx *ctx)
     return VSOM_OK;
 }
 
-// Halo exchange of the sharded U-matrix: one grid row of MEANS per border (sigma is the centre's own), read
-// straight out of the owner's plane over NVLink (peer-mapped pointer, device-to-device copy).
-static int fetch_halo(vsom_ctx *ctx)
-{
-    const size_t rowFloats = static_cast<size_t>(ctx->W) * ctx->rowStride;
-    for (size_t i = 0; i < ctx->haloRows.size(); ++i)
-    {
-        const int y = ctx->haloRows[i], owner = (y / ctx->shardBlock) % ctx->world;
-        const int lr = shard_local_row(y, ctx->shardBlock, owner, ctx->world);
-        if (!ctx->peerMean[owner])
-            return set_error(ctx, VSOM_ERR_INVALID, "vsom_update_umatrix: sharded context without vsom_peer_import_planes / vsom_peer_attach for every rank");
-        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->haloBuf + i * rowFloats, ctx->peerMean[owner] + lr * rowFloats, sizeof(float) * rowFloats, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    return VSOM_OK;
-}
-
 int vsom_update_umatrix(vsom_ctx *ctx, double *out)
 {
     if (!ctx)
@@ -904,12 +884,6 @@ int vsom_update_umatrix(vsom_ctx *ctx, double *out)
     int rc = umatrix_tables(ctx);
     if (rc)
         return rc;
-    if (ctx->world > 1)
-    {
-        rc = fetch_halo(ctx);
-        if (rc)
-            return rc;
-    }
     const float *const *meanRows = static_cast<const float *const *>(ctx->umTab);
     const int *rowsDev = reinterpret_cast<const int *>(meanRows + 2 * ctx->H);
     const char *kenv = getenv("VSOM_UMATRIX_KERNEL"); // "rows": the one-thread-per-pair kernel without shared-memory tiles (A/B measurements)

@@ -89,9 +89,7 @@ struct vsom_ctx
     std::vector<int> localRowY;   // global grid row of every local row
     float *peerMean[8] = {};      // mean planes of the ranks (U-matrix halo rows), peer-mapped; peerMean[rank] == mean
     bool peerMeanOpened[8] = {};
-    float *haloBuf = nullptr;     // neighbour rows fetched from other ranks for the U-matrix
-    size_t haloCap = 0;
-    std::vector<int> haloRows;    // the grid rows held in haloBuf, in order
+    std::vector<int> haloRows;    // grid rows of other ranks that border this rank's rows (read in place for the U-matrix)
     vsom::u64 *rankSlots = nullptr;
     vsom::u64 *peerSlots[8] = {};
     bool peerOpened[8] = {};
