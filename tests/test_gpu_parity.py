@@ -549,3 +549,30 @@ def test_umatrix_division_corner_cases(vsom, po, Dm, order):
     ctx.upload_state(mean=mean2, sigma=sigma2)
     assert_bit_equal(ctx.update_umatrix(), o.update_umatrix(), "umatrix (ordinary values)")
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ soft assignment (f3)
+@pytest.mark.parametrize("order", [0, 2], ids=["seq", "eigen_sse"])
+@pytest.mark.parametrize("tr,Din", [(0, 12), (1, 33), (2, 6)])
+def test_soft_assign_matches_find_restricted_bmd(vsom, po, tr, Din, order):
+    """vsom_soft_assign = Som::findRestrictedBmd (src/Som.cpp:457-487) per row: exp(-d^2 / 2) of the (already squared) distance for
+    nodes with enough hits, normalised.  Distances are the reference's bits; exp() is the device's f64 exp, so the tolerance is
+    1e-13 relative (stated in include/vsom_b200.h); the zero pattern (nodes below min_hits) must be identical."""
+    rng = np.random.default_rng(Din)
+    W, H = 9, 7
+    o = po.Oracle(W, H, Din, tr, order)
+    o.random_initialize(3, 0.2)
+    st = o.get_state()
+    st["hits"] = rng.integers(0, 4, W * H).astype(np.uint64)
+    o.set_state(**st)
+    ctx = vsom.VsomContext(W, H, Din, tr, order)
+    upload_like(ctx, st)
+    x = (0.2 * synth(rng, 7, Din, tr)).astype(np.float32)  # close to the map: probabilities that do not underflow
+    for min_hits in (0, 2):
+        got = ctx.soft_assign(x, min_hits)
+        for r in range(len(x)):
+            want = o.find_restricted_bmd(x[r], min_hits)
+            assert np.array_equal(got[r] == 0, want == 0), "zero pattern"
+            np.testing.assert_allclose(got[r], want, rtol=1e-13, atol=0)
+            assert abs(got[r].sum() - 1.0) < 1e-12
+    ctx.close()
