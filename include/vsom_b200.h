@@ -207,6 +207,10 @@ VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_
  * value per operand element, 2 = hi / lo pairs (three products per element; chosen when a probe of the first rows shows that
  * tier 1 cannot separate the BMU from its neighbours on this map). */
 VSOM_API int vsom_debug_last_score_tc(const vsom_ctx *ctx);
+/* Why rows of the tensor-core path went to the exact scan, counted since vsom_create: out[0] candidate list overflowed (more
+ * than 32 nodes inside the margin), out[1] NaN distance / no eligible candidate, out[2] the certificate could not exclude an
+ * unlisted node. */
+VSOM_API int vsom_debug_tc_stats(const vsom_ctx *ctx, uint64_t out[3]);
 
 /* Som::evaluate for all-continuous columns (src/Som.cpp:490-523): f64 running mean of the BMU distance in row
  * order.  (With binary columns the reference adds a cross-entropy term; that is host work on top of the

@@ -32,5 +32,5 @@ for name, schedule in (("random init", ()), ("trained, sigma 32 -> 2", ((32, .5)
         ctx.synchronize()
         best = min(best, time.perf_counter() - t0)
     print(f"{name:24s} {n / best / 1e6:8.2f} M rows/s  {best * 1e3:8.2f} ms  {2 * W * H * D * n / best / 1e12 / 1401.7 * 100:5.1f}% of sustained peak, "
-          f"fallback {fb} ({100.0 * fb / n:.3f}%), distinct BMUs {len(torch.unique(ob))}, training {ttrain:.2f}s", flush=True)
+          f"fallback {fb} ({100.0 * fb / n:.3f}%), tier {ctx.last_score_tc}, causes {ctx.tc_stats()}, distinct BMUs {len(torch.unique(ob))}, training {ttrain:.2f}s", flush=True)
     ctx.close()

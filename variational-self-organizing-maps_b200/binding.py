@@ -54,6 +54,7 @@ _PROTOS = {
     "vsom_find_bmu_exact": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
     "vsom_find_bmu_exact_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
     "vsom_debug_last_score_tc": (C.c_int, [_vp]),
+    "vsom_debug_tc_stats": (C.c_int, [_vp, _u64p]),
     "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
     "vsom_find_bmu_batch_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, _u64p]),
     "vsom_evaluate": (C.c_int, [_vp, _f32p, C.c_size_t, _f64p]),
@@ -238,6 +239,11 @@ class VsomContext:
         """0 when the last scoring call ran the exact scan, else the precision tier (1 or 2) of K2 (tcgen05 candidate search +
         exact rescore)."""
         return int(lib().vsom_debug_last_score_tc(self._h))
+
+    def tc_stats(self):
+        out = np.zeros(3, np.uint64)
+        self._check(lib().vsom_debug_tc_stats(self._h, _p(out, _u64p)))
+        return {"list_overflow": int(out[0]), "nan_or_none": int(out[1]), "certificate": int(out[2])}
 
     def find_bmu_batch(self, x, min_hits=0):
         """Tensor-core candidate search + exact rescore; returns (bmu, dist, rows that took the exact full scan)."""

@@ -750,6 +750,15 @@ int vsom_find_bmu_batch(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hi
     return find_bmu_host_impl(ctx, x, n, min_hits, out_bmu, out_dist, true, fallback_rows, "vsom_find_bmu_batch");
 }
 
+int vsom_debug_tc_stats(const vsom_ctx *ctx, uint64_t out[3])
+{
+    if (!ctx || !out)
+        return VSOM_ERR_INVALID;
+    for (int i = 0; i < 3; ++i)
+        out[i] = ctx->tcStats[i];
+    return VSOM_OK;
+}
+
 int vsom_debug_last_score_tc(const vsom_ctx *ctx) { return ctx ? (ctx->lastScoreTc ? ctx->lastScoreTier : 0) : 0; }
 
 int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)

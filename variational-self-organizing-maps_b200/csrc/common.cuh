@@ -120,6 +120,7 @@ struct vsom_ctx
     size_t stageCap[10] = {};
     bool trainEnqueued = false;              // vsom_train_chunk_device work not yet checked for an abort
     bool poisoned = false;                   // an online-step chunk aborted: the context refuses further chunks
+    unsigned long long tcStats[3] = {0, 0, 0}; // K2 fallback causes since creation: list overflow, NaN / nothing eligible, certificate
     int lastScoreTier = 0;                   // precision tier of the last K2 call (1: one half per operand, 2: hi / lo pairs)
     int lastScoreTc = 0;                     // the last scoring call ran K2 (tensor-core search + exact rescore)
     unsigned long long lastFallbackRows = 0; // rows of the last tensor-core scoring call that needed the exact full scan

@@ -181,7 +181,7 @@ struct TcShared
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, int kSteps, int rowsTotal,
-                int numRowTiles, int numNodeTiles, int kBlocks, int stagger, int D, const float *__restrict__ xnorm2, const float *__restrict__ xratio, const TcScale *__restrict__ scale,
+                int numRowTiles, int numNodeTiles, int kBlocks, int kCols, int stagger, int D, const float *__restrict__ xnorm2, const float *__restrict__ xratio, const TcScale *__restrict__ scale,
                 unsigned *__restrict__ candOut,
                 unsigned *__restrict__ countOut, float *__restrict__ bestOut, int *err)
 {
@@ -368,7 +368,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
             const float xn = row < rowsTotal ? xnorm2[row] : 0.0f, ratio = row < rowsTotal ? xratio[row] : 1.0f;
             float E, delta;
-            tc_margins(xn, mm, ratio, kBlocks * TC_BK, D, scale->split, E, delta);
+            tc_margins(xn, mm, ratio, kCols, D, scale->split, E, delta);
             float best = inf, thr = inf;
             int cnt = 0;
             bool ovf = false;
@@ -636,7 +636,8 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
                                                              const unsigned *__restrict__ cand, const unsigned *__restrict__ count, const float *__restrict__ bestA,
                                                              const float *__restrict__ xnorm2, const float *__restrict__ xratio, const TcScale *__restrict__ scale,
                                                              int Kpad, int order, int N, const u64 *__restrict__ hits, u64 minHits, unsigned *__restrict__ outBmu,
-                                                             float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount)
+                                                             float *__restrict__ outDist, unsigned *__restrict__ fallbackRows, unsigned *__restrict__ fallbackCount,
+                                                             unsigned long long *__restrict__ stats)
 {
     __shared__ unsigned sOff[RS_ROWS + 1];
     __shared__ unsigned sWarpTot[RS_ROWS / 32];
@@ -709,7 +710,11 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
             certified = lower > sd;
         }
         if (!certified)
+        {
             fallbackRows[atomicAdd(fallbackCount, 1u)] = static_cast<unsigned>(row);
+            // diagnostics: why (1: list overflow / empty, 2: NaN or nothing eligible, 3: the certificate's bound did not clear d*)
+            atomicAdd(stats + (cnt == TC_OVERFLOW ? 1 : (nan || key == ~0ull ? 2 : 3)), 1ull);
+        }
         else
         {
             if (outBmu)
@@ -825,8 +830,8 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     c.N = N;
     c.split = split;
     c.kSteps = ((split ? 3 * D : D) + 3 + 15) / 16; // K = 16 per MMA: the model vector (three segments in the precise tier) + the three node-constant columns
-    c.Kpad = (c.kSteps * 16 + TC_BK - 1) / TC_BK * TC_BK; // operand rows are whole 128-byte swizzle rows
-    c.kBlocks = c.Kpad / TC_BK;
+    c.Kpad = c.kSteps * 16; // columns of the operand rows; the last 64-wide TMA box may reach past them: zero fill, no memory traffic
+    c.kBlocks = (c.Kpad + TC_BK - 1) / TC_BK;
     c.Npad = (N + TC_BN - 1) / TC_BN * TC_BN;
     c.nodeTiles = c.Npad / TC_BN;
     c.minHits = minHits;
@@ -884,7 +889,7 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     }
     c.Xb = static_cast<__half *>(ctx->stage[7]);
     c.totalDev = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(ctx->stage[8]) + 2 * c.setBytes);
-    VSOM_CUDA(ctx, cudaMemsetAsync(c.totalDev, 0, sizeof(unsigned long long), ctx->stream));
+    VSOM_CUDA(ctx, cudaMemsetAsync(c.totalDev, 0, 4 * sizeof(unsigned long long), ctx->stream));
     VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
     c.slab = 0;
     return VSOM_OK;
@@ -915,13 +920,13 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
     const int grid = std::min(rowTiles, ctx->numSMs);
     VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.kSteps, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.stagger, c.D, xnorm, xratio, c.scale,
+    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.kSteps, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.Kpad, c.stagger, c.D, xnorm, xratio, c.scale,
                                                                         cand, candCount, bestA, ctx->errFlag);
     cudaStream_t rs = c.overlap ? ctx->auxStream : ctx->stream;
     VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
     VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
     rescore_kernel<<<static_cast<unsigned>((rows + RS_ROWS - 1) / RS_ROWS), RS_THREADS, 0, rs>>>(xs, static_cast<long long>(rows), c.D, ctx->mean, ctx->rowStride, cand, candCount, bestA,
-                                                                                                 xnorm, xratio, c.scale, c.Kpad, order, c.N, ctx->hits, c.minHits, outBmuDev, outDistDev, fbRows, fbCount);
+                                                                                                 xnorm, xratio, c.scale, c.Kpad, order, c.N, ctx->hits, c.minHits, outBmuDev, outDistDev, fbRows, fbCount, c.totalDev);
     // rows the certificate rejected: exact scan (K3 tiles over the row list; the count stays on the device)
     add_count_kernel<<<1, 1, 0, rs>>>(fbCount, c.totalDev);
     rc = launch_find_bmu_list(ctx, xs, rows, fbRows, fbCount, c.minHits, outBmuDev, outDistDev, rs);
@@ -943,14 +948,17 @@ static int tc_finish(vsom_ctx *ctx, TcCall &c, unsigned long long *fallbackRowsO
     // the context's stream owns the results again
     for (int i = 0; i < 2 && static_cast<size_t>(i) < c.slab; ++i)
         VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evDone[i], 0));
-    unsigned long long totalFallback = 0;
+    unsigned long long totalFallback = 0, st[4] = {0, 0, 0, 0};
     int flag = 0;
-    VSOM_CUDA(ctx, cudaMemcpyAsync(&totalFallback, c.totalDev, sizeof(totalFallback), cudaMemcpyDeviceToHost, ctx->stream));
+    VSOM_CUDA(ctx, cudaMemcpyAsync(st, c.totalDev, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
     VSOM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flag)
         return set_error(ctx, VSOM_ERR_TIMEOUT, "score_tc: pipeline barrier timed out (kernel bug)");
     VSOM_CUDA(ctx, cudaGetLastError());
+    totalFallback = st[0];
+    for (int i = 0; i < 3; ++i)
+        ctx->tcStats[i] += st[i + 1];
     if (fallbackRowsOut)
         *fallbackRowsOut = totalFallback;
     ctx->lastFallbackRows = totalFallback;
@@ -967,7 +975,7 @@ static const double kTcTierSwitch = 0.04;
 // rows per slab such that the fp16 operand staging of a slab stays below 2.5 GiB
 static size_t tc_slab_cap(const vsom_ctx *ctx, int split)
 {
-    const size_t kext = static_cast<size_t>(split ? 3 * ctx->Dm : ctx->Dm) + 3, kpad = (kext + TC_BK - 1) / TC_BK * TC_BK;
+    const size_t kext = static_cast<size_t>(split ? 3 * ctx->Dm : ctx->Dm) + 3, kpad = (kext + 15) / 16 * 16;
     return std::max<size_t>(TC_BM, ((size_t{5} << 29) / (kpad * 2)) & ~static_cast<size_t>(TC_BM - 1));
 }
 
