@@ -671,7 +671,7 @@ def main():
                                     "resident in HBM, data-sharded over the ranks",
                         "note": score_note,
                         "call": "vsom_find_bmu_device (the reference-facing scoring call: Som::evaluate / measureSimilarity / mapDataSet dispatch to it)",
-                        "kernel": "K2 score_tc_kernel (tcgen05 fp16 candidate search, margin lists of <= 32 nodes) + exact f32 rescore + certificate + exact scan of rejected rows",
+                        "kernel": "K2 score_tc_kernel (tcgen05 fp16 candidate search, margin lists of <= 48 nodes) + exact f32 rescore + certificate + exact scan of rejected rows",
                         "tier": score_tier, "tier_note": "1 = one fp16 value per operand element (2 N D tensor flops per row); 2 = hi / lo pairs (6 N D), chosen by the library's probe "
                                                          "when the map's neighbouring nodes are closer than a single pass can resolve; frac is always against 2 N D",
                         "tensor_flops_issued_frac_of_peak": score_rows_s / world * 2 * SW_ * SH_ * SD_ * (3 if score_tier == 2 else 1) / 1e12 / bf16_tf,

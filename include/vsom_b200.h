@@ -188,7 +188,7 @@ VSOM_API int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double si
  * This is the call behind Som::evaluate (:490-523), Som::measureSimilarity (:631-714) and Som::mapDataSet.
  * Dispatch: batches of >= 1024 rows on shapes K2 covers (Standard / Median, Dm <= 2048) run the tensor-core candidate
  * search (tcgen05 + TMA, fp16 operands with exact power-of-two scaling; one value per element, or hi / lo pairs when a probe
- * of the first rows shows the map needs the precision) + exact f32 rescore of the <= 32 listed candidates per row + a
+ * of the first rows shows the map needs the precision) + exact f32 rescore of the <= 48 listed candidates per row + a
  * certificate that no unlisted node can win; rows that fail it are re-scored by the exact scan.  Everything else runs the
  * exact scan.
  * Results are bit-identical either way.  The host-pointer form streams the rows through two staging buffers (H2D of the
@@ -208,7 +208,7 @@ VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_
  * tier 1 cannot separate the BMU from its neighbours on this map). */
 VSOM_API int vsom_debug_last_score_tc(const vsom_ctx *ctx);
 /* Why rows of the tensor-core path went to the exact scan, counted since vsom_create: out[0] candidate list overflowed (more
- * than 32 nodes inside the margin), out[1] NaN distance / no eligible candidate, out[2] the certificate could not exclude an
+ * than 48 nodes inside the margin), out[1] NaN distance / no eligible candidate, out[2] the certificate could not exclude an
  * unlisted node. */
 VSOM_API int vsom_debug_tc_stats(const vsom_ctx *ctx, uint64_t out[3]);
 

@@ -30,7 +30,7 @@
 // bound is strictly above S_r times the best EXACT distance among the listed nodes, no unlisted node can be the BMU or tie
 // with it, and the row is done; otherwise the row is re-scored by the exact full scan.  So the result never depends on a
 // statistical recall argument: Delta' only trades list length against the share of rows that need the full scan.  Up to
-// 32 survivors per row go to the exact rescore (which also re-checks min_hits eligibility, so nothing depends on the large
+// 48 survivors per row go to the exact rescore (which also re-checks min_hits eligibility, so nothing depends on the large
 // constant given to excluded nodes); rows with more (or whose list overflowed) take the exact full scan as well.
 //
 // Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
@@ -55,9 +55,9 @@
 namespace vsom
 {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 32, TC_THREADS = 384;
-constexpr int TC_LIST = 16;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
-constexpr int TC_LIST_HI = 10; // lists are compacted against the current threshold when one passes this length
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 48, TC_THREADS = 384;
+constexpr int TC_LIST = 24;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
+constexpr int TC_LIST_HI = 16; // lists are compacted against the current threshold when one passes this length
 constexpr unsigned TC_OVERFLOW = 255;
 constexpr int TC_MAXK = 256;   // longest model vector; the operands carry 3 more columns for the node constant (below)
 constexpr int TC_MAXKB = (TC_MAXK + 16 + TC_BK - 1) / TC_BK; // k-blocks of the extended operands at most (5)
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
             base += sWarpTot[w];
         const unsigned off = sOff[tid] + base;
         for (unsigned j = 0; j < c; ++j)
-            sItem[off + j] = static_cast<unsigned short>((tid << 5) | j);
+            sItem[off + j] = static_cast<unsigned short>((tid << 6) | j);
         if (tid == RS_ROWS - 1)
             sOff[RS_ROWS] = off + c;
     }
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_kernel(const float *__rest
     for (unsigned i = tid; i < total; i += RS_THREADS)
     {
         const unsigned it = sItem[i];
-        const int r = static_cast<int>(it >> 5), j = static_cast<int>(it & 31u);
+        const int r = static_cast<int>(it >> 6), j = static_cast<int>(it & 63u);
         const long long row = row0 + r;
         const unsigned node = cand[row * TC_TOPK + j];
         // eligibility is re-checked here: padding nodes and nodes below min_hits may be listed when their large constant does
