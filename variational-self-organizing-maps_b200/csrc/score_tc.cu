@@ -369,7 +369,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             const float xn = row < rowsTotal ? xnorm2[row] : 0.0f, ratio = row < rowsTotal ? xratio[row] : 1.0f;
             float E, delta;
             tc_margins(xn, mm, ratio, kCols, D, scale->split, E, delta);
-            float best = inf, thr = inf;
+            float best = inf, thr = inf, thrC = inf; // thrC: threshold at this list's last compaction
             int cnt = 0;
             bool ovf = false;
             unsigned wp = mineAddr; // shared address of the next free entry of this thread's list (2048 bytes apart)
@@ -390,9 +390,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         if (c + 1 < TC_BN / 64)
                             tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
                         cnt = static_cast<int>((wp - mineAddr) >> 11);
-                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI))
+                        // a long list is compacted only when the threshold has tightened since its last compaction: otherwise
+                        // nothing would go, and rows with many genuine near-candidates would pay the loop at every chunk
+                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
                         {
                             compact(cnt, thr);
+                            thrC = thr;
                             wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
                         }
                         unsigned(&w)[32] = v[c & 1];
