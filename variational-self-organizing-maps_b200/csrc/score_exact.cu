@@ -17,6 +17,8 @@
 // commutes, so every lane ends with the same bits), then the scalar tail.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace vsom
 {
 
@@ -28,7 +30,7 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
                                                                        const u64 *__restrict__ hits, u64 minHits, int N, int Din, int Dr, int P,
                                                                        int rowStride, const unsigned short *__restrict__ pairI,
                                                                        const unsigned short *__restrict__ pairJ, unsigned *__restrict__ outBmu,
-                                                                       float *__restrict__ outDist)
+                                                                       float *__restrict__ outDist, int splits, u64 *__restrict__ keyBuf)
 {
     __shared__ float xa[RT][KC + 1];
     __shared__ float ma[NT][KC + 1];
@@ -37,19 +39,26 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4; // nodes tx + 16 j, rows ty + 16 i
-    const u64 row0 = static_cast<u64>(blockIdx.x) * RT;
-    // with a row list (the rows a tensor-core slab could not certify): item i is row rowList[i], the count lives on the device
-    const u64 n = rowList ? static_cast<u64>(*rowCount) : nIn;
-    if (row0 >= n)
-        return;
-    auto src_row = [&](u64 item) -> u64 { return rowList ? static_cast<u64>(rowList[item]) : item; };
+    // List mode (the rows a tensor-core slab could not certify): item i is row rowList[i], the count lives on the device, and a
+    // fixed grid walks (row tile, node split) work items — few rows must not mean few CTAs with the whole map each; the splits
+    // of a row meet in keyBuf[item] by atomic min of the (distance, node) key, written out by finalize_list_kernel.
+    const bool listMode = rowList != nullptr;
+    const u64 n = listMode ? static_cast<u64>(*rowCount) : nIn;
+    const u64 rowTiles = (n + RT - 1) / RT, nWork = listMode ? rowTiles * static_cast<u64>(splits) : rowTiles;
+    auto src_row = [&](u64 item) -> u64 { return listMode ? static_cast<u64>(rowList[item]) : item; };
+    const int nodeTilesTotal = (N + NT - 1) / NT, tilesPerSplit = listMode ? (nodeTilesTotal + splits - 1) / splits : nodeTilesTotal;
+  for (u64 w = blockIdx.x; w < nWork; w += gridDim.x)
+  {
+    const u64 row0 = (listMode ? w / static_cast<u64>(splits) : w) * RT;
+    const int split = listMode ? static_cast<int>(w % static_cast<u64>(splits)) : 0;
+    const int nodeLo = split * tilesPerSplit * NT, nodeHi = min(N, nodeLo + tilesPerSplit * NT);
 
     u64 best[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         best[i] = ~0ull;
 
-    for (int node0 = 0; node0 < N; node0 += NT)
+    for (int node0 = nodeLo; node0 < nodeHi; node0 += NT)
     {
         float acc[4][4];
 #pragma unroll
@@ -154,18 +163,24 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_kernel(const flo
         const u64 item = row0 + ty + 16 * i;
         if (tx == 0 && item < n)
         {
-            const u64 row = src_row(item);
-            if (outBmu)
-                outBmu[row] = key_node(k);
-            if (outDist)
+            if (listMode)
+                atomicMin(keyBuf + item, k);
+            else
             {
-                float d = __uint_as_float(static_cast<unsigned>(k >> 32));
-                if (k & 1ull)
-                    d = __uint_as_float(0x7fc00000u);
-                outDist[row] = d;
+                if (outBmu)
+                    outBmu[item] = key_node(k);
+                if (outDist)
+                {
+                    float d = __uint_as_float(static_cast<unsigned>(k >> 32));
+                    if (k & 1ull)
+                        d = __uint_as_float(0x7fc00000u);
+                    outDist[item] = d;
+                }
             }
         }
     }
+    __syncthreads(); // the staging arrays are reused by the next work item
+  }
 }
 
 // ---------------------------------------------------------------------------------------- Eigen SSE2 order
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
                                                                              const u64 *__restrict__ hits, u64 minHits, int N, int Din, int Dr, int P,
                                                                              int rowStride, const unsigned short *__restrict__ pairI,
                                                                              const unsigned short *__restrict__ pairJ, unsigned *__restrict__ outBmu,
-                                                                             float *__restrict__ outDist)
+                                                                             float *__restrict__ outDist, int splits, u64 *__restrict__ keyBuf)
 {
     constexpr bool kClr = TR == VSOM_CLR;
     __shared__ float xa[ER][KC + 1], ma[EN][EMS];
@@ -188,11 +203,16 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = tid & 7, g = tid >> 3, gx = g & 7, gy = g >> 3; // chain; nodes gx + 8 j (j < 4), rows gy + 4 i (i < 8)
-    const u64 row0 = static_cast<u64>(blockIdx.x) * ER;
     const int n8 = Dr & ~7, nrest = Dr - n8;
-    const u64 n = rowList ? static_cast<u64>(*rowCount) : nIn; // see find_bmu_exact_kernel
-    if (row0 >= n)
-        return;
+    const bool listMode = rowList != nullptr; // see find_bmu_exact_kernel
+    const u64 n = listMode ? static_cast<u64>(*rowCount) : nIn;
+    const u64 rowTiles = (n + ER - 1) / ER, nWork = listMode ? rowTiles * static_cast<u64>(splits) : rowTiles;
+    const int nodeTilesTotal = (N + EN - 1) / EN, tilesPerSplit = listMode ? (nodeTilesTotal + splits - 1) / splits : nodeTilesTotal;
+  for (u64 w = blockIdx.x; w < nWork; w += gridDim.x)
+  {
+    const u64 row0 = (listMode ? w / static_cast<u64>(splits) : w) * ER;
+    const int split = listMode ? static_cast<int>(w % static_cast<u64>(splits)) : 0;
+    const int nodeLo = split * tilesPerSplit * EN, nodeHi = min(N, nodeLo + tilesPerSplit * EN);
 
     u64 best[8];
 #pragma unroll
@@ -209,7 +229,7 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
         bq = 0.0f;
         if (item < n && k < Dr)
         {
-            const u64 row = rowList ? static_cast<u64>(rowList[item]) : item;
+            const u64 row = listMode ? static_cast<u64>(rowList[item]) : item;
             if (!kClr)
                 a = x[row * Din + k];
             else
@@ -229,6 +249,7 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
                 bq = mean[static_cast<size_t>(node) * rowStride + P + k];
         }
     };
+    __syncthreads(); // (list mode) the previous work item's readers of xr are done
     {
         const int r = tid >> 3, e = tid & 7; // 32 rows x 8 rest elements
         float a, bq;
@@ -237,8 +258,7 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
         if (kClr)
             xrb[r][e] = bq;
     }
-
-    for (int node0 = 0; node0 < N; node0 += EN)
+    for (int node0 = nodeLo; node0 < nodeHi; node0 += EN)
     {
         float acc[8][4];
 #pragma unroll
@@ -334,16 +354,39 @@ __global__ void __launch_bounds__(kScoreThreads) find_bmu_exact_eigen_kernel(con
 #pragma unroll
         for (int q = 1; q < 8; ++q)
             k = u64_min(k, sBest[tid][q]);
-        const u64 row = rowList ? static_cast<u64>(rowList[row0 + tid]) : row0 + tid;
+        const u64 item = row0 + tid;
+        if (listMode)
+            atomicMin(keyBuf + item, k);
+        else
+        {
+            if (outBmu)
+                outBmu[item] = key_node(k);
+            if (outDist)
+            {
+                float d = __uint_as_float(static_cast<unsigned>(k >> 32));
+                if (k & 1ull)
+                    d = __uint_as_float(0x7fc00000u);
+                outDist[item] = d;
+            }
+        }
+    }
+    __syncthreads(); // sBest and the staging arrays are reused by the next work item
+  }
+}
+
+// list mode: keys of the work items' splits -> outputs of the listed rows
+__global__ void finalize_list_kernel(const unsigned *__restrict__ rowList, const unsigned *__restrict__ rowCount, const u64 *__restrict__ keyBuf,
+                                     unsigned *__restrict__ outBmu, float *__restrict__ outDist)
+{
+    const unsigned n = *rowCount;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const u64 k = keyBuf[i];
+        const unsigned row = rowList[i];
         if (outBmu)
             outBmu[row] = key_node(k);
         if (outDist)
-        {
-            float d = __uint_as_float(static_cast<unsigned>(k >> 32));
-            if (k & 1ull)
-                d = __uint_as_float(0x7fc00000u);
-            outDist[row] = d;
-        }
+            outDist[row] = (k & 1ull) ? __uint_as_float(0x7fc00000u) : __uint_as_float(static_cast<unsigned>(k >> 32));
     }
 }
 
@@ -418,42 +461,48 @@ int launch_soft_assign(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
     return VSOM_OK;
 }
 
-// rowListDev == null: rows 0 .. n-1 of xDev.  Otherwise the rows rowListDev[0 .. *rowCountDev) (at most n of them: the grid
-// covers n, tiles past the count return at once) — the exact scan of the rows a tensor-core slab could not certify, with
-// the count staying on the device.
+// rowListDev == null: rows 0 .. n-1 of xDev.  Otherwise the rows rowListDev[0 .. *rowCountDev) (at most n of them) — the exact
+// scan of the rows a tensor-core slab could not certify, the count staying on the device; keyBufDev: n u64 of scratch.
 int launch_find_bmu_list(vsom_ctx *ctx, const float *xDev, size_t n, const unsigned *rowListDev, const unsigned *rowCountDev, uint64_t minHits, unsigned *outBmuDev,
-                         float *outDistDev, cudaStream_t stream)
+                         float *outDistDev, cudaStream_t stream, u64 *keyBufDev)
 {
     if (n == 0)
         return VSOM_OK;
-    if (ctx->order == VSOM_ORDER_EIGEN_SSE)
+    const bool list = rowListDev != nullptr;
+    const bool eigen = ctx->order == VSOM_ORDER_EIGEN_SSE;
+    const int tileRows = eigen ? ER : RT, tileNodes = eigen ? EN : NT;
+    // list mode: a fixed grid (a few CTAs per SM) walks (row tile, node split) work items; 32 splits of the node range
+    const int nodeTiles = (ctx->N + tileNodes - 1) / tileNodes, splits = list ? std::max(1, std::min(32, nodeTiles)) : 1;
+    const unsigned grid = list ? static_cast<unsigned>(std::min<size_t>((n + tileRows - 1) / tileRows * splits, static_cast<size_t>(ctx->numSMs) * 4))
+                               : static_cast<unsigned>((n + tileRows - 1) / tileRows);
+    if (list)
+        VSOM_CUDA(ctx, cudaMemsetAsync(keyBufDev, 0xff, sizeof(u64) * n, stream));
+#define VSOM_SCORE_ARGS xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev, splits, keyBufDev
+    if (eigen)
     {
-        const unsigned egrid = static_cast<unsigned>((n + ER - 1) / ER);
         if (ctx->transform == VSOM_CLR)
-            find_bmu_exact_eigen_kernel<VSOM_CLR><<<egrid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr,
-                                                                                   ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+            find_bmu_exact_eigen_kernel<VSOM_CLR><<<grid, kScoreThreads, 0, stream>>>(VSOM_SCORE_ARGS);
         else
-            find_bmu_exact_eigen_kernel<VSOM_STANDARD><<<egrid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din,
-                                                                                        ctx->Dr, ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
-        VSOM_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 1;
-        return VSOM_OK;
+            find_bmu_exact_eigen_kernel<VSOM_STANDARD><<<grid, kScoreThreads, 0, stream>>>(VSOM_SCORE_ARGS);
     }
-    const unsigned grid = static_cast<unsigned>((n + RT - 1) / RT);
-    if (ctx->transform == VSOM_CLR)
-        find_bmu_exact_kernel<VSOM_CLR><<<grid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr, ctx->P,
-                                                                          ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
+    else if (ctx->transform == VSOM_CLR)
+        find_bmu_exact_kernel<VSOM_CLR><<<grid, kScoreThreads, 0, stream>>>(VSOM_SCORE_ARGS);
     else // Standard and Median share the Comparer (src/Transformation.cpp:7-8, :45-46)
-        find_bmu_exact_kernel<VSOM_STANDARD><<<grid, kScoreThreads, 0, stream>>>(xDev, n, rowListDev, rowCountDev, ctx->mean, ctx->hits, minHits, ctx->N, ctx->Din, ctx->Dr,
-                                                                               ctx->P, ctx->rowStride, ctx->pairI, ctx->pairJ, outBmuDev, outDistDev);
-    VSOM_CUDA(ctx, cudaGetLastError());
+        find_bmu_exact_kernel<VSOM_STANDARD><<<grid, kScoreThreads, 0, stream>>>(VSOM_SCORE_ARGS);
+#undef VSOM_SCORE_ARGS
     ctx->launches += 1;
+    if (list)
+    {
+        finalize_list_kernel<<<std::min(1024u, static_cast<unsigned>((n + 255) / 256)), 256, 0, stream>>>(rowListDev, rowCountDev, keyBufDev, outBmuDev, outDistDev);
+        ctx->launches += 1;
+    }
+    VSOM_CUDA(ctx, cudaGetLastError());
     return VSOM_OK;
 }
 
 int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev)
 {
-    return launch_find_bmu_list(ctx, xDev, n, nullptr, nullptr, minHits, outBmuDev, outDistDev, ctx->stream);
+    return launch_find_bmu_list(ctx, xDev, n, nullptr, nullptr, minHits, outBmuDev, outDistDev, ctx->stream, nullptr);
 }
 
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev)

@@ -874,8 +874,8 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     if (rc)
         return rc;
     // per-row scratch: candidates, their count, |s_r x|^2, s_m / s_r, best approximate score, fallback list; per set: fallback count
-    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + 3 * sizeof(float) + sizeof(unsigned);
-    c.setBytes = (perRow * c.slabRows + 256 + 255) & ~static_cast<size_t>(255);
+    const size_t perRow = sizeof(unsigned) * TC_TOPK + sizeof(unsigned) + 3 * sizeof(float) + sizeof(unsigned) + sizeof(u64); // + key of the exact scan's node splits
+    c.setBytes = (perRow * c.slabRows + 512 + 255) & ~static_cast<size_t>(255);
     rc = stage_reserve(ctx, 8, 2 * c.setBytes + 256);
     if (rc)
         return rc;
@@ -910,7 +910,8 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     float *xratio = xnorm + c.slabRows;
     float *bestA = xratio + c.slabRows;
     unsigned *fbRows = reinterpret_cast<unsigned *>(bestA + c.slabRows);
-    unsigned *fbCount = fbRows + c.slabRows;
+    u64 *fbKeys = reinterpret_cast<u64 *>(set + ((reinterpret_cast<unsigned char *>(fbRows + c.slabRows) - set + 7) & ~static_cast<size_t>(7)));
+    unsigned *fbCount = reinterpret_cast<unsigned *>(fbKeys + c.slabRows);
     const int order = ctx->order == VSOM_ORDER_EIGEN_SSE ? VSOM_ORDER_EIGEN_SSE : VSOM_ORDER_REFERENCE;
 
     if (c.slab >= 2)
@@ -932,7 +933,7 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
                                                                                                  xnorm, xratio, c.scale, c.Kpad, order, c.N, ctx->hits, c.minHits, outBmuDev, outDistDev, fbRows, fbCount, c.totalDev);
     // rows the certificate rejected: exact scan (K3 tiles over the row list; the count stays on the device)
     add_count_kernel<<<1, 1, 0, rs>>>(fbCount, c.totalDev);
-    rc = launch_find_bmu_list(ctx, xs, rows, fbRows, fbCount, c.minHits, outBmuDev, outDistDev, rs);
+    rc = launch_find_bmu_list(ctx, xs, rows, fbRows, fbCount, c.minHits, outBmuDev, outDistDev, rs, fbKeys);
     if (rc)
         return rc;
     if (outBmuHost && outBmuDev)
