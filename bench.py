@@ -61,8 +61,8 @@ def peaks_burst():
 
 
 def measured_traffic(kernel, units):
-    """DRAM bytes of one launch processing `units`, scaled from the committed ncu capture (profiles/r01_traffic.json)."""
-    p = os.path.join(REPO, "profiles", "r01_traffic.json")
+    """DRAM bytes of one launch processing `units`, scaled from the committed ncu captures (profiles/r02_traffic.json)."""
+    p = os.path.join(REPO, "profiles", "r02_traffic.json")
     if not os.path.exists(p):
         return None
     k = json.load(open(p)).get(kernel)
@@ -541,7 +541,7 @@ def main():
                  "planes_resident_in_smem": lctx.planes_resident, "reduction_order": args.order}
         if world == 1:
             large["roofline"]["traffic"] = measured_traffic("online_step_kernel_large_map", LROWS)
-            large["roofline"]["traffic_source"] = "profiles/r01_traffic.json (ncu --set full of the streamed-scan kernel, scaled per sample)"
+            large["roofline"]["traffic_source"] = "profiles/r02_traffic.json (ncu --set full of the streamed-scan kernel, scaled per sample)"
         # full U-matrix of the large map (config 5: "plus full UMatrix"): every rank computes its own grid rows; on sharded
         # contexts the border rows of means are read from the neighbours' planes over NVLink first (inside the timed call)
         barrier()
@@ -659,7 +659,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "smem" if resident else "hbm", "achieved": achieved, "peak": onchip["smem_gbs"] if resident else hbm_gbs, "unit": "GB/s",
                          "frac": achieved / (onchip["smem_gbs"] if resident else hbm_gbs), "traffic": measured_traffic(k1_name, n),
-                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, scaled per sample): DRAM bytes, a tiny fraction of the algorithmic bytes because the map stays on chip",
+                         "traffic_source": "profiles/r02_traffic.json (ncu --set full, scaled per sample): DRAM bytes, a tiny fraction of the algorithmic bytes because the map stays on chip",
                          "peak_source": "measured in this run (vsom_debug_measure_peaks, csrc/peaks.cu): aggregate conflict-free LDS.128 read bandwidth of the 148 SMs" if resident else peak_src,
                          "algorithmic_bytes_per_sample": bps, "window_nodes": k, "kernel": k1_name, "kernel_ms_per_launch": kern_s * 1e3,
                          "measured_peaks_gbs": {"smem_all_sms": onchip["smem_gbs"], "smem_per_sm": onchip["smem_gbs_per_sm"], "l2_read": onchip["l2_gbs"], "l2_set_mib": onchip["l2_set_mib"], "hbm_copy": hbm_gbs},
@@ -679,7 +679,7 @@ def main():
                         "parity": "see cpu_baseline.scoring_agreement (measured in this run) and tests/test_gpu_parity.py",
                         "fallback_rows": fallback_rows, "fallback_frac": fallback_rows / rows_rank, "gpu_launches": score_launches, "clocks": score_clocks,
                         "roofline": {"bound": "tensor", "achieved": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12, "peak": bf16_tf, "unit": "TFLOP/s",
-                                     "frac": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12 / bf16_tf, "traffic": measured_traffic("score_tc_kernel", rows_rank),
+                                     "frac": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12 / bf16_tf, "traffic": measured_traffic(f"score_tc_kernel_tier{score_tier}", rows_rank),
                                      "flops_per_row": 2 * SW_ * SH_ * SD_, "peak_source": peak_src + " (sustained bf16; the timed region is > 1 s per GPU at N=1)",
                                      "frac_of_burst_peak": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12 / bf16_burst},
                         "e2e": {"value": score_e2e, "unit": "rows/s", "rows": e2e_rows * world, "h2d_bytes_per_step": e2e_rows * SD_ * 4, "d2h_bytes_per_step": e2e_rows * 8,
