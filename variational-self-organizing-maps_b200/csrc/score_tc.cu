@@ -382,65 +382,73 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 unsigned v[2][32];
                 if ((stagger & 2) == 0) // bit 1 of the debug word: skip the column work (pipeline-only timing)
                 {
-                    tmem_ld32(taddr, v[0]);
+                    // one 32-column chunk of this thread's row.  Kept as ONE copy of the code per TMEM buffer (the loop below is
+                    // not unrolled further): fully unrolled, the epilogue was 48 KB of SASS and its warps spent 40 % of their
+                    // time waiting for instructions (ncu: stall_no_inst, profiles/r02_k2_ncu_details.txt)
+                    auto chunk = [&](unsigned(&w)[32], int c) {
+                    cnt = static_cast<int>((wp - mineAddr) >> 11);
+                    // a long list is compacted only when the threshold has tightened since its last compaction: otherwise
+                    // nothing would go, and rows with many genuine near-candidates would pay the loop at every chunk
+                    if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
+                    {
+                        compact(cnt, thr);
+                        thrC = thr;
+                        wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
+                    }
+                                        const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
+                    // The accumulators ARE the scores.  Group minima (of four columns) and the chunk minimum first: a tree of
+                    // independent min instructions (FMNMX3 where it fits), nothing else on the common path.
+                    float m4[8];
 #pragma unroll
-                    for (int c = 0; c < TC_BN / 64; ++c)
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        m4[j4] = fminf(fminf(__uint_as_float(w[j4 * 4 + 0]), __uint_as_float(w[j4 * 4 + 1])),
+                                       fminf(__uint_as_float(w[j4 * 4 + 2]), __uint_as_float(w[j4 * 4 + 3])));
+                    const float cm = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+                    const float thrOld = thr; // valid, possibly stale: whatever must be appended lies below it
+                    // the chunk's own minimum tightens the threshold BEFORE anything is appended
+                    best = fminf(best, cm);
+                    thr = best + delta;
+                    if (!__any_sync(0xffffffffu, cm < thrOld))
+                        return; // no lane of the warp has a candidate in this chunk (the common case once the rows have settled)
+                    unsigned gm = 0; // groups of four columns in which this row may have something to append
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        gm |= (m4[j4] < thrOld) ? (1u << j4) : 0u;
+                    // one REDUX tells the whole warp which groups need the (predicated) appends; the branches
+                    // below are on a warp-uniform value
+                    const unsigned any = __reduce_or_sync(0xffffffffu, gm);
+                    if (any)
+                    {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            if (any & (1u << j4))
+                            {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (__uint_as_float(w[j4 * 4 + k]) < thr)
+                                    {
+                                        if (wp < mineEnd)
+                                        {
+                                            sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
+                                            wp += 2048;
+                                        }
+                                        else
+                                            ovf = true; // list full: this row takes the exact scan
+                                    }
+                            }
+                    }
+                    };
+                    tmem_ld32(taddr, v[0]);
+#pragma unroll 1
+                    for (int cp = 0; cp < TC_BN / 128; ++cp)
                     {
                         tmem_wait_ld();
-                        if (c + 1 < TC_BN / 64)
-                            tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-                        cnt = static_cast<int>((wp - mineAddr) >> 11);
-                        // a long list is compacted only when the threshold has tightened since its last compaction: otherwise
-                        // nothing would go, and rows with many genuine near-candidates would pay the loop at every chunk
-                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
-                        {
-                            compact(cnt, thr);
-                            thrC = thr;
-                            wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
-                        }
-                        unsigned(&w)[32] = v[c & 1];
-                        const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
-                        // The accumulators ARE the scores.  Group minima (of four columns) and the chunk minimum first: a tree of
-                        // independent min instructions (FMNMX3 where it fits), nothing else on the common path.
-                        float m4[8];
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)
-                            m4[j4] = fminf(fminf(__uint_as_float(w[j4 * 4 + 0]), __uint_as_float(w[j4 * 4 + 1])),
-                                           fminf(__uint_as_float(w[j4 * 4 + 2]), __uint_as_float(w[j4 * 4 + 3])));
-                        const float cm = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
-                        const float thrOld = thr; // valid, possibly stale: whatever must be appended lies below it
-                        // the chunk's own minimum tightens the threshold BEFORE anything is appended
-                        best = fminf(best, cm);
-                        thr = best + delta;
-                        if (!__any_sync(0xffffffffu, cm < thrOld))
-                            continue; // no lane of the warp has a candidate in this chunk (the common case once the rows have settled)
-                        unsigned gm = 0; // groups of four columns in which this row may have something to append
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4)
-                            gm |= (m4[j4] < thrOld) ? (1u << j4) : 0u;
-                        // one REDUX tells the whole warp which groups need the (predicated) appends; the branches
-                        // below are on a warp-uniform value
-                        const unsigned any = __reduce_or_sync(0xffffffffu, gm);
-                        if (any)
-                        {
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4)
-                                if (any & (1u << j4))
-                                {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        if (__uint_as_float(w[j4 * 4 + k]) < thr)
-                                        {
-                                            if (wp < mineEnd)
-                                            {
-                                                sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
-                                                wp += 2048;
-                                            }
-                                            else
-                                                ovf = true; // list full: this row takes the exact scan
-                                        }
-                                }
-                        }
+                        tmem_ld32(taddr + (2 * cp + 1) * 32, v[1]);
+                        chunk(v[0], 2 * cp);
+                        tmem_wait_ld();
+                        if (2 * cp + 2 < TC_BN / 64)
+                            tmem_ld32(taddr + (2 * cp + 2) * 32, v[0]);
+                        chunk(v[1], 2 * cp + 1);
                     }
                 }
                 tc_fence_before();
