@@ -56,6 +56,7 @@ namespace vsom
 {
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 3, TC_TOPK = 48, TC_THREADS = 384;
+constexpr int TC_MAXSTAGES = 6; // ring stages at most (CTA pairs hold half B tiles: twice the stages in the same space)
 constexpr int TC_LIST = 24;    // per-thread candidate list (shared memory); a full list sends the row to the exact scan
 constexpr int TC_LIST_HI = 16; // lists are compacted against the current threshold when one passes this length
 constexpr unsigned TC_OVERFLOW = 255;
@@ -91,27 +92,68 @@ __device__ __forceinline__ bool mbar_try_wait(void *bar, unsigned parity)
 // bounded wait: a pipeline bug must end the kernel (error flag), not hang the GPU
 __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity, int *err)
 {
-    for (long long spin = 0; spin < (1ll << 26); ++spin)
+    unsigned long long t0 = 0;
+#pragma unroll 1
+    for (unsigned spin = 1;; ++spin)
+    {
         if (mbar_try_wait(bar, parity))
             return true;
+        if ((spin & 1023u) == 0)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0)
+                t0 = t;
+            else if (t - t0 > 4000000000ull) // 4 s: no legitimate wait of this pipeline lasts longer than a tile
+                break;
+        }
+    }
     *err = 2;
     return false;
 }
+// In a CTA pair the shared::cluster address of the SAME offset in the even (leader) CTA: clear the peer bit (cute's Sm100MmaPeerBitMask)
+constexpr unsigned TC_LEADER_MASK = 0xFEFFFFFFu;
+// PAIR: the load lands in this CTA's shared memory, its bytes complete on the LEADER CTA's barrier
+template <bool PAIR>
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, void *bar, int c0, int c1)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
+    if (PAIR)
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                     "l"(map), "r"(smem_u32(bar) & TC_LEADER_MASK), "r"(c0), "r"(c1)
+                     : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                     "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                     : "memory");
 }
+// PAIR: the arrival is delivered to the barrier at this offset in BOTH CTAs
+template <bool PAIR>
 __device__ __forceinline__ void umma_commit(void *bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if (PAIR)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(static_cast<unsigned short>(3))
+                     : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void umma_f16(unsigned tmemC, u64 descA, u64 descB, unsigned idesc, unsigned accumulate)
+template <bool PAIR>
+__device__ __forceinline__ void mbar_arrive_leader(void *bar)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemC), "l"(descA),
-                 "l"(descB), "r"(idesc), "r"(accumulate)
-                 : "memory");
+    if (PAIR)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC_LEADER_MASK) : "memory");
+    else
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one lane of a converged warp (elect.sync): the compiler knows the guarded code runs in exactly one thread
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld32(unsigned addr, unsigned (&v)[32])
 {
@@ -123,6 +165,10 @@ __device__ __forceinline__ void tmem_ld32(unsigned addr, unsigned (&v)[32])
                    "=r"(v[31])
                  : "r"(addr)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(unsigned addr, unsigned (&v)[4])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void sts64(unsigned addr, unsigned lo, unsigned hi)
 {
@@ -140,7 +186,22 @@ __device__ __forceinline__ u64 umma_desc_sw128(unsigned smemAddr)
     return static_cast<u64>((smemAddr & 0x3ffff) >> 4) | (1ull << 16) | (static_cast<u64>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=f16 (format 0 at bits 7 and 10; bf16 would be 1), both K-major, N>>3 at 17, M>>4 at 24
-constexpr unsigned kIdesc = (1u << 4) | (static_cast<unsigned>(TC_BN >> 3) << 17) | (static_cast<unsigned>(TC_BM >> 4) << 24);
+__host__ __device__ constexpr unsigned tc_idesc(int m) { return (1u << 4) | (static_cast<unsigned>(TC_BN >> 3) << 17) | (static_cast<unsigned>(m >> 4) << 24); }
+constexpr unsigned kIdesc = tc_idesc(TC_BM), kIdescPair = tc_idesc(2 * TC_BM);
+// PAIR: one instruction for both CTAs (M = 256: rows 0..127 from the leader's A tile into its TMEM, 128..255 the peer's);
+// each CTA's shared memory supplies its 128 of the 256 B rows; the descriptors address the same offsets in both
+template <bool PAIR>
+__device__ __forceinline__ void umma_f16(unsigned tmemC, u64 descA, u64 descB, unsigned accumulate)
+{
+    if (PAIR)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemC), "l"(descA),
+                     "l"(descB), "r"(kIdescPair), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmemC), "l"(descA),
+                     "l"(descB), "r"(kIdesc), "r"(accumulate)
+                     : "memory");
+}
 
 // scales of one scoring call, computed on the device (tc_scale_kernel)
 struct TcScale
@@ -179,6 +240,14 @@ struct TcShared
     static constexpr int TOTAL = MERGE_OFF + 256 * 8;
 };
 
+// PAIR = true: two CTAs of a cluster (the two SMs of a TPC) work as one tcgen05 cta_group::2 unit on 256 rows.  Each CTA
+// holds its own 128 rows of A and HALF of the B tile (128 of the 256 nodes); one MMA (M = 256) issued by the even CTA reads
+// both halves, so every B byte crosses L2 -> SMEM once per 256 rows instead of once per 128, and each SM's shared memory
+// serves 8 KB per K = 16 step instead of 12 KB.  Barrier protocol (same offsets in both CTAs):
+//   bFull / aFull : the LEADER's; its producer expects both CTAs' bytes, the peer's TMA completes on it (cta_group::2 load)
+//   bEmpty / aEmpty / tFull : each CTA's own, signalled by the leader's tcgen05.commit multicast to both
+//   tEmpty : the leader's; one arrival per epilogue warp of BOTH CTAs (the peer's arrive through shared::cluster)
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM, int kSteps, int rowsTotal,
                 int numRowTiles, int numNodeTiles, int kBlocks, int kCols, int stagger, int D, const float *__restrict__ xnorm2, const float *__restrict__ xratio, const TcScale *__restrict__ scale,
@@ -188,10 +257,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     // 128-byte-swizzled TMA / UMMA tiles need a 1024-byte aligned base; declaring the alignment (instead of rounding
     // a pointer up by hand) also lets the compiler keep every derived pointer in the shared address space (LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int BST = PAIR ? TC_B_BYTES / 2 : TC_B_BYTES;       // B bytes of one stage in THIS CTA's shared memory
+    constexpr int NCTA = PAIR ? 2 : 1;
     unsigned char *sA = smem + TcShared::A_OFF;
     unsigned char *sB = smem + TcShared::B_OFF;
     u64 *bars = reinterpret_cast<u64 *>(smem + TcShared::BAR_OFF);
-    u64 *bFull = bars, *bEmpty = bars + TC_STAGES, *aFull = bars + 2 * TC_STAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
+    u64 *bFull = bars, *bEmpty = bars + TC_MAXSTAGES, *aFull = bars + 2 * TC_MAXSTAGES, *aEmpty = aFull + 1, *tFull = aEmpty + 1, *tEmpty = tFull + 2;
     unsigned *tmemBaseSlot = reinterpret_cast<unsigned *>(tEmpty + 2);
     uint2 *lists = reinterpret_cast<uint2 *>(smem + TcShared::LIST_OFF);
     float *sBest = reinterpret_cast<float *>(smem + TcShared::MERGE_OFF);
@@ -199,13 +270,25 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool streamed = kBlocks > TC_MAXKB; // the row tile's K does not fit the resident A area: A k-blocks ride in the stage ring
-    // CTAs walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
+    const int stageBytes = streamed ? TC_A_BYTES + BST : BST;
+    // stages of the ring: whatever fits the operand area (resident: the 96 KB behind A; streamed: A and B areas together)
+    const unsigned numStages = streamed ? static_cast<unsigned>((TcShared::BAR_OFF) / (TC_A_BYTES + BST) < TC_MAXSTAGES ? (TcShared::BAR_OFF) / (TC_A_BYTES + BST) : TC_MAXSTAGES)
+                                        : static_cast<unsigned>(TC_STAGES * TC_B_BYTES / BST);
+    unsigned char *ring = streamed ? smem : sB;
+    unsigned crank = 0;
+    if (PAIR)
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const bool leader = crank == 0;
+    // work units: PAIR -> 256 rows (row tiles 2u and 2u + 1, one per CTA; an odd last one is a tile of zero rows)
+    const int unitIdx = PAIR ? blockIdx.x >> 1 : blockIdx.x, unitStride = PAIR ? gridDim.x >> 1 : gridDim.x;
+    const int numUnits = PAIR ? (numRowTiles + 1) >> 1 : numRowTiles;
+    // units walk the node tiles from different starting points so that at any moment they pull DIFFERENT B tiles out
     // of L2 (all starting at tile 0 makes 148 SMs ask the same lines at once)
-    const int ntStart = (stagger & 1) ? static_cast<int>((static_cast<unsigned>(blockIdx.x) * 7u) % static_cast<unsigned>(numNodeTiles)) : 0;
+    const int ntStart = (stagger & 1) ? static_cast<int>((static_cast<unsigned>(unitIdx) * 7u) % static_cast<unsigned>(numNodeTiles)) : 0;
 
     if (warp == 1 && lane == 0)
     {
-        for (int s = 0; s < TC_STAGES; ++s)
+        for (int s = 0; s < TC_MAXSTAGES; ++s)
         {
             mbar_init(&bFull[s], 1);
             mbar_init(&bEmpty[s], 1);
@@ -215,14 +298,24 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         for (int a = 0; a < 2; ++a)
         {
             mbar_init(&tFull[a], 1);
-            mbar_init(&tEmpty[a], 256);
+            mbar_init(&tEmpty[a], 8 * NCTA); // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (PAIR)
+        cluster_sync(); // the peer's barriers exist before anything of ours can reach them; both CTAs are resident for the paired allocation
     if (warp == 2)
     {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemBaseSlot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR)
+        {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemBaseSlot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+        else
+        {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemBaseSlot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -231,56 +324,70 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 
     if (warp == 0)
     {
-        // ===================================================== TMA producer
-        if (lane == 0)
+        // ===================================================== TMA producer (both CTAs of a pair: own A rows, own half of B)
+        // The WHOLE warp walks the loop (waits included) and one elected lane issues: with a divergent `if (lane == 0)` around
+        // the loop every TMA / MMA instruction (uniform datapath) is wrapped in an ELECT / R2UR.BROADCAST retry loop and the
+        // per-k-block issue path grows to ~150 dependent instructions — as long as the 4 MMAs it feeds (ncu, round 2).
         {
             unsigned stage = 0, phase = 0, aPhase = 0;
             bool ok = true;
-            for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
+            for (int u = unitIdx; u < numUnits && ok; u += unitStride)
             {
+                const int rt = PAIR ? 2 * u + static_cast<int>(crank) : u;
                 if (!streamed)
                 {
                     ok = mbar_wait(aEmpty, aPhase ^ 1, err); // previous row tile's MMAs are done with A
                     aPhase ^= 1;
-                    mbar_expect_tx(aFull, static_cast<unsigned>(kBlocks) * TC_A_BYTES);
-                    for (int kb = 0; kb < kBlocks; ++kb)
-                        tma_load_2d(sA + kb * TC_A_BYTES, &mapX, aFull, kb * TC_BK, rt * TC_BM);
+                    if (elect_one())
+                    {
+                        if (leader)
+                            mbar_expect_tx(aFull, static_cast<unsigned>(kBlocks) * TC_A_BYTES * NCTA);
+                        for (int kb = 0; kb < kBlocks; ++kb)
+                            tma_load_2d<PAIR>(sA + kb * TC_A_BYTES, &mapX, aFull, kb * TC_BK, rt * TC_BM);
+                    }
+                    __syncwarp();
                 }
                 for (int i = 0; i < numNodeTiles && ok; ++i)
+                {
+                    int nt = i + ntStart;
+                    nt -= nt >= numNodeTiles ? numNodeTiles : 0;
+                    const int node0 = nt * TC_BN + static_cast<int>(crank) * (TC_BN / 2); // PAIR: this CTA's half of the node tile (box of 128 rows)
                     for (int kb = 0; kb < kBlocks && ok; ++kb)
                     {
-                        const int nt = (i + ntStart) % numNodeTiles;
                         ok = mbar_wait(&bEmpty[stage], phase ^ 1, err);
-                        if (!streamed)
+                        unsigned char *st = ring + stage * stageBytes;
+                        if (elect_one())
                         {
-                            mbar_expect_tx(&bFull[stage], TC_B_BYTES);
-                            tma_load_2d(sB + stage * TC_B_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
+                            if (leader)
+                                mbar_expect_tx(&bFull[stage], static_cast<unsigned>(stageBytes) * NCTA);
+                            if (streamed)
+                            {
+                                // long rows: the A k-block travels with the B k-block (re-read from L2 for every node tile)
+                                tma_load_2d<PAIR>(st, &mapX, &bFull[stage], kb * TC_BK, rt * TC_BM);
+                                st += TC_A_BYTES;
+                            }
+                            tma_load_2d<PAIR>(st, &mapM, &bFull[stage], kb * TC_BK, node0);
                         }
-                        else
-                        {
-                            // long rows: the A k-block travels with the B k-block (re-read from L2 for every node tile)
-                            unsigned char *st = smem + stage * (TC_A_BYTES + TC_B_BYTES);
-                            mbar_expect_tx(&bFull[stage], TC_A_BYTES + TC_B_BYTES);
-                            tma_load_2d(st, &mapX, &bFull[stage], kb * TC_BK, rt * TC_BM);
-                            tma_load_2d(st + TC_A_BYTES, &mapM, &bFull[stage], kb * TC_BK, nt * TC_BN);
-                        }
-                        if (++stage == TC_STAGES)
+                        __syncwarp();
+                        if (++stage == numStages)
                         {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
+                }
             }
         }
     }
     else if (warp == 1)
     {
-        // ===================================================== MMA issuer (one lane)
-        if (lane == 0)
+        // ===================================================== MMA issuer (whole warp walks, one elected lane issues; PAIR: leader CTA only)
+        if (leader)
         {
             unsigned stage = 0, phase = 0, aPhase = 0, acc = 0, accPhase = 0;
             bool ok = true;
-            for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
+            const unsigned ringAddr = smem_u32(ring), sAAddr = smem_u32(sA);
+            for (int u = unitIdx; u < numUnits && ok; u += unitStride)
             {
                 if (!streamed)
                 {
@@ -290,31 +397,34 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 for (int nt = 0; nt < numNodeTiles && ok; ++nt)
                 {
                     ok = mbar_wait(&tEmpty[acc], accPhase ^ 1, err); // epilogue drained this accumulator
-                    tc_fence_after();
                     const unsigned tmemC = tmemBase + acc * TC_BN;
                     for (int kb = 0; kb < kBlocks && ok; ++kb)
                     {
                         ok = mbar_wait(&bFull[stage], phase, err);
                         tc_fence_after();
-                        const unsigned aAddr = streamed ? smem_u32(smem + stage * (TC_A_BYTES + TC_B_BYTES)) : smem_u32(sA + kb * TC_A_BYTES);
-                        const unsigned bAddr = streamed ? aAddr + TC_A_BYTES : smem_u32(sB + stage * TC_B_BYTES);
+                        const unsigned stAddr = ringAddr + stage * static_cast<unsigned>(stageBytes);
+                        const unsigned aAddr = streamed ? stAddr : sAAddr + static_cast<unsigned>(kb) * TC_A_BYTES;
+                        const unsigned bAddr = streamed ? stAddr + TC_A_BYTES : stAddr;
                         const int steps = min(TC_BK / 16, kSteps - kb * (TC_BK / 16)); // the last k-block may be partly used
+                        if (elect_one())
+                        {
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the descriptor's address field
+                            const u64 da = umma_desc_sw128(aAddr), db = umma_desc_sw128(bAddr);
 #pragma unroll
-                        for (int k = 0; k < TC_BK / 16; ++k)
-                            if (k < steps)
-                            {
-                                // +32 bytes per K=16 step inside the 128-byte swizzle row
-                                const u64 da = umma_desc_sw128(aAddr + k * 32), db = umma_desc_sw128(bAddr + k * 32);
-                                umma_f16(tmemC, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
-                            }
-                        umma_commit(&bEmpty[stage]); // frees the B stage when the MMAs above have read it
-                        if (++stage == TC_STAGES)
+                            for (int k = 0; k < TC_BK / 16; ++k)
+                                if (k < steps)
+                                    umma_f16<PAIR>(tmemC, da + 2u * k, db + 2u * k, (kb | k) != 0 ? 1u : 0u);
+                            umma_commit<PAIR>(&bEmpty[stage]); // frees the stage (in both CTAs) when the MMAs above have read it
+                            if (kb == kBlocks - 1)
+                                umma_commit<PAIR>(&tFull[acc]); // accumulator complete
+                        }
+                        __syncwarp();
+                        if (++stage == numStages)
                         {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
-                    umma_commit(&tFull[acc]); // accumulator complete
                     if (++acc == 2)
                     {
                         acc = 0;
@@ -322,7 +432,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     }
                 }
                 if (!streamed)
-                    umma_commit(aEmpty); // all MMAs of this row tile are done reading A
+                {
+                    if (elect_one())
+                        umma_commit<PAIR>(aEmpty); // all MMAs of this row tile are done reading A
+                    __syncwarp();
+                }
             }
         }
     }
@@ -363,8 +477,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             cnt = k;
         };
 
-        for (int rt = blockIdx.x; rt < numRowTiles && ok; rt += gridDim.x)
+        for (int u = unitIdx; u < numUnits && ok; u += unitStride)
         {
+            const int rt = PAIR ? 2 * u + static_cast<int>(crank) : u;
             const long long row = static_cast<long long>(rt) * TC_BM + rowInTile;
             const float xn = row < rowsTotal ? xnorm2[row] : 0.0f, ratio = row < rowsTotal ? xratio[row] : 1.0f;
             float E, delta;
@@ -386,57 +501,58 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     // not unrolled further): fully unrolled, the epilogue was 48 KB of SASS and its warps spent 40 % of their
                     // time waiting for instructions (ncu: stall_no_inst, profiles/r02_k2_ncu_details.txt)
                     auto chunk = [&](unsigned(&w)[32], int c) {
-                    cnt = static_cast<int>((wp - mineAddr) >> 11);
-                    // a long list is compacted only when the threshold has tightened since its last compaction: otherwise
-                    // nothing would go, and rows with many genuine near-candidates would pay the loop at every chunk
-                    if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
-                    {
-                        compact(cnt, thr);
-                        thrC = thr;
-                        wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
-                    }
-                                        const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
-                    // The accumulators ARE the scores.  Group minima (of four columns) and the chunk minimum first: a tree of
-                    // independent min instructions (FMNMX3 where it fits), nothing else on the common path.
-                    float m4[8];
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4)
-                        m4[j4] = fminf(fminf(__uint_as_float(w[j4 * 4 + 0]), __uint_as_float(w[j4 * 4 + 1])),
-                                       fminf(__uint_as_float(w[j4 * 4 + 2]), __uint_as_float(w[j4 * 4 + 3])));
-                    const float cm = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
-                    const float thrOld = thr; // valid, possibly stale: whatever must be appended lies below it
-                    // the chunk's own minimum tightens the threshold BEFORE anything is appended
-                    best = fminf(best, cm);
-                    thr = best + delta;
-                    if (!__any_sync(0xffffffffu, cm < thrOld))
-                        return; // no lane of the warp has a candidate in this chunk (the common case once the rows have settled)
-                    unsigned gm = 0; // groups of four columns in which this row may have something to append
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4)
-                        gm |= (m4[j4] < thrOld) ? (1u << j4) : 0u;
-                    // one REDUX tells the whole warp which groups need the (predicated) appends; the branches
-                    // below are on a warp-uniform value
-                    const unsigned any = __reduce_or_sync(0xffffffffu, gm);
-                    if (any)
-                    {
+                        cnt = static_cast<int>((wp - mineAddr) >> 11);
+                        // a long list is compacted only when the threshold has tightened since its last compaction: otherwise
+                        // nothing would go, and rows with many genuine near-candidates would pay the loop at every chunk
+                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
+                        {
+                            compact(cnt, thr);
+                            thrC = thr;
+                            wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
+                        }
+                        const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
+                        // The accumulators ARE the scores.  Group minima (of four columns) and the chunk minimum first: a tree of
+                        // independent min instructions (FMNMX3 where it fits), nothing else on the common path.
+                        float m4[8];
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
-                            if (any & (1u << j4))
-                            {
+                            m4[j4] = fminf(fminf(__uint_as_float(w[j4 * 4 + 0]), __uint_as_float(w[j4 * 4 + 1])),
+                                           fminf(__uint_as_float(w[j4 * 4 + 2]), __uint_as_float(w[j4 * 4 + 3])));
+                        const float cm = fminf(fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])), fminf(fminf(m4[4], m4[5]), fminf(m4[6], m4[7])));
+                        const float thrOld = thr; // valid, possibly stale: whatever must be appended lies below it
+                        // the chunk's own minimum tightens the threshold BEFORE anything is appended
+                        best = fminf(best, cm);
+                        thr = best + delta;
+                        if (!__any_sync(0xffffffffu, cm < thrOld))
+                            return; // no lane of the warp has a candidate in this chunk (the common case once the rows have settled)
+                        unsigned gm = 0; // groups of four columns in which this row may have something to append
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (__uint_as_float(w[j4 * 4 + k]) < thr)
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            gm |= (m4[j4] < thrOld) ? (1u << j4) : 0u;
+                        // one REDUX tells the whole warp which groups hold something; each flagged group is re-read from TMEM (4
+                        // columns) in a short loop — 32 predicated appends per chunk copy in the instruction stream cost more in
+                        // instruction fetch than the re-read does in latency
+                        const unsigned cAddr = taddr + static_cast<unsigned>(c * 32);
+#pragma unroll 1
+                        for (unsigned left = __reduce_or_sync(0xffffffffu, gm); left; left &= left - 1)
+                        {
+                            const unsigned j4 = static_cast<unsigned>(__ffs(static_cast<int>(left)) - 1);
+                            unsigned r[4];
+                            tmem_ld4(cAddr + j4 * 4, r);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (__uint_as_float(r[k]) < thr)
+                                {
+                                    if (wp < mineEnd)
                                     {
-                                        if (wp < mineEnd)
-                                        {
-                                            sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
-                                            wp += 2048;
-                                        }
-                                        else
-                                            ovf = true; // list full: this row takes the exact scan
+                                        sts64(wp, r[k], nodeBase + j4 * 4 + k);
+                                        wp += 2048;
                                     }
-                            }
-                    }
+                                    else
+                                        ovf = true; // list full: this row takes the exact scan
+                                }
+                        }
                     };
                     tmem_ld32(taddr, v[0]);
 #pragma unroll 1
@@ -452,7 +568,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&tEmpty[acc]);
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive_leader<PAIR>(&tEmpty[acc]);
                 if (++acc == 2)
                 {
                     acc = 0;
@@ -489,9 +607,17 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync(); // neither CTA leaves (or frees TMEM) while the other may still signal its barriers
+    else
+        __syncthreads();
     if (warp == 2)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512) : "memory");
+    {
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ operand preparation
@@ -825,7 +951,7 @@ bool score_tc_supported(const vsom_ctx *ctx) { return ctx->transform != VSOM_CLR
 struct TcCall
 {
     int D = 0, N = 0, Kpad = 0, kBlocks = 0, kSteps = 0, Npad = 0, nodeTiles = 0, stagger = 1, split = 0;
-    bool overlap = true;
+    bool overlap = true, pair = true;
     uint64_t minHits = 0;
     size_t slabRows = 0, setBytes = 0, slab = 0;
     __half *Xb = nullptr;
@@ -860,13 +986,17 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     tc_scale_kernel<<<1, 1, 0, ctx->stream>>>(c.scale, split);
     map_operand_kernel<<<(c.Npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, mnorm, ctx->hits, minHits, N, c.Npad, D, ctx->rowStride, c.scale, Mb, c.Kpad);
     ctx->launches += 3;
-    rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, TC_BN);
+    // CTA pairs (tcgen05 cta_group::2, the default): each CTA of a pair loads half of a node tile (box of 128 nodes)
+    static const bool pairEnv = [] { const char *e = getenv("VSOM_TC_PAIR"); return e ? atoi(e) != 0 : true; }();
+    c.pair = pairEnv && ctx->numSMs >= 2;
+    rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, c.pair ? TC_BN / 2 : TC_BN);
     if (rc)
         return rc;
     // function attributes are per device: set it for every context (not once per process)
     if (!ctx->tcAttrSet)
     {
-        VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShared::TOTAL));
+        VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShared::TOTAL));
+        VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShared::TOTAL));
         ctx->tcAttrSet = 1;
     }
 
@@ -930,10 +1060,33 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     if (rc)
         return rc;
     const int rowTiles = static_cast<int>((rows + TC_BM - 1) / TC_BM);
-    const int grid = std::min(rowTiles, ctx->numSMs);
     VSOM_CUDA(ctx, cudaMemsetAsync(fbCount, 0, sizeof(unsigned), ctx->stream));
-    score_tc_kernel<<<grid, TC_THREADS, TcShared::TOTAL, ctx->stream>>>(mapX, c.mapM, c.kSteps, static_cast<int>(rows), rowTiles, c.nodeTiles, c.kBlocks, c.Kpad, c.stagger, c.D, xnorm, xratio, c.scale,
-                                                                        cand, candCount, bestA, ctx->errFlag);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = TcShared::TOTAL;
+        cfg.stream = ctx->stream;
+        if (c.pair)
+        {
+            // one cluster of two CTAs (the two SMs of a TPC) per 256 rows
+            const int units = (rowTiles + 1) / 2;
+            cfg.gridDim = dim3(static_cast<unsigned>(2 * std::min(units, ctx->numSMs / 2)));
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+        }
+        else
+            cfg.gridDim = dim3(static_cast<unsigned>(std::min(rowTiles, ctx->numSMs)));
+        const int rowsI = static_cast<int>(rows);
+        const float *xn = xnorm, *xr = xratio;
+        const TcScale *sc = c.scale;
+        VSOM_CUDA(ctx, cudaLaunchKernelEx(&cfg, c.pair ? score_tc_kernel<true> : score_tc_kernel<false>, mapX, c.mapM, c.kSteps, rowsI, rowTiles, c.nodeTiles, c.kBlocks, c.Kpad, c.stagger, c.D,
+                                          xn, xr, sc, cand, candCount, bestA, ctx->errFlag));
+    }
     cudaStream_t rs = c.overlap ? ctx->auxStream : ctx->stream;
     VSOM_CUDA(ctx, cudaEventRecord(ctx->evScore[par], ctx->stream));
     VSOM_CUDA(ctx, cudaStreamWaitEvent(rs, ctx->evScore[par], 0));
