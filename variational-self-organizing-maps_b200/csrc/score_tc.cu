@@ -33,16 +33,22 @@
 // 48 survivors per row go to the exact rescore (which also re-checks min_hits eligibility, so nothing depends on the large
 // constant given to excluded nodes); rows with more (or whose list overflowed) take the exact full scan as well.
 //
-// Kernel structure (one CTA per SM, persistent over 128-row tiles; 256 threads):
-//   warp 0   TMA producer : A tile (128 rows x K, resident for the row tile) + B tiles (256 nodes x 64) through a
-//                           3-stage mbarrier ring
-//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) into one
-//                           of two 256-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes
-//                           the accumulator
+// Kernel structure (one CTA per SM, persistent; 384 threads; by default two CTAs — the SMs of a TPC — form a cluster and
+// work as ONE tcgen05 cta_group::2 unit on 256 rows, see score_tc_kernel):
+//   warp 0   TMA producer : A tile (128 rows x K; resident for the row tile when K <= 320, else its k-blocks ride in the
+//                           ring) + B tiles (this CTA's half of 256 nodes x 64) through an mbarrier ring (6 / 5 stages)
+//   warp 1   MMA issuer   : the whole warp walks the loop, one elected lane (elect.sync) issues tcgen05.mma kind::f16
+//                           (M = 128 per CTA, N = 256, K = 16) into one of two 256-column TMEM accumulators;
+//                           tcgen05.commit frees the smem stage / publishes the accumulator (multicast to both CTAs)
 //   warp 2   TMEM allocator (512 columns)
-//   warps 4-7 epilogue    : thread = one row (TMEM lane); tcgen05.ld 32 columns at a time (next chunk in flight),
-//                           per column: FFMA (score), compare, predicated append; running best via FMNMX
-// Limits of this version: Standard / Median transformation, Dm <= 256 (A tile resident); other shapes use K3.
+//   warps 4-11 epilogue   : two threads per row (TMEM lane), 128 columns each; tcgen05.ld 32 columns at a time (next
+//                           chunk in flight); per chunk a tree of FMNMX3 (the accumulators ARE the scores), one vote, and
+//                           only for flagged groups of four columns the predicated appends to the thread's list
+// Two precision tiers (one fp16 per operand element / hi-lo pairs, three products) — see launch_find_bmu_tc.
+// Measured (round 2, 128x128x256, ncu): pipeline without epilogue 93 % / 97 % tensor-pipe active (tier 1 / 2); with it
+// 67 % / 91 %.  Tier 1 is bounded by the epilogue's TMEM reads (4 B per row-node pair at ~64 B/clk/SM is as long as the
+// K = 272 MMA work of the tile); tier 2 runs into the chip's power limit (SM clock 1.35-1.5 GHz at > 90 % activity).
+// Limits: Standard / Median transformation (not CLR), Dm <= 2048; other shapes use K3.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -140,7 +146,7 @@ template <bool PAIR>
 __device__ __forceinline__ void mbar_arrive_leader(void *bar)
 {
     if (PAIR)
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC_LEADER_MASK) : "memory");
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC_LEADER_MASK) : "memory"); // no .release.cluster: that is a MEMBAR.GPU per tile; the TMEM reads are ordered by tcgen05.fence::before_thread_sync
     else
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -165,10 +171,6 @@ __device__ __forceinline__ void tmem_ld32(unsigned addr, unsigned (&v)[32])
                    "=r"(v[31])
                  : "r"(addr)
                  : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(unsigned addr, unsigned (&v)[4])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void sts64(unsigned addr, unsigned lo, unsigned hi)
 {
@@ -495,7 +497,22 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                 tc_fence_after();
                 const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
                 unsigned v[2][32];
-                if ((stagger & 2) == 0) // bit 1 of the debug word: skip the column work (pipeline-only timing)
+                if (stagger & 4) // bit 2 of the debug word: read the accumulator, do nothing with it (TMEM-read-only timing)
+                {
+#pragma unroll 1
+                    for (int c = 0; c < TC_BN / 64; ++c)
+                    {
+                        tmem_ld32(taddr + c * 32, v[0]);
+                        tmem_wait_ld();
+                        unsigned x = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            x |= v[0][j];
+                        if (x == 0x7fc00123u) // keeps the loads alive; never true for sums of finite products
+                            ovf = true;
+                    }
+                }
+                else if ((stagger & 2) == 0) // bit 1 of the debug word: skip the column work (pipeline-only timing)
                 {
                     // one 32-column chunk of this thread's row.  Kept as ONE copy of the code per TMEM buffer (the loop below is
                     // not unrolled further): fully unrolled, the epilogue was 48 KB of SASS and its warps spent 40 % of their
@@ -529,30 +546,27 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
                             gm |= (m4[j4] < thrOld) ? (1u << j4) : 0u;
-                        // one REDUX tells the whole warp which groups hold something; each flagged group is re-read from TMEM (4
-                        // columns) in a short loop — 32 predicated appends per chunk copy in the instruction stream cost more in
-                        // instruction fetch than the re-read does in latency
-                        const unsigned cAddr = taddr + static_cast<unsigned>(c * 32);
-#pragma unroll 1
-                        for (unsigned left = __reduce_or_sync(0xffffffffu, gm); left; left &= left - 1)
-                        {
-                            const unsigned j4 = static_cast<unsigned>(__ffs(static_cast<int>(left)) - 1);
-                            unsigned r[4];
-                            tmem_ld4(cAddr + j4 * 4, r);
-                            tmem_wait_ld();
+                        // one REDUX tells the whole warp which groups need the (predicated) appends; the branches below are on a
+                        // warp-uniform value.  (Re-reading the flagged groups from TMEM in a short loop makes the code 4x smaller and measured the same on a
+                        // random map, 5 % slower on a candidate-rich one: its tcgen05.wait::ld also waits for the prefetched next chunk.)
+                        const unsigned any = __reduce_or_sync(0xffffffffu, gm);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (__uint_as_float(r[k]) < thr)
-                                {
-                                    if (wp < mineEnd)
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            if (any & (1u << j4))
+                            {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (__uint_as_float(w[j4 * 4 + k]) < thr)
                                     {
-                                        sts64(wp, r[k], nodeBase + j4 * 4 + k);
-                                        wp += 2048;
+                                        if (wp < mineEnd)
+                                        {
+                                            sts64(wp, w[j4 * 4 + k], nodeBase + j4 * 4 + k);
+                                            wp += 2048;
+                                        }
+                                        else
+                                            ovf = true; // list full: this row takes the exact scan
                                     }
-                                    else
-                                        ovf = true; // list full: this row takes the exact scan
-                                }
-                        }
+                            }
                     };
                     tmem_ld32(taddr, v[0]);
 #pragma unroll 1
