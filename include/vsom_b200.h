@@ -205,7 +205,8 @@ VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_
                                         uint64_t *fallback_rows);
 /* 0 when the last scoring call on ctx ran the exact scan, else the precision tier of its tensor-core search: 1 = one fp16
  * value per operand element, 2 = hi / lo pairs (three products per element; chosen when a probe of the first rows shows that
- * tier 1 cannot separate the BMU from its neighbours on this map). */
+ * tier 1 cannot separate the BMU from its neighbours on this map), 3 = both probes (8192 rows each, whose results stand)
+ * left more than a quarter of their rows uncertified and the remainder went to the exact scan. */
 VSOM_API int vsom_debug_last_score_tc(const vsom_ctx *ctx);
 /* Why rows of the tensor-core path went to the exact scan, counted since vsom_create: out[0] candidate list overflowed (more
  * than 48 nodes inside the margin), out[1] NaN distance / no eligible candidate, out[2] the certificate could not exclude an

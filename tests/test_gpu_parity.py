@@ -360,6 +360,35 @@ def test_tensor_core_scoring_ties_and_overflow_take_the_exact_scan(vsom):
     ctx.close()
 
 
+def test_tensor_core_probes_hand_hopeless_batches_to_the_exact_scan(vsom):
+    """A map whose nodes nearly coincide (what a batch-map epoch with a wide neighbourhood leaves): every node is inside every
+    row's margin, no candidate list can be certified at either precision.  The tier-1 and tier-2 probes (8192 rows each, results
+    kept) must notice and send the remainder to the exact scan; results stay bit-exact, through the device call and the
+    host-buffer call."""
+    rng = np.random.default_rng(77)
+    W, H, D, n = 20, 20, 96, 3 * 8192 + 1234
+    base = rng.standard_normal(D).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, vsom.STANDARD, vsom.ORDER_EIGEN_SSE)
+    ctx.upload_state(mean=(base[None, :] + 1e-4 * rng.standard_normal((W * H, D))).astype(np.float32))
+    x = (base[None, :] + rng.standard_normal((n, D))).astype(np.float32)
+    eb, ed = ctx.find_bmu_exact(x)
+    tb, td, fb = ctx.find_bmu_batch(x)
+    print(f"probes: tier {ctx.last_score_tc}, {fb} of {n} rows took the exact scan")
+    assert ctx.last_score_tc == 3 and fb >= n - 2 * 8192
+    assert_bit_equal(tb, eb, "bmu")
+    assert_bit_equal(td, ed, "dist")
+    import torch
+    xd = torch.from_numpy(x).cuda()
+    ob = torch.empty(n, dtype=torch.int32, device="cuda")
+    od = torch.empty(n, dtype=torch.float32, device="cuda")
+    fbd = ctx.find_bmu_batch_device(xd, n, ob, od)
+    ctx.synchronize()
+    assert ctx.last_score_tc == 3 and fbd >= n - 2 * 8192
+    assert_bit_equal(ob.cpu().numpy().astype(eb.dtype), eb, "device bmu")
+    assert_bit_equal(od.cpu().numpy(), ed, "device dist")
+    ctx.close()
+
+
 def test_tc_scoring_pipelines_slabs(vsom, monkeypatch):
     monkeypatch.setenv("VSOM_TC_SLAB_LOG2", "20")  # 1M-row slabs instead of 4M, so that three of them fit a test
     _tc_scoring_pipelines_slabs(vsom)

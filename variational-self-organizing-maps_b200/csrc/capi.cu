@@ -686,11 +686,24 @@ static int find_bmu_host_impl(vsom_ctx *ctx, const float *x, size_t n, uint64_t 
     {
         // pipelined: H2D of slab i + 1, search + re-scoring of slab i and D2H of slab i - 1 overlap (score_tc.cu)
         unsigned long long fb = 0;
+        size_t done = 0;
         ctx->lastScoreTc = 1;
-        const int rc = launch_find_bmu_tc_host(ctx, x, n, min_hits, out_bmu, out_dist, &fb);
+        const int rc = launch_find_bmu_tc_host(ctx, x, n, min_hits, out_bmu, out_dist, &fb, &done);
+        if (rc)
+            return rc;
+        if (done < n) // the probes found the map / data unsuited to the candidate search: the rest takes the exact path below
+        {
+            uint64_t rest = 0;
+            const int rc2 = find_bmu_host_impl(ctx, x + done * ctx->Din, n - done, min_hits, out_bmu ? out_bmu + done : nullptr, out_dist ? out_dist + done : nullptr, false,
+                                               &rest, who);
+            ctx->lastScoreTc = 1;
+            fb += rest;
+            if (rc2)
+                return rc2;
+        }
         if (fallback_rows)
             *fallback_rows = fb;
-        return rc;
+        return VSOM_OK;
     }
     int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
     if (rc)

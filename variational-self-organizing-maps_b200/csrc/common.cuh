@@ -175,7 +175,8 @@ int launch_find_bmu_list(vsom_ctx *ctx, const float *xDev, size_t n, const unsig
                          float *outDistDev, cudaStream_t stream, u64 *keyBufDev);
 bool score_tc_supported(const vsom_ctx *ctx);
 int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, unsigned *outBmuDev, float *outDistDev, unsigned long long *fallbackRowsOut);
-int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut);
+int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut,
+                            size_t *rowsDoneOut);
 int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma, int isFirst, const u64 *lastDev, unsigned *bmuDev, float *distDev);
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
 int launch_soft_assign(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, double *probDev, double *sumsDev);
@@ -217,6 +218,11 @@ __device__ __forceinline__ void cp_async4(void *smemDst, const void *gmemSrc)
 {
     unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smemDst, const void *gmemSrc)
+{
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void *smemDst, const void *gmemSrc)
 {

@@ -1150,6 +1150,7 @@ static int tc_finish(vsom_ctx *ctx, TcCall &c, unsigned long long *fallbackRowsO
 // (tier 1 at f fallback costs ~ t1 + f t_exact per row, tier 2 ~ 3 t1: break-even near 4 %).  VSOM_TC_TIER=1|2 forces one.
 static const size_t kTcProbeRows = 8192;
 static const double kTcTierSwitch = 0.04;
+static const double kTcExactSwitch = 0.25; // tier-2 probe fallback above this: the tensor cores select nothing useful, the rest is scanned exactly (tier "3")
 
 // rows per slab such that the fp16 operand staging of a slab stays below 2.5 GiB
 static size_t tc_slab_cap(const vsom_ctx *ctx, int split)
@@ -1205,8 +1206,28 @@ int launch_find_bmu_tc(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minH
         total += fb;
         tier = static_cast<double>(fb) > kTcTierSwitch * static_cast<double>(done) ? 2 : 1;
     }
+    if (tier == 2 && !tc_forced_tier() && n - done > kTcProbeRows)
+    {
+        // second probe: the next rows through tier 2 (their results stand).  Data whose norms dwarf the map's (or a map whose nodes
+        // nearly coincide) leaves more candidates than the lists hold even at 2^-20: the remainder goes straight to the exact scan
+        const int rc = tc_run_device(ctx, xDev + done * ctx->Dm, kTcProbeRows, minHits, 1, slab2, outBmuDev ? outBmuDev + done : nullptr,
+                                     outDistDev ? outDistDev + done : nullptr, &fb);
+        if (rc)
+            return rc;
+        total += fb;
+        done += kTcProbeRows;
+        if (static_cast<double>(fb) > kTcExactSwitch * static_cast<double>(kTcProbeRows))
+            tier = 3;
+    }
     ctx->lastScoreTier = tier;
-    if (done < n)
+    if (done < n && tier == 3)
+    {
+        const int rc = launch_find_bmu(ctx, xDev + done * ctx->Dm, n - done, minHits, outBmuDev ? outBmuDev + done : nullptr, outDistDev ? outDistDev + done : nullptr);
+        if (rc)
+            return rc;
+        total += n - done;
+    }
+    else if (done < n)
     {
         const int rc = tc_run_device(ctx, xDev + done * ctx->Dm, n - done, minHits, tier == 2 ? 1 : 0, tier == 2 ? slab2 : slab1, outBmuDev ? outBmuDev + done : nullptr,
                                      outDistDev ? outDistDev + done : nullptr, &fb);
@@ -1281,7 +1302,8 @@ static int tc_run_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t min
 // return to the host behind its re-scoring.  With pinned host memory the three engines (H2D, SMs, D2H) overlap fully; the
 // call is then bound by the slower of PCIe (4 D bytes per row) and the kernel.  stage slots: 0 = two row slabs,
 // 1 / 2 = BMU / distance of the whole call.  Same probe and tier choice as the device form.
-int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut)
+int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t minHits, unsigned *outBmuHost, float *outDistHost, unsigned long long *fallbackRowsOut,
+                            size_t *rowsDoneOut)
 {
     if (!score_tc_supported(ctx))
         return set_error(ctx, VSOM_ERR_UNSUPPORTED, "score_tc: needs a Standard/Median transformation and Dm <= 2048");
@@ -1303,15 +1325,30 @@ int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_
         total += fb;
         tier = static_cast<double>(fb) > kTcTierSwitch * static_cast<double>(done) ? 2 : 1;
     }
+    if (tier == 2 && !tc_forced_tier() && n - done > kTcProbeRows)
+    {
+        const int rc = tc_run_host(ctx, xHost + done * ctx->Dm, kTcProbeRows, minHits, 1, slabRows, outBmuHost ? outBmuHost + done : nullptr,
+                                   outDistHost ? outDistHost + done : nullptr, &fb);
+        if (rc)
+            return rc;
+        total += fb;
+        done += kTcProbeRows;
+        if (static_cast<double>(fb) > kTcExactSwitch * static_cast<double>(kTcProbeRows))
+            tier = 3;
+    }
     ctx->lastScoreTier = tier;
-    if (done < n)
+    if (done < n && tier != 3)
     {
         const int rc = tc_run_host(ctx, xHost + done * ctx->Dm, n - done, minHits, tier == 2 ? 1 : 0, slabRows, outBmuHost ? outBmuHost + done : nullptr,
                                    outDistHost ? outDistHost + done : nullptr, &fb);
         if (rc)
             return rc;
         total += fb;
+        done = n;
     }
+    // tier 3: rows [done, n) are left to the caller's exact path
+    if (rowsDoneOut)
+        *rowsDoneOut = done;
     if (fallbackRowsOut)
         *fallbackRowsOut = total;
     ctx->lastFallbackRows = total;
