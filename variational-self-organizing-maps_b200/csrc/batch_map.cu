@@ -49,17 +49,19 @@ __global__ void hits_add_kernel(const unsigned *__restrict__ bmu, u64 n, u64 *__
         atomicAdd(hits + bmu[j], 1ull);
 }
 
-// ---- phase A for the later epochs: findLocalBmu (src/Som.cpp:335-454) per row, one warp per row.  Lanes 0..7 evaluate
-// the candidate cells' distances (each a sequential f32 chain like the reference), every lane then replays the
-// reference's comparisons on the shuffled values, so the walk state stays warp-uniform.
+// ---- phase A for the later epochs: findLocalBmu (src/Som.cpp:335-454) per row, EIGHT lanes per row (four rows per warp).
+// The lanes of a group evaluate the candidate cells' distances (each a sequential f32 chain like the reference — one lane per
+// distance is all the parallelism a strict summation order leaves, so a whole warp per row kept 24 lanes idle), every lane of
+// the group then replays the reference's comparisons on the shuffled values, so the walk state stays group-uniform.
 template <int TR>
 __global__ void __launch_bounds__(256) local_bmu_rows_kernel(const float *__restrict__ x, u64 n, const float *__restrict__ mean, int W, int H, int Din,
                                                              int Dr, int P, int rowStride, const unsigned short *__restrict__ pairI,
                                                              const unsigned short *__restrict__ pairJ, int order, const u64 *__restrict__ start,
                                                              unsigned *__restrict__ outBmu, float *__restrict__ outDist)
 {
-    const u64 row = static_cast<u64>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const u64 row = (static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;                              // lane inside the group of eight
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);            // the group's lanes inside the warp
     if (row >= n)
         return;
     const float *xr = x + row * Din;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) local_bmu_rows_kernel(const float *__rest
     const u64 uW = static_cast<u64>(W), uH = static_cast<u64>(H), M1 = ~0ull;
     const u64 fx[8] = {M1, 0, 1, 1, 1, 0, M1, M1}, fy[8] = {1, 1, 1, 0, M1, M1, M1, 0};
     u64 lastBMU = start ? start[row] : 0ull, minIndex = lastBMU, lastMeasured = lastBMU;
-    float minDist = __shfl_sync(0xffffffffu, lane == 0 ? dist(lastBMU) : 0.0f, 0);
+    float minDist = __shfl_sync(gmask, lane == 0 ? dist(lastBMU) : 0.0f, 0, 8);
     for (;;)
     {
         const u64 lmX = lastMeasured % uW, lmY = lastMeasured / uW, lbX = lastBMU % uW;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(256) local_bmu_rows_kernel(const float *__rest
 #pragma unroll
             for (int i = 0; i < 8; ++i)
             {
-                const float v = __shfl_sync(0xffffffffu, mine, i);
+                const float v = __shfl_sync(gmask, mine, i, 8);
                 if (v < minDist)
                 {
                     minDist = v;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) local_bmu_rows_kernel(const float *__rest
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                 {
-                    const float v = __shfl_sync(0xffffffffu, mine, i);
+                    const float v = __shfl_sync(gmask, mine, i, 8);
                     if (v < minDist)
                     {
                         minDist = v;
@@ -366,7 +368,7 @@ int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma,
     }
     else
     {
-        const unsigned grid = static_cast<unsigned>((n + 7) / 8);
+        const unsigned grid = static_cast<unsigned>((n + 31) / 32);
         if (ctx->transform == VSOM_CLR)
             local_bmu_rows_kernel<VSOM_CLR><<<grid, 256, 0, ctx->stream>>>(xDev, n, ctx->mean, ctx->W, ctx->H, ctx->Din, ctx->Dr, ctx->P, ctx->rowStride,
                                                                            ctx->pairI, ctx->pairJ, ctx->order, lastDev, bmuDev, distDev);
