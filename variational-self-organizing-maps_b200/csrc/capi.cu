@@ -353,7 +353,11 @@ void vsom_destroy(vsom_ctx *ctx)
         {
             cudaEventDestroy(ctx->evScore[i]);
             cudaEventDestroy(ctx->evDone[i]);
+        }
+        for (int i = 0; i < 3; ++i)
+        {
             cudaEventDestroy(ctx->evCopied[i]);
+            cudaEventDestroy(ctx->evSlabDone[i]);
         }
     }
     if (ctx->stream)

@@ -101,7 +101,7 @@ struct vsom_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t auxStream = nullptr;           // K2: re-scoring of slab i overlaps the search of slab i + 1
     cudaStream_t copyStream = nullptr;          // host-buffer scoring: H2D of slab i + 1 overlaps the search of slab i
-    cudaEvent_t evScore[2] = {}, evDone[2] = {}, evCopied[2] = {};
+    cudaEvent_t evScore[2] = {}, evDone[2] = {}, evCopied[3] = {}, evSlabDone[3] = {}; // evCopied / evSlabDone: per host staging buffer (three)
     int tcAttrSet = 0;                          // K2's dynamic shared-memory opt-in was set on this context's device
     float *mean = nullptr, *S = nullptr, *sigma = nullptr, *weight = nullptr;
     vsom::u64 *hits = nullptr;
