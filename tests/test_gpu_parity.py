@@ -307,6 +307,32 @@ def test_tensor_core_scoring_unsupported_shapes_use_exact(vsom):
     ctx.close()
 
 
+@pytest.mark.parametrize("tier", ["1", "2"])
+@pytest.mark.parametrize("shape", [(64, 64, 128, 3000 + 77), (40, 25, 300, 1300)])
+def test_tensor_core_single_cta_variant_equals_the_pair_kernel(vsom, monkeypatch, shape, tier):
+    """score_tc_kernel<PAIR=false> (VSOM_TC_PAIR=0: one CTA per 128 rows, whole B tile per SM) is kept beside the default CTA-pair
+    kernel; both must return the exact scan's results on a trained map, resident and streamed A alike, with an odd number of
+    row tiles (the pair's last unit is half empty)."""
+    monkeypatch.setenv("VSOM_TC_TIER", tier)
+    W, H, D, n = shape
+    rng = np.random.default_rng(W + D)
+    centres = (rng.standard_normal((12, D)) * 2).astype(np.float32)
+    data = lambda k: (centres[rng.integers(0, 12, k)] + 0.4 * rng.standard_normal((k, D))).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, vsom.STANDARD, vsom.ORDER_EIGEN_SSE)
+    ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * H, D)) / 1000).astype(np.float32))
+    for sg, eta in ((W / 3.0, 0.4), (W / 8.0, 0.2), (2.0, 0.1)):
+        ctx.train_chunk(data(1500), eta, sg, vsom.EXPONENTIAL)
+    q = data(n)
+    eb, ed = ctx.find_bmu_exact(q)
+    for pair in ("1", "0"):
+        monkeypatch.setenv("VSOM_TC_PAIR", pair)
+        tb, td, fb = ctx.find_bmu_batch(q)
+        assert ctx.last_score_tc == int(tier)
+        assert_bit_equal(tb, eb, f"bmu, pair={pair}")
+        assert_bit_equal(td, ed, f"dist, pair={pair}")
+    ctx.close()
+
+
 @pytest.mark.parametrize("tier", ["1", "2", "auto"])
 @pytest.mark.parametrize("shape", [(20, 20, 784, 1500), (64, 64, 128, 3000), (128, 128, 256, 2500), (40, 25, 300, 1300), (9, 9, 5, 1100)])
 def test_tensor_core_tiers_and_long_rows(vsom, po, monkeypatch, shape, tier):

@@ -1001,8 +1001,8 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     map_operand_kernel<<<(c.Npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, mnorm, ctx->hits, minHits, N, c.Npad, D, ctx->rowStride, c.scale, Mb, c.Kpad);
     ctx->launches += 3;
     // CTA pairs (tcgen05 cta_group::2, the default): each CTA of a pair loads half of a node tile (box of 128 nodes)
-    static const bool pairEnv = [] { const char *e = getenv("VSOM_TC_PAIR"); return e ? atoi(e) != 0 : true; }();
-    c.pair = pairEnv && ctx->numSMs >= 2;
+    const char *pairEnv = getenv("VSOM_TC_PAIR"); // read per call: the tests run both variants in one process
+    c.pair = (pairEnv ? atoi(pairEnv) != 0 : true) && ctx->numSMs >= 2;
     rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, c.pair ? TC_BN / 2 : TC_BN);
     if (rc)
         return rc;
