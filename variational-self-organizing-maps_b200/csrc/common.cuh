@@ -214,6 +214,40 @@ __device__ __forceinline__ void st_relaxed_sys(u64 *p, u64 v)
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// ---- packed f32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 — one issue slot for two IEEE-rounded f32 operations; each half
+// rounds exactly like the scalar .rn instruction, so packed code stays bit-identical to the scalar chains it replaces)
+__device__ __forceinline__ u64 f2_pack(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 f2_add(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 f2_sub(u64 a, u64 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ void cp_async4(void *smemDst, const void *gmemSrc)
 {
     unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));

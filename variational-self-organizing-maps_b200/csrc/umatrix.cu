@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(UTHREADS) umatrix_tiled_kernel(const float *co
     const int muRow = active ? (ty + 1 + kDi[nb]) * (UTX + 2) + tx + 1 + kDj[nb] : mcRow; // no neighbour: distance to itself (0)
     const int sgRow = UMEANROWS + ty * UTX + tx;
 
-    EigenSseSum acc;
+    u64 acc2[4] = {0ull, 0ull, 0ull, 0ull}; // the eight chains of EigenSseSum as four packed pairs (+0.0f each)
     float s = 0.0f;
     const int blocks8 = Dm >> 3, nrest = Dm & 7;
     const int nSlices = (Dm + UKS - 1) / UKS;
@@ -279,28 +279,62 @@ __global__ void __launch_bounds__(UTHREADS) umatrix_tiled_kernel(const float *co
         for (int b8 = 0; b8 < UKS / 8; ++b8)
             if (b8 < fullHere)
             {
-                const float4 a0 = *reinterpret_cast<const float4 *>(mc + 8 * b8), a1 = *reinterpret_cast<const float4 *>(mc + 8 * b8 + 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(mu + 8 * b8), b1 = *reinterpret_cast<const float4 *>(mu + 8 * b8 + 4);
-                const float mcv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, muv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                // elements (0,1) (2,3) (4,5) (6,7) of the block as packed f32x2 pairs: the five rounded operations of a term cost
+                // five issue slots per TWO elements (FADD2 / FMUL2 / FFMA2), same bits as the scalar sequence in raw_term_fast
+                const ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(mc + 8 * b8), a1 = *reinterpret_cast<const ulonglong2 *>(mc + 8 * b8 + 4);
+                const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(mu + 8 * b8), b1 = *reinterpret_cast<const ulonglong2 *>(mu + 8 * b8 + 4);
+                const u64 mc2[4] = {a0.x, a0.y, a1.x, a1.y}, mu2[4] = {b0.x, b0.y, b1.x, b1.y};
                 const float sMown = clamp_sigma(sg[8 * b8 + nb]); // this lane's element of the block
-                const float yown = __frcp_rn(sMown);
-                float tv[8], sMv[8];
+                const float yown = __frcp_rn(sMown), nsMown = -sMown;
+                u64 t2[4];
+                float nsMv[8];
                 bool bad = ((__ballot_sync(0xffffffffu, !rcp_ok(sMown)) >> grp) & 0xffu) != 0;
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
+                for (int p = 0; p < 4; ++p)
                 {
-                    sMv[e] = __shfl_sync(0xffffffffu, sMown, grp + e);
-                    tv[e] = raw_term_fast(mcv[e], muv[e], sMv[e], __shfl_sync(0xffffffffu, yown, grp + e), bad);
+                    nsMv[2 * p] = __shfl_sync(0xffffffffu, nsMown, grp + 2 * p);
+                    nsMv[2 * p + 1] = __shfl_sync(0xffffffffu, nsMown, grp + 2 * p + 1);
+                    const u64 y2 = f2_pack(__shfl_sync(0xffffffffu, yown, grp + 2 * p), __shfl_sync(0xffffffffu, yown, grp + 2 * p + 1));
+                    const u64 d2 = f2_sub(mc2[p], mu2[p]);
+                    const u64 q2 = f2_mul(d2, y2);
+                    const u64 r2 = f2_fma(f2_pack(nsMv[2 * p], nsMv[2 * p + 1]), q2, d2);
+                    const u64 av = f2_fma(r2, y2, q2);
+                    t2[p] = f2_mul(av, av);
+                    float dl, dh;
+                    f2_unpack(d2, dl, dh);
+                    bad = bad || !(fabsf(dl) < 1.2676506e30f) || !(fabsf(dh) < 1.2676506e30f); // 2^100; NaN fails the comparison
                 }
                 if (bad)
+                {
+                    float mcv[8], muv[8], sMv[8], tv[8];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                    {
+                        f2_unpack(mc2[p], mcv[2 * p], mcv[2 * p + 1]);
+                        f2_unpack(mu2[p], muv[2 * p], muv[2 * p + 1]);
+                        sMv[2 * p] = -nsMv[2 * p];
+                        sMv[2 * p + 1] = -nsMv[2 * p + 1];
+                    }
                     raw_terms_exact(mcv, muv, sMv, tv);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        t2[p] = f2_pack(tv[2 * p], tv[2 * p + 1]);
+                }
                 if (ORDER == VSOM_ORDER_EIGEN_SSE)
-                    acc.block(tv);
+                {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        acc2[p] = f2_add(acc2[p], t2[p]); // EigenSseSum::block on chains (2p, 2p + 1)
+                }
                 else
                 {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        s = __fadd_rn(s, tv[e]);
+                    for (int p = 0; p < 4; ++p)
+                    {
+                        float tl, th;
+                        f2_unpack(t2[p], tl, th);
+                        s = __fadd_rn(__fadd_rn(s, tl), th);
+                    }
                 }
             }
         if (sl == nSlices - 1)
@@ -322,7 +356,13 @@ __global__ void __launch_bounds__(UTHREADS) umatrix_tiled_kernel(const float *co
             if (bad)
                 raw_terms_exact(mcv, muv, sMv, tv);
             if (ORDER == VSOM_ORDER_EIGEN_SSE)
+            {
+                EigenSseSum acc;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    f2_unpack(acc2[p], acc.a[2 * p], acc.a[2 * p + 1]);
                 s = acc.finish(tv, nrest);
+            }
             else
                 for (int e = 0; e < nrest; ++e)
                     s = __fadd_rn(s, tv[e]);
@@ -350,6 +390,204 @@ __global__ void __launch_bounds__(UTHREADS) umatrix_tiled_kernel(const float *co
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tiled, Eigen order, element-major
+// In Eigen's packet order the eight chains of a dot product are indexed by the element's position inside its block of eight
+// (EigenSseSum).  So lane e of a node's eight lanes can own ELEMENT e of every block for ALL eight neighbours: its own-node
+// value, sigma and reciprocal are private (no shuffles at all), each neighbour costs one conflict-free LDS.32, and the lane's
+// eight accumulators ARE chain e of the eight pairs.  The kernel above needs 4 LDS.128 + 16 SHFL per block and warp and is bound
+// by the shared-memory / shuffle pipe (32 of its cycles per block and warp, measured: halving the FP issue slots changed nothing);
+// this one needs 10 LDS.32.  Neighbours are processed as packed f32x2 pairs.  The chains meet once, at the end (finish()).
+// The sequential order has no such decomposition (its single chain runs across the elements) and keeps the kernel above.
+constexpr int USTRE = 40; // row stride: rows of consecutive nodes 8 banks apart -> the 4 x 8 lanes of a warp hit 32 different banks
+
+__global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const float *const *__restrict__ meanRow, const float *const *__restrict__ sigmaRow,
+                                                                       const int2 *__restrict__ tiles, int W, int H, int Dm, int rowStride, double *__restrict__ out)
+{
+    extern __shared__ __align__(16) float usmem[];
+    float(*sbuf)[UROWS * USTRE] = reinterpret_cast<float(*)[UROWS * USTRE]>(usmem); // two slice buffers; reused for the chains at the end
+    float(*res)[8] = reinterpret_cast<float(*)[8]>(usmem + 2 * UROWS * USTRE);      // [UTX * UTY][8]
+
+    const int tid = threadIdx.x;
+    const int2 tile = tiles[blockIdx.y]; // first grid row, number of rows (<= UTY)
+    const int y0 = tile.x, ny = tile.y, x0 = blockIdx.x * UTX;
+    const int e = tid & 7, tx = (tid >> 3) % UTX, ty = tid / (8 * UTX);
+    const int i = y0 + ty, j = x0 + tx;
+    const bool node = ty < ny && j < W;
+
+    const float *csrc[UCHUNKS];
+    int cdst[UCHUNKS];
+#pragma unroll
+    for (int c = 0; c < UCHUNKS; ++c)
+    {
+        const int id = tid + c * UTHREADS, row = id >> 3, part = id & 7;
+        csrc[c] = nullptr;
+        cdst[c] = row < UROWS ? row * USTRE + part * 4 : -1;
+        if (row < UMEANROWS)
+        {
+            const int ry = row / (UTX + 2), rx = row - ry * (UTX + 2), y = y0 - 1 + ry, x = x0 - 1 + rx;
+            if (ry < ny + 2 && y >= 0 && y < H && x >= 0 && x < W && meanRow[y])
+                csrc[c] = meanRow[y] + static_cast<size_t>(x) * rowStride + part * 4;
+        }
+        else if (row < UROWS)
+        {
+            const int r2 = row - UMEANROWS, ry = r2 / UTX, rx = r2 - ry * UTX, y = y0 + ry, x = x0 + rx;
+            if (ry < ny && x < W)
+                csrc[c] = sigmaRow[y] + static_cast<size_t>(x) * rowStride + part * 4;
+        }
+    }
+    auto load_slice = [&](int sl, float *buf) {
+        const int k0 = sl * UKS;
+#pragma unroll
+        for (int c = 0; c < UCHUNKS; ++c)
+            if (cdst[c] >= 0)
+            {
+                const int part4 = (cdst[c] % USTRE);
+                if (csrc[c] && k0 + part4 < rowStride)
+                    cp_async16(buf + cdst[c], csrc[c] + k0);
+                else
+                    *reinterpret_cast<float4 *>(buf + cdst[c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int mcOff = ((ty + 1) * (UTX + 2) + tx + 1) * USTRE + e;
+    const int sgOff = (UMEANROWS + ty * UTX + tx) * USTRE + e;
+    int muOff[8];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb)
+    {
+        const int ni = i + kDi[nb], nj = j + kDj[nb];
+        const bool act = node && ni >= 0 && ni < H && nj >= 0 && nj < W;
+        muOff[nb] = act ? ((ty + 1 + kDi[nb]) * (UTX + 2) + tx + 1 + kDj[nb]) * USTRE + e : mcOff; // no neighbour: distance to itself (0)
+    }
+
+    // one block of eight elements (this lane: element e) against the eight neighbours -> four packed terms.  The pointers already
+    // include the slice buffer, the row and e; `o` is a compile-time offset in the unrolled callers (LDS [reg + imm]).
+    auto block_terms = [&](const float *mcp, const float *sgp, const float *const (&mup)[8], int o, u64 (&t2)[4]) {
+        const float mcv = mcp[o], sM = clamp_sigma(sgp[o]);
+        // sM in [1e-5, 2^100]: inside the range where __frcp_rn is its fast path (MUFU.RCP + one FMA-residual Newton step, the
+        // correctly rounded reciprocal for biased exponents 1..252); written out to drop the range test and the slow-path call.
+        // Outside (NaN, > 2^100) the block takes the exact path below and y is not used.
+        float y0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(sM));
+        const float y = __fmaf_rn(y0, -__fmaf_rn(sM, y0, -1.0f), y0);
+        const u64 mc2 = f2_pack(mcv, mcv), y2 = f2_pack(y, y), nsM2 = f2_pack(-sM, -sM);
+        bool bad = !rcp_ok(sM);
+        float muv[8];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+            muv[nb] = mup[nb][o];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+        {
+            const u64 d2 = f2_sub(mc2, f2_pack(muv[2 * p], muv[2 * p + 1]));
+            const u64 q2 = f2_mul(d2, y2);
+            const u64 r2 = f2_fma(nsM2, q2, d2);
+            const u64 av = f2_fma(r2, y2, q2);
+            t2[p] = f2_mul(av, av);
+            float dl, dh;
+            f2_unpack(d2, dl, dh);
+            bad = bad || !(fabsf(dl) < 1.2676506e30f) || !(fabsf(dh) < 1.2676506e30f); // 2^100; NaN fails the comparison
+        }
+        if (bad) // the reference's own arithmetic for what the correction step is not proven for (rare, per lane)
+        {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+            {
+                const float a0 = __fdiv_rn(__fsub_rn(mcv, muv[2 * p]), sM), a1 = __fdiv_rn(__fsub_rn(mcv, muv[2 * p + 1]), sM);
+                t2[p] = f2_pack(__fmul_rn(a0, a0), __fmul_rn(a1, a1));
+            }
+        }
+    };
+
+    u64 acc2[4] = {0ull, 0ull, 0ull, 0ull}; // chain e of the pairs (0,1) (2,3) (4,5) (6,7)
+    u64 rest2[4] = {0ull, 0ull, 0ull, 0ull}; // term of element e of the trailing partial block (e < Dm % 8)
+    const int blocks8 = Dm >> 3, nrest = Dm & 7;
+    const int nSlices = (Dm + UKS - 1) / UKS;
+    load_slice(0, sbuf[0]);
+    for (int sl = 0; sl < nSlices; ++sl)
+    {
+        if (sl + 1 < nSlices)
+        {
+            load_slice(sl + 1, sbuf[(sl + 1) & 1]);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+        else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const float *buf = sbuf[sl & 1];
+        const float *mcp = buf + mcOff, *sgp = buf + sgOff;
+        const float *mup[8];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+            mup[nb] = buf + muOff[nb];
+        const int fullHere = min(UKS / 8, blocks8 - sl * (UKS / 8)); // full blocks of eight inside this slice
+#pragma unroll
+        for (int b8 = 0; b8 < UKS / 8; ++b8)
+            if (b8 < fullHere)
+            {
+                u64 t2[4];
+                block_terms(mcp, sgp, mup, 8 * b8, t2);
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    acc2[p] = f2_add(acc2[p], t2[p]);
+            }
+        if (sl == nSlices - 1 && e < nrest)
+            block_terms(mcp, sgp, mup, (blocks8 << 3) - sl * UKS, rest2); // the last Dm % 8 elements sit behind this slice's full blocks
+        __syncthreads(); // this buffer is refilled by the next iteration's load
+    }
+    // the chains meet: [node][neighbour][chain] and [node][neighbour][rest element] through shared memory, then finish() per pair
+    float *fin = usmem, *finRest = usmem + UTX * UTY * 64;
+    {
+        const int nodeAt = (tid >> 3) * 64;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+        {
+            float lo, hi;
+            f2_unpack(acc2[p], lo, hi);
+            fin[nodeAt + (2 * p) * 8 + e] = lo;
+            fin[nodeAt + (2 * p + 1) * 8 + e] = hi;
+            f2_unpack(rest2[p], lo, hi);
+            finRest[nodeAt + (2 * p) * 8 + e] = lo;
+            finRest[nodeAt + (2 * p + 1) * 8 + e] = hi;
+        }
+    }
+    __syncthreads();
+    {
+        // this thread: pair (node, neighbour e)
+        EigenSseSum acc;
+        float rest[8];
+        const int at = (tid >> 3) * 64 + e * 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+        {
+            acc.a[c] = fin[at + c];
+            rest[c] = finRest[at + c];
+        }
+        const float sres = acc.finish(rest, nrest);
+        __syncthreads(); // res lies behind the slice buffers, but keep the phases apart anyway
+        res[tid >> 3][e] = sres;
+    }
+    __syncthreads();
+    if (e == 0 && node)
+    {
+        double u = 0.0;
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+            const int qi = i + kDi[q], qj = j + kDj[q];
+            if (qi >= 0 && qi < H && qj >= 0 && qj < W)
+            {
+                const double r = static_cast<double>(res[tid >> 3][q]);
+                u = __dadd_rn(u, q < 4 ? r : __dmul_rn(r, 0.3));
+                ++cnt;
+            }
+        }
+        out[static_cast<size_t>(i) * W + j] = __ddiv_rn(u, static_cast<double>(cnt));
+    }
+}
+
 int launch_umatrix_tiles(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int2 *tilesDev, int nTiles)
 {
     if (ctx->W < 2 || ctx->H < 2)
@@ -358,7 +596,15 @@ int launch_umatrix_tiles(vsom_ctx *ctx, const float *const *meanRowDev, const fl
         return VSOM_OK;
     dim3 grid((ctx->W + UTX - 1) / UTX, nTiles);
     const int smem = static_cast<int>(sizeof(float) * (2 * UROWS * USTR + UTX * UTY * 8));
-    if (ctx->order == VSOM_ORDER_EIGEN_SSE)
+    static const bool lanesPerPair = [] { const char *e = getenv("VSOM_UMATRIX_EIGEN_KERNEL"); return e && atoi(e) == 0; }(); // 0: the (node, neighbour) kernel also in Eigen order
+    if (ctx->order == VSOM_ORDER_EIGEN_SSE && !lanesPerPair)
+    {
+        const int smemE = static_cast<int>(sizeof(float) * (2 * UROWS * USTRE + UTX * UTY * 8));
+        static_assert(2 * UROWS * USTRE >= 2 * UTX * UTY * 64, "the chains are exchanged through the slice buffers");
+        VSOM_CUDA(ctx, cudaFuncSetAttribute(umatrix_tiled_eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemE));
+        umatrix_tiled_eigen_kernel<<<grid, UTHREADS, smemE, ctx->stream>>>(meanRowDev, sigmaRowDev, tilesDev, ctx->W, ctx->H, ctx->Dm, ctx->rowStride, ctx->umatrix);
+    }
+    else if (ctx->order == VSOM_ORDER_EIGEN_SSE)
     {
         VSOM_CUDA(ctx, cudaFuncSetAttribute(umatrix_tiled_kernel<VSOM_ORDER_EIGEN_SSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         umatrix_tiled_kernel<VSOM_ORDER_EIGEN_SSE><<<grid, UTHREADS, smem, ctx->stream>>>(meanRowDev, sigmaRowDev, tilesDev, ctx->W, ctx->H, ctx->Dm, ctx->rowStride, ctx->umatrix);
