@@ -398,7 +398,9 @@ __global__ void __launch_bounds__(UTHREADS) umatrix_tiled_kernel(const float *co
 // by the shared-memory / shuffle pipe (32 of its cycles per block and warp, measured: halving the FP issue slots changed nothing);
 // this one needs 10 LDS.32.  Neighbours are processed as packed f32x2 pairs.  The chains meet once, at the end (finish()).
 // The sequential order has no such decomposition (its single chain runs across the elements) and keeps the kernel above.
-constexpr int USTRE = 40; // row stride: rows of consecutive nodes 8 banks apart -> the 4 x 8 lanes of a warp hit 32 different banks
+constexpr int UKSE = 64;  // elements per slice (two barriers and one round of copy bookkeeping per slice)
+constexpr int USTRE = UKSE + 8; // row stride: rows of consecutive nodes 8 banks apart -> the 4 x 8 lanes of a warp hit 32 different banks
+constexpr int UCHUNKSE = (UROWS * (UKSE / 4) + UTHREADS - 1) / UTHREADS; // 16-byte copies per thread and slice
 
 __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const float *const *__restrict__ meanRow, const float *const *__restrict__ sigmaRow,
                                                                        const int2 *__restrict__ tiles, int W, int H, int Dm, int rowStride, double *__restrict__ out)
@@ -414,12 +416,14 @@ __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const 
     const int i = y0 + ty, j = x0 + tx;
     const bool node = ty < ny && j < W;
 
-    const float *csrc[UCHUNKS];
-    int cdst[UCHUNKS];
+    // per 16-byte copy of a slice: source (null: the chunk is zero-filled), destination offset, and the number of elements the
+    // chunk may start at before it leaves the row (<= 0: never copy)
+    const float *csrc[UCHUNKSE];
+    int cdst[UCHUNKSE], clim[UCHUNKSE];
 #pragma unroll
-    for (int c = 0; c < UCHUNKS; ++c)
+    for (int c = 0; c < UCHUNKSE; ++c)
     {
-        const int id = tid + c * UTHREADS, row = id >> 3, part = id & 7;
+        const int id = tid + c * UTHREADS, row = id / (UKSE / 4), part = id % (UKSE / 4);
         csrc[c] = nullptr;
         cdst[c] = row < UROWS ? row * USTRE + part * 4 : -1;
         if (row < UMEANROWS)
@@ -434,37 +438,39 @@ __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const 
             if (ry < ny && x < W)
                 csrc[c] = sigmaRow[y] + static_cast<size_t>(x) * rowStride + part * 4;
         }
+        clim[c] = csrc[c] ? rowStride - part * 4 : 0; // copy while k0 < clim (0: no source, or no such chunk)
     }
+    // Rows without a source (outside the grid, absent halo) are zeroed ONCE; a chunk past the end of the rows is simply not copied:
+    // what it would hold is never read (full blocks end at 8 (Dm / 8), the rest block reads its first Dm % 8 elements).
+    for (int q = tid; q < 2 * UROWS * USTRE / 4; q += UTHREADS)
+        reinterpret_cast<float4 *>(usmem)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
     auto load_slice = [&](int sl, float *buf) {
-        const int k0 = sl * UKS;
+        const int k0 = sl * UKSE;
 #pragma unroll
-        for (int c = 0; c < UCHUNKS; ++c)
-            if (cdst[c] >= 0)
-            {
-                const int part4 = (cdst[c] % USTRE);
-                if (csrc[c] && k0 + part4 < rowStride)
-                    cp_async16(buf + cdst[c], csrc[c] + k0);
-                else
-                    *reinterpret_cast<float4 *>(buf + cdst[c]) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int c = 0; c < UCHUNKSE; ++c)
+            if (k0 < clim[c])
+                cp_async16(buf + cdst[c], csrc[c] + k0);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const int mcOff = ((ty + 1) * (UTX + 2) + tx + 1) * USTRE + e;
-    const int sgOff = (UMEANROWS + ty * UTX + tx) * USTRE + e;
-    int muOff[8];
+    // BYTE offsets of this lane's element inside a slice buffer (the buffer base stays in a uniform register: LDS [R + UR + imm])
+    const unsigned mcOff = static_cast<unsigned>(((ty + 1) * (UTX + 2) + tx + 1) * USTRE + e) * 4u;
+    const unsigned sgOff = static_cast<unsigned>((UMEANROWS + ty * UTX + tx) * USTRE + e) * 4u;
+    unsigned muOff[8];
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb)
     {
         const int ni = i + kDi[nb], nj = j + kDj[nb];
         const bool act = node && ni >= 0 && ni < H && nj >= 0 && nj < W;
-        muOff[nb] = act ? ((ty + 1 + kDi[nb]) * (UTX + 2) + tx + 1 + kDj[nb]) * USTRE + e : mcOff; // no neighbour: distance to itself (0)
+        muOff[nb] = act ? static_cast<unsigned>(((ty + 1 + kDi[nb]) * (UTX + 2) + tx + 1 + kDj[nb]) * USTRE + e) * 4u : mcOff; // no neighbour: distance to itself (0)
     }
 
     // one block of eight elements (this lane: element e) against the eight neighbours -> four packed terms.  The pointers already
     // include the slice buffer, the row and e; `o` is a compile-time offset in the unrolled callers (LDS [reg + imm]).
-    auto block_terms = [&](const float *mcp, const float *sgp, const float *const (&mup)[8], int o, u64 (&t2)[4]) {
-        const float mcv = mcp[o], sM = clamp_sigma(sgp[o]);
+    auto at = [](const float *buf, unsigned byteOff, int o) { return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(buf) + byteOff + 4 * o); };
+    auto block_terms = [&](const float *buf, int o, u64 (&t2)[4]) {
+        const float mcv = at(buf, mcOff, o), sM = clamp_sigma(at(buf, sgOff, o));
         // sM in [1e-5, 2^100]: inside the range where __frcp_rn is its fast path (MUFU.RCP + one FMA-residual Newton step, the
         // correctly rounded reciprocal for biased exponents 1..252); written out to drop the range test and the slow-path call.
         // Outside (NaN, > 2^100) the block takes the exact path below and y is not used.
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const 
         float muv[8];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb)
-            muv[nb] = mup[nb][o];
+            muv[nb] = at(buf, muOff[nb], o);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
         {
@@ -503,7 +509,7 @@ __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const 
     u64 acc2[4] = {0ull, 0ull, 0ull, 0ull}; // chain e of the pairs (0,1) (2,3) (4,5) (6,7)
     u64 rest2[4] = {0ull, 0ull, 0ull, 0ull}; // term of element e of the trailing partial block (e < Dm % 8)
     const int blocks8 = Dm >> 3, nrest = Dm & 7;
-    const int nSlices = (Dm + UKS - 1) / UKS;
+    const int nSlices = (Dm + UKSE - 1) / UKSE;
     load_slice(0, sbuf[0]);
     for (int sl = 0; sl < nSlices; ++sl)
     {
@@ -516,24 +522,19 @@ __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const 
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const float *buf = sbuf[sl & 1];
-        const float *mcp = buf + mcOff, *sgp = buf + sgOff;
-        const float *mup[8];
+        const int fullHere = min(UKSE / 8, blocks8 - sl * (UKSE / 8)); // full blocks of eight inside this slice
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb)
-            mup[nb] = buf + muOff[nb];
-        const int fullHere = min(UKS / 8, blocks8 - sl * (UKS / 8)); // full blocks of eight inside this slice
-#pragma unroll
-        for (int b8 = 0; b8 < UKS / 8; ++b8)
+        for (int b8 = 0; b8 < UKSE / 8; ++b8)
             if (b8 < fullHere)
             {
                 u64 t2[4];
-                block_terms(mcp, sgp, mup, 8 * b8, t2);
+                block_terms(buf, 8 * b8, t2);
 #pragma unroll
                 for (int p = 0; p < 4; ++p)
                     acc2[p] = f2_add(acc2[p], t2[p]);
             }
         if (sl == nSlices - 1 && e < nrest)
-            block_terms(mcp, sgp, mup, (blocks8 << 3) - sl * UKS, rest2); // the last Dm % 8 elements sit behind this slice's full blocks
+            block_terms(buf, (blocks8 << 3) - sl * UKSE, rest2); // the last Dm % 8 elements sit behind this slice's full blocks
         __syncthreads(); // this buffer is refilled by the next iteration's load
     }
     // the chains meet: [node][neighbour][chain] and [node][neighbour][rest element] through shared memory, then finish() per pair
