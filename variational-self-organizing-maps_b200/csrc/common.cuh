@@ -241,6 +241,17 @@ __device__ __forceinline__ u64 f2_mul(u64 a, u64 b)
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// CAUTION (ptxas 12.9, seen in SASS): a mul.rn.f32x2 whose only consumer is an add.rn.f32x2 IS contracted into one FFMA2 — with
+// -fmad=false, with the explicit .rn forms that are never fused for scalars, even when the product is written as fma(a, b, -0).
+// That changes the rounding.  Whenever a product feeds an addition, multiply the halves with scalar __fmul_rn (f2_mul_halves) and
+// add packed: one more issue slot per pair, bits identical to the scalar chain.
+__device__ __forceinline__ u64 f2_mul_halves(u64 a, u64 b)
+{
+    float al, ah, bl, bh;
+    f2_unpack(a, al, ah);
+    f2_unpack(b, bl, bh);
+    return f2_pack(__fmul_rn(al, bl), __fmul_rn(ah, bh));
+}
 __device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c)
 {
     u64 d;

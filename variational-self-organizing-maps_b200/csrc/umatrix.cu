@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(UTHREADS) umatrix_tiled_kernel(const float *co
                     const u64 q2 = f2_mul(d2, y2);
                     const u64 r2 = f2_fma(f2_pack(nsMv[2 * p], nsMv[2 * p + 1]), q2, d2);
                     const u64 av = f2_fma(r2, y2, q2);
-                    t2[p] = f2_mul(av, av);
+                    t2[p] = f2_mul_halves(av, av); // feeds the chain's addition: scalar products (see f2_mul_halves)
                     float dl, dh;
                     f2_unpack(d2, dl, dh);
                     bad = bad || !(fabsf(dl) < 1.2676506e30f) || !(fabsf(dh) < 1.2676506e30f); // 2^100; NaN fails the comparison
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(UTHREADS, 2) umatrix_tiled_eigen_kernel(const 
             const u64 q2 = f2_mul(d2, y2);
             const u64 r2 = f2_fma(nsM2, q2, d2);
             const u64 av = f2_fma(r2, y2, q2);
-            t2[p] = f2_mul(av, av);
+            t2[p] = f2_mul_halves(av, av); // feeds the chain's addition: scalar products (see f2_mul_halves)
             float dl, dh;
             f2_unpack(d2, dl, dh);
             bad = bad || !(fabsf(dl) < 1.2676506e30f) || !(fabsf(dh) < 1.2676506e30f); // 2^100; NaN fails the comparison
