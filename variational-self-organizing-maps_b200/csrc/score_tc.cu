@@ -45,9 +45,11 @@
 //                           chunk in flight); per chunk a tree of FMNMX3 (the accumulators ARE the scores), one vote, and
 //                           only for flagged groups of four columns the predicated appends to the thread's list
 // Two precision tiers (one fp16 per operand element / hi-lo pairs, three products) — see launch_find_bmu_tc.
-// Measured (round 2, 128x128x256, ncu): pipeline without epilogue 93 % / 97 % tensor-pipe active (tier 1 / 2); with it
-// 67 % / 91 %.  Tier 1 is bounded by the epilogue's TMEM reads (4 B per row-node pair at ~64 B/clk/SM is as long as the
-// K = 272 MMA work of the tile); tier 2 runs into the chip's power limit (SM clock 1.35-1.5 GHz at > 90 % activity).
+// Measured (round 2, 128x128x256, ncu): pipeline without epilogue 93 % / 97 % tensor-pipe active (tier 1 / 2); an epilogue that only
+// reads the accumulators (tcgen05.ld, no scoring) 92 % / 97 %; the real one 72 % / 95 %.  So the TMEM reads fit under the K = 272
+// contraction of a tile; what costs tier 1 its last 20 % is the latency chain of the scoring code (min tree -> vote -> branch) with two
+// epilogue warps per scheduler, and the per-tile handshake of 16 warps in two CTAs.  Tier 2 runs into the chip's power limit
+// (SM clock 1.35-1.5 GHz at > 90 % activity).
 // Limits: Standard / Median transformation (not CLR), Dm <= 2048; other shapes use K3.
 #include "common.cuh"
 
@@ -492,22 +494,28 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             unsigned wp = mineAddr; // shared address of the next free entry of this thread's list (2048 bytes apart)
             for (int i = 0; i < numNodeTiles && ok; ++i)
             {
-                const int nt = (i + ntStart) % numNodeTiles;
+                int nt = i + ntStart; // ntStart < numNodeTiles: one conditional subtraction instead of a division per tile
+                nt -= nt >= numNodeTiles ? numNodeTiles : 0;
                 ok = mbar_wait(&tFull[acc], accPhase, err);
                 tc_fence_after();
                 const unsigned taddr = tmemBase + (static_cast<unsigned>(q * 32) << 16) + acc * TC_BN + half * (TC_BN / 2);
                 unsigned v[2][32];
+                bool released = false;
                 if (stagger & 4) // bit 2 of the debug word: read the accumulator, do nothing with it (TMEM-read-only timing)
                 {
+                    // bit 3: two loads in flight per warp (is the read rate bound by the port or by the requests in flight?)
 #pragma unroll 1
-                    for (int c = 0; c < TC_BN / 64; ++c)
+                    for (int c = 0; c < TC_BN / 64; c += 2)
                     {
                         tmem_ld32(taddr + c * 32, v[0]);
+                        if (!(stagger & 8))
+                            tmem_wait_ld();
+                        tmem_ld32(taddr + (c + 1) * 32, v[1]);
                         tmem_wait_ld();
                         unsigned x = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            x |= v[0][j];
+                            x |= v[0][j] | v[1][j];
                         if (x == 0x7fc00123u) // keeps the loads alive; never true for sums of finite products
                             ovf = true;
                     }
@@ -518,15 +526,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                     // not unrolled further): fully unrolled, the epilogue was 48 KB of SASS and its warps spent 40 % of their
                     // time waiting for instructions (ncu: stall_no_inst, profiles/r02_k2_ncu_details.txt)
                     auto chunk = [&](unsigned(&w)[32], int c) {
-                        cnt = static_cast<int>((wp - mineAddr) >> 11);
-                        // a long list is compacted only when the threshold has tightened since its last compaction: otherwise
-                        // nothing would go, and rows with many genuine near-candidates would pay the loop at every chunk
-                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
-                        {
-                            compact(cnt, thr);
-                            thrC = thr;
-                            wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
-                        }
                         const unsigned nodeBase = static_cast<unsigned>(nt * TC_BN + half * (TC_BN / 2) + c * 32);
                         // The accumulators ARE the scores.  Group minima (of four columns) and the chunk minimum first: a tree of
                         // independent min instructions (FMNMX3 where it fits), nothing else on the common path.
@@ -542,6 +541,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         thr = best + delta;
                         if (!__any_sync(0xffffffffu, cm < thrOld))
                             return; // no lane of the warp has a candidate in this chunk (the common case once the rows have settled)
+                        // Lists only grow here, so this is where a long one is compacted — and only when the threshold has tightened
+                        // since its last compaction: otherwise nothing would go, and rows with many genuine near-candidates would pay
+                        // the loop at every chunk.  (The check used to sit at the top of every chunk: a second vote on the common path.)
+                        cnt = static_cast<int>((wp - mineAddr) >> 11);
+                        if (__any_sync(0xffffffffu, cnt > TC_LIST_HI && thr < thrC))
+                        {
+                            compact(cnt, thr);
+                            thrC = thr;
+                            wp = mineAddr + (static_cast<unsigned>(cnt) << 11);
+                        }
                         unsigned gm = 0; // groups of four columns in which this row may have something to append
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
@@ -578,13 +587,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                         tmem_wait_ld();
                         if (2 * cp + 2 < TC_BN / 64)
                             tmem_ld32(taddr + (2 * cp + 2) * 32, v[0]);
+                        else
+                        {
+                            // the tile's last chunk is in registers: the accumulator goes back to the MMA warp BEFORE that chunk is
+                            // scored (the slowest of the 16 epilogue warps of a pair gates the next tile but one)
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0)
+                                mbar_arrive_leader<PAIR>(&tEmpty[acc]);
+                            released = true;
+                        }
                         chunk(v[1], 2 * cp + 1);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0)
-                    mbar_arrive_leader<PAIR>(&tEmpty[acc]);
+                if (!released)
+                {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive_leader<PAIR>(&tEmpty[acc]);
+                }
                 if (++acc == 2)
                 {
                     acc = 0;
