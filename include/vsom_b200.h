@@ -191,7 +191,7 @@ VSOM_API int vsom_batch_epoch(vsom_ctx *ctx, const float *x, size_t n, double si
  * of the first rows shows the map needs the precision) + exact f32 rescore of the <= 48 listed candidates per row + a
  * certificate that no unlisted node can win; rows that fail it are re-scored by the exact scan.  Everything else runs the
  * exact scan.
- * Results are bit-identical either way.  The host-pointer form streams the rows through two staging buffers (H2D of the
+ * Results are bit-identical either way.  The host-pointer form streams the rows through three staging buffers (H2D of the
  * next slab overlaps the search of the current one; pinned host memory gives full overlap). */
 VSOM_API int vsom_find_bmu(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, uint32_t *out_bmu, float *out_dist);
 VSOM_API int vsom_find_bmu_device(vsom_ctx *ctx, const float *x_dev, size_t n, uint64_t min_hits, uint32_t *out_bmu_dev, float *out_dist_dev);
