@@ -472,6 +472,18 @@ def main():
         sctx.find_bmu_host_ptr(q_pin.data_ptr(), e2e_rows, b_pin.data_ptr(), d_pin.data_ptr())
     se2e_s = (time.perf_counter() - t0) / se2e_calls
     score_err = float(d_pin.double().mean())  # Som::evaluate's mean BMU distance from the returned host array (outside the timed region)
+    # anomaly scoring end to end (the per-row pass of Som::measureSimilarity): BMU + largest normalised deviation per row, same rows
+    r_pin = torch.empty(e2e_rows, dtype=torch.float32, pin_memory=True)
+    sctx.measure_similarity_host_ptr(q_pin.data_ptr(), min(e2e_rows, 1 << 20), 3, b_pin.data_ptr(), r_pin.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    sctx.measure_similarity_host_ptr(q_pin.data_ptr(), e2e_rows, 3, b_pin.data_ptr(), r_pin.data_ptr())
+    sim_s = time.perf_counter() - t0
+    tsim = torch.tensor([sim_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tsim, op=dist.ReduceOp.MAX)
+    sim_e2e = world * e2e_rows / float(tsim.item())
+    sim_finite = float(torch.isfinite(r_pin).float().mean())
     tt = torch.tensor([se2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -688,7 +700,8 @@ def main():
                                      "frac_of_burst_peak": score_rows_s / world * 2 * SW_ * SH_ * SD_ / 1e12 / bf16_burst},
                         "e2e": {"value": score_e2e, "unit": "rows/s", "rows": e2e_rows * world, "h2d_bytes_per_step": e2e_rows * SD_ * 4, "d2h_bytes_per_step": e2e_rows * 8,
                                 "call": "vsom_find_bmu with pinned host rows (H2D of slab i+1 / search of slab i / D2H of slab i-1 overlap)", "mean_bmu_distance": score_err,
-                                "matches_device_run": e2e_matches, "pcie_h2d_gbs_measured": h2d_gbs, "pcie_ceiling_rows_per_s": world * h2d_gbs * 1e9 / (SD_ * 4),
+                                "matches_device_run": e2e_matches,
+                                "measure_similarity": {"value": sim_e2e, "unit": "rows/s", "call": "vsom_measure_similarity (what Som::measureSimilarity makes: restricted BMU + the row's largest ((x - m) / sM) / numOfSigmas, one trip over PCIe)", "finite_share": sim_finite}, "pcie_h2d_gbs_measured": h2d_gbs, "pcie_ceiling_rows_per_s": world * h2d_gbs * 1e9 / (SD_ * 4),
                                 "frac_of_pcie_ceiling": score_e2e / (world * h2d_gbs * 1e9 / (SD_ * 4))},
                         "exact_scan_rows_per_s": exact_rows_s, "exact_scan_rows": exact_rows * world,
                         "scaling": "row-sharded, no communication"},

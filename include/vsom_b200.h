@@ -217,6 +217,13 @@ VSOM_API int vsom_debug_tc_stats(const vsom_ctx *ctx, uint64_t out[3]);
  * order.  (With binary columns the reference adds a cross-entropy term; that is host work on top of the
  * BMU indices this call family returns.) */
 VSOM_API int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error);
+/* The per-row pass of Som::measureSimilarity (src/Som.cpp:631-714) for n host rows in ONE trip over PCIe: every row's restricted
+ * BMU (as vsom_find_bmu, out_bmu may be NULL) and out_row_max[i] = max over the columns of ((x - m_bmu) / sM) / number_of_sigmas
+ * with the reference's capped sigma sM (:648) and its three f32 operations; NaN deltas never win (the reference compares with
+ * `>`), -inf when a row has none.  The reference's running maximum over all rows and columns is, after its first update, the
+ * running maximum of these values in row order, which is how Som::measureSimilarity (host/Som.cpp) finds the row it judges.
+ * Needs a Standard / Median context (model vector as long as the rows). */
+VSOM_API int vsom_measure_similarity(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, int number_of_sigmas, uint32_t *out_bmu, float *out_row_max);
 /* Distance of one row to every node: N x euclidianWeightedDist (src/Som.cpp:124-141), as the double it returns. */
 VSOM_API int vsom_all_dists(vsom_ctx *ctx, const float *v, double *out);
 

@@ -415,6 +415,40 @@ def test_tensor_core_probes_hand_hopeless_batches_to_the_exact_scan(vsom):
     ctx.close()
 
 
+@pytest.mark.parametrize("n, slab_log2", [(300, None), (3 * 8192 + 777, "12"), (20000, None)])
+def test_measure_similarity_row_pass_matches_the_reference_formula(vsom, monkeypatch, n, slab_log2):
+    """vsom_measure_similarity (the per-row pass of Som::measureSimilarity, src/Som.cpp:631-714): restricted BMU + the row's largest
+    ((x - m_bmu) / sM) / numOfSigmas, on the exact-scan path (300 rows), through the tensor-core pipeline with many small slabs and
+    both probes, and in one slab — against the same three f32 operations in numpy on the exact scan's BMUs."""
+    if slab_log2:
+        monkeypatch.setenv("VSOM_TC_HOST_SLAB_LOG2", slab_log2)
+    rng = np.random.default_rng(n)
+    W, H, D = 24, 20, 48
+    centres = (rng.standard_normal((10, D)) * 2).astype(np.float32)
+    data = lambda k: (centres[rng.integers(0, 10, k)] + 0.4 * rng.standard_normal((k, D))).astype(np.float32)
+    ctx = vsom.VsomContext(W, H, D, vsom.STANDARD, vsom.ORDER_EIGEN_SSE)
+    ctx.upload_state(mean=(rng.integers(-1000, 1000, (W * H, D)) / 1000).astype(np.float32))
+    for sg, eta in ((8.0, 0.4), (3.0, 0.2), (1.5, 0.1)):
+        ctx.train_chunk(data(1500), eta, sg, vsom.EXPONENTIAL)
+    st = ctx.download_state()
+    sigma = st["sigma"].copy()
+    sigma[::7] *= np.float32(1e-6)  # some sigmas below the reference's cap of 1e-5 (src/Som.cpp:648 caps, it does not floor)
+    ctx.upload_state(mean=st["mean"], sigma=sigma)
+    x = data(n)
+    x[5, 3] = np.nan
+    min_hits = 1
+    eb, _ = ctx.find_bmu_exact(x, min_hits)
+    bmu, row_max = ctx.measure_similarity(x, 3, min_hits)
+    assert_bit_equal(bmu, eb, "bmu")
+    m, s = st["mean"][eb], sigma[eb]
+    sM = np.where(s > np.float32(0.00001), np.float32(0.00001), s).astype(np.float32)
+    with np.errstate(all="ignore"):
+        delta = (((x - m).astype(np.float32) / sM).astype(np.float32) / np.float32(3)).astype(np.float32)
+    want = np.where(np.isnan(delta), -np.inf, delta).max(axis=1).astype(np.float32)
+    assert_bit_equal(row_max, want, "row maxima")
+    ctx.close()
+
+
 def test_tc_scoring_pipelines_slabs(vsom, monkeypatch):
     monkeypatch.setenv("VSOM_TC_SLAB_LOG2", "20")  # 1M-row slabs instead of 4M, so that three of them fit a test
     _tc_scoring_pipelines_slabs(vsom)

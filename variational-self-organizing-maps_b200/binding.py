@@ -58,6 +58,7 @@ _PROTOS = {
     "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
     "vsom_find_bmu_batch_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, _u64p]),
     "vsom_evaluate": (C.c_int, [_vp, _f32p, C.c_size_t, _f64p]),
+    "vsom_measure_similarity": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, C.c_int, _u32p, _f32p]),
     "vsom_soft_assign": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _f64p]),
     "vsom_all_dists": (C.c_int, [_vp, _f32p, _f64p]),
     "vsom_update_umatrix": (C.c_int, [_vp, _f64p]),
@@ -261,6 +262,19 @@ class VsomContext:
                                                      out_bmu_dev.data_ptr() if out_bmu_dev is not None else None,
                                                      out_dist_dev.data_ptr() if out_dist_dev is not None else None, C.byref(fb)))
         return int(fb.value)
+
+    def measure_similarity(self, x, number_of_sigmas, min_hits=0):
+        """Per-row pass of Som::measureSimilarity: (restricted BMU, largest normalised deviation from it) for every row."""
+        x = _f32(x).reshape(-1, self.Din)
+        n = x.shape[0]
+        bmu = np.empty(n, np.uint32)
+        row_max = np.empty(n, np.float32)
+        self._check(lib().vsom_measure_similarity(self._h, _p(x, _f32p), n, min_hits, int(number_of_sigmas), _p(bmu, _u32p), _p(row_max, _f32p)))
+        return bmu, row_max
+
+    def measure_similarity_host_ptr(self, x_ptr: int, n: int, number_of_sigmas: int, bmu_ptr: int, row_max_ptr: int, min_hits=0):
+        """vsom_measure_similarity on raw HOST addresses (e.g. pinned torch tensors)."""
+        self._check(lib().vsom_measure_similarity(self._h, C.cast(x_ptr, _f32p), n, min_hits, int(number_of_sigmas), C.cast(bmu_ptr, _u32p), C.cast(row_max_ptr, _f32p)))
 
     def evaluate(self, x):
         x = _f32(x).reshape(-1, self.Din)

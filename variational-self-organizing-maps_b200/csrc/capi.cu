@@ -728,6 +728,10 @@ static int find_bmu_host_impl(vsom_ctx *ctx, const float *x, size_t n, uint64_t 
     rc = launch_find_bmu(ctx, xDev, n, min_hits, bmuDev, distDev);
     if (rc)
         return rc;
+    rc = similarity_hook(ctx, xDev, n, bmuDev, 0, ctx->stream); // armed by vsom_measure_similarity only
+    if (rc)
+        return rc;
+    ctx->simRowBase += n;
     if (out_bmu)
         VSOM_CUDA(ctx, cudaMemcpyAsync(out_bmu, bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_dist)
@@ -792,6 +796,35 @@ int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)
     for (size_t i = 0; i < n; ++i)
         error += 1. / (static_cast<double>(i) + 1.0) * (static_cast<double>(dist[i]) + 0.0 - error);
     *mean_error = error;
+    return VSOM_OK;
+}
+
+int vsom_measure_similarity(vsom_ctx *ctx, const float *x, size_t n, uint64_t min_hits, int number_of_sigmas, uint32_t *out_bmu, float *out_row_max)
+{
+    if (!ctx || (!x && n) || (!out_row_max && n))
+        return ctx ? set_error(ctx, VSOM_ERR_INVALID, "vsom_measure_similarity: NULL argument") : VSOM_ERR_INVALID;
+    if (ctx->world > 1)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, kUnshardedOnly);
+    if (ctx->Dm != ctx->Din)
+        return set_error(ctx, VSOM_ERR_UNSUPPORTED, "vsom_measure_similarity: the model vector must have the rows' length (Standard / Median transformation)");
+    if (number_of_sigmas == 0)
+        return set_error(ctx, VSOM_ERR_INVALID, "vsom_measure_similarity: number_of_sigmas is 0");
+    if (n == 0)
+        return VSOM_OK;
+    VSOM_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = stage_reserve(ctx, 9, sizeof(float) * n);
+    if (rc)
+        return rc;
+    ctx->simK = static_cast<float>(number_of_sigmas);
+    ctx->simHost = out_row_max;
+    ctx->simRowBase = 0;
+    rc = find_bmu_host_impl(ctx, x, n, min_hits, out_bmu, nullptr, true, nullptr, "vsom_measure_similarity");
+    ctx->simK = 0.0f;
+    ctx->simHost = nullptr;
+    if (rc)
+        return rc;
+    // the tensor-core path's result copies run on its re-scoring stream; tc_finish joined it to the context's stream
+    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VSOM_OK;
 }
 

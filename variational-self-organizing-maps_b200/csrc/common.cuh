@@ -124,6 +124,11 @@ struct vsom_ctx
     int lastScoreTier = 0;                   // precision tier of the last K2 call (1: one half per operand, 2: hi / lo pairs)
     int lastScoreTc = 0;                     // the last scoring call ran K2 (tensor-core search + exact rescore)
     unsigned long long lastFallbackRows = 0; // rows of the last tensor-core scoring call that needed the exact full scan
+    // vsom_measure_similarity: while simK != 0 every host-buffer scoring slab also gets its rows' largest normalised deviation
+    // from their BMU (stage slot 9, absolute row index = simRowBase + row inside the running sub-call), copied to simHost
+    float simK = 0.0f;
+    float *simHost = nullptr;
+    size_t simRowBase = 0;
     int gridTrain = 0, residentTrain = 0, smStrideTrain = 0;
     size_t smemTrain = 0;
     uint64_t launches = 0;
@@ -180,6 +185,8 @@ int launch_find_bmu_tc_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_
 int launch_batch_epoch(vsom_ctx *ctx, const float *xDev, size_t n, double sigma, int isFirst, const u64 *lastDev, unsigned *bmuDev, float *distDev);
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev);
 int launch_soft_assign(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits, double *probDev, double *sumsDev);
+int launch_similarity_rowmax(vsom_ctx *ctx, const float *xDev, size_t rows, const unsigned *bmuDev, float k, float *outDev, cudaStream_t stream);
+int similarity_hook(vsom_ctx *ctx, const float *xDev, size_t rows, const unsigned *bmuDev, size_t rowInCall, cudaStream_t stream);
 int launch_umatrix_tiles(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int2 *tilesDev, int nTiles);
 int umatrix_tile_rows();
 int launch_umatrix_rows(vsom_ctx *ctx, const float *const *meanRowDev, const float *const *sigmaRowDev, const int *rowsDev, int nRows);

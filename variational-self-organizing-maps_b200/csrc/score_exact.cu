@@ -505,6 +505,64 @@ int launch_find_bmu(vsom_ctx *ctx, const float *xDev, size_t n, uint64_t minHits
     return launch_find_bmu_list(ctx, xDev, n, nullptr, nullptr, minHits, outBmuDev, outDistDev, ctx->stream, nullptr);
 }
 
+// ---- Som::measureSimilarity's per-row pass (src/Som.cpp:631-714): delta_n = ((v_n - m_n) / sM_n) / numOfSigmas against the row's BMU,
+// sM = the reference's capped sigma (:648: sigma > 1e-5 -> 1e-5).  The reference keeps a running "largest delta" over all rows and
+// columns; once that value is >= 0 (after its first update) a row can only raise it to the row's own maximum, so the device returns
+// max_n delta_n per row (NaN never wins a `>`; -inf when every delta is NaN) and the host replays the scan over rows.
+// One warp per row; the three IEEE operations are the reference's (fsub, fdiv, fdiv).
+__global__ void __launch_bounds__(256) similarity_rowmax_kernel(const float *__restrict__ x, u64 rows, int D, const float *__restrict__ mean, const float *__restrict__ sigma,
+                                                                int rowStride, const unsigned *__restrict__ bmu, float k, float *__restrict__ out)
+{
+    const u64 row = static_cast<u64>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows)
+        return;
+    const float *v = x + row * D;
+    const size_t at = static_cast<size_t>(bmu[row]) * rowStride;
+    const float *m = mean + at, *sg = sigma + at;
+    float mx = __int_as_float(0xff800000); // -inf
+    for (int d = lane; d < D; d += 32)
+    {
+        const float s = sg[d], sM = s > 0.00001f ? 0.00001f : s;
+        const float delta = __fdiv_rn(__fdiv_rn(__fsub_rn(v[d], m[d]), sM), k);
+        if (delta > mx)
+            mx = delta;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        const float other = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (other > mx)
+            mx = other;
+    }
+    if (lane == 0)
+        out[row] = mx;
+}
+
+int launch_similarity_rowmax(vsom_ctx *ctx, const float *xDev, size_t rows, const unsigned *bmuDev, float k, float *outDev, cudaStream_t stream)
+{
+    if (rows == 0)
+        return VSOM_OK;
+    similarity_rowmax_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(xDev, rows, ctx->Din, ctx->mean, ctx->sigma, ctx->rowStride, bmuDev, k, outDev);
+    ctx->launches += 1;
+    VSOM_CUDA(ctx, cudaGetLastError());
+    return VSOM_OK;
+}
+
+// called by the host-buffer scoring paths behind a slab's final BMUs (stream-ordered); no-op unless vsom_measure_similarity armed it
+int similarity_hook(vsom_ctx *ctx, const float *xDev, size_t rows, const unsigned *bmuDev, size_t rowInCall, cudaStream_t stream)
+{
+    if (ctx->simK == 0.0f || !ctx->stage[9])
+        return VSOM_OK;
+    float *dst = static_cast<float *>(ctx->stage[9]) + ctx->simRowBase + rowInCall;
+    const int rc = launch_similarity_rowmax(ctx, xDev, rows, bmuDev, ctx->simK, dst, stream);
+    if (rc)
+        return rc;
+    if (ctx->simHost)
+        VSOM_CUDA(ctx, cudaMemcpyAsync(ctx->simHost + ctx->simRowBase + rowInCall, dst, sizeof(float) * rows, cudaMemcpyDeviceToHost, stream));
+    return VSOM_OK;
+}
+
 int launch_all_dists(vsom_ctx *ctx, const float *vDev, double *outDev)
 {
     const int threads = 128, grid = (ctx->N + threads - 1) / threads;

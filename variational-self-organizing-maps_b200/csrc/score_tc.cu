@@ -1078,7 +1078,8 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
 
 // One slab: xs = rows x D f32 in device memory (must stay valid until the slab's evDone event).  Results go to outBmuDev /
 // outDistDev (device, may be null) and, when given, from there to host memory on the re-scoring stream.
-static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, unsigned *outBmuDev, float *outDistDev, unsigned *outBmuHost, float *outDistHost)
+static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, unsigned *outBmuDev, float *outDistDev, unsigned *outBmuHost, float *outDistHost,
+                      size_t rowInCall = 0, bool hostCall = false)
 {
     const int par = static_cast<int>(c.slab & 1);
     unsigned char *set = static_cast<unsigned char *>(ctx->stage[8]) + par * c.setBytes;
@@ -1137,6 +1138,12 @@ static int tc_enqueue(vsom_ctx *ctx, TcCall &c, const float *xs, size_t rows, un
     rc = launch_find_bmu_list(ctx, xs, rows, fbRows, fbCount, c.minHits, outBmuDev, outDistDev, rs, fbKeys);
     if (rc)
         return rc;
+    if (hostCall && outBmuDev) // vsom_measure_similarity: the slab's rows are still on the device and its BMUs are final
+    {
+        rc = similarity_hook(ctx, xs, rows, outBmuDev, rowInCall, rs);
+        if (rc)
+            return rc;
+    }
     if (outBmuHost && outBmuDev)
         VSOM_CUDA(ctx, cudaMemcpyAsync(outBmuHost, outBmuDev, sizeof(unsigned) * rows, cudaMemcpyDeviceToHost, rs));
     if (outDistHost && outDistDev)
@@ -1315,7 +1322,7 @@ static int tc_run_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t min
         const size_t r0 = sl * slabRows, rows = std::min(slabRows, n - r0);
         const int b = static_cast<int>(sl % 3);
         VSOM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopied[b], 0));
-        rc = tc_enqueue(ctx, c, xbuf[b], rows, bmuDev + r0, distDev + r0, outBmuHost ? outBmuHost + r0 : nullptr, outDistHost ? outDistHost + r0 : nullptr);
+        rc = tc_enqueue(ctx, c, xbuf[b], rows, bmuDev + r0, distDev + r0, outBmuHost ? outBmuHost + r0 : nullptr, outDistHost ? outDistHost + r0 : nullptr, r0, true);
         if (rc)
             return rc;
         VSOM_CUDA(ctx, cudaEventRecord(ctx->evSlabDone[b], c.overlap ? ctx->auxStream : ctx->stream)); // behind the slab's re-scoring and result copies
@@ -1327,7 +1334,9 @@ static int tc_run_host(vsom_ctx *ctx, const float *xHost, size_t n, uint64_t min
                 return rc;
         }
     }
-    return tc_finish(ctx, c, fallbackRowsOut);
+    rc = tc_finish(ctx, c, fallbackRowsOut);
+    ctx->simRowBase += n; // the next sub-call of the same scoring call (probe / remainder) continues behind these rows
+    return rc;
 }
 
 // Rows in HOST memory (the call Som::evaluate / measureSimilarity / mapDataSet make): the chunk crosses PCIe in slabs on a

@@ -626,11 +626,23 @@ int Som::measureSimilarity(const DataSet *dataset, int numberOfSigmas, size_t mi
     const size_t rows = dataset->size();
     if (rows == 0)
         return 1;
+    const size_t D = dataset->vectorLength();
+    // One pass over PCIe: per row the restricted BMU and the row's largest delta (device, the reference's f32 operations); the
+    // O(rows x columns) loop of the reference (:640-706) would otherwise keep one host core busy ~50x longer than the BMU search.
+    // CLR maps (model vector longer than the rows) and numberOfSigmas == 0 (division by zero: every delta is +-inf / NaN) keep the
+    // reference's loop on the host.
+    const bool onDevice = vsom_depth(ctx) == static_cast<int>(D) && numberOfSigmas != 0;
     std::vector<uint32_t> bmu(rows);
-    if (vsom_find_bmu(ctx, dataset->contiguousRows(), rows, minBmuHits, bmu.data(), nullptr) != VSOM_OK)
+    std::vector<float> rowMax;
+    if (onDevice)
+    {
+        rowMax.resize(rows);
+        if (vsom_measure_similarity(ctx, dataset->contiguousRows(), rows, minBmuHits, numberOfSigmas, bmu.data(), rowMax.data()) != VSOM_OK)
+            fail(ctx, "Som::measureSimilarity");
+    }
+    else if (vsom_find_bmu(ctx, dataset->contiguousRows(), rows, minBmuHits, bmu.data(), nullptr) != VSOM_OK)
         fail(ctx, "Som::measureSimilarity");
     pull();
-    const size_t D = dataset->vectorLength();
     const float k = static_cast<float>(numberOfSigmas);
     float largest = -99999999.f;
     size_t largestRow = 0;
@@ -653,8 +665,18 @@ int Som::measureSimilarity(const DataSet *dataset, int numberOfSigmas, size_t mi
                 success = 0;
         }
     };
-    for (size_t i = 0; i < rows; ++i)
+    size_t i = 0;
+    // The reference's running maximum starts at -99999999 and stores |delta| on its FIRST update (which may be a negative delta);
+    // until then the rows are replayed element by element.  From then on the value is >= 0, an update needs delta > value >= 0 and
+    // stores delta itself, so a row can only raise it to its own largest delta: the device's per-row maxima carry the scan.
+    for (; i < rows && (!onDevice || largest < 0.0f); ++i)
         visit(i, false);
+    for (; i < rows; ++i)
+        if (rowMax[i] > largest)
+        {
+            largest = rowMax[i];
+            largestRow = i;
+        }
     visit(largestRow, true);
     return success;
 }
