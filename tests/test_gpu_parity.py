@@ -198,7 +198,7 @@ def test_online_step_lanes_order_near_tie_rule(vsom, po, shape):
     ctx.close()
 
 
-@pytest.mark.parametrize("n,N", [(0, 12), (1, 12), (2047, 100), (2048, 400), (2049, 4096), (100000, 16384), (70001, 70000)])
+@pytest.mark.parametrize("n,N", [(0, 12), (1, 12), (2047, 100), (2048, 400), (2049, 4096), (100000, 16384), (300000, 24576), (70001, 70000)])
 def test_build_index(vsom, po, n, N):
     W = N // 4 if N % 4 == 0 else N
     H = N // W

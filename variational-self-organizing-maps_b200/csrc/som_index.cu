@@ -30,6 +30,35 @@ __global__ void index_hist_kernel(const unsigned *__restrict__ bmu, u64 n, int N
     }
 }
 
+// the same histogram with a CTA-private copy in shared memory (maps of up to 24 576 nodes): 16.8 M global 64-bit atomics on 16 384
+// addresses took 313 us (L2 atomic throughput); shared-memory atomics + one flush per CTA and bin do not
+__global__ void __launch_bounds__(1024) index_hist_smem_kernel(const unsigned *__restrict__ bmu, u64 n, int N, u64 *__restrict__ counts, int *__restrict__ bad)
+{
+    extern __shared__ unsigned histS[];
+    for (int k = threadIdx.x; k < N; k += blockDim.x)
+        histS[k] = 0u;
+    __syncthreads();
+    const u64 stride = static_cast<u64>(gridDim.x) * blockDim.x;
+    bool anyBad = false;
+    for (u64 r = static_cast<u64>(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += stride)
+    {
+        const unsigned k = bmu[r];
+        if (k < static_cast<unsigned>(N))
+            atomicAdd(histS + k, 1u);
+        else
+            anyBad = true;
+    }
+    if (anyBad)
+        *bad = 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x)
+    {
+        const unsigned c = histS[k];
+        if (c)
+            atomicAdd(counts + k, static_cast<u64>(c));
+    }
+}
+
 // exclusive scan of counts[N] into offsets[N+1]; one CTA, each thread owns a contiguous run
 __global__ void __launch_bounds__(1024) index_scan_kernel(const u64 *__restrict__ counts, int N, u64 *__restrict__ offsets)
 {
@@ -233,8 +262,18 @@ int launch_build_index(vsom_ctx *ctx, const unsigned *bmuDev, size_t n, u64 *cou
     VSOM_CUDA(ctx, cudaMemsetAsync(ctx->errFlag, 0, sizeof(int), ctx->stream));
     if (n > 0)
     {
-        const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(ctx->numSMs) * 8));
-        index_hist_kernel<<<grid, 256, 0, ctx->stream>>>(bmuDev, n, N, countsDev, ctx->errFlag);
+        const size_t histBytes = sizeof(unsigned) * static_cast<size_t>(N);
+        if (histBytes <= 96 * 1024 && n >= (1u << 16))
+        {
+            // one CTA per SM, each with its own shared-memory histogram (a CTA sees at most n / numSMs + 1024 rows: 32-bit counts)
+            VSOM_CUDA(ctx, cudaFuncSetAttribute(index_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(histBytes)));
+            index_hist_smem_kernel<<<static_cast<unsigned>(ctx->numSMs), 1024, histBytes, ctx->stream>>>(bmuDev, n, N, countsDev, ctx->errFlag);
+        }
+        else
+        {
+            const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(ctx->numSMs) * 8));
+            index_hist_kernel<<<grid, 256, 0, ctx->stream>>>(bmuDev, n, N, countsDev, ctx->errFlag);
+        }
         ctx->launches += 1;
     }
     index_scan_kernel<<<1, 1024, 0, ctx->stream>>>(countsDev, N, offsetsDev);
