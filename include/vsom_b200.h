@@ -208,6 +208,9 @@ VSOM_API int vsom_find_bmu_batch_device(vsom_ctx *ctx, const float *x_dev, size_
  * tier 1 cannot separate the BMU from its neighbours on this map), 3 = both probes (8192 rows each, whose results stand)
  * left more than a quarter of their rows uncertified and the remainder went to the exact scan. */
 VSOM_API int vsom_debug_last_score_tc(const vsom_ctx *ctx);
+/* 1 when that search ran as CTA pairs (tcgen05 cta_group::2, the default wherever the device can co-schedule clusters of two),
+ * 0 for the single-CTA kernel (VSOM_TC_PAIR=0, or a device partition without whole TPCs). */
+VSOM_API int vsom_debug_last_score_pair(const vsom_ctx *ctx);
 /* Why rows of the tensor-core path went to the exact scan, counted since vsom_create: out[0] candidate list overflowed (more
  * than 48 nodes inside the margin), out[1] NaN distance / no eligible candidate, out[2] the certificate could not exclude an
  * unlisted node. */

@@ -327,7 +327,7 @@ def test_tensor_core_single_cta_variant_equals_the_pair_kernel(vsom, monkeypatch
     for pair in ("1", "0"):
         monkeypatch.setenv("VSOM_TC_PAIR", pair)
         tb, td, fb = ctx.find_bmu_batch(q)
-        assert ctx.last_score_tc == int(tier)
+        assert ctx.last_score_tc == int(tier) and ctx.last_score_pair == int(pair)  # a whole B200 schedules clusters of two
         assert_bit_equal(tb, eb, f"bmu, pair={pair}")
         assert_bit_equal(td, ed, f"dist, pair={pair}")
     ctx.close()

@@ -54,6 +54,7 @@ _PROTOS = {
     "vsom_find_bmu_exact": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p]),
     "vsom_find_bmu_exact_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp]),
     "vsom_debug_last_score_tc": (C.c_int, [_vp]),
+    "vsom_debug_last_score_pair": (C.c_int, [_vp]),
     "vsom_debug_tc_stats": (C.c_int, [_vp, _u64p]),
     "vsom_find_bmu_batch": (C.c_int, [_vp, _f32p, C.c_size_t, C.c_uint64, _u32p, _f32p, _u64p]),
     "vsom_find_bmu_batch_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint64, _vp, _vp, _u64p]),
@@ -240,6 +241,11 @@ class VsomContext:
         """0 when the last scoring call ran the exact scan, else the precision tier (1 or 2) of K2 (tcgen05 candidate search +
         exact rescore)."""
         return int(lib().vsom_debug_last_score_tc(self._h))
+
+    @property
+    def last_score_pair(self) -> int:
+        """1 when the last K2 search ran as CTA pairs (cta_group::2), 0 for the single-CTA kernel."""
+        return int(lib().vsom_debug_last_score_pair(self._h))
 
     def tc_stats(self):
         out = np.zeros(3, np.uint64)

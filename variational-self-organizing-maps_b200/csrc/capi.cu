@@ -781,6 +781,7 @@ int vsom_debug_tc_stats(const vsom_ctx *ctx, uint64_t out[3])
 }
 
 int vsom_debug_last_score_tc(const vsom_ctx *ctx) { return ctx ? (ctx->lastScoreTc ? ctx->lastScoreTier : 0) : 0; }
+int vsom_debug_last_score_pair(const vsom_ctx *ctx) { return ctx ? (ctx->lastScoreTc ? ctx->lastScorePair : 0) : 0; }
 
 int vsom_evaluate(vsom_ctx *ctx, const float *x, size_t n, double *mean_error)
 {

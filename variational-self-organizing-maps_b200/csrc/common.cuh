@@ -103,6 +103,8 @@ struct vsom_ctx
     cudaStream_t copyStream = nullptr;          // host-buffer scoring: H2D of slab i + 1 overlaps the search of slab i
     cudaEvent_t evScore[2] = {}, evDone[2] = {}, evCopied[3] = {}, evSlabDone[3] = {}; // evCopied / evSlabDone: per host staging buffer (three)
     int tcAttrSet = 0;                          // K2's dynamic shared-memory opt-in was set on this context's device
+    int tcPairOk = 0;                           // ... and the device can co-schedule a cluster of two K2 CTAs (cta_group::2 kernel)
+    int lastScorePair = 0;                      // the last K2 call ran the CTA-pair kernel
     float *mean = nullptr, *S = nullptr, *sigma = nullptr, *weight = nullptr;
     vsom::u64 *hits = nullptr;
     double *umatrix = nullptr;

@@ -1022,20 +1022,37 @@ static int tc_begin(vsom_ctx *ctx, TcCall &c, size_t maxSlabRows, uint64_t minHi
     tc_scale_kernel<<<1, 1, 0, ctx->stream>>>(c.scale, split);
     map_operand_kernel<<<(c.Npad + 7) / 8, 256, 0, ctx->stream>>>(ctx->mean, mnorm, ctx->hits, minHits, N, c.Npad, D, ctx->rowStride, c.scale, Mb, c.Kpad);
     ctx->launches += 3;
-    // CTA pairs (tcgen05 cta_group::2, the default): each CTA of a pair loads half of a node tile (box of 128 nodes)
-    const char *pairEnv = getenv("VSOM_TC_PAIR"); // read per call: the tests run both variants in one process
-    c.pair = (pairEnv ? atoi(pairEnv) != 0 : true) && ctx->numSMs >= 2;
-    rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, c.pair ? TC_BN / 2 : TC_BN);
-    if (rc)
-        return rc;
-    // function attributes are per device: set it for every context (not once per process)
+    // function attributes are per device: set them for every context (not once per process), and ask once whether the device can
+    // co-schedule a cluster of two of these CTAs (it cannot on a partition without whole TPCs; then the single-CTA kernel runs)
     if (!ctx->tcAttrSet)
     {
         VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShared::TOTAL));
         VSOM_CUDA(ctx, cudaFuncSetAttribute(score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShared::TOTAL));
+        cudaLaunchConfig_t q = {};
+        cudaLaunchAttribute qa[1];
+        q.gridDim = dim3(2);
+        q.blockDim = dim3(TC_THREADS);
+        q.dynamicSmemBytes = TcShared::TOTAL;
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 2;
+        qa[0].val.clusterDim.y = 1;
+        qa[0].val.clusterDim.z = 1;
+        q.attrs = qa;
+        q.numAttrs = 1;
+        int clusters = 0;
+        const cudaError_t qe = cudaOccupancyMaxActiveClusters(&clusters, score_tc_kernel<true>, &q);
+        if (qe != cudaSuccess)
+            cudaGetLastError(); // not an error of the scoring call
+        ctx->tcPairOk = qe == cudaSuccess && clusters >= 1 ? 1 : 0;
         ctx->tcAttrSet = 1;
     }
-
+    // CTA pairs (tcgen05 cta_group::2, the default): each CTA of a pair loads half of a node tile (box of 128 nodes)
+    const char *pairEnv = getenv("VSOM_TC_PAIR"); // read per call: the tests run both variants in one process
+    c.pair = (pairEnv ? atoi(pairEnv) != 0 : true) && ctx->numSMs >= 2 && ctx->tcPairOk;
+    ctx->lastScorePair = c.pair ? 1 : 0;
+    rc = make_map(ctx, &c.mapM, Mb, static_cast<unsigned long long>(c.Npad), c.Kpad, c.pair ? TC_BN / 2 : TC_BN);
+    if (rc)
+        return rc;
     // ---- rows go through in slabs (the fp16 staging buffer: 2.7 GB at K = 256 + 3 for 4M rows).  Two streams: the context's
     // stream converts a slab and runs the tensor-core search; an auxiliary stream re-scores the slab's candidates (and scans
     // the few rows the certificate rejected) while the next slab is already being searched.  Candidate scratch is
