@@ -422,6 +422,8 @@ def test_measure_similarity_row_pass_matches_the_reference_formula(vsom, monkeyp
     both probes, and in one slab — against the same three f32 operations in numpy on the exact scan's BMUs."""
     if slab_log2:
         monkeypatch.setenv("VSOM_TC_HOST_SLAB_LOG2", slab_log2)
+    if n < 1024:
+        monkeypatch.setenv("VSOM_EXACT_HOST_SLAB_LOG2", "7")  # the exact host path in three slabs of 128 rows
     rng = np.random.default_rng(n)
     W, H, D = 24, 20, 48
     centres = (rng.standard_normal((10, D)) * 2).astype(np.float32)

@@ -709,34 +709,42 @@ static int find_bmu_host_impl(vsom_ctx *ctx, const float *x, size_t n, uint64_t 
             *fallback_rows = fb;
         return VSOM_OK;
     }
-    int rc = stage_reserve(ctx, 0, sizeof(float) * n * ctx->Din);
+    // exact scan from host rows, in slabs (a call can be the remainder of a very large batch that the probes took off the
+    // tensor-core path): staging stays bounded, results return per slab
+    const char *slabEnv = getenv("VSOM_EXACT_HOST_SLAB_LOG2"); // test knob
+    const size_t slab = std::min(n, static_cast<size_t>(1) << (slabEnv ? atoi(slabEnv) : 20));
+    int rc = stage_reserve(ctx, 0, sizeof(float) * slab * ctx->Din);
     if (rc)
         return rc;
-    rc = stage_reserve(ctx, 1, sizeof(unsigned) * n);
+    rc = stage_reserve(ctx, 1, sizeof(unsigned) * slab);
     if (rc)
         return rc;
-    rc = stage_reserve(ctx, 2, sizeof(float) * n);
+    rc = stage_reserve(ctx, 2, sizeof(float) * slab);
     if (rc)
         return rc;
     float *xDev = static_cast<float *>(ctx->stage[0]);
     unsigned *bmuDev = static_cast<unsigned *>(ctx->stage[1]);
     float *distDev = static_cast<float *>(ctx->stage[2]);
-    VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x, sizeof(float) * n * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
     if (fallback_rows)
         *fallback_rows = n;
     ctx->lastScoreTc = 0;
-    rc = launch_find_bmu(ctx, xDev, n, min_hits, bmuDev, distDev);
-    if (rc)
-        return rc;
-    rc = similarity_hook(ctx, xDev, n, bmuDev, 0, ctx->stream); // armed by vsom_measure_similarity only
-    if (rc)
-        return rc;
-    ctx->simRowBase += n;
-    if (out_bmu)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(out_bmu, bmuDev, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_dist)
-        VSOM_CUDA(ctx, cudaMemcpyAsync(out_dist, distDev, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t r0 = 0; r0 < n; r0 += slab)
+    {
+        const size_t rows = std::min(slab, n - r0);
+        VSOM_CUDA(ctx, cudaMemcpyAsync(xDev, x + r0 * ctx->Din, sizeof(float) * rows * ctx->Din, cudaMemcpyHostToDevice, ctx->stream));
+        rc = launch_find_bmu(ctx, xDev, rows, min_hits, bmuDev, distDev);
+        if (rc)
+            return rc;
+        rc = similarity_hook(ctx, xDev, rows, bmuDev, 0, ctx->stream); // armed by vsom_measure_similarity only
+        if (rc)
+            return rc;
+        ctx->simRowBase += rows;
+        if (out_bmu)
+            VSOM_CUDA(ctx, cudaMemcpyAsync(out_bmu + r0, bmuDev, sizeof(unsigned) * rows, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_dist)
+            VSOM_CUDA(ctx, cudaMemcpyAsync(out_dist + r0, distDev, sizeof(float) * rows, cudaMemcpyDeviceToHost, ctx->stream));
+        VSOM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the staging buffers are reused by the next slab
+    }
     return VSOM_OK;
 }
 
